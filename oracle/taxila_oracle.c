@@ -1,0 +1,857 @@
+/* taxila_oracle.c -- CPU restatement of Taxila-LBM's flow time step.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under taxila-lbm_b200/ links, loads or calls
+ * this file; it is the checker for the CUDA path (tests/, __graft_entry__.smoke(),
+ * and the cpu_baseline / --impl reference legs of bench.py).
+ *
+ * It follows the reference's algorithm in the reference's own structure:
+ * array-of-structures fields with PETSc-DMDA style ghost layers, one full sweep
+ * per phase, a full-size streaming temporary, push streaming followed by a
+ * bounce-back sweep over the ghosted box.  Every function cites the reference
+ * file:line it restates (paths relative to the reference tree).  No reference
+ * source is copied: the Fortran is restated in C, and the fluid-fluid stencil
+ * rows are numbers extracted by oracle/gen_stencil_tables.py.
+ *
+ * Parity pinning: tests/test_oracle_golden.py checks this oracle against the
+ * reference's shipped golden vector tests/bubble_2D/reference_solution/fi001.dat
+ * (committed copy: tests/golden/bubble_2D_fi001.f64be) -- D2Q9/SRT/iso-4 directly,
+ * the MRT tables through MRT(all rates 1) == SRT, and the D3Q19 tables through a
+ * z-invariant extrusion projected onto the same golden.  D3Q19 MRT with general
+ * rates, iso-8/10, walls, minerals and body force have no golden in the
+ * reference ("parity unpinned" for those features).
+ *
+ * Floating point: compile with -ffp-contract=off and without -ffast-math so the
+ * evaluation order below is the one executed.  Default-real Fortran literals
+ * that are NOT exactly representable are reproduced as float constants
+ * (1./6., 1./12., 1./3. in the fluid-solid force, 1.e-12 for eps).
+ *
+ * Layout (first index fastest, as in lbm_flow.F90:963-970):
+ *   fi    [S][Q][gx][gy][gz]      ghost width 1
+ *   rho   [S][rgx][rgy][rgz]      ghost width R = stencil_size_rho
+ *   flux, forces [S][D][gx][gy][gz]
+ *   walls [rgx][rgy][rgz]         doubles holding small integers
+ * For ndims == 2 the z extent is 1 with no z ghost.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/taxila_gpu.h"
+#include "ff_stencil_tables.h"
+
+#define MAXQ 19
+#define MAXS TXG_NMAX_COMPONENTS
+
+typedef struct txo_state {
+  txg_config cfg;
+  int D, Q, S, R;
+  int NX, NY, NZ;
+  int gz;  /* ghost width in z for "g" arrays: 1 (3-D) or 0 (2-D) */
+  int rgz; /* ghost width in z for "rg" arrays: R or 0 */
+  int gnx, gny, gnz;    /* ghosted extents, width 1 */
+  int rgnx, rgny, rgnz; /* ghosted extents, width R */
+  /* lattice (lbm_discretization_d3q19.F90:64-232, lbm_discretization_d2q9.F90:53-144) */
+  int ci[MAXQ][3];
+  double weights[MAXQ];
+  int opposites[MAXQ], reflect[3][MAXQ];
+  double mt_mrt[MAXQ][MAXQ]; /* mt_mrt[n][i] = M(n, i): row n of M */
+  double mmt_mrt[MAXQ];
+  double ffw[41];
+  double c_0;
+  /* per component */
+  double tau_mrt[MAXS][MAXQ];
+  double d_k[MAXS], c_s2[MAXS], s_c[MAXS];
+  /* fields */
+  double *fi, *fi_eq, *rho, *psi, *flux, *forces, *walls, *stream_tmp;
+  double *fi_old; /* DistributionCalcDeltaNorm */
+  int have_old;
+  int threads; /* 1 = literal serial order everywhere */
+} txo_state;
+
+/* ---------------------------------------------------------------- indexing */
+static inline size_t gnode(const txo_state *s, int i, int j, int k) {
+  return ((size_t)(k + s->gz) * s->gny + (size_t)(j + 1)) * s->gnx + (size_t)(i + 1);
+}
+static inline size_t rgnode(const txo_state *s, int i, int j, int k) {
+  return ((size_t)(k + s->rgz) * s->rgny + (size_t)(j + s->R)) * s->rgnx + (size_t)(i + s->R);
+}
+#define FI(s, m, n, i, j, k) ((s)->fi[gnode(s, i, j, k) * (size_t)((s)->S * (s)->Q) + (size_t)(n) * (s)->S + (m)])
+#define FEQ(s, m, n, i, j, k) ((s)->fi_eq[gnode(s, i, j, k) * (size_t)((s)->S * (s)->Q) + (size_t)(n) * (s)->S + (m)])
+#define RHO(s, m, i, j, k) ((s)->rho[rgnode(s, i, j, k) * (size_t)(s)->S + (m)])
+#define PSI(s, m, i, j, k) ((s)->psi[rgnode(s, i, j, k) * (size_t)(s)->S + (m)])
+#define FLUX(s, m, d, i, j, k) ((s)->flux[gnode(s, i, j, k) * (size_t)((s)->S * (s)->D) + (size_t)(d) * (s)->S + (m)])
+#define FRC(s, m, d, i, j, k) ((s)->forces[gnode(s, i, j, k) * (size_t)((s)->S * (s)->D) + (size_t)(d) * (s)->S + (m)])
+#define WALLS(s, i, j, k) ((s)->walls[rgnode(s, i, j, k)])
+
+/* ---------------------------------------------------------------- lattices */
+/* DiscretizationSetup_D3Q19, lbm_discretization_d3q19.F90:64-232 */
+static void setup_d3q19(txo_state *s) {
+  static const int cx[19] = {0, 1, 0, -1, 0, 0, 0, 1, -1, -1, 1, 1, -1, -1, 1, 0, 0, 0, 0};
+  static const int cy[19] = {0, 0, 1, 0, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, -1, 1};
+  static const int cz[19] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1};
+  static const int M[19][19] = {
+      {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1},
+      {-30, -11, -11, -11, -11, -11, -11, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8},
+      {12, -4, -4, -4, -4, -4, -4, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1},
+      {0, 1, 0, -1, 0, 0, 0, 1, -1, -1, 1, 1, -1, -1, 1, 0, 0, 0, 0},
+      {0, -4, 0, 4, 0, 0, 0, 1, -1, -1, 1, 1, -1, -1, 1, 0, 0, 0, 0},
+      {0, 0, 1, 0, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, -1, 1},
+      {0, 0, -4, 0, 4, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, -1, 1},
+      {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1},
+      {0, 0, 0, 0, 0, -4, 4, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1},
+      {0, 2, -1, 2, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, 1, -2, -2, -2, -2},
+      {0, -4, 2, -4, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, -2, -2, -2, -2},
+      {0, 0, 1, 0, 1, -1, -1, 1, 1, 1, 1, -1, -1, -1, -1, 0, 0, 0, 0},
+      {0, 0, -2, 0, -2, 2, 2, 1, 1, 1, 1, -1, -1, -1, -1, 0, 0, 0, 0},
+      {0, 0, 0, 0, 0, 0, 0, 1, -1, 1, -1, 0, 0, 0, 0, 0, 0, 0, 0},
+      {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, -1, 1, -1},
+      {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, -1, 1, -1, 0, 0, 0, 0},
+      {0, 0, 0, 0, 0, 0, 0, 1, -1, -1, 1, -1, 1, 1, -1, 0, 0, 0, 0},
+      {0, 0, 0, 0, 0, 0, 0, -1, -1, 1, 1, 0, 0, 0, 0, 1, -1, -1, 1},
+      {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, -1, -1, -1, -1, 1, 1}};
+  static const int mmt[19] = {19, 2394, 252, 10, 40, 10, 40, 10, 40, 36, 72, 12, 24, 4, 4, 4, 8, 8, 8};
+  s->Q = 19;
+  s->D = 3;
+  for (int n = 0; n < 19; ++n) {
+    s->ci[n][0] = cx[n];
+    s->ci[n][1] = cy[n];
+    s->ci[n][2] = cz[n];
+    s->weights[n] = n == 0 ? 1.0 / 3.0 : (n <= 6 ? 1.0 / 18.0 : 1.0 / 36.0);
+    s->mmt_mrt[n] = mmt[n];
+    for (int i = 0; i < 19; ++i) s->mt_mrt[n][i] = M[n][i];
+  }
+  s->c_0 = 6.0;
+  memset(s->ffw, 0, sizeof s->ffw);
+  if (s->cfg.isotropy_order == 4) {
+    s->ffw[1] = 1.0 / 6.;
+    s->ffw[2] = 1.0 / 12.;
+  } else if (s->cfg.isotropy_order == 8) {
+    s->ffw[1] = 4.0 / 45.;
+    s->ffw[2] = 1.0 / 21.;
+    s->ffw[3] = 2.0 / 105.;
+    s->ffw[4] = 5.0 / 504.;
+    s->ffw[5] = 1.0 / 315.;
+    s->ffw[6] = 1.0 / 630.;
+    s->ffw[8] = 1.0 / 5040.;
+  }
+}
+
+/* DiscretizationSetUp_D2Q9, lbm_discretization_d2q9.F90:53-144 */
+static void setup_d2q9(txo_state *s) {
+  static const int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+  static const int cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+  static const int M[9][9] = {{1, 1, 1, 1, 1, 1, 1, 1, 1},     {-4, -1, -1, -1, -1, 2, 2, 2, 2},
+                              {4, -2, -2, -2, -2, 1, 1, 1, 1}, {0, 1, 0, -1, 0, 1, -1, -1, 1},
+                              {0, -2, 0, 2, 0, 1, -1, -1, 1},  {0, 0, 1, 0, -1, 1, 1, -1, -1},
+                              {0, 0, -2, 0, 2, 1, 1, -1, -1},  {0, 1, -1, 1, -1, 0, 0, 0, 0},
+                              {0, 0, 0, 0, 0, 1, -1, 1, -1}};
+  static const int mmt[9] = {9, 36, 36, 6, 12, 6, 12, 4, 4};
+  s->Q = 9;
+  s->D = 2;
+  for (int n = 0; n < 9; ++n) {
+    s->ci[n][0] = cx[n];
+    s->ci[n][1] = cy[n];
+    s->ci[n][2] = 0;
+    s->weights[n] = n == 0 ? 4.0 / 9.0 : (n <= 4 ? 1.0 / 9.0 : 1.0 / 36.0);
+    s->mmt_mrt[n] = mmt[n];
+    for (int i = 0; i < 9; ++i) s->mt_mrt[n][i] = M[n][i];
+  }
+  s->c_0 = 6.0;
+  memset(s->ffw, 0, sizeof s->ffw);
+  if (s->cfg.isotropy_order == 4) {
+    s->ffw[1] = 1.0 / 3.;
+    s->ffw[2] = 1.0 / 12.;
+  } else if (s->cfg.isotropy_order == 8) {
+    s->ffw[1] = 4.0 / 21.;
+    s->ffw[2] = 4.0 / 45.;
+    s->ffw[4] = 1.0 / 60.;
+    s->ffw[5] = 2.0 / 315.;
+    s->ffw[8] = 1.0 / 5040.;
+  } else if (s->cfg.isotropy_order == 10) {
+    s->ffw[1] = 262.0 / 1785.;
+    s->ffw[2] = 93.0 / 1190.;
+    s->ffw[4] = 7.0 / 340.;
+    s->ffw[5] = 6.0 / 595.;
+    s->ffw[8] = 9.0 / 9520.;
+    s->ffw[9] = 2.0 / 5355.;
+    s->ffw[10] = 1.0 / 7140.;
+  }
+}
+
+/* opposites / reflect_{x,y,z}: the reference spells them out direction by direction
+ * (lbm_discretization_d3q19.F90:83-161, lbm_discretization_d2q9.F90:68-97); they are
+ * exactly "negate all / one component of c_n", which is what is computed here. */
+static int find_dir(const txo_state *s, int x, int y, int z) {
+  for (int n = 0; n < s->Q; ++n)
+    if (s->ci[n][0] == x && s->ci[n][1] == y && s->ci[n][2] == z) return n;
+  return -1;
+}
+static void setup_permutations(txo_state *s) {
+  for (int n = 0; n < s->Q; ++n) {
+    const int *c = s->ci[n];
+    s->opposites[n] = find_dir(s, -c[0], -c[1], -c[2]);
+    s->reflect[0][n] = find_dir(s, -c[0], c[1], c[2]);
+    s->reflect[1][n] = find_dir(s, c[0], -c[1], c[2]);
+    s->reflect[2][n] = find_dir(s, c[0], c[1], -c[2]);
+  }
+}
+
+/* DiscretizationSetupRelax_D3Q19 (lbm_discretization_d3q19.F90:234-263),
+ * DiscretizationSetUpRelax_D2Q9 (lbm_discretization_d2q9.F90:147-166),
+ * RelaxationSetFromOptions (lbm_relaxation.F90:117-151),
+ * ComponentSetFromOptions d_k (lbm_component.F90:158) */
+static void setup_relaxation(txo_state *s) {
+  const txg_config *c = &s->cfg;
+  for (int m = 0; m < s->S; ++m) {
+    s->c_s2[m] = 1.0 / 3.;
+    s->d_k[m] = 1. - 2. / (3. * c->mm[m]);
+    if (c->relaxation_mode == TXG_RELAXATION_MODE_SRT)
+      s->s_c[m] = 1.0 / c->tau[m];
+    else
+      s->s_c[m] = c->s_c[m];
+    double *t = s->tau_mrt[m];
+    if (s->D == 3) {
+      const double r[19] = {c->s_c[m],  c->s_e[m],  c->s_e2[m], c->s_c[m],  c->s_q[m],  c->s_c[m], c->s_q[m],
+                            c->s_c[m],  c->s_q[m],  c->s_nu[m], c->s_pi[m], c->s_nu[m], c->s_pi[m], c->s_nu[m],
+                            c->s_nu[m], c->s_nu[m], c->s_m[m],  c->s_m[m],  c->s_m[m]};
+      memcpy(t, r, sizeof r);
+    } else {
+      const double r[9] = {c->s_c[m], c->s_e[m], c->s_e2[m], c->s_c[m], c->s_q[m],
+                           c->s_c[m], c->s_q[m], c->s_nu[m], c->s_nu[m]};
+      memcpy(t, r, sizeof r);
+    }
+  }
+}
+
+/* ---------------------------------------------------------------- lifecycle */
+txo_state *txo_create(const txg_config *cfg) {
+  if (!cfg || cfg->struct_bytes != (int32_t)sizeof(txg_config)) return NULL;
+  txo_state *s = (txo_state *)calloc(1, sizeof *s);
+  s->cfg = *cfg;
+  s->S = cfg->ncomponents;
+  s->R = cfg->stencil_size_rho;
+  s->NX = cfg->NX;
+  s->NY = cfg->NY;
+  s->NZ = cfg->ndims == 3 ? cfg->NZ : 1;
+  if (cfg->discretization == TXG_D3Q19_DISCRETIZATION)
+    setup_d3q19(s);
+  else
+    setup_d2q9(s);
+  setup_permutations(s);
+  setup_relaxation(s);
+  s->gz = s->D == 3 ? 1 : 0;
+  s->rgz = s->D == 3 ? s->R : 0;
+  s->gnx = s->NX + 2;
+  s->gny = s->NY + 2;
+  s->gnz = s->NZ + 2 * s->gz;
+  s->rgnx = s->NX + 2 * s->R;
+  s->rgny = s->NY + 2 * s->R;
+  s->rgnz = s->NZ + 2 * s->rgz;
+  size_t ng = (size_t)s->gnx * s->gny * s->gnz, nrg = (size_t)s->rgnx * s->rgny * s->rgnz;
+  /* PETSc Vecs start zeroed (VecSet in WallsSetUp lbm_walls.F90:146-147; local
+   * vectors from DMCreateLocalVector are zero-filled) */
+  s->fi = (double *)calloc(ng * s->S * s->Q, sizeof(double));
+  s->fi_eq = (double *)calloc(ng * s->S * s->Q, sizeof(double));
+  s->stream_tmp = (double *)calloc(ng * s->S * s->Q, sizeof(double));
+  s->rho = (double *)calloc(nrg * s->S, sizeof(double));
+  s->psi = (double *)calloc(nrg * s->S, sizeof(double));
+  s->flux = (double *)calloc(ng * s->S * s->D, sizeof(double));
+  s->forces = (double *)calloc(ng * s->S * s->D, sizeof(double));
+  s->walls = (double *)calloc(nrg, sizeof(double));
+  s->fi_old = NULL;
+  s->threads = 1;
+  return s;
+}
+
+void txo_destroy(txo_state *s) {
+  if (!s) return;
+  free(s->fi);
+  free(s->fi_eq);
+  free(s->stream_tmp);
+  free(s->rho);
+  free(s->psi);
+  free(s->flux);
+  free(s->forces);
+  free(s->walls);
+  free(s->fi_old);
+  free(s);
+}
+
+void txo_set_threads(txo_state *s, int n) {
+  s->threads = n < 1 ? 1 : n;
+#ifdef _OPENMP
+  omp_set_num_threads(s->threads);
+#endif
+}
+
+/* ---------------------------------------------------------------- ghost exchange
+ * DMLocalToLocalBegin/End on a DMDA with a box stencil of width w, single rank:
+ * a ghost entry is overwritten by its periodic image iff every out-of-range
+ * coordinate lies in a DM_BOUNDARY_PERIODIC direction; ghosts beyond a
+ * DM_BOUNDARY_GHOSTED face are left alone (lbm_grid.F90:150-157). */
+static void local_to_local(const txo_state *s, double *a, int dof, int w, int wz) {
+  const int NX = s->NX, NY = s->NY, NZ = s->NZ;
+  const int nx = NX + 2 * w, ny = NY + 2 * w;
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+  for (int k = -wz; k < NZ + wz; ++k)
+    for (int j = -w; j < NY + w; ++j)
+      for (int i = -w; i < NX + w; ++i) {
+        int oi = i < 0 || i >= NX, oj = j < 0 || j >= NY, ok = k < 0 || k >= NZ;
+        if (!(oi || oj || ok)) continue;
+        if ((oi && !s->cfg.periodic[0]) || (oj && !s->cfg.periodic[1]) || (ok && !s->cfg.periodic[2])) continue;
+        int si = ((i % NX) + NX) % NX, sj = ((j % NY) + NY) % NY, sk = ((k % NZ) + NZ) % NZ;
+        size_t dst = ((size_t)(k + wz) * ny + (size_t)(j + w)) * nx + (size_t)(i + w);
+        size_t src = ((size_t)(sk + wz) * ny + (size_t)(sj + w)) * nx + (size_t)(si + w);
+        memcpy(a + dst * dof, a + src * dof, sizeof(double) * (size_t)dof);
+      }
+}
+/* DistributionCommunicateFi, lbm_distribution_function.F90:309-334 */
+static void communicate_fi(txo_state *s) { local_to_local(s, s->fi, s->S * s->Q, 1, s->gz); }
+/* DistributionCommunicateDensityBegin/End, lbm_distribution_function.F90:342-357 */
+static void communicate_density(txo_state *s) { local_to_local(s, s->rho, s->S, s->R, s->rgz); }
+
+/* WallsSetGhostNodesD2/D3 (lbm_walls.F90:190-231) then WallsCommunicate (:233-244).
+ * `walls_natural` is the global Vec in natural ordering (x fastest). */
+void txo_set_walls(txo_state *s, const double *walls_natural) {
+  const int NX = s->NX, NY = s->NY, NZ = s->NZ, R = s->R, RZ = s->rgz;
+  for (int k = 0; k < NZ; ++k)
+    for (int j = 0; j < NY; ++j)
+      for (int i = 0; i < NX; ++i) WALLS(s, i, j, k) = walls_natural[((size_t)k * NY + j) * NX + i];
+  for (int k = -RZ; k < NZ + RZ; ++k)
+    for (int j = -R; j < NY + R; ++j)
+      for (int i = -R; i < NX + R; ++i) {
+        int ghost = 0;
+        if ((i < 0 || i >= NX) && !s->cfg.periodic[0]) ghost = 1;
+        if ((j < 0 || j >= NY) && !s->cfg.periodic[1]) ghost = 1;
+        if (s->D == 3 && (k < 0 || k >= NZ) && !s->cfg.periodic[2]) ghost = 1;
+        if (ghost) WALLS(s, i, j, k) = TXG_WALL_GHOST;
+      }
+  local_to_local(s, s->walls, 1, R, RZ);
+}
+
+/* the ghosted walls array as the Fortran side would hold it */
+void txo_get_walls_rg(const txo_state *s, double *out) {
+  memcpy(out, s->walls, sizeof(double) * (size_t)s->rgnx * s->rgny * s->rgnz);
+}
+
+/* LBMInitializeState (lbm.F90:444-453): rho from natural order [node][m], u = 0 */
+void txo_set_rho(txo_state *s, const double *rho_natural) {
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i)
+        for (int m = 0; m < s->S; ++m)
+          RHO(s, m, i, j, k) = rho_natural[(((size_t)k * s->NY + j) * s->NX + i) * s->S + m];
+  memset(s->flux, 0, sizeof(double) * (size_t)s->gnx * s->gny * s->gnz * s->S * s->D);
+}
+
+void txo_set_fi(txo_state *s, const double *fi_natural) {
+  const int SQ = s->S * s->Q;
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i)
+        memcpy(&FI(s, 0, 0, i, j, k), fi_natural + (((size_t)k * s->NY + j) * s->NX + i) * SQ, sizeof(double) * SQ);
+}
+
+/* ---------------------------------------------------------------- equilibrium
+ * DiscretizationEquilf_D3Q19 (lbm_discretization_d3q19.F90:265-305),
+ * DiscretizationEquilf_D2Q9 (lbm_discretization_d2q9.F90:168-205),
+ * driver FlowUpdateFeq (lbm_flow.F90:822-834). */
+static void update_feq(txo_state *s) {
+  const int D = s->D, Q = s->Q;
+  for (int m = 0; m < s->S; ++m) {
+    const double d_k = s->d_k[m], c_s2 = s->c_s2[m];
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+    for (int k = 0; k < s->NZ; ++k)
+      for (int j = 0; j < s->NY; ++j)
+        for (int i = 0; i < s->NX; ++i) {
+          if (WALLS(s, i, j, k) != 0.) continue;
+          double usqr = 0.;
+          for (int d = 0; d < D; ++d) usqr += FLUX(s, m, d, i, j, k) * FLUX(s, m, d, i, j, k);
+          const double rho = RHO(s, m, i, j, k);
+          if (D == 3)
+            FEQ(s, m, 0, i, j, k) = rho * (d_k - usqr / 2.);
+          else
+            FEQ(s, m, 0, i, j, k) = rho * ((1. + d_k * 5.) / 6. - 2. * usqr / 3.);
+          for (int n = 1; n < Q; ++n) {
+            double udote = 0.;
+            for (int d = 0; d < D; ++d) udote += s->ci[n][d] * FLUX(s, m, d, i, j, k);
+            FEQ(s, m, n, i, j, k) =
+                s->weights[n] * rho *
+                (1.5 * (1. - d_k) + udote / c_s2 + udote * udote / (2. * c_s2 * c_s2) - usqr / (2. * c_s2));
+          }
+        }
+  }
+}
+
+/* FlowFiBarEqPrefactor, lbm_flow.F90:836-851 */
+static void prefactor_node(const txo_state *s, int i, int j, int k, double pref[MAXS][MAXQ]) {
+  for (int n = 0; n < s->Q; ++n)
+    for (int m = 0; m < s->S; ++m) {
+      double acc = 0.;
+      for (int d = 0; d < s->D; ++d) acc += FRC(s, m, d, i, j, k) * (s->ci[n][d] - FLUX(s, m, d, i, j, k));
+      pref[m][n] = acc / (RHO(s, m, i, j, k) * s->c_s2[m]);
+    }
+}
+
+/* RelaxationCollideSRT (lbm_relaxation.F90:171-180), RelaxationCollideMRT (:182-200) */
+static void relaxation_collide(const txo_state *s, int m, double f[MAXS][MAXQ], double feqbar[MAXS][MAXQ]) {
+  const int Q = s->Q;
+  if (s->cfg.relaxation_mode == TXG_RELAXATION_MODE_SRT) {
+    const double tau = s->cfg.tau[m];
+    for (int n = 0; n < Q; ++n) f[m][n] = f[m][n] - (f[m][n] - feqbar[m][n]) / tau;
+  } else {
+    double d_fi[MAXQ];
+    for (int n = 0; n < Q; ++n) d_fi[n] = f[m][n] - feqbar[m][n];
+    for (int n = 0; n < Q; ++n) {
+      double mdiff = 0.;
+      for (int i = 0; i < Q; ++i) mdiff += s->mt_mrt[n][i] * d_fi[i];
+      for (int i = 0; i < Q; ++i) f[m][i] = f[m][i] - s->tau_mrt[m][n] * mdiff / s->mmt_mrt[n] * s->mt_mrt[n][i];
+    }
+  }
+}
+
+/* FlowCollision -> FlowCollisionD3/D2, lbm_flow.F90:936-1029 */
+static void flow_collision(txo_state *s) {
+  update_feq(s);
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i) {
+        if (WALLS(s, i, j, k) != 0.) continue;
+        double pref[MAXS][MAXQ], f[MAXS][MAXQ], feqbar[MAXS][MAXQ];
+        prefactor_node(s, i, j, k, pref);
+        for (int m = 0; m < s->S; ++m)
+          for (int n = 0; n < s->Q; ++n) {
+            f[m][n] = FI(s, m, n, i, j, k);
+            feqbar[m][n] = (1. - .5 * pref[m][n]) * FEQ(s, m, n, i, j, k);
+          }
+        for (int m = 0; m < s->S; ++m) relaxation_collide(s, m, f, feqbar);
+        for (int m = 0; m < s->S; ++m)
+          for (int n = 0; n < s->Q; ++n) FI(s, m, n, i, j, k) = f[m][n] + pref[m][n] * FEQ(s, m, n, i, j, k);
+      }
+}
+
+/* ---------------------------------------------------------------- streaming
+ * DistributionStreamD3/D2, lbm_distribution_function.F90:560-652.  The reference
+ * streams into an uninitialised automatic array and copies it back; entries it
+ * never writes are garbage.  They are NaN here so that any dependence on them
+ * would poison the result and fail the golden comparison. */
+static void stream(txo_state *s) {
+  const int S = s->S, Q = s->Q, SQ = S * Q;
+  const size_t ng = (size_t)s->gnx * s->gny * s->gnz;
+  double *tmp = s->stream_tmp;
+  const double qnan = NAN;
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+  for (size_t a = 0; a < ng * SQ; ++a) tmp[a] = qnan;
+  for (int n = 0; n < Q; ++n) {
+    const int cx = s->ci[n][0], cy = s->ci[n][1], cz = s->ci[n][2];
+    /* destination box = owned box extended by one cell along +c_n */
+    int xs = 0, xe = s->NX - 1, ys = 0, ye = s->NY - 1, zs = 0, ze = s->NZ - 1;
+    if (cx < 0) xs += cx; else if (cx > 0) xe += cx;
+    if (cy < 0) ys += cy; else if (cy > 0) ye += cy;
+    if (cz < 0) zs += cz; else if (cz > 0) ze += cz;
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+    for (int k = zs; k <= ze; ++k)
+      for (int j = ys; j <= ye; ++j)
+        for (int i = xs; i <= xe; ++i) {
+          const double *src = &FI(s, 0, n, i - cx, j - cy, k - cz);
+          double *dst = tmp + gnode(s, i, j, k) * SQ + (size_t)n * S;
+          for (int m = 0; m < S; ++m) dst[m] = src[m];
+        }
+  }
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+  for (size_t a = 0; a < ng * SQ; ++a) s->fi[a] = tmp[a];
+}
+
+/* DistributionBouncebackD3/D2, lbm_distribution_function.F90:669-784: literal
+ * serial sweep over the ghosted (width 1) box in k, j, i order. */
+static inline int owned(const txo_state *s, int i, int j, int k) {
+  return i >= 0 && i < s->NX && j >= 0 && j < s->NY && k >= 0 && k < s->NZ;
+}
+static void bounceback_node(txo_state *s, int i, int j, int k, int zero) {
+  const double w = WALLS(s, i, j, k);
+  const int S = s->S, Q = s->Q;
+  if (!(w > 0)) return;
+  int axis = -1;
+  if (w == TXG_WALL_NORMAL_X) axis = 0;
+  else if (w == TXG_WALL_NORMAL_Y) axis = 1;
+  else if (w == TXG_WALL_NORMAL_Z && s->D == 3) axis = 2;
+  if (zero != 1) {
+    for (int n = 0; n < Q; ++n) {
+      int ni = i, nj = j, nk = k, nn;
+      if (axis < 0) {
+        ni = i - s->ci[n][0];
+        nj = j - s->ci[n][1];
+        nk = k - s->ci[n][2];
+        nn = s->opposites[n];
+      } else {
+        if (axis == 0) ni = i - s->ci[n][0];
+        if (axis == 1) nj = j - s->ci[n][1];
+        if (axis == 2) nk = k - s->ci[n][2];
+        nn = s->reflect[axis][n];
+      }
+      if (owned(s, ni, nj, nk))
+        for (int m = 0; m < S; ++m) FI(s, m, nn, ni, nj, nk) = FI(s, m, n, i, j, k);
+    }
+  }
+  if (zero != 0)
+    for (int a = 0; a < S * Q; ++a) (&FI(s, 0, 0, i, j, k))[a] = 0.;
+}
+static void bounceback(txo_state *s) {
+  const int gz = s->gz;
+  if (s->threads <= 1) {
+    for (int k = -gz; k < s->NZ + gz; ++k)
+      for (int j = -1; j <= s->NY; ++j)
+        for (int i = -1; i <= s->NX; ++i) bounceback_node(s, i, j, k, 2);
+  } else {
+    /* timing variant: all pushes, then all zeroing.  Identical to the serial sweep
+     * whenever solid nodes hold f = 0 on entry (true for every state the flow
+     * update itself produces) and no 900-902 codes are present; checked in
+     * tests/test_oracle_selfchecks.py. */
+#pragma omp parallel for schedule(static)
+    for (int k = -gz; k < s->NZ + gz; ++k)
+      for (int j = -1; j <= s->NY; ++j)
+        for (int i = -1; i <= s->NX; ++i) bounceback_node(s, i, j, k, 0);
+#pragma omp parallel for schedule(static)
+    for (int k = -gz; k < s->NZ + gz; ++k)
+      for (int j = -1; j <= s->NY; ++j)
+        for (int i = -1; i <= s->NX; ++i) bounceback_node(s, i, j, k, 1);
+  }
+}
+
+/* ---------------------------------------------------------------- moments */
+/* DistributionCalcDensityD3/D2, lbm_distribution_function.F90:379-428 */
+static void calc_density(txo_state *s) {
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i)
+        for (int m = 0; m < s->S; ++m) {
+          double acc = 0.;
+          if (WALLS(s, i, j, k) == 0.)
+            for (int n = 0; n < s->Q; ++n) acc += FI(s, m, n, i, j, k);
+          RHO(s, m, i, j, k) = acc;
+        }
+}
+
+/* DistributionCalcFluxD3/D2, lbm_distribution_function.F90:451-508 */
+static void calc_flux_into(const txo_state *s, double *flux) {
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i)
+        for (int m = 0; m < s->S; ++m)
+          for (int d = 0; d < s->D; ++d) {
+            double acc = 0.;
+            if (WALLS(s, i, j, k) == 0.)
+              for (int n = 0; n < s->Q; ++n) acc += FI(s, m, n, i, j, k) * (double)s->ci[n][d];
+            flux[gnode(s, i, j, k) * (size_t)(s->S * s->D) + (size_t)d * s->S + m] = acc;
+          }
+}
+
+/* FlowUpdateUED3/D2, lbm_flow.F90:494-574 */
+static void update_ue(txo_state *s) {
+  double mmot[MAXS];
+  for (int m = 0; m < s->S; ++m) mmot[m] = s->cfg.mm[m] * s->s_c[m];
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i) {
+        if (WALLS(s, i, j, k) != 0.) continue;
+        double up[3];
+        for (int d = 0; d < s->D; ++d)
+          for (int m = 0; m < s->S; ++m) FLUX(s, m, d, i, j, k) = FLUX(s, m, d, i, j, k) + .5 * FRC(s, m, d, i, j, k);
+        for (int d = 0; d < s->D; ++d) {
+          double num = 0., den = 0.;
+          for (int m = 0; m < s->S; ++m) num += FLUX(s, m, d, i, j, k) * mmot[m];
+          for (int m = 0; m < s->S; ++m) den += RHO(s, m, i, j, k) * mmot[m];
+          up[d] = num / den;
+        }
+        for (int m = 0; m < s->S; ++m)
+          for (int d = 0; d < s->D; ++d) FLUX(s, m, d, i, j, k) = up[d];
+      }
+}
+
+/* ---------------------------------------------------------------- forces */
+/* EOSApply_Rho / EOSApply_SC, lbm_eos.F90:183-229 (whole ghosted array) */
+static void eos_apply(txo_state *s) {
+  const size_t nrg = (size_t)s->rgnx * s->rgny * s->rgnz;
+  for (int m = 0; m < s->S; ++m) {
+    const int type = s->cfg.eos_type[m];
+    const double rho0 = s->cfg.eos_rho0[m];
+    for (size_t a = 0; a < nrg; ++a) {
+      const double r = s->rho[a * s->S + m];
+      s->psi[a * s->S + m] = type == TXG_EOS_SC ? rho0 * (1. - exp(-r / rho0)) : r;
+    }
+  }
+}
+
+/* LBMAddFluidSolidForcesD3/D2, lbm_forcing.F90:1326-1421 (+ the neighbour gather
+ * DistributionGatherValueToDirectionD*, lbm_distribution_function.F90:525-542,786-807).
+ * 1./6., 1./12., 1./3. are default-real (single precision) literals there.
+ * Codes >= nminerals+1 below 998 (800, 900-902) index minerals(:) out of bounds in
+ * the reference; they contribute nothing here. */
+static void add_fluid_solid(txo_state *s) {
+  const float w_axis_f = s->D == 3 ? 1.f / 6.f : 1.f / 3.f;
+  const float w_diag_f = 1.f / 12.f;
+  const int naxis = 2 * s->D;
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i) {
+        if (WALLS(s, i, j, k) != 0.) continue;
+        for (int n = 1; n < s->Q; ++n) {
+          const double t = WALLS(s, i + s->ci[n][0], j + s->ci[n][1], k + s->ci[n][2]);
+          if (!(t > 0. && t < 998.)) continue;
+          const int mineral = (int)t;
+          if (mineral > s->cfg.nminerals) continue;
+          const double w = n <= naxis ? (double)w_axis_f : (double)w_diag_f;
+          for (int d = 0; d < s->D; ++d)
+            for (int m = 0; m < s->S; ++m)
+              FRC(s, m, d, i, j, k) =
+                  FRC(s, m, d, i, j, k) - w * RHO(s, m, i, j, k) * s->cfg.gw[mineral - 1][m] * s->ci[n][d];
+        }
+      }
+}
+
+/* LBMAddBodyForcesD3/D2, lbm_forcing.F90:1440-1496 */
+static void add_body(txo_state *s) {
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i) {
+        if (WALLS(s, i, j, k) != 0.) continue;
+        for (int m = 0; m < s->S; ++m)
+          for (int d = 0; d < s->D; ++d)
+            FRC(s, m, d, i, j, k) = FRC(s, m, d, i, j, k) + s->cfg.gvt[d] * s->cfg.mm[m] * RHO(s, m, i, j, k);
+      }
+}
+
+/* LBMAddFluidFluidForcesD3 (lbm_forcing.F90:51-958) / D2 (:960-1299).  One BLOCK
+ * row per `if (walls...) then` block of the reference, in source order. */
+static void add_fluid_fluid(txo_state *s, const double *field /* rho or psi, rg layout */) {
+  const int S = s->S, D = s->D, order = s->cfg.isotropy_order;
+  const double eps = (double)1.e-12f;
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i) {
+        if (WALLS(s, i, j, k) != 0.) continue;
+        double gradrho[3][MAXS];
+        double weightsum[3] = {0., 0., 0.};
+        for (int d = 0; d < 3; ++d)
+          for (int m = 0; m < S; ++m) gradrho[d][m] = 0.;
+        const double *here = field + rgnode(s, i, j, k) * (size_t)S;
+#define F(a, b, c) (WALLS(s, i + (a), j + (b), k + (c)) == 0.)
+#define BLOCK(minorder, L, dx, dy, dz, cx, cy, cz, wx, wy, wz, los)                         \
+  if (order >= (minorder) && (los)) {                                                       \
+    const double *there = field + rgnode(s, i + (dx), j + (dy), k + (dz)) * (size_t)S;      \
+    const int cc[3] = {cx, cy, cz};                                                          \
+    const int ww[3] = {wx, wy, wz};                                                          \
+    for (int d = 0; d < D; ++d)                                                              \
+      if (cc[d] != 0) {                                                                      \
+        const double coef = (cc[d] > 0 ? cc[d] : -cc[d]) * s->ffw[L];                        \
+        for (int m = 0; m < S; ++m) {                                                        \
+          if (cc[d] > 0)                                                                     \
+            gradrho[d][m] = gradrho[d][m] + coef * (there[m] - here[m]);                     \
+          else                                                                               \
+            gradrho[d][m] = gradrho[d][m] - coef * (there[m] - here[m]);                     \
+        }                                                                                    \
+        weightsum[d] = weightsum[d] + s->ffw[L] * ww[d];                                     \
+      }                                                                                      \
+  }
+        if (D == 3) {
+          TXO_FF_BLOCKS_D3(BLOCK)
+        } else {
+          TXO_FF_BLOCKS_D2(BLOCK)
+        }
+#undef BLOCK
+#undef F
+        for (int m = 0; m < S; ++m)
+          for (int d = 0; d < D; ++d)
+            if (weightsum[d] > eps) {
+              double acc = 0.;
+              for (int mp = 0; mp < S; ++mp) acc += s->cfg.gf[m][mp] * (gradrho[d][mp] / weightsum[d]);
+              FRC(s, m, d, i, j, k) = FRC(s, m, d, i, j, k) - s->c_0 * here[m] * acc;
+            }
+      }
+}
+
+/* FlowCalcForces, lbm_flow.F90:760-808 */
+static void calc_forces(txo_state *s) {
+  memset(s->forces, 0, sizeof(double) * (size_t)s->gnx * s->gny * s->gnz * s->S * s->D);
+  if (s->cfg.fluidsolid_forces) add_fluid_solid(s);
+  if (s->cfg.body_forces) add_body(s);
+  if (s->cfg.fluidfluid_forces) {
+    communicate_density(s);
+    if (s->cfg.use_nonideal_eos) {
+      eos_apply(s);
+      add_fluid_fluid(s, s->psi);
+    } else {
+      add_fluid_fluid(s, s->rho);
+    }
+  }
+}
+
+/* ---------------------------------------------------------------- init */
+/* FlowFiInit (lbm_flow.F90:923-934) with FlowFiBarInit -> FlowFeqBarD3/D2 (:853-921) */
+void txo_fi_init(txo_state *s) {
+  calc_forces(s);
+  update_feq(s);
+#pragma omp parallel for schedule(static) if (s->threads > 1)
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i) {
+        if (WALLS(s, i, j, k) != 0.) continue;
+        double pref[MAXS][MAXQ];
+        prefactor_node(s, i, j, k, pref);
+        for (int m = 0; m < s->S; ++m)
+          for (int n = 0; n < s->Q; ++n) FI(s, m, n, i, j, k) = (1. - 0.5 * pref[m][n]) * FEQ(s, m, n, i, j, k);
+      }
+}
+
+/* FlowUpdateMoments, lbm_flow.F90:466-478 */
+void txo_update_moments(txo_state *s) {
+  calc_density(s);
+  calc_flux_into(s, s->flux);
+  calc_forces(s);
+  update_ue(s);
+}
+
+/* ---------------------------------------------------------------- time step
+ * LBMRun2 body, lbm.F90:286-361, for periodic / bounce-back faces:
+ * FlowCollision; DistributionCommunicateFi; FlowStream; FlowBounceback;
+ * FlowApplyBCs (= FlowCalcRhoForces, lbm_flow.F90:445-456,1958-1991);
+ * FlowUpdateFlux (:458-464). */
+void txo_step(txo_state *s, int nsteps) {
+  for (int it = 0; it < nsteps; ++it) {
+    flow_collision(s);
+    communicate_fi(s);
+    stream(s);
+    bounceback(s);
+    calc_density(s);
+    calc_forces(s);
+    calc_flux_into(s, s->flux);
+    update_ue(s);
+  }
+}
+
+/* the phases individually, for white-box tests */
+void txo_phase_collision(txo_state *s) { flow_collision(s); }
+void txo_phase_communicate_fi(txo_state *s) { communicate_fi(s); }
+void txo_phase_stream(txo_state *s) { stream(s); }
+void txo_phase_bounceback(txo_state *s) { bounceback(s); }
+void txo_phase_apply_bcs(txo_state *s) {
+  calc_density(s);
+  calc_forces(s);
+}
+void txo_phase_update_flux(txo_state *s) {
+  calc_flux_into(s, s->flux);
+  update_ue(s);
+}
+
+/* ---------------------------------------------------------------- export (natural order, owned only) */
+void txo_get_fi(const txo_state *s, double *out) {
+  const int SQ = s->S * s->Q;
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i)
+        memcpy(out + (((size_t)k * s->NY + j) * s->NX + i) * SQ, &FI(s, 0, 0, i, j, k), sizeof(double) * SQ);
+}
+void txo_get_rho(const txo_state *s, double *out) {
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i)
+        for (int m = 0; m < s->S; ++m) out[(((size_t)k * s->NY + j) * s->NX + i) * s->S + m] = RHO(s, m, i, j, k);
+}
+static void get_sd(const txo_state *s, const double *a, double *out) {
+  const int SD = s->S * s->D;
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i)
+        memcpy(out + (((size_t)k * s->NY + j) * s->NX + i) * SD, a + gnode(s, i, j, k) * SD, sizeof(double) * SD);
+}
+void txo_get_u(const txo_state *s, double *out) { get_sd(s, s->flux, out); }
+void txo_get_forces(const txo_state *s, double *out) { get_sd(s, s->forces, out); }
+
+/* FlowUpdateDiagnostics -> FlowUpdateDiagnosticsD3/D2, lbm_flow.F90:603-758.
+ * rhot, prs: [node]; velt: [node][d].  Solid nodes: prs = null_pressure, rhot and
+ * velt keep their initial zero. */
+void txo_diagnostics(txo_state *s, double *rhot, double *prs, double *velt) {
+  const int S = s->S, D = s->D;
+  const size_t ng = (size_t)s->gnx * s->gny * s->gnz;
+  double *u = (double *)calloc(ng * S * D, sizeof(double));
+  calc_flux_into(s, u);
+  if (s->cfg.use_nonideal_eos) eos_apply(s);
+  const double *psi = s->cfg.use_nonideal_eos ? s->psi : s->rho;
+  for (int k = 0; k < s->NZ; ++k)
+    for (int j = 0; j < s->NY; ++j)
+      for (int i = 0; i < s->NX; ++i) {
+        const size_t o = ((size_t)k * s->NY + j) * s->NX + i;
+        if (WALLS(s, i, j, k) != 0.) {
+          prs[o] = s->cfg.null_pressure;
+          rhot[o] = 0.;
+          for (int d = 0; d < D; ++d) velt[o * D + d] = 0.;
+          continue;
+        }
+        double rt = 0.;
+        for (int m = 0; m < S; ++m) rt += RHO(s, m, i, j, k) * s->cfg.mm[m];
+        rhot[o] = rt;
+        double p = rt / 3.;
+        if (s->cfg.use_nonideal_eos || S > 1) {
+          const double *ps = psi + rgnode(s, i, j, k) * (size_t)S;
+          for (int m = 0; m < S; ++m) {
+            double acc = 0.;
+            for (int mp = 0; mp < S; ++mp) acc += s->cfg.gf[m][mp] * ps[mp];
+            p = p + s->c_0 / 2. * ps[m] * acc;
+          }
+        }
+        prs[o] = p;
+        double *un = u + gnode(s, i, j, k) * (size_t)(S * D);
+        for (int m = 0; m < S; ++m)
+          for (int d = 0; d < D; ++d) un[d * S + m] = un[d * S + m] + .5 * FRC(s, m, d, i, j, k);
+        for (int d = 0; d < D; ++d) {
+          double acc = 0.;
+          for (int m = 0; m < S; ++m) acc += un[d * S + m] * s->cfg.mm[m];
+          velt[o * D + d] = acc / rt;
+        }
+      }
+  free(u);
+}
+
+/* DistributionCalcDeltaNorm (fi variant), lbm_distribution_function.F90:809-833:
+ * || (fi_old - fi) / fi ||_inf over the global (owned) vector. */
+double txo_delta_norm(txo_state *s) {
+  const size_t n = (size_t)s->NX * s->NY * s->NZ * s->S * s->Q;
+  double *cur = (double *)malloc(n * sizeof(double));
+  txo_get_fi(s, cur);
+  double norm = 1.e99;
+  if (s->fi_old) {
+    norm = 0.;
+    for (size_t a = 0; a < n; ++a) {
+      double v = fabs((s->fi_old[a] - cur[a]) / cur[a]);
+      if (v > norm || v != v) norm = v;
+    }
+    free(s->fi_old);
+  }
+  s->fi_old = cur;
+  return norm;
+}
+
+/* lattice tables, for table-identity tests */
+void txo_get_lattice(const txo_state *s, int *ci /*Q*3*/, double *weights, int *opp, double *mt /*Q*Q rows of M*/,
+                     double *mmt, double *ffw /*41*/) {
+  for (int n = 0; n < s->Q; ++n) {
+    for (int d = 0; d < 3; ++d) ci[n * 3 + d] = s->ci[n][d];
+    weights[n] = s->weights[n];
+    opp[n] = s->opposites[n];
+    mmt[n] = s->mmt_mrt[n];
+    for (int i = 0; i < s->Q; ++i) mt[n * s->Q + i] = s->mt_mrt[n][i];
+  }
+  memcpy(ffw, s->ffw, sizeof s->ffw);
+}
