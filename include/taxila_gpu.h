@@ -32,6 +32,12 @@
 
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define TXG_API __attribute__((visibility("default")))
+#else
+#define TXG_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -99,7 +105,7 @@ typedef struct txg_config {
   double s_pi[TXG_NMAX_COMPONENTS];
   double s_m[TXG_NMAX_COMPONENTS];
   double mm[TXG_NMAX_COMPONENTS];    /* molecular mass; d_k = 1 - 2/(3 mm)          */
-  double gf[TXG_NMAX_COMPONENTS][TXG_NMAX_COMPONENTS]; /* gf[m][m'] = -g_<m+1><m'+1>*/
+  double gf[TXG_NMAX_COMPONENTS][TXG_NMAX_COMPONENTS]; /* gf[m][m'] = option -g_<m+1><m'+1> */
   double eos_rho0[TXG_NMAX_COMPONENTS];                /* EOS_SC rho0               */
   double gw[TXG_MAX_MINERALS][TXG_NMAX_COMPONENTS];    /* gw[mineral-1][m]          */
   double gvt[3];                     /* body acceleration, lbm_flow.F90:226-231     */
@@ -112,62 +118,62 @@ typedef struct txg_flow *txg_handle;
 /* Fill *cfg with the reference's defaults (OptionsCreate lbm_options.F90:93-152,
  * RelaxationCreate lbm_relaxation.F90:60-83: tau = s_* = 1, mm = 1, isotropy 4,
  * nminerals 1, everything periodic = 0).  Not a reference procedure. */
-int txg_config_defaults(txg_config *cfg);
+TXG_API int txg_config_defaults(txg_config *cfg);
 
 /* FlowCreate/FlowSetUp (lbm_flow.F90:104-154,378-428): validates cfg, selects
  * cuda device `device`, allocates the device-resident SoA lattice for the slab. */
-int txg_create(txg_handle *h, const txg_config *cfg, int device);
+TXG_API int txg_create(txg_handle *h, const txg_config *cfg, int device);
 
 /* FlowDestroy (lbm_flow.F90:156-184). */
-int txg_destroy(txg_handle h);
+TXG_API int txg_destroy(txg_handle h);
 
 /* Message of the last failing call on this handle ("" if none).  h may be NULL
  * for failures of txg_create itself. */
-const char *txg_last_error(txg_handle h);
+TXG_API const char *txg_last_error(txg_handle h);
 
 /* Multi-GPU wiring (replaces the DMDA communicator set up in lbm_grid.F90:159-212).
  * Rank 0 calls txg_nccl_unique_id and broadcasts the 128 bytes with whatever
  * the host program has (MPI_Bcast in the Fortran driver, torch.distributed in
  * bench.py); then every rank calls txg_comm_init.  Not needed for nranks == 1. */
-int txg_nccl_unique_id(unsigned char id_out[128]);
-int txg_comm_init(txg_handle h, const unsigned char id[128]);
+TXG_API int txg_nccl_unique_id(unsigned char id_out[128]);
+TXG_API int txg_comm_init(txg_handle h, const unsigned char id[128]);
 
 /* WallsSetValues + WallsSetGhostNodes + WallsCommunicate result
  * (lbm_walls.F90:151-244, called lbm.F90:162-163,189): the local ghosted
  * walls(rg..) array of doubles.  Classified into u8 node classes on the device. */
-int txg_set_walls(txg_handle h, const double *walls_rg);
+TXG_API int txg_set_walls(txg_handle h, const double *walls_rg);
 
 /* LBMInitializeState result (lbm.F90:444-453): host rho(S,rg..) and u(S,ndims,g..)
  * as filled by the user's initialize_state.  u may be NULL (= 0, what every
  * shipped initialize_state sets). */
-int txg_set_rho_u(txg_handle h, const double *rho_rg, const double *u_g);
+TXG_API int txg_set_rho_u(txg_handle h, const double *rho_rg, const double *u_g);
 
 /* Restart / IC-from-file (lbm.F90:482-544): host fi(S,0:b,g..). */
-int txg_set_fi(txg_handle h, const double *fi_g);
+TXG_API int txg_set_fi(txg_handle h, const double *fi_g);
 
 /* FlowFiInit (lbm_flow.F90:923-934): forces from rho0, fi = (1 - prefactor/2) feq(rho0, u0). */
-int txg_fi_init(txg_handle h);
+TXG_API int txg_fi_init(txg_handle h);
 
 /* FlowUpdateMoments (lbm_flow.F90:466-478): rho, flux, forces, common velocity
  * from the current fi.  On the device these are recomputed inside every step, so
  * this only refreshes the exported copies (txg_get_*). */
-int txg_update_moments(txg_handle h);
+TXG_API int txg_update_moments(txg_handle h);
 
 /* LBMRun2 inner body (lbm.F90:286-361), nsteps times: FlowCollision,
  * DistributionCommunicateFi, FlowStream, FlowBounceback, FlowApplyBCs (periodic /
  * bounce-back faces), FlowUpdateFlux.  Asynchronous on the handle's streams. */
-int txg_step(txg_handle h, int nsteps);
+TXG_API int txg_step(txg_handle h, int nsteps);
 
 /* The six reference procedures individually, for a shim that keeps LBMRun2's
  * loop body unchanged.  The fused device step runs when txg_update_flux is
  * reached; the other five only check the call order (a call out of the
  * reference's order is an error, not a silent no-op). */
-int txg_collision(txg_handle h);      /* FlowCollision             lbm_flow.F90:936  */
-int txg_communicate_fi(txg_handle h); /* DistributionCommunicateFi lbm_distribution_function.F90:309 */
-int txg_stream(txg_handle h);         /* FlowStream                lbm_flow.F90:810  */
-int txg_bounceback(txg_handle h);     /* FlowBounceback            lbm_flow.F90:816  */
-int txg_apply_bcs(txg_handle h);      /* FlowApplyBCs              lbm_flow.F90:1958 */
-int txg_update_flux(txg_handle h);    /* FlowUpdateFlux            lbm_flow.F90:458  */
+TXG_API int txg_collision(txg_handle h);      /* FlowCollision             lbm_flow.F90:936  */
+TXG_API int txg_communicate_fi(txg_handle h); /* DistributionCommunicateFi lbm_distribution_function.F90:309 */
+TXG_API int txg_stream(txg_handle h);         /* FlowStream                lbm_flow.F90:810  */
+TXG_API int txg_bounceback(txg_handle h);     /* FlowBounceback            lbm_flow.F90:816  */
+TXG_API int txg_apply_bcs(txg_handle h);      /* FlowApplyBCs              lbm_flow.F90:1958 */
+TXG_API int txg_update_flux(txg_handle h);    /* FlowUpdateFlux            lbm_flow.F90:458  */
 
 /* FlowGetArrays view of the state (lbm_flow.F90:431-436): copy the device state
  * back into the reference's host arrays.  Any pointer may be NULL.  Synchronises.
@@ -175,33 +181,33 @@ int txg_update_flux(txg_handle h);    /* FlowUpdateFlux            lbm_flow.F90:
  *   rho_rg    rho(S,rg..)       DistributionCalcDensity (owned entries; ghosts untouched)
  *   u_g       flux(S,ndims,g..) common velocity u' after FlowUpdateUE (lbm_flow.F90:494-574)
  *   forces_g  forces(S,ndims,g..) after FlowCalcForces (lbm_flow.F90:760-808)          */
-int txg_get_fi(txg_handle h, double *fi_g);
-int txg_get_state(txg_handle h, double *rho_rg, double *u_g, double *forces_g);
+TXG_API int txg_get_fi(txg_handle h, double *fi_g);
+TXG_API int txg_get_state(txg_handle h, double *rho_rg, double *u_g, double *forces_g);
 
 /* FlowUpdateDiagnostics (lbm_flow.F90:603-758): owned-only arrays in the
  * reference's global (natural) layout: rhot(x,y,z), prs(x,y,z), velt(ndims,x,y,z). */
-int txg_get_diagnostics(txg_handle h, double *rhot, double *prs, double *velt);
+TXG_API int txg_get_diagnostics(txg_handle h, double *rhot, double *prs, double *velt);
 
 /* The device node-class array of the slab with its ghost layers, as u8 in the
  * layout of walls(rg..) -- for the bit-exact classification check. */
-int txg_get_node_class(txg_handle h, uint8_t *class_rg);
+TXG_API int txg_get_node_class(txg_handle h, uint8_t *class_rg);
 
 /* DistributionCalcDeltaNorm (lbm_distribution_function.F90:809-833), fi variant:
  * max |(fi_old - fi)/fi| over owned entries, then fi_old = fi.  First call
  * returns 1e99 like the reference's initial value. */
-int txg_delta_norm(txg_handle h, double *norm);
+TXG_API int txg_delta_norm(txg_handle h, double *norm);
 
 /* Block until all device work queued on the handle is done. */
-int txg_synchronize(txg_handle h);
+TXG_API int txg_synchronize(txg_handle h);
 
 /* ---- measurement hooks (not reference procedures) ---------------------------- */
 /* Device-side time of the last txg_step call in milliseconds (CUDA events on the
  * handle's compute stream), kernel launches it issued, and accumulated per-kernel
  * time: names/ms/launches for up to `cap` kernels; returns the count in *n.      */
-int txg_last_step_ms(txg_handle h, float *ms, int64_t *launches);
-int txg_enable_kernel_timing(txg_handle h, int on);
-int txg_kernel_times(txg_handle h, int cap, const char **names, double *ms, int64_t *launches, int *n);
-int txg_reset_kernel_times(txg_handle h);
+TXG_API int txg_last_step_ms(txg_handle h, float *ms, int64_t *launches);
+TXG_API int txg_enable_kernel_timing(txg_handle h, int on);
+TXG_API int txg_kernel_times(txg_handle h, int cap, const char **names, double *ms, int64_t *launches, int *n);
+TXG_API int txg_reset_kernel_times(txg_handle h);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,955 @@
+// flow.cu -- the handle behind include/taxila_gpu.h: device storage, halo exchange, step loop,
+// host <-> device layout conversion, and the extern "C" entry points.
+//
+// There is no CPU fallback anywhere in this file: every entry point that computes launches CUDA
+// kernels on the handle's device and fails with a non-zero code if it cannot.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/taxila_gpu.h"
+#include "flow.h"
+#include "setup_kernels.cuh"
+
+using namespace txg;
+
+// PETSc error codes (petscerror.h) -- the reference's convention, lbm_error.F90:30-45
+enum {
+  TXG_ERR_MEM = 55,
+  TXG_ERR_SUP = 56,
+  TXG_ERR_ORDER = 58,
+  TXG_ERR_ARG_WRONG = 62,
+  TXG_ERR_ARG_OUTOFRANGE = 63,
+  TXG_ERR_ARG_NULL = 85,
+  TXG_ERR_LIB = 76
+};
+
+// ------------------------------------------------------------------ NCCL, bound at run time
+// The single-GPU path needs no NCCL at all; multi-GPU binds libnccl.so.2 on first use so that a host
+// program that already loaded NCCL (torch.distributed, an MPI+NCCL Fortran driver) shares it.
+namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8 };
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+  bool load() {
+    if (lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) {
+      err = std::string("cannot load libnccl.so.2: ") + dlerror();
+      return false;
+    }
+#define TXG_SYM(field, name)                                  \
+  field = (decltype(field))dlsym(lib, name);                  \
+  if (!field) {                                               \
+    err = std::string("libnccl lacks symbol ") + name;        \
+    return false;                                             \
+  }
+    TXG_SYM(GetUniqueId, "ncclGetUniqueId")
+    TXG_SYM(CommInitRank, "ncclCommInitRank")
+    TXG_SYM(CommDestroy, "ncclCommDestroy")
+    TXG_SYM(Send, "ncclSend")
+    TXG_SYM(Recv, "ncclRecv")
+    TXG_SYM(GroupStart, "ncclGroupStart")
+    TXG_SYM(GroupEnd, "ncclGroupEnd")
+    TXG_SYM(GetErrorString, "ncclGetErrorString")
+#undef TXG_SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+std::string g_create_error;
+}  // namespace
+
+// ------------------------------------------------------------------ the handle
+struct KernelTimer {
+  std::string name;
+  double ms = 0.;
+  int64_t launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct txg_flow {
+  txg_config cfg;
+  Grid g;
+  Phys p;
+  KernelSet ks;
+  int device = 0;
+  int S = 0, Q = 0, D = 0, R = 1;
+  cudaStream_t s_main = nullptr, s_comm = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_step0 = nullptr, ev_step1 = nullptr;
+  double *f[2] = {nullptr, nullptr};  // f[cur] holds the pull-form populations
+  int cur = 0;
+  double *rho = nullptr;       // stencil field (rho, or psi with an EOS), R ghost planes
+  double *rho_true = nullptr;  // true density (only allocated with an EOS; else == rho)
+  double *u0 = nullptr;        // initial per-component velocity [S][D][nnodes], optional
+  double *gw = nullptr;
+  uint8_t *cls = nullptr;
+  uint32_t *nbmask = nullptr, *ffmask = nullptr;
+  int *counters = nullptr;  // [0] bad wall codes, [1] fluid nodes next to 900-902 walls
+  double *staging = nullptr;
+  size_t staging_bytes = 0;
+  double *f_old = nullptr;  // DistributionCalcDeltaNorm
+  bool have_old = false;
+  unsigned long long *norm_bits = nullptr;
+  // exported copies (lazily allocated)
+  double *x_rho = nullptr, *x_u = nullptr, *x_F = nullptr, *x_rhot = nullptr, *x_prs = nullptr, *x_velt = nullptr;
+  bool walls_set = false, state_set = false, rho_current = false;
+  int phase = 0;  // position in the six-procedure sequence of LBMRun2
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int up = -1, down = -1;  // z-neighbour ranks (or -1)
+  // measurement
+  bool timing = false;
+  std::vector<KernelTimer> timers;
+  float last_ms = 0.f;
+  int64_t last_launches = 0, launches = 0;
+  std::string err;
+};
+
+#define TXG_FAIL(h, code, ...)                      \
+  do {                                              \
+    char buf_[512];                                 \
+    snprintf(buf_, sizeof buf_, __VA_ARGS__);       \
+    if (h) (h)->err = buf_; else g_create_error = buf_; \
+    return (code);                                  \
+  } while (0)
+
+#define TXG_CUDA(h, call)                                                                       \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      TXG_FAIL(h, TXG_ERR_LIB, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, \
+               cudaGetErrorString(e_));                                                         \
+  } while (0)
+
+#define TXG_NCCL(h, call)                                                                          \
+  do {                                                                                             \
+    ncclResult_t r_ = (call);                                                                      \
+    if (r_ != 0)                                                                                   \
+      TXG_FAIL(h, TXG_ERR_LIB, "NCCL error %d at %s:%d: %s", r_, __FILE__, __LINE__, g_nccl.GetErrorString(r_)); \
+  } while (0)
+
+#define TXG_TRY(expr)        \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_) return rc_;     \
+  } while (0)
+
+static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ------------------------------------------------------------------ kernel timing
+static KernelTimer *timer_for(txg_flow *h, const char *name) {
+  for (auto &t : h->timers)
+    if (t.name == name) return &t;
+  h->timers.push_back(KernelTimer());
+  h->timers.back().name = name;
+  return &h->timers.back();
+}
+struct ScopedKernel {
+  txg_flow *h;
+  KernelTimer *t = nullptr;
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t s;
+  ScopedKernel(txg_flow *h_, const char *name, cudaStream_t s_) : h(h_), s(s_) {
+    h->launches++;
+    if (h->timing) {
+      t = timer_for(h, name);
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, s);
+    } else {
+      t = timer_for(h, name);
+    }
+    t->launches++;
+  }
+  ~ScopedKernel() {
+    if (h->timing) {
+      cudaEventRecord(b, s);
+      t->pending.emplace_back(a, b);
+    }
+  }
+};
+static void drain_timers(txg_flow *h) {
+  for (auto &t : h->timers) {
+    for (auto &pr : t.pending) {
+      float ms = 0.f;
+      cudaEventSynchronize(pr.second);
+      cudaEventElapsedTime(&ms, pr.first, pr.second);
+      t.ms += ms;
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    t.pending.clear();
+  }
+}
+
+// ------------------------------------------------------------------ set-up
+static int select_kernels(txg_flow *h) {
+  const txg_config &c = h->cfg;
+  const bool mrt = c.relaxation_mode == TXG_RELAXATION_MODE_MRT;
+  bool ok = false;
+  if (c.discretization == TXG_D3Q19_DISCRETIZATION) {
+    if (h->S == 1) ok = kernel_set_d3q19_s1(mrt, c.isotropy_order, &h->ks);
+    if (h->S == 2) ok = kernel_set_d3q19_s2(mrt, c.isotropy_order, &h->ks);
+    if (h->S == 3) ok = kernel_set_d3q19_s3(mrt, c.isotropy_order, &h->ks);
+  } else {
+    if (h->S == 1) ok = kernel_set_d2q9_s1(mrt, c.isotropy_order, &h->ks);
+    if (h->S == 2) ok = kernel_set_d2q9_s2(mrt, c.isotropy_order, &h->ks);
+    if (h->S == 3) ok = kernel_set_d2q9_s3(mrt, c.isotropy_order, &h->ks);
+  }
+  if (!ok)
+    TXG_FAIL(h, TXG_ERR_SUP,
+             "no device kernels for discretization %d, ncomponents %d, isotropy order %d (built: D3Q19 order 4/8, "
+             "D2Q9 order 4/8/10, 1-3 components; D3 order 10 is an LBMError in the reference too)",
+             c.discretization, h->S, c.isotropy_order);
+  return 0;
+}
+
+static void fill_phys(txg_flow *h) {
+  const txg_config &c = h->cfg;
+  Phys &p = h->p;
+  memset(&p, 0, sizeof p);
+  const bool d3 = c.discretization == TXG_D3Q19_DISCRETIZATION;
+  for (int m = 0; m < h->S; ++m) {
+    const bool mrt = c.relaxation_mode == TXG_RELAXATION_MODE_MRT;
+    p.inv_tau[m] = 1.0 / c.tau[m];
+    const double s_c = mrt ? c.s_c[m] : 1.0 / c.tau[m];  // lbm_relaxation.F90:133
+    const double rates[7] = {c.s_c[m], c.s_e[m], c.s_e2[m], c.s_q[m], c.s_nu[m], c.s_pi[m], c.s_m[m]};
+    for (int r = 0; r < h->Q; ++r) {
+      const int which = d3 ? D3Q19::rate_of(r) : D2Q9::rate_of(r);
+      const int norm = d3 ? D3Q19::Mnorm(r) : D2Q9::Mnorm(r);
+      p.mrt_rate[m][r] = rates[which] / (double)norm;
+    }
+    p.mm[m] = c.mm[m];
+    p.d_k[m] = 1. - 2. / (3. * c.mm[m]);  // lbm_component.F90:158
+    p.mmot[m] = c.mm[m] * s_c;            // lbm_flow.F90:519-521
+    for (int k = 0; k < h->S; ++k) p.gf[m][k] = c.gf[m][k];
+    p.eos_rho0[m] = c.eos_rho0[m];
+    p.eos_sc[m] = c.use_nonideal_eos && c.eos_type[m] == TXG_EOS_SC;
+  }
+  for (int d = 0; d < 3; ++d) p.gvt[d] = c.gvt[d];
+  p.nminerals = c.nminerals;
+  p.fluidfluid = c.fluidfluid_forces;
+  p.fluidsolid = c.fluidsolid_forces;
+  p.body = c.body_forces;
+  p.eos = c.use_nonideal_eos;
+  p.gw = h->gw;
+}
+
+static int validate(const txg_config *c) {
+  txg_flow *h = nullptr;
+  if (!c) TXG_FAIL(h, TXG_ERR_ARG_NULL, "txg_create: null config");
+  if (c->struct_bytes != (int32_t)sizeof(txg_config))
+    TXG_FAIL(h, TXG_ERR_ARG_WRONG, "txg_config.struct_bytes = %d but the library was built with %zu", c->struct_bytes,
+             sizeof(txg_config));
+  const bool d3 = c->discretization == TXG_D3Q19_DISCRETIZATION, d2 = c->discretization == TXG_D2Q9_DISCRETIZATION;
+  if (!d3 && !d2) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "invalid discretization %d", c->discretization);
+  if (c->ndims != (d3 ? 3 : 2)) TXG_FAIL(h, TXG_ERR_ARG_WRONG, "ndims %d does not match the discretization", c->ndims);
+  if (c->ncomponents < 1 || c->ncomponents > TXG_NMAX_COMPONENTS)
+    TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "ncomponents %d out of range", c->ncomponents);
+  if (c->NX < 1 || c->NY < 1 || c->NZ < 1) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "invalid box %d x %d x %d", c->NX, c->NY, c->NZ);
+  if (d2 && c->NZ != 1) TXG_FAIL(h, TXG_ERR_ARG_WRONG, "NZ must be 1 for D2Q9");
+  if (c->relaxation_mode != TXG_RELAXATION_MODE_SRT && c->relaxation_mode != TXG_RELAXATION_MODE_MRT)
+    TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "invalid relaxation mode in LBM");  // lbm_relaxation.F90:166
+  const int Rneed = stencil_radius(c->isotropy_order);
+  if (c->stencil_size_rho < Rneed || c->stencil_size_rho > 3)
+    TXG_FAIL(h, TXG_ERR_ARG_WRONG, "stencil_size_rho %d too small for isotropy order %d (needs %d)", c->stencil_size_rho,
+             c->isotropy_order, Rneed);
+  if (c->NX <= 2 * c->stencil_size_rho || c->NY <= 2 * c->stencil_size_rho)
+    TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "box too small for the stencil");
+  if (c->nminerals < 1 || c->nminerals > TXG_MAX_MINERALS) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "nminerals %d out of range", c->nminerals);
+  if (c->nranks < 1 || c->rank < 0 || c->rank >= c->nranks) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "invalid rank %d of %d", c->rank, c->nranks);
+  if (d2 && c->nranks != 1) TXG_FAIL(h, TXG_ERR_SUP, "D2Q9 runs on one rank (z-slab decomposition is 3-D only)");
+  if (c->zs < 0 || c->zl < 1 || c->zs + c->zl > c->NZ) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "invalid z-slab [%d, %d) of %d", c->zs, c->zs + c->zl, c->NZ);
+  if (c->nranks == 1 && (c->zs != 0 || c->zl != c->NZ)) TXG_FAIL(h, TXG_ERR_ARG_WRONG, "a single rank must own the whole box");
+  if (c->nranks > 1 && c->zl < c->stencil_size_rho) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "z-slab thinner than the stencil");
+  for (int m = 0; m < c->ncomponents; ++m) {
+    if (!(c->tau[m] > 0.) || !(c->mm[m] > 0.)) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "component %d: tau and mm must be positive", m + 1);
+    if (c->use_nonideal_eos && c->eos_type[m] != TXG_EOS_DENSITY && c->eos_type[m] != TXG_EOS_SC)
+      TXG_FAIL(h, TXG_ERR_SUP, "component %d: only EOS_DENSITY and EOS_SC are implemented on the device", m + 1);
+  }
+  return 0;
+}
+
+extern "C" int txg_config_defaults(txg_config *c) {
+  if (!c) return TXG_ERR_ARG_NULL;
+  memset(c, 0, sizeof *c);
+  c->struct_bytes = (int32_t)sizeof *c;
+  c->ndims = 3;
+  c->discretization = TXG_D3Q19_DISCRETIZATION;
+  c->ncomponents = 1;
+  c->NX = c->NY = c->NZ = 1;
+  c->zs = 0;
+  c->zl = 1;
+  c->stencil_size_rho = 1;
+  c->relaxation_mode = TXG_RELAXATION_MODE_SRT;
+  c->isotropy_order = 4;
+  c->nminerals = 1;
+  c->nranks = 1;
+  for (int m = 0; m < TXG_NMAX_COMPONENTS; ++m) {
+    c->tau[m] = c->s_c[m] = c->s_e[m] = c->s_e2[m] = c->s_q[m] = c->s_nu[m] = c->s_pi[m] = c->s_m[m] = 1.0;
+    c->mm[m] = 1.0;
+    c->eos_rho0[m] = 1.0;
+    c->eos_type[m] = TXG_EOS_DENSITY;
+  }
+  return 0;
+}
+
+extern "C" const char *txg_last_error(txg_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static int alloc_zero(txg_flow *h, void **p, size_t bytes) {
+  TXG_CUDA(h, cudaMalloc(p, bytes));
+  TXG_CUDA(h, cudaMemsetAsync(*p, 0, bytes, h->s_main));
+  return 0;
+}
+
+extern "C" int txg_destroy(txg_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  drain_timers(h);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
+                  h->nbmask, h->ffmask, h->counters, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
+                  h->x_rhot, h->x_prs, h->x_velt};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (h->ev_a) cudaEventDestroy(h->ev_a);
+  if (h->ev_b) cudaEventDestroy(h->ev_b);
+  if (h->ev_step0) cudaEventDestroy(h->ev_step0);
+  if (h->ev_step1) cudaEventDestroy(h->ev_step1);
+  if (h->s_main) cudaStreamDestroy(h->s_main);
+  if (h->s_comm) cudaStreamDestroy(h->s_comm);
+  delete h;
+  return 0;
+}
+
+extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
+  if (!out) {
+    g_create_error = "txg_create: null handle pointer";
+    return TXG_ERR_ARG_NULL;
+  }
+  *out = nullptr;
+  TXG_TRY(validate(cfg));
+  int ndev = 0;
+  {
+    txg_flow *h = nullptr;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      TXG_FAIL(h, TXG_ERR_LIB, "no CUDA device available (%s); this library has no CPU path",
+               e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "device %d out of range (%d devices)", device, ndev);
+  }
+  txg_flow *h = new txg_flow();
+  h->cfg = *cfg;
+  h->device = device;
+  h->S = cfg->ncomponents;
+  h->D = cfg->ndims;
+  h->Q = cfg->discretization == TXG_D3Q19_DISCRETIZATION ? 19 : 9;
+  h->R = cfg->stencil_size_rho;
+  int rc = 0;
+  auto fail = [&](int code) {
+    g_create_error = h->err;
+    txg_destroy(h);
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) {
+    h->err = "cudaSetDevice failed";
+    return fail(TXG_ERR_LIB);
+  }
+  if ((rc = select_kernels(h))) return fail(rc);
+  Grid &g = h->g;
+  g.NX = cfg->NX;
+  g.NY = cfg->NY;
+  g.NZl = cfg->ndims == 3 ? cfg->zl : 1;
+  g.R = h->R;
+  g.Rz = cfg->ndims == 3 ? h->R : 0;
+  g.perx = cfg->periodic[0];
+  g.pery = cfg->periodic[1];
+  g.plane = (long long)g.NX * g.NY;
+  g.fstride = (long long)(g.NZl + 2) * g.plane;
+  g.rstride = (long long)(g.NZl + 2 * g.R) * g.plane;
+  g.nnodes = (long long)g.NZl * g.plane;
+  g.cnx = g.NX + 2 * g.R;
+  g.cny = g.NY + 2 * g.R;
+  auto body = [&]() -> int {
+    TXG_CUDA(h, cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
+    TXG_CUDA(h, cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking));
+    TXG_CUDA(h, cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+    TXG_CUDA(h, cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+    TXG_CUDA(h, cudaEventCreate(&h->ev_step0));
+    TXG_CUDA(h, cudaEventCreate(&h->ev_step1));
+    const size_t fbytes = (size_t)h->S * h->Q * g.fstride * sizeof(double);
+    TXG_TRY(alloc_zero(h, (void **)&h->f[0], fbytes));
+    TXG_TRY(alloc_zero(h, (void **)&h->f[1], fbytes));
+    TXG_TRY(alloc_zero(h, (void **)&h->rho, (size_t)h->S * g.rstride * sizeof(double)));
+    if (cfg->use_nonideal_eos)
+      TXG_TRY(alloc_zero(h, (void **)&h->rho_true, (size_t)h->S * g.rstride * sizeof(double)));
+    else
+      h->rho_true = h->rho;
+    TXG_TRY(alloc_zero(h, (void **)&h->cls, (size_t)(g.NZl + 2 * g.Rz) * g.cny * g.cnx));
+    TXG_TRY(alloc_zero(h, (void **)&h->nbmask, (size_t)g.nnodes * sizeof(uint32_t)));
+    if (h->ks.ff_words) TXG_TRY(alloc_zero(h, (void **)&h->ffmask, (size_t)h->ks.ff_words * g.nnodes * sizeof(uint32_t)));
+    TXG_TRY(alloc_zero(h, (void **)&h->counters, 4 * sizeof(int)));
+    TXG_TRY(alloc_zero(h, (void **)&h->norm_bits, sizeof(unsigned long long)));
+    std::vector<double> gw((size_t)cfg->nminerals * h->S);
+    for (int k = 0; k < cfg->nminerals; ++k)
+      for (int m = 0; m < h->S; ++m) gw[(size_t)k * h->S + m] = cfg->gw[k][m];
+    TXG_CUDA(h, cudaMalloc((void **)&h->gw, gw.size() * sizeof(double)));
+    TXG_CUDA(h, cudaMemcpy(h->gw, gw.data(), gw.size() * sizeof(double), cudaMemcpyHostToDevice));
+    TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+    return 0;
+  };
+  if ((rc = body())) return fail(rc);
+  fill_phys(h);
+  // z neighbours of the slab ring
+  const int nr = cfg->nranks, r = cfg->rank;
+  if (cfg->ndims == 3) {
+    h->up = r + 1 < nr ? r + 1 : (cfg->periodic[2] ? 0 : -1);
+    h->down = r > 0 ? r - 1 : (cfg->periodic[2] ? nr - 1 : -1);
+  }
+  *out = h;
+  return 0;
+}
+
+extern "C" int txg_nccl_unique_id(unsigned char id_out[128]) {
+  txg_flow *h = nullptr;
+  if (!g_nccl.load()) TXG_FAIL(h, TXG_ERR_LIB, "%s", g_nccl.err.c_str());
+  ncclUniqueId id;
+  TXG_NCCL(h, g_nccl.GetUniqueId(&id));
+  memcpy(id_out, id.internal, 128);
+  return 0;
+}
+
+extern "C" int txg_comm_init(txg_handle h, const unsigned char id_in[128]) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (h->cfg.nranks == 1) return 0;
+  if (!g_nccl.load()) TXG_FAIL(h, TXG_ERR_LIB, "%s", g_nccl.err.c_str());
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  ncclUniqueId id;
+  memcpy(id.internal, id_in, 128);
+  TXG_NCCL(h, g_nccl.CommInitRank(&h->comm, h->cfg.nranks, id, h->cfg.rank));
+  return 0;
+}
+
+// ------------------------------------------------------------------ halo exchange along z
+// One ghost plane of f each side; R ghost planes of rho each side.  `n_up`/`n_down` are the chunk
+// lists (offset into the buffer of the plane to send / the ghost plane to fill).
+struct Chunk {
+  long long send_off, recv_off;
+  long long count;
+};
+
+static int exchange(txg_flow *h, double *buf, const std::vector<Chunk> &to_up, const std::vector<Chunk> &to_down,
+                    cudaStream_t s) {
+  // to_up: my top planes -> up neighbour's bottom ghost; I receive my bottom ghost from `down`.
+  // to_down: my bottom planes -> down neighbour's top ghost; I receive my top ghost from `up`.
+  const int nr = h->cfg.nranks;
+  if (nr == 1) {
+    if (h->up < 0) return 0;  // not periodic in z: ghosts are never read
+    // periodic single rank: my own top plane is my bottom ghost and vice versa
+    for (const Chunk &c : to_up)
+      TXG_CUDA(h, cudaMemcpyAsync(buf + c.recv_off, buf + c.send_off, c.count * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    for (const Chunk &c : to_down)
+      TXG_CUDA(h, cudaMemcpyAsync(buf + c.recv_off, buf + c.send_off, c.count * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    h->launches += (int64_t)(to_up.size() + to_down.size());
+    return 0;
+  }
+  if (!h->comm) TXG_FAIL(h, TXG_ERR_ORDER, "nranks > 1 but txg_comm_init was not called");
+  TXG_NCCL(h, g_nccl.GroupStart());
+  for (const Chunk &c : to_up) {
+    if (h->up >= 0) TXG_NCCL(h, g_nccl.Send(buf + c.send_off, (size_t)c.count, ncclFloat64, h->up, h->comm, s));
+    if (h->down >= 0) TXG_NCCL(h, g_nccl.Recv(buf + c.recv_off, (size_t)c.count, ncclFloat64, h->down, h->comm, s));
+  }
+  for (const Chunk &c : to_down) {
+    if (h->down >= 0) TXG_NCCL(h, g_nccl.Send(buf + c.send_off, (size_t)c.count, ncclFloat64, h->down, h->comm, s));
+    if (h->up >= 0) TXG_NCCL(h, g_nccl.Recv(buf + c.recv_off, (size_t)c.count, ncclFloat64, h->up, h->comm, s));
+  }
+  TXG_NCCL(h, g_nccl.GroupEnd());
+  return 0;
+}
+
+// pull-form populations: the up-going directions (c_z = +1) of my top plane are pulled by the up
+// neighbour's bottom plane, so they fill its bottom ghost; mirror for c_z = -1.
+// `all_dirs`: node-value buffers (init / restart) need every z-moving direction both ways.
+static int exchange_f(txg_flow *h, double *buf, bool all_dirs, cudaStream_t s) {
+  if (h->D != 3) return 0;
+  const Grid &g = h->g;
+  std::vector<Chunk> upv, downv;
+  const bool d3 = true;
+  (void)d3;
+  for (int m = 0; m < h->S; ++m)
+    for (int n = 0; n < h->Q; ++n) {
+      const int cz = D3Q19::c(n, 2);
+      if (cz == 0) continue;
+      const long long base = (long long)(m * h->Q + n) * g.fstride;
+      if (cz > 0 || all_dirs) upv.push_back({base + (long long)g.NZl * g.plane, base, g.plane});
+      if (cz < 0 || all_dirs) downv.push_back({base + g.plane, base + (long long)(g.NZl + 1) * g.plane, g.plane});
+    }
+  return exchange(h, buf, upv, downv, s);
+}
+
+static int exchange_rho(txg_flow *h, double *buf, cudaStream_t s) {
+  if (h->D != 3) return 0;
+  const Grid &g = h->g;
+  const int R = g.R;
+  std::vector<Chunk> upv, downv;
+  for (int m = 0; m < h->S; ++m) {
+    const long long base = (long long)m * g.rstride;
+    // my top R owned planes [NZl, NZl+R) (ghosted index) -> neighbour's bottom ghost [0, R)
+    upv.push_back({base + (long long)g.NZl * g.plane, base, (long long)R * g.plane});
+    // my bottom R owned planes [R, 2R) -> neighbour's top ghost [NZl+R, NZl+2R)
+    downv.push_back({base + (long long)R * g.plane, base + (long long)(g.NZl + R) * g.plane, (long long)R * g.plane});
+  }
+  return exchange(h, buf, upv, downv, s);
+}
+
+// ------------------------------------------------------------------ host <-> device layout conversion
+static int ensure_staging(txg_flow *h, size_t bytes) {
+  if (h->staging_bytes >= bytes) return 0;
+  if (h->staging) cudaFree(h->staging);
+  h->staging = nullptr;
+  h->staging_bytes = 0;
+  TXG_CUDA(h, cudaMalloc((void **)&h->staging, bytes));
+  h->staging_bytes = bytes;
+  return 0;
+}
+
+// host array [gz][gy][gx][K*S] (ghost width gw in x,y; gwz in z) -> device SoA
+static int import_field(txg_flow *h, const double *host, int gw, int gwz, int K, double *dst, long long dst_stride,
+                        long long dst_plane0) {
+  const Grid &g = h->g;
+  const int dof = h->S * K;
+  const size_t plane_elems = (size_t)(g.NX + 2 * gw) * (g.NY + 2 * gw) * dof;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)g.NZl, ((size_t)256 << 20) / (plane_elems * 8)));
+  TXG_TRY(ensure_staging(h, plane_elems * 8 * chunk));
+  for (int z0 = 0; z0 < g.NZl; z0 += chunk) {
+    const int nz = std::min(chunk, g.NZl - z0);
+    TXG_CUDA(h, cudaMemcpyAsync(h->staging, host + (size_t)(z0 + gwz) * plane_elems, plane_elems * 8 * nz,
+                                cudaMemcpyHostToDevice, h->s_main));
+    const long long total = (long long)nz * g.plane * dof;
+    k_import_aos<<<blocks_for(total, 256), 256, 0, h->s_main>>>(h->staging, dst, g.NX, g.NY, gw, h->S, K, dst_stride,
+                                                                dst_plane0, z0, nz);
+    TXG_CUDA(h, cudaGetLastError());
+    TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  }
+  return 0;
+}
+
+static int export_field(txg_flow *h, double *host, int gw, int gwz, int K, int S, const double *src,
+                        long long src_stride, long long src_plane0) {
+  const Grid &g = h->g;
+  const int dof = S * K;
+  const size_t plane_elems = (size_t)(g.NX + 2 * gw) * (g.NY + 2 * gw) * dof;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)g.NZl, ((size_t)256 << 20) / (plane_elems * 8)));
+  TXG_TRY(ensure_staging(h, plane_elems * 8 * chunk));
+  for (int z0 = 0; z0 < g.NZl; z0 += chunk) {
+    const int nz = std::min(chunk, g.NZl - z0);
+    if (gw > 0)  // keep the caller's ghost entries: round-trip the planes through the staging buffer
+      TXG_CUDA(h, cudaMemcpyAsync(h->staging, host + (size_t)(z0 + gwz) * plane_elems, plane_elems * 8 * nz,
+                                  cudaMemcpyHostToDevice, h->s_main));
+    const long long total = (long long)nz * g.plane * dof;
+    k_export_aos<<<blocks_for(total, 256), 256, 0, h->s_main>>>(h->staging, src, g.NX, g.NY, gw, S, K, src_stride,
+                                                                src_plane0, z0, nz);
+    TXG_CUDA(h, cudaGetLastError());
+    TXG_CUDA(h, cudaMemcpyAsync(host + (size_t)(z0 + gwz) * plane_elems, h->staging, plane_elems * 8 * nz,
+                                cudaMemcpyDeviceToHost, h->s_main));
+    TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ walls
+extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (!walls_rg) TXG_FAIL(h, TXG_ERR_ARG_NULL, "txg_set_walls: null array");
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  const Grid &g = h->g;
+  const long long n = (long long)(g.NZl + 2 * g.Rz) * g.cny * g.cnx;
+  // classify in chunks through the staging buffer
+  const long long chunk = std::min<long long>(n, (long long)32 << 20);
+  TXG_TRY(ensure_staging(h, (size_t)chunk * 8));
+  TXG_CUDA(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(int), h->s_main));
+  for (long long o = 0; o < n; o += chunk) {
+    const long long c = std::min(chunk, n - o);
+    TXG_CUDA(h, cudaMemcpyAsync(h->staging, walls_rg + o, (size_t)c * 8, cudaMemcpyHostToDevice, h->s_main));
+    k_classify<<<blocks_for(c, 256), 256, 0, h->s_main>>>(h->staging, h->cls + o, c, h->counters);
+    TXG_CUDA(h, cudaGetLastError());
+    TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  }
+  h->ks.build_masks<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->cls, h->nbmask, h->ffmask, h->counters + 1);
+  TXG_CUDA(h, cudaGetLastError());
+  int counters[4];
+  TXG_CUDA(h, cudaMemcpyAsync(counters, h->counters, sizeof counters, cudaMemcpyDeviceToHost, h->s_main));
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  if (counters[0]) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "walls array holds %d negative or NaN codes", counters[0]);
+  if (counters[1])
+    TXG_FAIL(h, TXG_ERR_SUP,
+             "%d fluid/wall contacts with free-slip codes 900-902 (WALL_NORMAL_X/Y/Z): specular walls are not "
+             "implemented on the device yet",
+             counters[1]);
+  h->walls_set = true;
+  return 0;
+}
+
+extern "C" int txg_get_node_class(txg_handle h, uint8_t *out) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (!out) TXG_FAIL(h, TXG_ERR_ARG_NULL, "null array");
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  const Grid &g = h->g;
+  TXG_CUDA(h, cudaMemcpy(out, h->cls, (size_t)(g.NZl + 2 * g.Rz) * g.cny * g.cnx, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ------------------------------------------------------------------ state in
+static int run_moments(txg_flow *h, int z0, int nz, cudaStream_t s) {
+  if (nz <= 0) return 0;
+  ScopedKernel sk(h, "k_moments", s);
+  h->ks.moments<<<blocks_for((long long)nz * h->g.plane, 128), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, h->nbmask, z0, nz);
+  TXG_CUDA(h, cudaGetLastError());
+  return 0;
+}
+static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
+  if (nz <= 0) return 0;
+  ScopedKernel sk(h, "k_collide", s);
+  h->ks.collide<<<blocks_for((long long)nz * h->g.plane, 128), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho,
+                                                                           h->nbmask, h->ffmask, h->cls, z0, nz);
+  TXG_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+// node values in f[cur^1] (owned planes) -> pull form in f[cur], ghosts exchanged
+static int node_values_to_pull(txg_flow *h) {
+  const Grid &g = h->g;
+  double *fN = h->f[h->cur ^ 1], *fA = h->f[h->cur];
+  TXG_TRY(exchange_f(h, fN, true, h->s_main));
+  {
+    ScopedKernel sk(h, "k_unstream", h->s_main);
+    h->ks.unstream<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, fN, fA, h->nbmask, 0, g.NZl);
+    TXG_CUDA(h, cudaGetLastError());
+  }
+  TXG_TRY(exchange_f(h, fA, false, h->s_main));
+  h->state_set = true;
+  h->rho_current = false;
+  return 0;
+}
+
+extern "C" int txg_set_rho_u(txg_handle h, const double *rho_rg, const double *u_g) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (!rho_rg) TXG_FAIL(h, TXG_ERR_ARG_NULL, "txg_set_rho_u: null rho");
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  const Grid &g = h->g;
+  TXG_TRY(import_field(h, rho_rg, g.R, g.Rz, 1, h->rho_true, g.rstride, g.R));
+  if (u_g) {
+    if (!h->u0) TXG_CUDA(h, cudaMalloc((void **)&h->u0, (size_t)h->S * h->D * g.nnodes * sizeof(double)));
+    TXG_TRY(import_field(h, u_g, 1, h->D == 3 ? 1 : 0, h->D, h->u0, g.nnodes, 0));
+  } else if (h->u0) {
+    cudaFree(h->u0);
+    h->u0 = nullptr;
+  }
+  return 0;
+}
+
+extern "C" int txg_set_fi(txg_handle h, const double *fi_g) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (!fi_g) TXG_FAIL(h, TXG_ERR_ARG_NULL, "txg_set_fi: null fi");
+  if (!h->walls_set) TXG_FAIL(h, TXG_ERR_ORDER, "txg_set_fi before txg_set_walls");
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  const Grid &g = h->g;
+  TXG_TRY(import_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->f[h->cur ^ 1], g.fstride, 1));
+  return node_values_to_pull(h);
+}
+
+// psi = EOS(rho) over the owned planes of rho_true -> rho (stencil field); identity without an EOS
+__global__ void k_eos_field(Grid g, Phys p, int S, const double *__restrict__ rho_true, double *__restrict__ psi) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nnodes) return;
+  for (int m = 0; m < S; ++m) {
+    const long long o = m * g.rstride + (long long)g.R * g.plane + i;
+    psi[o] = eos_psi(p, m, rho_true[o]);
+  }
+}
+
+extern "C" int txg_fi_init(txg_handle h) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (!h->walls_set) TXG_FAIL(h, TXG_ERR_ORDER, "txg_fi_init before txg_set_walls");
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  const Grid &g = h->g;
+  if (h->cfg.use_nonideal_eos) {
+    k_eos_field<<<blocks_for(g.nnodes, 256), 256, 0, h->s_main>>>(g, h->p, h->S, h->rho_true, h->rho);
+    TXG_CUDA(h, cudaGetLastError());
+    h->launches++;
+  }
+  TXG_TRY(exchange_rho(h, h->rho, h->s_main));
+  {
+    ScopedKernel sk(h, "k_fi_init", h->s_main);
+    h->ks.fi_init<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->p, h->f[h->cur ^ 1], h->rho, h->rho_true, h->u0,
+                                                                     h->nbmask, h->ffmask, h->cls, 0, g.NZl);
+    TXG_CUDA(h, cudaGetLastError());
+  }
+  return node_values_to_pull(h);
+}
+
+// ------------------------------------------------------------------ the step
+// One reference time step = collide, communicate fi, stream, bounce-back, density, forces, flux,
+// common velocity (lbm.F90:286-361).  On the device: K1 moments (stream + bounce-back + density) with
+// the rho halo, then K2 (forces + momentum + velocity + collision) with the f halo.  Boundary planes
+// run first so that their halos travel on the communication stream while the interior computes.
+static int one_step(txg_flow *h) {
+  const Grid &g = h->g;
+  const bool split = h->cfg.nranks > 1 && g.NZl >= 4 * g.R + 2;
+  cudaStream_t sm = h->s_main, sc = h->s_comm;
+  if (!split) {
+    TXG_TRY(run_moments(h, 0, g.NZl, sm));
+    TXG_TRY(exchange_rho(h, h->rho, sm));
+    TXG_TRY(run_collide(h, 0, g.NZl, sm));
+    TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], false, sm));
+    h->cur ^= 1;
+    return 0;
+  }
+  const int R = g.R;
+  // K1: bottom and top R planes, then their halo on the comm stream, interior meanwhile
+  TXG_TRY(run_moments(h, 0, R, sm));
+  TXG_TRY(run_moments(h, g.NZl - R, R, sm));
+  TXG_CUDA(h, cudaEventRecord(h->ev_a, sm));
+  TXG_CUDA(h, cudaStreamWaitEvent(sc, h->ev_a, 0));
+  TXG_TRY(exchange_rho(h, h->rho, sc));
+  TXG_CUDA(h, cudaEventRecord(h->ev_b, sc));
+  TXG_TRY(run_moments(h, R, g.NZl - 2 * R, sm));
+  TXG_CUDA(h, cudaStreamWaitEvent(sm, h->ev_b, 0));
+  // K2: boundary planes (they need the rho halo), halo of the new populations, interior meanwhile
+  TXG_TRY(run_collide(h, 0, 1, sm));
+  TXG_TRY(run_collide(h, g.NZl - 1, 1, sm));
+  TXG_CUDA(h, cudaEventRecord(h->ev_a, sm));
+  TXG_CUDA(h, cudaStreamWaitEvent(sc, h->ev_a, 0));
+  TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], false, sc));
+  TXG_CUDA(h, cudaEventRecord(h->ev_b, sc));
+  TXG_TRY(run_collide(h, 1, g.NZl - 2, sm));
+  TXG_CUDA(h, cudaStreamWaitEvent(sm, h->ev_b, 0));
+  h->cur ^= 1;
+  return 0;
+}
+
+extern "C" int txg_step(txg_handle h, int nsteps) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "txg_step before txg_fi_init / txg_set_fi");
+  if (nsteps < 0) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "nsteps %d", nsteps);
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  const int64_t l0 = h->launches;
+  TXG_CUDA(h, cudaEventRecord(h->ev_step0, h->s_main));
+  for (int i = 0; i < nsteps; ++i) TXG_TRY(one_step(h));
+  TXG_CUDA(h, cudaEventRecord(h->ev_step1, h->s_main));
+  h->last_launches = h->launches - l0;
+  h->rho_current = false;
+  return 0;
+}
+
+// the six reference procedures: only the order is checked; the device step runs at the last one
+static int phase_call(txg_flow *h, int expect, const char *name) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (h->phase != expect)
+    TXG_FAIL(h, TXG_ERR_ORDER, "%s (procedure %d of 6) called out of the LBMRun2 order (lbm.F90:286-361): procedure %d is next", name,
+             expect + 1, h->phase + 1);
+  h->phase = (expect + 1) % 6;
+  return 0;
+}
+extern "C" int txg_collision(txg_handle h) { return phase_call(h, 0, "FlowCollision"); }
+extern "C" int txg_communicate_fi(txg_handle h) { return phase_call(h, 1, "DistributionCommunicateFi"); }
+extern "C" int txg_stream(txg_handle h) { return phase_call(h, 2, "FlowStream"); }
+extern "C" int txg_bounceback(txg_handle h) { return phase_call(h, 3, "FlowBounceback"); }
+extern "C" int txg_apply_bcs(txg_handle h) { return phase_call(h, 4, "FlowApplyBCs"); }
+extern "C" int txg_update_flux(txg_handle h) {
+  TXG_TRY(phase_call(h, 5, "FlowUpdateFlux"));
+  return txg_step(h, 1);
+}
+
+// ------------------------------------------------------------------ state out
+// refresh rho (+halo) from the current populations
+static int refresh_rho(txg_flow *h) {
+  if (h->rho_current) return 0;
+  TXG_TRY(run_moments(h, 0, h->g.NZl, h->s_main));
+  TXG_TRY(exchange_rho(h, h->rho, h->s_main));
+  h->rho_current = true;
+  return 0;
+}
+
+extern "C" int txg_update_moments(txg_handle h) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "txg_update_moments before txg_fi_init / txg_set_fi");
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  h->rho_current = false;
+  return refresh_rho(h);
+}
+
+static int run_export(txg_flow *h, double *rho_o, double *u_o, double *F_o, double *rhot, double *prs, double *velt) {
+  const Grid &g = h->g;
+  ScopedKernel sk(h, "k_export", h->s_main);
+  h->ks.export_state<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->p, h->f[h->cur], h->rho, h->nbmask, h->ffmask, h->cls,
+                                                                        rho_o, u_o, F_o, rhot, prs, velt,
+                                                                        h->cfg.null_pressure, 0, g.NZl);
+  TXG_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+static int ensure(txg_flow *h, double **p, size_t n) {
+  if (*p) return 0;
+  TXG_CUDA(h, cudaMalloc((void **)p, n * sizeof(double)));
+  return 0;
+}
+
+extern "C" int txg_get_fi(txg_handle h, double *fi_g) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (!fi_g) TXG_FAIL(h, TXG_ERR_ARG_NULL, "null array");
+  if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "no state on the device yet");
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  const Grid &g = h->g;
+  {
+    ScopedKernel sk(h, "k_stream_out", h->s_main);
+    h->ks.stream_out<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->f[h->cur], h->f[h->cur ^ 1], h->nbmask, 0, g.NZl);
+    TXG_CUDA(h, cudaGetLastError());
+  }
+  return export_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->S, h->f[h->cur ^ 1], g.fstride, 1);
+}
+
+extern "C" int txg_get_state(txg_handle h, double *rho_rg, double *u_g, double *forces_g) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "no state on the device yet");
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  const Grid &g = h->g;
+  TXG_TRY(refresh_rho(h));
+  const size_t n = (size_t)g.nnodes;
+  if (rho_rg) TXG_TRY(ensure(h, &h->x_rho, n * h->S));
+  if (u_g) TXG_TRY(ensure(h, &h->x_u, n * h->S * h->D));
+  if (forces_g) TXG_TRY(ensure(h, &h->x_F, n * h->S * h->D));
+  TXG_TRY(run_export(h, rho_rg ? h->x_rho : nullptr, u_g ? h->x_u : nullptr, forces_g ? h->x_F : nullptr, nullptr, nullptr, nullptr));
+  const int gz1 = h->D == 3 ? 1 : 0;
+  if (rho_rg) TXG_TRY(export_field(h, rho_rg, g.R, g.Rz, 1, h->S, h->x_rho, g.nnodes, 0));
+  if (u_g) TXG_TRY(export_field(h, u_g, 1, gz1, h->D, h->S, h->x_u, g.nnodes, 0));
+  if (forces_g) TXG_TRY(export_field(h, forces_g, 1, gz1, h->D, h->S, h->x_F, g.nnodes, 0));
+  return 0;
+}
+
+extern "C" int txg_get_diagnostics(txg_handle h, double *rhot, double *prs, double *velt) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "no state on the device yet");
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  const Grid &g = h->g;
+  TXG_TRY(refresh_rho(h));
+  const size_t n = (size_t)g.nnodes;
+  if (rhot) TXG_TRY(ensure(h, &h->x_rhot, n));
+  if (prs) TXG_TRY(ensure(h, &h->x_prs, n));
+  if (velt) TXG_TRY(ensure(h, &h->x_velt, n * h->D));
+  TXG_TRY(run_export(h, nullptr, nullptr, nullptr, rhot ? h->x_rhot : nullptr, prs ? h->x_prs : nullptr, velt ? h->x_velt : nullptr));
+  if (rhot) TXG_CUDA(h, cudaMemcpyAsync(rhot, h->x_rhot, n * 8, cudaMemcpyDeviceToHost, h->s_main));
+  if (prs) TXG_CUDA(h, cudaMemcpyAsync(prs, h->x_prs, n * 8, cudaMemcpyDeviceToHost, h->s_main));
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  if (velt) TXG_TRY(export_field(h, velt, 0, 0, h->D, 1, h->x_velt, g.nnodes, 0));
+  return 0;
+}
+
+extern "C" int txg_delta_norm(txg_handle h, double *norm) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (!norm) TXG_FAIL(h, TXG_ERR_ARG_NULL, "null norm");
+  if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "no state on the device yet");
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  const Grid &g = h->g;
+  const long long n = (long long)h->S * h->Q * g.fstride;
+  {
+    ScopedKernel sk(h, "k_stream_out", h->s_main);
+    h->ks.stream_out<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->f[h->cur], h->f[h->cur ^ 1], h->nbmask, 0, g.NZl);
+    TXG_CUDA(h, cudaGetLastError());
+  }
+  if (!h->f_old) {
+    TXG_CUDA(h, cudaMalloc((void **)&h->f_old, (size_t)n * 8));
+    TXG_CUDA(h, cudaMemsetAsync(h->f_old, 0, (size_t)n * 8, h->s_main));
+  }
+  TXG_CUDA(h, cudaMemsetAsync(h->norm_bits, 0, sizeof(unsigned long long), h->s_main));
+  // ghost planes of the node-value buffer hold stale data: compare owned planes only, per (m,n) block
+  for (int b = 0; b < h->S * h->Q; ++b) {
+    const long long off = (long long)b * g.fstride + g.plane;
+    k_delta_norm<<<blocks_for(g.nnodes, 256), 256, 0, h->s_main>>>(h->f[h->cur ^ 1] + off, h->f_old + off, g.nnodes, h->norm_bits);
+  }
+  TXG_CUDA(h, cudaGetLastError());
+  h->launches += h->S * h->Q;
+  unsigned long long bits = 0;
+  TXG_CUDA(h, cudaMemcpyAsync(&bits, h->norm_bits, sizeof bits, cudaMemcpyDeviceToHost, h->s_main));
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  double v;
+  memcpy(&v, &bits, sizeof v);
+  *norm = h->have_old ? v : 1.e99;  // lbm_distribution_function.F90:818
+  h->have_old = true;
+  return 0;
+}
+
+extern "C" int txg_synchronize(txg_handle h) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_comm));
+  return 0;
+}
+
+// ------------------------------------------------------------------ measurement hooks
+extern "C" int txg_last_step_ms(txg_handle h, float *ms, int64_t *launches) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  TXG_CUDA(h, cudaEventSynchronize(h->ev_step1));
+  float t = 0.f;
+  TXG_CUDA(h, cudaEventElapsedTime(&t, h->ev_step0, h->ev_step1));
+  if (ms) *ms = t;
+  if (launches) *launches = h->last_launches;
+  return 0;
+}
+extern "C" int txg_enable_kernel_timing(txg_handle h, int on) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  h->timing = on != 0;
+  return 0;
+}
+extern "C" int txg_reset_kernel_times(txg_handle h) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  drain_timers(h);
+  for (auto &t : h->timers) {
+    t.ms = 0.;
+    t.launches = 0;
+  }
+  return 0;
+}
+extern "C" int txg_kernel_times(txg_handle h, int cap, const char **names, double *ms, int64_t *launches, int *n) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  drain_timers(h);
+  int k = 0;
+  for (auto &t : h->timers) {
+    if (k >= cap) break;
+    if (names) names[k] = t.name.c_str();
+    if (ms) ms[k] = t.ms;
+    if (launches) launches[k] = t.launches;
+    ++k;
+  }
+  if (n) *n = k;
+  return 0;
+}

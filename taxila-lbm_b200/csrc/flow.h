@@ -1,0 +1,51 @@
+// flow.h -- host-side declarations shared by the translation units of libtaxila_gpu.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace txg {
+
+// One set of kernel entry points per (lattice, S, MRT, ISO) combination; the instantiations are
+// spread over inst_*.cu so they compile in parallel.
+struct KernelSet {
+  void (*moments)(Grid, Phys, const double *, double *, const uint32_t *, int, int);
+  void (*collide)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
+                  const uint8_t *, int, int);
+  void (*fi_init)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
+                  const uint32_t *, const uint8_t *, int, int);
+  void (*unstream)(Grid, const double *, double *, const uint32_t *, int, int);
+  void (*stream_out)(Grid, const double *, double *, const uint32_t *, int, int);
+  void (*export_state)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *,
+                       const uint8_t *, double *, double *, double *, double *, double *, double *, double, int, int);
+  void (*build_masks)(Grid, const uint8_t *, uint32_t *, uint32_t *, int *);
+  int ff_words;  // u32 words of ffmask per node (0 for isotropy order 4)
+  const char *name;
+};
+
+template <class L, int S, bool MRT, int ISO>
+KernelSet make_kernel_set(const char *name) {
+  KernelSet k;
+  k.moments = k_moments<L, S>;
+  k.collide = k_collide<L, S, MRT, ISO>;
+  k.fi_init = k_fi_init<L, S, ISO>;
+  k.unstream = k_unstream<L, S>;
+  k.stream_out = k_stream_out<L, S>;
+  k.export_state = k_export<L, S, ISO>;
+  k.build_masks = k_build_masks<L, ISO>;
+  k.ff_words = ISO == 4 ? 0 : ff_words<L>(ISO);
+  k.name = name;
+  return k;
+}
+
+// defined in inst_<lattice>_s<S>.cu; returns false if the combination is not built
+bool kernel_set_d3q19_s1(bool mrt, int iso, KernelSet *out);
+bool kernel_set_d3q19_s2(bool mrt, int iso, KernelSet *out);
+bool kernel_set_d3q19_s3(bool mrt, int iso, KernelSet *out);
+bool kernel_set_d2q9_s1(bool mrt, int iso, KernelSet *out);
+bool kernel_set_d2q9_s2(bool mrt, int iso, KernelSet *out);
+bool kernel_set_d2q9_s3(bool mrt, int iso, KernelSet *out);
+
+}  // namespace txg

@@ -1,0 +1,17 @@
+// inst_d3q19_s1.cu -- kernel instantiations for D3Q19, 1 component(s)
+#include "flow.h"
+namespace txg {
+bool kernel_set_d3q19_s1(bool mrt, int iso, KernelSet *out) {
+  if (iso == 4) {
+    *out = mrt ? make_kernel_set<D3Q19, 1, true, 4>("d3q19_s1_mrt_iso4")
+               : make_kernel_set<D3Q19, 1, false, 4>("d3q19_s1_srt_iso4");
+    return true;
+  }
+  if (iso == 8) {
+    *out = mrt ? make_kernel_set<D3Q19, 1, true, 8>("d3q19_s1_mrt_iso8")
+               : make_kernel_set<D3Q19, 1, false, 8>("d3q19_s1_srt_iso8");
+    return true;
+  }
+  return false;
+}
+}  // namespace txg

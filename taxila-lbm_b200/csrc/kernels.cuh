@@ -1,0 +1,613 @@
+// kernels.cuh -- device code of the flow hot path (sm_100a).
+//
+// Storage (all fp64, one slab per GPU, x fastest):
+//   f    [S][Q][NZl+2 ][NY][NX]   populations in PULL form: slot (m,n,X) holds the post-collision
+//                                 value that leaves X along c_n; the value a node sees after
+//                                 streaming + bounce-back is pull(X,n) below.  One ghost z-plane
+//                                 each side (filled by the halo exchange).
+//   rho  [S][NZl+2R][NY][NX]      per-component density (psi when a non-ideal EOS is on), R ghost planes
+//   cls  [NZl+2Rz][NY+2R][NX+2R]  u8 node class incl. ghosts, straight from the host walls(rg..) array
+//   nbmask [NZl][NY][NX]          u32: bit n = neighbour X+c_n is solid, bit 31 = X itself is solid
+//   ffmask [NW][NZl][NY][NX]      u32 words: bit e = fluid-fluid stencil entry e is active at X
+//                                 (isotropy order > 4 only; order 4 re-uses nbmask)
+//
+// Reference loops each kernel replaces are cited at the kernel.
+#pragma once
+#include <cstdint>
+
+#include "lattice.cuh"
+
+namespace txg {
+
+struct Grid {
+  int NX, NY, NZl;  // owned slab
+  int R, Rz;        // ghost width of rho/cls in x,y (R) and z (Rz = R in 3-D, 0 in 2-D)
+  int perx, pery;   // periodic flags (non-periodic neighbours are class 255 and never dereferenced)
+  long long plane;    // NX*NY
+  long long fstride;  // (NZl+2)*plane     distance between (m,n) blocks of f
+  long long rstride;  // (NZl+2R)*plane    distance between components of rho
+  long long nnodes;   // NZl*plane
+  int cnx, cny;       // NX+2R, NY+2R
+};
+
+constexpr int MAXS = 3;  // instantiated component counts: 1..3
+
+struct Phys {
+  // per component
+  double inv_tau[MAXS];        // SRT
+  double mrt_rate[MAXS][19];   // MRT: s_r / ||M_r||^2 per moment row
+  double mm[MAXS], d_k[MAXS], mmot[MAXS];
+  double gf[MAXS][MAXS];
+  double eos_rho0[MAXS];
+  int eos_sc[MAXS];            // 1: psi = rho0 (1 - exp(-rho/rho0)); 0: psi = rho
+  double gvt[3];
+  int nminerals;
+  int fluidfluid, fluidsolid, body, eos;
+  const double *gw;            // device [nminerals][S]
+};
+
+// ------------------------------------------------------------------ addressing helpers
+struct NodeIdx {
+  int x, y, z;      // owned coordinates
+  long long o;      // z*plane + y*NX + x  (nbmask / export index)
+};
+
+__device__ __forceinline__ bool node_of_thread(const Grid &g, int z0, int nz, NodeIdx &nd) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nz * g.plane) return false;
+  int zz = (int)(idx / g.plane);
+  int r = (int)(idx - (long long)zz * g.plane);
+  nd.y = r / g.NX;
+  nd.x = r - nd.y * g.NX;
+  nd.z = z0 + zz;
+  nd.o = (long long)nd.z * g.plane + r;
+  return true;
+}
+
+// wrapped neighbour coordinate (clamped when the direction is not periodic; such
+// neighbours are solid in the masks and never read)
+__device__ __forceinline__ int wrapc(int v, int N, int per) {
+  if (v < 0) return per ? v + N : 0;
+  if (v >= N) return per ? v - N : N - 1;
+  return v;
+}
+
+// ------------------------------------------------------------------ pull streaming with bounce-back
+// DistributionStreamD3/D2 + DistributionBouncebackD3/D2 (lbm_distribution_function.F90:560-784) in
+// pull form: f_n(X,t+1) = f*_n(X - c_n) if X - c_n is fluid, else f*_opp(n)(X)  (SURVEY.md 8a-11).
+template <class L, int S>
+__device__ __forceinline__ void pull(const Grid &g, const double *__restrict__ fA, const NodeIdx &nd, uint32_t mask,
+                                     double (&f)[S][L::Q]) {
+  const int xm = wrapc(nd.x - 1, g.NX, g.perx), xp = wrapc(nd.x + 1, g.NX, g.perx);
+  const int ym = wrapc(nd.y - 1, g.NY, g.pery), yp = wrapc(nd.y + 1, g.NY, g.pery);
+  static_for<0, L::Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    constexpr int on = opp<L>(n);
+    // source node X - c_n
+    const int sx = L::c(n, 0) == 0 ? nd.x : (L::c(n, 0) > 0 ? xm : xp);
+    const int sy = L::c(n, 1) == 0 ? nd.y : (L::c(n, 1) > 0 ? ym : yp);
+    const int sz = nd.z + 1 - L::c(n, 2);  // +1: ghost plane offset
+    const bool bounce = n != 0 && ((mask >> on) & 1u);
+    const long long src_node = bounce ? ((long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x)
+                                      : ((long long)sz * g.plane + (long long)sy * g.NX + sx);
+    const int src_dir = bounce ? on : n;
+#pragma unroll
+    for (int m = 0; m < S; ++m) f[m][n] = __ldg(fA + (long long)(m * L::Q + src_dir) * g.fstride + src_node);
+  });
+}
+
+// ------------------------------------------------------------------ forces
+// FlowCalcForces (lbm_flow.F90:760-808): F = 0; fluid-solid (LBMAddFluidSolidForcesD*,
+// lbm_forcing.F90:1326-1421); body (LBMAddBodyForcesD*, :1440-1496); fluid-fluid
+// (LBMAddFluidFluidForcesD*, :51-1299) -- in that order, entries in the reference's order.
+// `rho_here` is this node's density; `psi` the stencil field (rho, or psi(rho) with an EOS).
+template <class L, int S, int ISO>
+__device__ __forceinline__ void forces(const Grid &g, const Phys &p, const double *__restrict__ psi,
+                                       const uint8_t *__restrict__ cls, const uint32_t *__restrict__ ffmask,
+                                       const NodeIdx &nd, uint32_t mask, const double (&rho_here)[S],
+                                       double (&F)[S][L::D]) {
+  constexpr int D = L::D;
+#pragma unroll
+  for (int m = 0; m < S; ++m)
+#pragma unroll
+    for (int d = 0; d < D; ++d) F[m][d] = 0.;
+
+  if (p.fluidsolid && (mask & 0x7fffffffu)) {
+    const long long cbase = ((long long)(nd.z + g.Rz) * g.cny + (nd.y + g.R)) * g.cnx + (nd.x + g.R);
+    static_for<1, L::Q>([&](auto n_) {
+      constexpr int n = decltype(n_)::value;
+      if ((mask >> n) & 1u) {
+        const long long coff = ((long long)L::c(n, 2) * g.cny + L::c(n, 1)) * g.cnx + L::c(n, 0);
+        const int id = cls[cbase + coff];
+        // 0 < walls < 998 and a valid mineral (lbm_forcing.F90:1352); 800/900-902 index out of
+        // bounds in the reference and contribute nothing here
+        if (id >= 1 && id <= p.nminerals) {
+          constexpr double w = L::fs_weight(n);
+          static_for<0, D>([&](auto d_) {
+            constexpr int d = decltype(d_)::value;
+            if constexpr (L::c(n, d) != 0) {
+#pragma unroll
+              for (int m = 0; m < S; ++m)
+                F[m][d] = F[m][d] - w * rho_here[m] * p.gw[(id - 1) * S + m] * (double)L::c(n, d);
+            }
+          });
+        }
+      }
+    });
+  }
+
+  if (p.body) {
+#pragma unroll
+    for (int m = 0; m < S; ++m)
+#pragma unroll
+      for (int d = 0; d < D; ++d) F[m][d] = F[m][d] + p.gvt[d] * p.mm[m] * rho_here[m];
+  }
+
+  if (p.fluidfluid) {
+    using FF = typename L::FF;
+    constexpr int E = ff_entries<L>(ISO);
+    constexpr int RAD = stencil_radius(ISO);
+    double G[D][S], W[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      W[d] = 0.;
+#pragma unroll
+      for (int m = 0; m < S; ++m) G[d][m] = 0.;
+    }
+    // wrapped coordinates for every offset in [-RAD, RAD]
+    int xi[2 * RAD + 1], yi[2 * RAD + 1];
+#pragma unroll
+    for (int a = -RAD; a <= RAD; ++a) {
+      xi[a + RAD] = wrapc(nd.x + a, g.NX, g.perx);
+      yi[a + RAD] = wrapc(nd.y + a, g.NY, g.pery);
+    }
+    double psi_here[S];
+#pragma unroll
+    for (int m = 0; m < S; ++m) psi_here[m] = p.eos ? psi[m * g.rstride + (long long)(nd.z + g.R) * g.plane + (long long)nd.y * g.NX + nd.x] : rho_here[m];
+
+    uint32_t words[(E + 31) / 32];
+    if constexpr (ISO != 4) {
+#pragma unroll
+      for (int w = 0; w < (E + 31) / 32; ++w) words[w] = ffmask[(long long)w * g.nnodes + nd.o];
+    }
+    static_for<0, E>([&](auto e_) {
+      constexpr int e = decltype(e_)::value;
+      constexpr int dx = FF::off[e][0], dy = FF::off[e][1], dz = FF::off[e][2];
+      bool active;
+      if constexpr (ISO == 4) {
+        constexpr int n = dir_of<L>(dx, dy, dz);  // order-4 offsets are the lattice directions
+        active = !((mask >> n) & 1u);
+      } else {
+        active = (words[e / 32] >> (e % 32)) & 1u;
+      }
+      if (active) {
+        constexpr double wgt = L::ffw(ISO, FF::L[e]);
+        const long long nb = (long long)(nd.z + g.R + dz) * g.plane + (long long)yi[dy + RAD] * g.NX + xi[dx + RAD];
+        double diff[S];
+#pragma unroll
+        for (int m = 0; m < S; ++m) diff[m] = __ldg(psi + m * g.rstride + nb) - psi_here[m];
+        if constexpr (dx != 0) {
+#pragma unroll
+          for (int m = 0; m < S; ++m) G[0][m] = G[0][m] + ((double)dx * wgt) * diff[m];
+          W[0] = W[0] + wgt * (double)(dx * dx);
+        }
+        if constexpr (dy != 0) {
+#pragma unroll
+          for (int m = 0; m < S; ++m) G[1][m] = G[1][m] + ((double)dy * wgt) * diff[m];
+          W[1] = W[1] + wgt * (double)(dy * dy);
+        }
+        if constexpr (D == 3 && dz != 0) {
+#pragma unroll
+          for (int m = 0; m < S; ++m) G[D - 1][m] = G[D - 1][m] + ((double)dz * wgt) * diff[m];
+          W[D - 1] = W[D - 1] + wgt * (double)(dz * dz);
+        }
+      }
+    });
+    const double eps = (double)1.e-12f;  // default-real literal, lbm_forcing.F90:69
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      if (W[d] > eps) {
+#pragma unroll
+        for (int m = 0; m < S; ++m) {
+          double acc = 0.;
+#pragma unroll
+          for (int mp = 0; mp < S; ++mp) acc += p.gf[m][mp] * (G[d][mp] / W[d]);
+          F[m][d] = F[m][d] - 6.0 * psi_here[m] * acc;  // c_0 = 6 on both lattices
+        }
+      }
+  }
+}
+
+// ------------------------------------------------------------------ moments
+// density of the streamed populations, ascending n like sum(fi(:,:,i,j,k),2)
+// (DistributionCalcDensityD*, lbm_distribution_function.F90:379-428)
+template <class L, int S>
+__device__ __forceinline__ void density(const double (&f)[S][L::Q], double (&rho)[S]) {
+#pragma unroll
+  for (int m = 0; m < S; ++m) {
+    double a = 0.;
+#pragma unroll
+    for (int n = 0; n < L::Q; ++n) a += f[m][n];
+    rho[m] = a;
+  }
+}
+
+// momentum j (DistributionCalcFluxD*, :451-508) and the common velocity u'
+// (FlowUpdateUED*, lbm_flow.F90:494-574)
+template <class L, int S>
+__device__ __forceinline__ void common_velocity(const Phys &p, const double (&f)[S][L::Q], const double (&rho)[S],
+                                                const double (&F)[S][L::D], double (&up)[L::D]) {
+  constexpr int D = L::D;
+  double ue[S][D];
+#pragma unroll
+  for (int m = 0; m < S; ++m)
+    static_for<0, D>([&](auto d_) {
+      constexpr int d = decltype(d_)::value;
+      double a = 0.;
+      static_for<0, L::Q>([&](auto n_) {
+        constexpr int n = decltype(n_)::value;
+        if constexpr (L::c(n, d) != 0) a += f[m][n] * (double)L::c(n, d);
+      });
+      ue[m][d] = a + .5 * F[m][d];
+    });
+  double den = 0.;
+#pragma unroll
+  for (int m = 0; m < S; ++m) den += rho[m] * p.mmot[m];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double num = 0.;
+#pragma unroll
+    for (int m = 0; m < S; ++m) num += ue[m][d] * p.mmot[m];
+    up[d] = num / den;
+  }
+}
+
+// equilibrium (DiscretizationEquilf_D3Q19/D2Q9) for one component
+template <class L>
+__device__ __forceinline__ void equilibrium(double rho, double d_k, const double (&u)[L::D], double (&feq)[L::Q]) {
+  constexpr double c_s2 = 1.0 / 3.0;
+  double usqr = 0.;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) usqr += u[d] * u[d];
+  feq[0] = rho * L::feq0(d_k, usqr);
+  const double base = 1.5 * (1. - d_k) - usqr / (2. * c_s2);
+  static_for<1, L::Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    double udote = 0.;
+    static_for<0, L::D>([&](auto d_) {
+      constexpr int d = decltype(d_)::value;
+      if constexpr (L::c(n, d) != 0) udote += (double)L::c(n, d) * u[d];
+    });
+    feq[n] = L::w(n) * rho * (base + udote / c_s2 + udote * udote / (2. * c_s2 * c_s2));
+  });
+}
+
+// prefactor(m,n) = sum_d F(m,d)(c_n,d - u_d) / (rho_m c_s2)  (FlowFiBarEqPrefactor, lbm_flow.F90:836-851)
+template <class L>
+__device__ __forceinline__ void prefactor(double rho, const double (&F)[L::D], const double (&u)[L::D],
+                                          double (&pref)[L::Q]) {
+  const double inv = 1. / (rho * (1.0 / 3.0));
+  static_for<0, L::Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    double a = 0.;
+#pragma unroll
+    for (int d = 0; d < L::D; ++d) a += F[d] * ((double)L::c(n, d) - u[d]);
+    pref[n] = a * inv;
+  });
+}
+
+// collision of one component (FlowCollisionD3/D2 lbm_flow.F90:960-1029 with
+// RelaxationCollideSRT/MRT lbm_relaxation.F90:171-200): f <- relax(f, (1-pref/2) feq) + pref feq
+template <class L, bool MRT>
+__device__ __forceinline__ void collide_component(const Phys &p, int m, double (&f)[L::Q], const double (&feq)[L::Q],
+                                                  const double (&pref)[L::Q]) {
+  constexpr int Q = L::Q;
+  if constexpr (!MRT) {
+    const double it = p.inv_tau[m];
+#pragma unroll
+    for (int n = 0; n < Q; ++n) {
+      const double fbar = (1. - .5 * pref[n]) * feq[n];
+      f[n] = f[n] - (f[n] - fbar) * it + pref[n] * feq[n];
+    }
+  } else {
+    double dfi[Q];
+#pragma unroll
+    for (int n = 0; n < Q; ++n) dfi[n] = f[n] - (1. - .5 * pref[n]) * feq[n];
+    static_for<0, Q>([&](auto r_) {
+      constexpr int r = decltype(r_)::value;
+      double mom = 0.;
+      static_for<0, Q>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        if constexpr (L::M(r, i) != 0) mom += (double)L::M(r, i) * dfi[i];
+      });
+      const double cr = p.mrt_rate[m][r] * mom;
+      static_for<0, Q>([&](auto i_) {
+        constexpr int i = decltype(i_)::value;
+        if constexpr (L::M(r, i) != 0) f[i] = f[i] - cr * (double)L::M(r, i);
+      });
+    });
+#pragma unroll
+    for (int n = 0; n < Q; ++n) f[n] = f[n] + pref[n] * feq[n];
+  }
+}
+
+__device__ __forceinline__ double eos_psi(const Phys &p, int m, double rho) {
+  return p.eos_sc[m] ? p.eos_rho0[m] * (1. - exp(-rho / p.eos_rho0[m])) : rho;
+}
+
+// ================================================================== kernels
+
+// K1 moments: stream + bounce-back folded into the read, rho_m = sum_n f_n; writes rho (psi with an
+// EOS).  Replaces DistributionStreamD*, DistributionBouncebackD*, DistributionCalcDensityD*, EOSApply.
+// Solid nodes are never written: rho stays 0 there from allocation.
+template <class L, int S>
+__global__ void __launch_bounds__(128) k_moments(Grid g, Phys p, const double *__restrict__ fA,
+                                                 double *__restrict__ rho, const uint32_t *__restrict__ nbmask, int z0,
+                                                 int nz) {
+  NodeIdx nd;
+  if (!node_of_thread(g, z0, nz, nd)) return;
+  const uint32_t mask = nbmask[nd.o];
+  if (mask >> 31) return;
+  double f[S][L::Q], r[S];
+  pull<L, S>(g, fA, nd, mask, f);
+  density<L, S>(f, r);
+  const long long o = (long long)(nd.z + g.R) * g.plane + (long long)nd.y * g.NX + nd.x;
+#pragma unroll
+  for (int m = 0; m < S; ++m) rho[m * g.rstride + o] = p.eos ? eos_psi(p, m, r[m]) : r[m];
+}
+
+// K2 collide: pull again, forces from the rho stencil, momentum, common velocity, equilibrium,
+// prefactor, SRT/MRT relaxation, forcing term; writes the post-collision populations.
+// Replaces LBMAddFluidFluid/FluidSolid/BodyForcesD*, DistributionCalcFluxD*, FlowUpdateUED*,
+// DiscretizationEquilf_*, FlowFiBarEqPrefactor, FlowCollisionD*, RelaxationCollide*.
+template <class L, int S, bool MRT, int ISO>
+__global__ void __launch_bounds__(128) k_collide(Grid g, Phys p, const double *__restrict__ fA,
+                                                 double *__restrict__ fB, const double *__restrict__ rho,
+                                                 const uint32_t *__restrict__ nbmask,
+                                                 const uint32_t *__restrict__ ffmask, const uint8_t *__restrict__ cls,
+                                                 int z0, int nz) {
+  NodeIdx nd;
+  if (!node_of_thread(g, z0, nz, nd)) return;
+  const uint32_t mask = nbmask[nd.o];
+  if (mask >> 31) return;
+  constexpr int Q = L::Q, D = L::D;
+  double f[S][Q], r[S], F[S][D], up[D];
+  pull<L, S>(g, fA, nd, mask, f);
+  density<L, S>(f, r);
+  forces<L, S, ISO>(g, p, rho, cls, ffmask, nd, mask, r, F);
+  common_velocity<L, S>(p, f, r, F, up);
+  const long long o = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
+#pragma unroll
+  for (int m = 0; m < S; ++m) {
+    double feq[Q], pref[Q];
+    equilibrium<L>(r[m], p.d_k[m], up, feq);
+    prefactor<L>(r[m], F[m], up, pref);
+    collide_component<L, MRT>(p, m, f[m], feq, pref);
+#pragma unroll
+    for (int n = 0; n < Q; ++n) fB[(long long)(m * Q + n) * g.fstride + o] = f[m][n];
+  }
+}
+
+// K3 fi_init (FlowFiInit lbm_flow.F90:923-934, FlowFeqBarD* :867-921): F from rho0, feq(rho0, u0),
+// f = (1 - prefactor/2) feq, written as NODE values (post-stream form) into fN; k_unstream then
+// converts to pull form.  u0 is [S][D][nnodes] or null (= 0).
+template <class L, int S, int ISO>
+__global__ void __launch_bounds__(128) k_fi_init(Grid g, Phys p, double *__restrict__ fN,
+                                                 const double *__restrict__ rho, const double *__restrict__ rho_true,
+                                                 const double *__restrict__ u0, const uint32_t *__restrict__ nbmask,
+                                                 const uint32_t *__restrict__ ffmask, const uint8_t *__restrict__ cls,
+                                                 int z0, int nz) {
+  NodeIdx nd;
+  if (!node_of_thread(g, z0, nz, nd)) return;
+  const uint32_t mask = nbmask[nd.o];
+  if (mask >> 31) return;
+  constexpr int Q = L::Q, D = L::D;
+  double r[S], F[S][D];
+  const long long ro = (long long)(nd.z + g.R) * g.plane + (long long)nd.y * g.NX + nd.x;
+#pragma unroll
+  for (int m = 0; m < S; ++m) r[m] = rho_true[m * g.rstride + ro];
+  forces<L, S, ISO>(g, p, rho, cls, ffmask, nd, mask, r, F);
+  const long long o = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
+#pragma unroll
+  for (int m = 0; m < S; ++m) {
+    double u[D], feq[Q], pref[Q];
+#pragma unroll
+    for (int d = 0; d < D; ++d) u[d] = u0 ? u0[(long long)(m * D + d) * g.nnodes + nd.o] : 0.;
+    equilibrium<L>(r[m], p.d_k[m], u, feq);
+    prefactor<L>(r[m], F[m], u, pref);
+#pragma unroll
+    for (int n = 0; n < Q; ++n) fN[(long long)(m * Q + n) * g.fstride + o] = (1. - 0.5 * pref[n]) * feq[n];
+  }
+}
+
+// node values -> pull form: A_n(Y) = f_n(Y + c_n) if Y + c_n is fluid, else f_opp(n)(Y).
+// Exact inverse of pull(); used after fi_init and txg_set_fi.
+template <class L, int S>
+__global__ void __launch_bounds__(128) k_unstream(Grid g, const double *__restrict__ fN, double *__restrict__ fA,
+                                                  const uint32_t *__restrict__ nbmask, int z0, int nz) {
+  NodeIdx nd;
+  if (!node_of_thread(g, z0, nz, nd)) return;
+  const uint32_t mask = nbmask[nd.o];
+  if (mask >> 31) return;
+  const int xm = wrapc(nd.x - 1, g.NX, g.perx), xp = wrapc(nd.x + 1, g.NX, g.perx);
+  const int ym = wrapc(nd.y - 1, g.NY, g.pery), yp = wrapc(nd.y + 1, g.NY, g.pery);
+  const long long o = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
+  static_for<0, L::Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    const int tx = L::c(n, 0) == 0 ? nd.x : (L::c(n, 0) > 0 ? xp : xm);
+    const int ty = L::c(n, 1) == 0 ? nd.y : (L::c(n, 1) > 0 ? yp : ym);
+    const int tz = nd.z + 1 + L::c(n, 2);
+    const bool solid = n != 0 && ((mask >> n) & 1u);
+    const long long src = solid ? o : ((long long)tz * g.plane + (long long)ty * g.NX + tx);
+    const int sd = solid ? opp<L>(n) : n;
+#pragma unroll
+    for (int m = 0; m < S; ++m)
+      fA[(long long)(m * L::Q + n) * g.fstride + o] = fN[(long long)(m * L::Q + sd) * g.fstride + src];
+  });
+}
+
+// pull form -> node values (what the reference holds in fi after FlowBounceback); solid nodes 0.
+template <class L, int S>
+__global__ void __launch_bounds__(128) k_stream_out(Grid g, const double *__restrict__ fA, double *__restrict__ fN,
+                                                    const uint32_t *__restrict__ nbmask, int z0, int nz) {
+  NodeIdx nd;
+  if (!node_of_thread(g, z0, nz, nd)) return;
+  const uint32_t mask = nbmask[nd.o];
+  const long long o = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
+  double f[S][L::Q];
+  if (mask >> 31) {
+#pragma unroll
+    for (int m = 0; m < S; ++m)
+#pragma unroll
+      for (int n = 0; n < L::Q; ++n) f[m][n] = 0.;
+  } else {
+    pull<L, S>(g, fA, nd, mask, f);
+  }
+#pragma unroll
+  for (int m = 0; m < S; ++m)
+#pragma unroll
+    for (int n = 0; n < L::Q; ++n) fN[(long long)(m * L::Q + n) * g.fstride + o] = f[m][n];
+}
+
+// K6 state/diagnostics export: from the pull-form populations and the current rho field compute
+// what the reference holds after FlowUpdateMoments (rho, forces, common velocity u') and what
+// FlowUpdateDiagnosticsD* (lbm_flow.F90:654-758) derives (rhot, prs, velt).  Any output may be null.
+template <class L, int S, int ISO>
+__global__ void __launch_bounds__(128) k_export(Grid g, Phys p, const double *__restrict__ fA,
+                                                const double *__restrict__ rho, const uint32_t *__restrict__ nbmask,
+                                                const uint32_t *__restrict__ ffmask, const uint8_t *__restrict__ cls,
+                                                double *__restrict__ rho_out /*[S][nnodes]*/,
+                                                double *__restrict__ u_out /*[S][D][nnodes]*/,
+                                                double *__restrict__ F_out /*[S][D][nnodes]*/,
+                                                double *__restrict__ rhot, double *__restrict__ prs,
+                                                double *__restrict__ velt /*[D][nnodes]*/, double null_pressure,
+                                                int z0, int nz) {
+  NodeIdx nd;
+  if (!node_of_thread(g, z0, nz, nd)) return;
+  const uint32_t mask = nbmask[nd.o];
+  constexpr int Q = L::Q, D = L::D;
+  if (mask >> 31) {
+#pragma unroll
+    for (int m = 0; m < S; ++m) {
+      if (rho_out) rho_out[m * g.nnodes + nd.o] = 0.;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        if (u_out) u_out[(long long)(m * D + d) * g.nnodes + nd.o] = 0.;
+        if (F_out) F_out[(long long)(m * D + d) * g.nnodes + nd.o] = 0.;
+      }
+    }
+    if (rhot) rhot[nd.o] = 0.;
+    if (prs) prs[nd.o] = null_pressure;
+    if (velt)
+#pragma unroll
+      for (int d = 0; d < D; ++d) velt[(long long)d * g.nnodes + nd.o] = 0.;
+    return;
+  }
+  double f[S][Q], r[S], F[S][D], up[D];
+  pull<L, S>(g, fA, nd, mask, f);
+  density<L, S>(f, r);
+  forces<L, S, ISO>(g, p, rho, cls, ffmask, nd, mask, r, F);
+  common_velocity<L, S>(p, f, r, F, up);
+#pragma unroll
+  for (int m = 0; m < S; ++m) {
+    if (rho_out) rho_out[m * g.nnodes + nd.o] = r[m];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      if (u_out) u_out[(long long)(m * D + d) * g.nnodes + nd.o] = up[d];
+      if (F_out) F_out[(long long)(m * D + d) * g.nnodes + nd.o] = F[m][d];
+    }
+  }
+  if (rhot || prs || velt) {
+    double rt = 0.;
+#pragma unroll
+    for (int m = 0; m < S; ++m) rt += r[m] * p.mm[m];
+    if (rhot) rhot[nd.o] = rt;
+    if (prs) {
+      double pr = rt / 3.;
+      if (p.eos || S > 1) {
+        double ps[S];
+#pragma unroll
+        for (int m = 0; m < S; ++m) ps[m] = p.eos ? eos_psi(p, m, r[m]) : r[m];
+#pragma unroll
+        for (int m = 0; m < S; ++m) {
+          double acc = 0.;
+#pragma unroll
+          for (int mp = 0; mp < S; ++mp) acc += p.gf[m][mp] * ps[mp];
+          pr = pr + 6.0 / 2. * ps[m] * acc;
+        }
+      }
+      prs[nd.o] = pr;
+    }
+    if (velt) {
+      static_for<0, D>([&](auto d_) {
+        constexpr int d = decltype(d_)::value;
+        double a = 0.;
+#pragma unroll
+        for (int m = 0; m < S; ++m) {
+          double j = 0.;
+          static_for<0, Q>([&](auto n_) {
+            constexpr int n = decltype(n_)::value;
+            if constexpr (L::c(n, d) != 0) j += f[m][n] * (double)L::c(n, d);
+          });
+          a += (j + .5 * F[m][d]) * p.mm[m];
+        }
+        velt[(long long)d * g.nnodes + nd.o] = a / rt;
+      });
+    }
+  }
+}
+
+// ------------------------------------------------------------------ set-up kernels
+
+// nbmask and the fluid-fluid activity bits, evaluated once per walls upload.
+// Line-of-sight rule: SURVEY.md 8a-15 / ff_stencil.cuh.
+template <class L, int ISO>
+__global__ void k_build_masks(Grid g, const uint8_t *__restrict__ cls, uint32_t *__restrict__ nbmask,
+                              uint32_t *__restrict__ ffmask, int *__restrict__ specular) {
+  NodeIdx nd;
+  if (!node_of_thread(g, 0, g.NZl, nd)) return;
+  const long long cbase = ((long long)(nd.z + g.Rz) * g.cny + (nd.y + g.R)) * g.cnx + (nd.x + g.R);
+  auto solid = [&](int dx, int dy, int dz) -> bool {
+    return cls[cbase + ((long long)dz * g.cny + dy) * g.cnx + dx] != 0;
+  };
+  uint32_t mask = solid(0, 0, 0) ? 0x80000000u : 0u;
+  static_for<1, L::Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    const uint8_t c = cls[cbase + ((long long)L::c(n, 2) * g.cny + L::c(n, 1)) * g.cnx + L::c(n, 0)];
+    if (c != 0) mask |= 1u << n;
+    if (c >= 250 && c <= 252 && !(mask >> 31)) atomicAdd(specular, 1);
+  });
+  nbmask[nd.o] = mask;
+  if constexpr (ISO != 4) {
+    using FF = typename L::FF;
+    constexpr int E = ff_entries<L>(ISO);
+    uint32_t words[(E + 31) / 32];
+#pragma unroll
+    for (int w = 0; w < (E + 31) / 32; ++w) words[w] = 0u;
+    static_for<0, E>([&](auto e_) {
+      constexpr int e = decltype(e_)::value;
+      constexpr int ox = FF::off[e][0], oy = FF::off[e][1], oz = FF::off[e][2];
+      bool ok = !solid(ox, oy, oz);
+      bool any = false;
+      static_for<0, FF::MAXALT>([&](auto a_) {
+        constexpr int a = decltype(a_)::value;
+        if constexpr (a < FF::nalt[e]) {
+          bool all = true;
+          static_for<0, FF::MAXLEN>([&](auto j_) {
+            constexpr int j = decltype(j_)::value;
+            if constexpr (j < FF::altlen[e][a]) {
+              constexpr int lx = FF::los[e][a][j][0], ly = FF::los[e][a][j][1], lz = FF::los[e][a][j][2];
+              all = all && !solid(lx, ly, lz);
+            }
+          });
+          any = any || all;
+        }
+      });
+      if (ok && any) words[e / 32] |= 1u << (e % 32);
+    });
+#pragma unroll
+    for (int w = 0; w < (E + 31) / 32; ++w) ffmask[(long long)w * g.nnodes + nd.o] = words[w];
+  }
+}
+
+}  // namespace txg

@@ -1,0 +1,204 @@
+"""Host-side mirror of the reference's flow interface over the C ABI.
+
+Method names follow the reference's module procedures (src/lbm/lbm_flow.F90 public list :84-102,
+src/lbm/lbm.F90 LBMInit2/LBMRun2) so a driver written against `Flow` reads like lbm.F90:
+
+    flow = Flow(cfg)                      # FlowCreate + FlowSetUp
+    flow.walls_set_values(walls_rg)       # WallsSetValues/WallsCommunicate result
+    flow.initialize_state(rho_rg)         # LBMInitializeState result
+    flow.fi_init()                        # FlowFiInit            lbm.F90:212
+    flow.update_moments()                 # FlowUpdateMoments     lbm.F90:238
+    flow.run(istep, kstep)                # LBMRun2 loop body x (kstep-istep)
+    flow.get_arrays() / update_diagnostics()
+
+All arrays are numpy float64 in the reference's local ghosted layouts (see geometry.ghosted).
+Everything computes on the GPU through libtaxila_gpu.so; nothing here does arithmetic.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .config import TxgConfig
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _c(a):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+class Flow:
+    def __init__(self, cfg: TxgConfig, device=0, nccl_id=None):
+        self.lib = capi.load()
+        self.cfg = cfg.copy()
+        self.h = C.c_void_p()
+        rc = self.lib.txg_create(C.byref(self.h), C.byref(self.cfg), int(device))
+        if rc:
+            msg = self.lib.txg_last_error(None)
+            raise capi.TaxilaGpuError(rc, msg.decode() if msg else "")
+        c = self.cfg
+        self.S, self.Q, self.D, self.R = c.ncomponents, c.Q, c.ndims, c.stencil_size_rho
+        self.NZl = c.zl if c.ndims == 3 else 1
+        self.NY, self.NX = c.NY, c.NX
+        if c.nranks > 1:
+            if nccl_id is None:
+                raise ValueError("nranks > 1 needs the NCCL unique id broadcast from rank 0")
+            buf = (C.c_ubyte * 128).from_buffer_copy(bytes(nccl_id))
+            self._check(self.lib.txg_comm_init(self.h, buf))
+
+    # ---- plumbing
+    def _check(self, rc):
+        capi.check(self.lib, self.h, rc)
+
+    def close(self):
+        if self.h:
+            self.lib.txg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def nccl_unique_id():
+        lib = capi.load()
+        buf = (C.c_ubyte * 128)()
+        rc = lib.txg_nccl_unique_id(buf)
+        if rc:
+            raise capi.TaxilaGpuError(rc, lib.txg_last_error(None).decode())
+        return bytes(buf)
+
+    # ---- local ghosted shapes (C order == the reference's Fortran arrays)
+    def _gz(self, w):
+        return w if self.D == 3 else 0
+
+    def shape_walls(self):
+        R = self.R
+        return (self.NZl + 2 * self._gz(R), self.NY + 2 * R, self.NX + 2 * R)
+
+    def shape_rho(self):
+        return self.shape_walls() + (self.S,)
+
+    def shape_fi(self):
+        return (self.NZl + 2 * self._gz(1), self.NY + 2, self.NX + 2, self.Q, self.S)
+
+    def shape_u(self):
+        return (self.NZl + 2 * self._gz(1), self.NY + 2, self.NX + 2, self.D, self.S)
+
+    def _expect(self, a, shape, what):
+        if a.shape != shape:
+            raise ValueError("%s: expected local ghosted shape %s, got %s" % (what, shape, a.shape))
+
+    # ---- set-up (lbm.F90:140-175,183-253,444-453)
+    def walls_set_values(self, walls_rg):
+        w = _c(walls_rg)
+        self._expect(w, self.shape_walls(), "walls")
+        self._check(self.lib.txg_set_walls(self.h, _dp(w)))
+
+    def initialize_state(self, rho_rg, u_g=None):
+        r = _c(rho_rg)
+        self._expect(r, self.shape_rho(), "rho")
+        u = _c(u_g)
+        if u is not None:
+            self._expect(u, self.shape_u(), "u")
+        self._check(self.lib.txg_set_rho_u(self.h, _dp(r), _dp(u)))
+
+    def set_fi(self, fi_g):
+        f = _c(fi_g)
+        self._expect(f, self.shape_fi(), "fi")
+        self._check(self.lib.txg_set_fi(self.h, _dp(f)))
+
+    def fi_init(self):
+        self._check(self.lib.txg_fi_init(self.h))
+
+    def update_moments(self):
+        self._check(self.lib.txg_update_moments(self.h))
+
+    # ---- time stepping (lbm.F90:262-422)
+    def step(self, nsteps=1):
+        self._check(self.lib.txg_step(self.h, int(nsteps)))
+
+    def run(self, istep, kstep):
+        """LBMRun2's loop `do lcv_step = istep+1, kstep`."""
+        self.step(kstep - istep)
+
+    def collision(self):
+        self._check(self.lib.txg_collision(self.h))
+
+    def communicate_fi(self):
+        self._check(self.lib.txg_communicate_fi(self.h))
+
+    def stream(self):
+        self._check(self.lib.txg_stream(self.h))
+
+    def bounceback(self):
+        self._check(self.lib.txg_bounceback(self.h))
+
+    def apply_bcs(self):
+        self._check(self.lib.txg_apply_bcs(self.h))
+
+    def update_flux(self):
+        self._check(self.lib.txg_update_flux(self.h))
+
+    def synchronize(self):
+        self._check(self.lib.txg_synchronize(self.h))
+
+    # ---- state out
+    def get_fi(self, out=None):
+        f = np.zeros(self.shape_fi()) if out is None else out
+        self._check(self.lib.txg_get_fi(self.h, _dp(f)))
+        return f
+
+    def get_arrays(self, rho=True, u=True, forces=True):
+        """FlowGetArrays view: (rho_rg, u_g, forces_g); ghost entries are left as passed (zero)."""
+        r = np.zeros(self.shape_rho()) if rho else None
+        uu = np.zeros(self.shape_u()) if u else None
+        ff = np.zeros(self.shape_u()) if forces else None
+        self._check(self.lib.txg_get_state(self.h, _dp(r), _dp(uu), _dp(ff)))
+        return r, uu, ff
+
+    def update_diagnostics(self):
+        """FlowUpdateDiagnostics: (rhot[z,y,x], prs[z,y,x], velt[z,y,x,d]) owned only."""
+        n = (self.NZl, self.NY, self.NX)
+        rhot, prs, velt = np.zeros(n), np.zeros(n), np.zeros(n + (self.D,))
+        self._check(self.lib.txg_get_diagnostics(self.h, _dp(rhot), _dp(prs), _dp(velt)))
+        return rhot, prs, velt
+
+    def node_class(self):
+        out = np.zeros(self.shape_walls(), dtype=np.uint8)
+        self._check(self.lib.txg_get_node_class(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def delta_norm(self):
+        v = C.c_double()
+        self._check(self.lib.txg_delta_norm(self.h, C.byref(v)))
+        return v.value
+
+    # ---- measurement
+    def last_step_ms(self):
+        ms, n = C.c_float(), C.c_int64()
+        self._check(self.lib.txg_last_step_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def enable_kernel_timing(self, on=True):
+        self._check(self.lib.txg_enable_kernel_timing(self.h, int(on)))
+
+    def reset_kernel_times(self):
+        self._check(self.lib.txg_reset_kernel_times(self.h))
+
+    def kernel_times(self):
+        cap = 32
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        ln = (C.c_int64 * cap)()
+        n = C.c_int()
+        self._check(self.lib.txg_kernel_times(self.h, cap, names, ms, ln, C.byref(n)))
+        return {names[i].decode(): (ms[i], ln[i]) for i in range(n.value)}

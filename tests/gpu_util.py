@@ -1,0 +1,33 @@
+"""Drive the CUDA path through the C ABI the way lbm.F90 drives the reference (LBMInit2 + LBMRun2)."""
+import numpy as np
+
+import taxila_lbm_b200 as tx
+from taxila_lbm_b200 import geometry as geo
+
+
+def make_flow(cfg, walls, rho, device=0):
+    """FlowSetUp, walls, initial state, FlowFiInit, FlowUpdateMoments on one GPU."""
+    D = cfg.ndims
+    R = cfg.stencil_size_rho
+    flow = tx.Flow(cfg, device=device)
+    walls_rg = geo.ghosted(walls, R, cfg.periodic, D, wall_ghost=True)
+    flow.walls_set_values(walls_rg)
+    rho_rg = geo.ghosted(rho, R, cfg.periodic, D)
+    flow.initialize_state(rho_rg)
+    flow.fi_init()
+    flow.update_moments()
+    return flow
+
+
+def fields(flow):
+    """(fi, rho, u, forces) in natural order, owned nodes only."""
+    D = flow.D
+    fi = geo.owned(flow.get_fi(), 1, D)
+    rho, u, F = flow.get_arrays()
+    return fi, geo.owned(rho, flow.R, D), geo.owned(u, 1, D), geo.owned(F, 1, D)
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b| (the parity definition of SURVEY.md 8d)."""
+    den = np.abs(b).max()
+    return np.abs(a - b).max() / (den if den > 0 else 1.0)
