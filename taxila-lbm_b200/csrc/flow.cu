@@ -109,6 +109,11 @@ struct txg_flow {
   double *gw = nullptr;
   uint8_t *cls = nullptr;
   uint32_t *nbmask = nullptr, *ffmask = nullptr;
+  // ascending list of fluid node indices (nullptr: every node is fluid) and, per owned z-plane, the
+  // offset of its first entry; plane_off[NZl] = number of fluid nodes
+  uint32_t *flist = nullptr;
+  std::vector<long long> plane_off;
+  long long nfluid = 0;
   int *counters = nullptr;  // [0] bad wall codes, [1] fluid nodes next to 900-902 walls
   double *staging = nullptr;
   size_t staging_bytes = 0;
@@ -279,6 +284,8 @@ static int validate(const txg_config *c) {
   if (c->stencil_size_rho < Rneed || c->stencil_size_rho > 3)
     TXG_FAIL(h, TXG_ERR_ARG_WRONG, "stencil_size_rho %d too small for isotropy order %d (needs %d)", c->stencil_size_rho,
              c->isotropy_order, Rneed);
+  if ((long long)c->NX * c->NY * (c->ndims == 3 ? c->zl : 1) >= (1ll << 32))
+    TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "slab of %d x %d x %d nodes exceeds the 32-bit node index of the fluid list", c->NX, c->NY, c->zl);
   if (c->NX <= 2 * c->stencil_size_rho || c->NY <= 2 * c->stencil_size_rho)
     TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "box too small for the stencil");
   if (c->nminerals < 1 || c->nminerals > TXG_MAX_MINERALS) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "nminerals %d out of range", c->nminerals);
@@ -334,7 +341,7 @@ extern "C" int txg_destroy(txg_handle h) {
   drain_timers(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
-                  h->nbmask, h->ffmask, h->counters, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
+                  h->nbmask, h->ffmask, h->flist, h->counters, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -583,6 +590,59 @@ static int export_field(txg_flow *h, double *host, int gw, int gwz, int K, int S
   return 0;
 }
 
+// ------------------------------------------------------------------ fluid-node list
+// Ascending indices of the fluid nodes of the slab, so that the hot kernels put only fluid nodes on
+// lanes.  Count per 256-slot chunk of each plane, scan the chunk counts on the host (NZl * plane/256
+// integers), then fill with a ballot rank inside each chunk.
+static int build_fluid_list(txg_flow *h) {
+  const Grid &g = h->g;
+  if (h->flist) {
+    cudaFree(h->flist);
+    h->flist = nullptr;
+  }
+  const int bpp = (int)((g.plane + 255) / 256);  // chunks per plane
+  const long long nchunks = (long long)bpp * g.NZl;
+  unsigned *d_cnt = nullptr;
+  TXG_CUDA(h, cudaMalloc((void **)&d_cnt, (size_t)nchunks * sizeof(unsigned)));
+  k_count_fluid<<<(unsigned)nchunks, 256, 0, h->s_main>>>(h->nbmask, g.plane, bpp, d_cnt);
+  TXG_CUDA(h, cudaGetLastError());
+  std::vector<unsigned> cnt((size_t)nchunks);
+  TXG_CUDA(h, cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nchunks * sizeof(unsigned), cudaMemcpyDeviceToHost, h->s_main));
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  h->plane_off.assign((size_t)g.NZl + 1, 0);
+  long long run = 0;
+  for (long long c = 0; c < nchunks; ++c) {
+    if (c % bpp == 0) h->plane_off[(size_t)(c / bpp)] = run;
+    const unsigned k = cnt[(size_t)c];
+    cnt[(size_t)c] = (unsigned)run;
+    run += k;
+  }
+  h->plane_off[(size_t)g.NZl] = run;
+  h->nfluid = run;
+  if (run == g.nnodes || run == 0) {  // no solids (dense identity) or nothing to do
+    cudaFree(d_cnt);
+    return 0;
+  }
+  TXG_CUDA(h, cudaMemcpyAsync(d_cnt, cnt.data(), (size_t)nchunks * sizeof(unsigned), cudaMemcpyHostToDevice, h->s_main));
+  TXG_CUDA(h, cudaMalloc((void **)&h->flist, (size_t)run * sizeof(uint32_t)));
+  k_fill_fluid<<<(unsigned)nchunks, 256, 0, h->s_main>>>(h->nbmask, g.plane, bpp, d_cnt, h->flist);
+  TXG_CUDA(h, cudaGetLastError());
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  cudaFree(d_cnt);
+  return 0;
+}
+
+// (first, count) of the list entries of owned planes [z0, z0 + nz)
+static inline void plane_range(const txg_flow *h, int z0, int nz, long long *first, long long *count) {
+  if (h->flist) {
+    *first = h->plane_off[(size_t)z0];
+    *count = h->plane_off[(size_t)(z0 + nz)] - *first;
+  } else {
+    *first = (long long)z0 * h->g.plane;
+    *count = h->nfluid ? (long long)nz * h->g.plane : 0;
+  }
+}
+
 // ------------------------------------------------------------------ walls
 extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   if (!h) return TXG_ERR_ARG_NULL;
@@ -612,6 +672,7 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
              "%d fluid/wall contacts with free-slip codes 900-902 (WALL_NORMAL_X/Y/Z): specular walls are not "
              "implemented on the device yet",
              counters[1]);
+  TXG_TRY(build_fluid_list(h));
   h->walls_set = true;
   return 0;
 }
@@ -626,18 +687,29 @@ extern "C" int txg_get_node_class(txg_handle h, uint8_t *out) {
 }
 
 // ------------------------------------------------------------------ state in
+// blocks of 128 threads = 4 warps of npw (fluid node, all components) items
+static inline unsigned hot_blocks(const txg_flow *h, long long count) {
+  const long long warps = (count + h->ks.npw - 1) / h->ks.npw;
+  return (unsigned)((warps + 3) / 4);
+}
 static int run_moments(txg_flow *h, int z0, int nz, cudaStream_t s) {
   if (nz <= 0) return 0;
+  long long first, count;
+  plane_range(h, z0, nz, &first, &count);
+  if (count == 0) return 0;
   ScopedKernel sk(h, "k_moments", s);
-  h->ks.moments<<<blocks_for((long long)nz * h->g.plane, 128), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, h->nbmask, z0, nz);
+  h->ks.moments<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, h->nbmask, h->flist, first, count);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
 static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   if (nz <= 0) return 0;
+  long long first, count;
+  plane_range(h, z0, nz, &first, &count);
+  if (count == 0) return 0;
   ScopedKernel sk(h, "k_collide", s);
-  h->ks.collide<<<blocks_for((long long)nz * h->g.plane, 128), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho,
-                                                                           h->nbmask, h->ffmask, h->cls, z0, nz);
+  h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->nbmask,
+                                                      h->ffmask, h->cls, h->flist, first, count);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }

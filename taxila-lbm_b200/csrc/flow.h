@@ -4,16 +4,18 @@
 
 #include <cstdint>
 
-#include "kernels.cuh"
+#include "hot_kernels.cuh"
 
 namespace txg {
 
 // One set of kernel entry points per (lattice, S, MRT, ISO) combination; the instantiations are
 // spread over inst_*.cu so they compile in parallel.
 struct KernelSet {
-  void (*moments)(Grid, Phys, const double *, double *, const uint32_t *, int, int);
+  // hot path: one lane per (fluid node, component); (list, first, count) select the entries
+  void (*moments)(Grid, Phys, const double *, double *, const uint32_t *, const uint32_t *, long long, long long);
   void (*collide)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
-                  const uint8_t *, int, int);
+                  const uint8_t *, const uint32_t *, long long, long long);
+  int npw;  // fluid nodes per warp of the hot kernels (32 / S)
   void (*fi_init)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
                   const uint32_t *, const uint8_t *, int, int);
   void (*unstream)(Grid, const double *, double *, const uint32_t *, int, int);
@@ -30,6 +32,7 @@ KernelSet make_kernel_set(const char *name) {
   KernelSet k;
   k.moments = k_moments<L, S>;
   k.collide = k_collide<L, S, MRT, ISO>;
+  k.npw = Lanes<S>::NPW;
   k.fi_init = k_fi_init<L, S, ISO>;
   k.unstream = k_unstream<L, S>;
   k.stream_out = k_stream_out<L, S>;

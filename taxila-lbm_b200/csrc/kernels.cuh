@@ -337,57 +337,6 @@ __device__ __forceinline__ double eos_psi(const Phys &p, int m, double rho) {
 
 // ================================================================== kernels
 
-// K1 moments: stream + bounce-back folded into the read, rho_m = sum_n f_n; writes rho (psi with an
-// EOS).  Replaces DistributionStreamD*, DistributionBouncebackD*, DistributionCalcDensityD*, EOSApply.
-// Solid nodes are never written: rho stays 0 there from allocation.
-template <class L, int S>
-__global__ void __launch_bounds__(128) k_moments(Grid g, Phys p, const double *__restrict__ fA,
-                                                 double *__restrict__ rho, const uint32_t *__restrict__ nbmask, int z0,
-                                                 int nz) {
-  NodeIdx nd;
-  if (!node_of_thread(g, z0, nz, nd)) return;
-  const uint32_t mask = nbmask[nd.o];
-  if (mask >> 31) return;
-  double f[S][L::Q], r[S];
-  pull<L, S>(g, fA, nd, mask, f);
-  density<L, S>(f, r);
-  const long long o = (long long)(nd.z + g.R) * g.plane + (long long)nd.y * g.NX + nd.x;
-#pragma unroll
-  for (int m = 0; m < S; ++m) rho[m * g.rstride + o] = p.eos ? eos_psi(p, m, r[m]) : r[m];
-}
-
-// K2 collide: pull again, forces from the rho stencil, momentum, common velocity, equilibrium,
-// prefactor, SRT/MRT relaxation, forcing term; writes the post-collision populations.
-// Replaces LBMAddFluidFluid/FluidSolid/BodyForcesD*, DistributionCalcFluxD*, FlowUpdateUED*,
-// DiscretizationEquilf_*, FlowFiBarEqPrefactor, FlowCollisionD*, RelaxationCollide*.
-template <class L, int S, bool MRT, int ISO>
-__global__ void __launch_bounds__(128) k_collide(Grid g, Phys p, const double *__restrict__ fA,
-                                                 double *__restrict__ fB, const double *__restrict__ rho,
-                                                 const uint32_t *__restrict__ nbmask,
-                                                 const uint32_t *__restrict__ ffmask, const uint8_t *__restrict__ cls,
-                                                 int z0, int nz) {
-  NodeIdx nd;
-  if (!node_of_thread(g, z0, nz, nd)) return;
-  const uint32_t mask = nbmask[nd.o];
-  if (mask >> 31) return;
-  constexpr int Q = L::Q, D = L::D;
-  double f[S][Q], r[S], F[S][D], up[D];
-  pull<L, S>(g, fA, nd, mask, f);
-  density<L, S>(f, r);
-  forces<L, S, ISO>(g, p, rho, cls, ffmask, nd, mask, r, F);
-  common_velocity<L, S>(p, f, r, F, up);
-  const long long o = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
-#pragma unroll
-  for (int m = 0; m < S; ++m) {
-    double feq[Q], pref[Q];
-    equilibrium<L>(r[m], p.d_k[m], up, feq);
-    prefactor<L>(r[m], F[m], up, pref);
-    collide_component<L, MRT>(p, m, f[m], feq, pref);
-#pragma unroll
-    for (int n = 0; n < Q; ++n) fB[(long long)(m * Q + n) * g.fstride + o] = f[m][n];
-  }
-}
-
 // K3 fi_init (FlowFiInit lbm_flow.F90:923-934, FlowFeqBarD* :867-921): F from rho0, feq(rho0, u0),
 // f = (1 - prefactor/2) feq, written as NODE values (post-stream form) into fN; k_unstream then
 // converts to pull form.  u0 is [S][D][nnodes] or null (= 0).

@@ -34,6 +34,31 @@ __global__ void k_classify(const double *__restrict__ walls, uint8_t *__restrict
   cls[i] = c;
 }
 
+// fluid-node list, pass 1: fluid nodes (nbmask bit 31 clear) per 256-slot chunk of each plane
+__global__ void k_count_fluid(const uint32_t *__restrict__ nbmask, long long plane, int bpp, unsigned *__restrict__ cnt) {
+  const long long z = blockIdx.x / bpp;
+  const long long r = (long long)(blockIdx.x % bpp) * 256 + threadIdx.x;
+  const bool fluid = r < plane && !(nbmask[z * plane + r] >> 31);
+  const int n = __syncthreads_count(fluid);
+  if (threadIdx.x == 0) cnt[blockIdx.x] = (unsigned)n;
+}
+
+// pass 2: off[chunk] = list position of the chunk's first fluid node; rank inside the chunk by ballot
+__global__ void k_fill_fluid(const uint32_t *__restrict__ nbmask, long long plane, int bpp,
+                             const unsigned *__restrict__ off, uint32_t *__restrict__ list) {
+  __shared__ unsigned warp_cnt[8];
+  const long long z = blockIdx.x / bpp;
+  const long long r = (long long)(blockIdx.x % bpp) * 256 + threadIdx.x;
+  const bool fluid = r < plane && !(nbmask[z * plane + r] >> 31);
+  const unsigned b = __ballot_sync(0xffffffffu, fluid);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) warp_cnt[w] = __popc(b);
+  __syncthreads();
+  unsigned base = off[blockIdx.x];
+  for (int k = 0; k < w; ++k) base += warp_cnt[k];
+  if (fluid) list[base + __popc(b & ((1u << lane) - 1u))] = (uint32_t)(z * plane + r);
+}
+
 // host AoS (ghosted, dof = K*S with index k*S+m) -> device SoA [(m*K+k)][z][y][x] and back.
 // The staging buffer holds the nzl ghosted (in x,y) z-planes of owned planes [zl0, zl0+nzl); only owned
 // nodes are touched.
