@@ -101,7 +101,7 @@ struct txg_flow {
   int S = 0, Q = 0, D = 0, R = 1;
   cudaStream_t s_main = nullptr, s_comm = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_step0 = nullptr, ev_step1 = nullptr;
-  double *f[2] = {nullptr, nullptr};  // f[cur] holds the pull-form populations
+  double *f[2] = {nullptr, nullptr};  // f[cur] holds the populations fi(m,n,X); collide pushes into f[cur^1]
   int cur = 0;
   double *rho = nullptr;       // stencil field (rho, or psi with an EOS), R ghost planes
   double *rho_true = nullptr;  // true density (only allocated with an EOS; else == rho)
@@ -112,6 +112,8 @@ struct txg_flow {
   // ascending list of fluid node indices (nullptr: every node is fluid) and, per owned z-plane, the
   // offset of its first entry; plane_off[NZl] = number of fluid nodes
   uint32_t *flist = nullptr;
+  double *wallrec = nullptr;   // [S*D + D][nfluid], see kernels.cuh
+  double *halo_recv = nullptr; // NCCL staging: [2 faces][S][NCROSS][plane]
   std::vector<long long> plane_off;
   long long nfluid = 0;
   int *counters = nullptr;  // [0] bad wall codes, [1] fluid nodes next to 900-902 walls
@@ -341,7 +343,7 @@ extern "C" int txg_destroy(txg_handle h) {
   drain_timers(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
-                  h->nbmask, h->ffmask, h->flist, h->counters, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
+                  h->nbmask, h->ffmask, h->flist, h->wallrec, h->halo_recv, h->counters, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -500,24 +502,54 @@ static int exchange(txg_flow *h, double *buf, const std::vector<Chunk> &to_up, c
   return 0;
 }
 
-// pull-form populations: the up-going directions (c_z = +1) of my top plane are pulled by the up
-// neighbour's bottom plane, so they fill its bottom ghost; mirror for c_z = -1.
-// `all_dirs`: node-value buffers (init / restart) need every z-moving direction both ways.
-static int exchange_f(txg_flow *h, double *buf, bool all_dirs, cudaStream_t s) {
+// Populations pushed across a z face sit in this slab's ghost plane; they belong in the
+// neighbour's boundary plane.  Single rank, periodic z: unpack straight from the own opposite
+// ghost plane.  Several ranks: send each ghost plane's crossing directions (one contiguous plane
+// per (m, n)), receive the neighbours' into the staging buffer, unpack from there.  The unpack is
+// masked (k_halo_unpack): a slot whose source node is solid keeps the bounce-back value its own
+// node wrote.
+static int exchange_f(txg_flow *h, double *buf, cudaStream_t s) {
   if (h->D != 3) return 0;
   const Grid &g = h->g;
-  std::vector<Chunk> upv, downv;
-  const bool d3 = true;
-  (void)d3;
-  for (int m = 0; m < h->S; ++m)
-    for (int n = 0; n < h->Q; ++n) {
+  const int nr = h->cfg.nranks;
+  const unsigned nb = blocks_for(g.plane, 256);
+  if (nr == 1) {
+    if (h->up < 0) return 0;  // not periodic in z: the ghost planes are solid (class 255), nothing is pushed
+    // plane 0 (bottom) takes c_z = +1 pushes that left through the top ghost plane NZl+1, and vice versa
+    h->ks.halo_unpack<<<nb, 256, 0, s>>>(g, buf, buf + (long long)(g.NZl + 1) * g.plane, g.fstride, 0, h->nbmask, 1);
+    h->ks.halo_unpack<<<nb, 256, 0, s>>>(g, buf, buf, g.fstride, 0, h->nbmask, 0);
+    TXG_CUDA(h, cudaGetLastError());
+    h->launches += 2;
+    return 0;
+  }
+  if (!h->comm) TXG_FAIL(h, TXG_ERR_ORDER, "nranks > 1 but txg_comm_init was not called");
+  const int NC = D3Q19::NCROSS;
+  const size_t face = (size_t)h->S * NC * g.plane;  // doubles per face
+  if (!h->halo_recv) TXG_CUDA(h, cudaMalloc((void **)&h->halo_recv, 2 * face * sizeof(double)));
+  double *from_down = h->halo_recv, *from_up = h->halo_recv + face;
+  TXG_NCCL(h, g_nccl.GroupStart());
+  for (int m = 0; m < h->S; ++m) {
+    int ku = 0, kd = 0;
+    for (int n = 1; n < h->Q; ++n) {
       const int cz = D3Q19::c(n, 2);
-      if (cz == 0) continue;
-      const long long base = (long long)(m * h->Q + n) * g.fstride;
-      if (cz > 0 || all_dirs) upv.push_back({base + (long long)g.NZl * g.plane, base, g.plane});
-      if (cz < 0 || all_dirs) downv.push_back({base + g.plane, base + (long long)(g.NZl + 1) * g.plane, g.plane});
+      const long long blk = (long long)(m * h->Q + n) * g.fstride;
+      if (cz > 0) {  // my top ghost plane -> up; the same directions arrive from down
+        if (h->up >= 0) TXG_NCCL(h, g_nccl.Send(buf + blk + (long long)(g.NZl + 1) * g.plane, (size_t)g.plane, ncclFloat64, h->up, h->comm, s));
+        if (h->down >= 0) TXG_NCCL(h, g_nccl.Recv(from_down + (size_t)(m * NC + ku) * g.plane, (size_t)g.plane, ncclFloat64, h->down, h->comm, s));
+        ++ku;
+      } else if (cz < 0) {  // my bottom ghost plane -> down; the same directions arrive from up
+        if (h->down >= 0) TXG_NCCL(h, g_nccl.Send(buf + blk, (size_t)g.plane, ncclFloat64, h->down, h->comm, s));
+        if (h->up >= 0) TXG_NCCL(h, g_nccl.Recv(from_up + (size_t)(m * NC + kd) * g.plane, (size_t)g.plane, ncclFloat64, h->up, h->comm, s));
+        ++kd;
+      }
     }
-  return exchange(h, buf, upv, downv, s);
+  }
+  TXG_NCCL(h, g_nccl.GroupEnd());
+  if (h->down >= 0) h->ks.halo_unpack<<<nb, 256, 0, s>>>(g, buf, from_down, 0, 1, h->nbmask, 1);
+  if (h->up >= 0) h->ks.halo_unpack<<<nb, 256, 0, s>>>(g, buf, from_up, 0, 1, h->nbmask, 0);
+  TXG_CUDA(h, cudaGetLastError());
+  h->launches += 2;
+  return 0;
 }
 
 static int exchange_rho(txg_flow *h, double *buf, cudaStream_t s) {
@@ -604,7 +636,7 @@ static int build_fluid_list(txg_flow *h) {
   const long long nchunks = (long long)bpp * g.NZl;
   unsigned *d_cnt = nullptr;
   TXG_CUDA(h, cudaMalloc((void **)&d_cnt, (size_t)nchunks * sizeof(unsigned)));
-  k_count_fluid<<<(unsigned)nchunks, 256, 0, h->s_main>>>(h->nbmask, g.plane, bpp, d_cnt);
+  k_count_fluid<<<(unsigned)nchunks, 256, 0, h->s_main>>>(h->nbmask, g.plane, bpp, d_cnt, h->counters + 2);
   TXG_CUDA(h, cudaGetLastError());
   std::vector<unsigned> cnt((size_t)nchunks);
   TXG_CUDA(h, cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nchunks * sizeof(unsigned), cudaMemcpyDeviceToHost, h->s_main));
@@ -619,7 +651,14 @@ static int build_fluid_list(txg_flow *h) {
   }
   h->plane_off[(size_t)g.NZl] = run;
   h->nfluid = run;
-  if (run == g.nnodes || run == 0) {  // no solids (dense identity) or nothing to do
+  if (h->wallrec) {
+    cudaFree(h->wallrec);
+    h->wallrec = nullptr;
+  }
+  int nrec = 0;
+  TXG_CUDA(h, cudaMemcpyAsync(&nrec, h->counters + 2, sizeof nrec, cudaMemcpyDeviceToHost, h->s_main));
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  if ((run == g.nnodes && nrec == 0) || run == 0) {  // nothing solid in reach (dense identity) or no fluid at all
     cudaFree(d_cnt);
     return 0;
   }
@@ -629,6 +668,14 @@ static int build_fluid_list(txg_flow *h) {
   TXG_CUDA(h, cudaGetLastError());
   TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
   cudaFree(d_cnt);
+  if (nrec) {
+    const size_t nk = (size_t)(h->S * h->D + h->D);
+    TXG_CUDA(h, cudaMalloc((void **)&h->wallrec, nk * (size_t)run * sizeof(double)));
+    TXG_CUDA(h, cudaMemsetAsync(h->wallrec, 0, nk * (size_t)run * sizeof(double), h->s_main));
+    h->ks.build_wallrec<<<blocks_for(run, 128), 128, 0, h->s_main>>>(g, h->p, h->cls, h->nbmask, h->ffmask, h->flist, run, h->wallrec);
+    TXG_CUDA(h, cudaGetLastError());
+    TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  }
   return 0;
 }
 
@@ -698,7 +745,7 @@ static int run_moments(txg_flow *h, int z0, int nz, cudaStream_t s) {
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
   ScopedKernel sk(h, "k_moments", s);
-  h->ks.moments<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, h->nbmask, h->flist, first, count);
+  h->ks.moments<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, h->flist, first, count);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -709,22 +756,13 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   if (count == 0) return 0;
   ScopedKernel sk(h, "k_collide", s);
   h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->nbmask,
-                                                      h->ffmask, h->cls, h->flist, first, count);
+                                                      h->ffmask, h->wallrec, h->nfluid, h->flist, first, count);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
 
-// node values in f[cur^1] (owned planes) -> pull form in f[cur], ghosts exchanged
-static int node_values_to_pull(txg_flow *h) {
-  const Grid &g = h->g;
-  double *fN = h->f[h->cur ^ 1], *fA = h->f[h->cur];
-  TXG_TRY(exchange_f(h, fN, true, h->s_main));
-  {
-    ScopedKernel sk(h, "k_unstream", h->s_main);
-    h->ks.unstream<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, fN, fA, h->nbmask, 0, g.NZl);
-    TXG_CUDA(h, cudaGetLastError());
-  }
-  TXG_TRY(exchange_f(h, fA, false, h->s_main));
+// the populations of the owned nodes are in f[cur]: with push storage that is the whole state
+static int state_ready(txg_flow *h) {
   h->state_set = true;
   h->rho_current = false;
   return 0;
@@ -752,8 +790,8 @@ extern "C" int txg_set_fi(txg_handle h, const double *fi_g) {
   if (!h->walls_set) TXG_FAIL(h, TXG_ERR_ORDER, "txg_set_fi before txg_set_walls");
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
-  TXG_TRY(import_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->f[h->cur ^ 1], g.fstride, 1));
-  return node_values_to_pull(h);
+  TXG_TRY(import_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->f[h->cur], g.fstride, 1));
+  return state_ready(h);
 }
 
 // psi = EOS(rho) over the owned planes of rho_true -> rho (stencil field); identity without an EOS
@@ -779,18 +817,19 @@ extern "C" int txg_fi_init(txg_handle h) {
   TXG_TRY(exchange_rho(h, h->rho, h->s_main));
   {
     ScopedKernel sk(h, "k_fi_init", h->s_main);
-    h->ks.fi_init<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->p, h->f[h->cur ^ 1], h->rho, h->rho_true, h->u0,
+    h->ks.fi_init<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->p, h->f[h->cur], h->rho, h->rho_true, h->u0,
                                                                      h->nbmask, h->ffmask, h->cls, 0, g.NZl);
     TXG_CUDA(h, cudaGetLastError());
   }
-  return node_values_to_pull(h);
+  return state_ready(h);
 }
 
 // ------------------------------------------------------------------ the step
 // One reference time step = collide, communicate fi, stream, bounce-back, density, forces, flux,
-// common velocity (lbm.F90:286-361).  On the device: K1 moments (stream + bounce-back + density) with
-// the rho halo, then K2 (forces + momentum + velocity + collision) with the f halo.  Boundary planes
-// run first so that their halos travel on the communication stream while the interior computes.
+// common velocity (lbm.F90:286-361).  On the device: K1 moments (density) with the rho halo, then K2
+// (forces + momentum + velocity + collision + push-streaming with bounce-back) with the halo of the
+// pushed populations.  Boundary planes run first so that their halos travel on the communication
+// stream while the interior computes.
 static int one_step(txg_flow *h) {
   const Grid &g = h->g;
   const bool split = h->cfg.nranks > 1 && g.NZl >= 4 * g.R + 2;
@@ -799,7 +838,7 @@ static int one_step(txg_flow *h) {
     TXG_TRY(run_moments(h, 0, g.NZl, sm));
     TXG_TRY(exchange_rho(h, h->rho, sm));
     TXG_TRY(run_collide(h, 0, g.NZl, sm));
-    TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], false, sm));
+    TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sm));
     h->cur ^= 1;
     return 0;
   }
@@ -818,7 +857,7 @@ static int one_step(txg_flow *h) {
   TXG_TRY(run_collide(h, g.NZl - 1, 1, sm));
   TXG_CUDA(h, cudaEventRecord(h->ev_a, sm));
   TXG_CUDA(h, cudaStreamWaitEvent(sc, h->ev_a, 0));
-  TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], false, sc));
+  TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sc));
   TXG_CUDA(h, cudaEventRecord(h->ev_b, sc));
   TXG_TRY(run_collide(h, 1, g.NZl - 2, sm));
   TXG_CUDA(h, cudaStreamWaitEvent(sm, h->ev_b, 0));
@@ -899,12 +938,7 @@ extern "C" int txg_get_fi(txg_handle h, double *fi_g) {
   if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "no state on the device yet");
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
-  {
-    ScopedKernel sk(h, "k_stream_out", h->s_main);
-    h->ks.stream_out<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->f[h->cur], h->f[h->cur ^ 1], h->nbmask, 0, g.NZl);
-    TXG_CUDA(h, cudaGetLastError());
-  }
-  return export_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->S, h->f[h->cur ^ 1], g.fstride, 1);
+  return export_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->S, h->f[h->cur], g.fstride, 1);
 }
 
 extern "C" int txg_get_state(txg_handle h, double *rho_rg, double *u_g, double *forces_g) {
@@ -950,20 +984,15 @@ extern "C" int txg_delta_norm(txg_handle h, double *norm) {
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
   const long long n = (long long)h->S * h->Q * g.fstride;
-  {
-    ScopedKernel sk(h, "k_stream_out", h->s_main);
-    h->ks.stream_out<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->f[h->cur], h->f[h->cur ^ 1], h->nbmask, 0, g.NZl);
-    TXG_CUDA(h, cudaGetLastError());
-  }
   if (!h->f_old) {
     TXG_CUDA(h, cudaMalloc((void **)&h->f_old, (size_t)n * 8));
     TXG_CUDA(h, cudaMemsetAsync(h->f_old, 0, (size_t)n * 8, h->s_main));
   }
   TXG_CUDA(h, cudaMemsetAsync(h->norm_bits, 0, sizeof(unsigned long long), h->s_main));
-  // ghost planes of the node-value buffer hold stale data: compare owned planes only, per (m,n) block
+  // ghost planes hold pushes in transit: compare owned planes only, per (m,n) block
   for (int b = 0; b < h->S * h->Q; ++b) {
     const long long off = (long long)b * g.fstride + g.plane;
-    k_delta_norm<<<blocks_for(g.nnodes, 256), 256, 0, h->s_main>>>(h->f[h->cur ^ 1] + off, h->f_old + off, g.nnodes, h->norm_bits);
+    k_delta_norm<<<blocks_for(g.nnodes, 256), 256, 0, h->s_main>>>(h->f[h->cur] + off, h->f_old + off, g.nnodes, h->norm_bits);
   }
   TXG_CUDA(h, cudaGetLastError());
   h->launches += h->S * h->Q;

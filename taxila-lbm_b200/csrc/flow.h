@@ -12,17 +12,19 @@ namespace txg {
 // spread over inst_*.cu so they compile in parallel.
 struct KernelSet {
   // hot path: one lane per (fluid node, component); (list, first, count) select the entries
-  void (*moments)(Grid, Phys, const double *, double *, const uint32_t *, const uint32_t *, long long, long long);
+  void (*moments)(Grid, Phys, const double *, double *, const uint32_t *, long long, long long);
   void (*collide)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
-                  const uint8_t *, const uint32_t *, long long, long long);
-  int npw;  // fluid nodes per warp of the hot kernels (32 / S)
+                  const double *, long long, const uint32_t *, long long, long long);
+  void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, int);
+  // set-up and export
   void (*fi_init)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
                   const uint32_t *, const uint8_t *, int, int);
-  void (*unstream)(Grid, const double *, double *, const uint32_t *, int, int);
-  void (*stream_out)(Grid, const double *, double *, const uint32_t *, int, int);
   void (*export_state)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *,
                        const uint8_t *, double *, double *, double *, double *, double *, double *, double, int, int);
   void (*build_masks)(Grid, const uint8_t *, uint32_t *, uint32_t *, int *);
+  void (*build_wallrec)(Grid, Phys, const uint8_t *, const uint32_t *, const uint32_t *, const uint32_t *, long long,
+                        double *);
+  int npw;       // fluid nodes per warp of the hot kernels (32 / S)
   int ff_words;  // u32 words of ffmask per node (0 for isotropy order 4)
   const char *name;
 };
@@ -32,12 +34,12 @@ KernelSet make_kernel_set(const char *name) {
   KernelSet k;
   k.moments = k_moments<L, S>;
   k.collide = k_collide<L, S, MRT, ISO>;
-  k.npw = Lanes<S>::NPW;
+  k.halo_unpack = k_halo_unpack<L, S>;
   k.fi_init = k_fi_init<L, S, ISO>;
-  k.unstream = k_unstream<L, S>;
-  k.stream_out = k_stream_out<L, S>;
   k.export_state = k_export<L, S, ISO>;
   k.build_masks = k_build_masks<L, ISO>;
+  k.build_wallrec = k_build_wallrec<L, S, ISO>;
+  k.npw = Lanes<S>::NPW;
   k.ff_words = ISO == 4 ? 0 : ff_words<L>(ISO);
   k.name = name;
   return k;

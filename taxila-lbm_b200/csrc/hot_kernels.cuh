@@ -1,16 +1,17 @@
-// hot_kernels.cuh -- the two per-timestep kernels of the flow hot path (sm_100a).
+// hot_kernels.cuh -- the per-timestep kernels of the flow hot path (sm_100a).
 //
 // Work decomposition: one lane per (fluid node, component).  A warp carries NPW = 32/S consecutive
 // entries of the fluid-node list for all S components: lanes [m*NPW, (m+1)*NPW) hold component m, so
-// every population load/store of a half-warp (S = 2) is one contiguous 128-byte run.  Quantities
-// that couple the components (Shan-Chen gradient of the other phases, common velocity) cross lanes
-// with warp shuffles, summed in ascending component order like the reference.  Splitting by
-// component halves the live register set (19 populations instead of 38) -- the fp64 collision is
-// otherwise register- and latency-bound on B200 long before HBM is.
+// every population load of a half-warp (S = 2) is one contiguous 128-byte run when the nodes are
+// x-neighbours.  Quantities that couple the components (Shan-Chen gradient of the other phases,
+// common velocity) cross lanes with warp shuffles, summed in ascending component order like the
+// reference.  Splitting by component halves the live register set (19 populations instead of 38):
+// the fp64 collision is otherwise register- and latency-bound on B200 long before HBM is.
 //
 // Only fluid nodes occupy lanes: `list` is the ascending list of fluid node indices of the slab
 // (built once per walls upload), so a porous medium does not waste fp64 issue slots on solid
-// voxels.  list == nullptr means "no solid node anywhere": entry i is node first + i.
+// voxels.  list == nullptr means "every node is fluid and none has a wall record": entry i is node
+// first + i.
 #pragma once
 #include "kernels.cuh"
 
@@ -21,38 +22,46 @@ struct Lanes {
   static constexpr int NPW = 32 / S;  // nodes per warp
 };
 
+struct Item {
+  int x, y, z;       // owned coordinates
+  unsigned o;        // z*plane + y*NX + x
+  long long li;      // position in the fluid list (index of the wall record)
+  int m, j;          // component, node slot inside the warp
+  bool active;       // false: replayed item, stores nothing
+};
+
 // (node, component) of this lane.  Returns false if the whole warp is beyond the range.  Lanes past
 // the end of the range (or the 32 - S*NPW spare lanes when S does not divide 32) replay a valid
 // item with active = false: they take part in the shuffles and store nothing.
 template <int S>
 __device__ __forceinline__ bool item_of_lane(const Grid &g, const uint32_t *__restrict__ list, long long first,
-                                             long long count, NodeIdx &nd, int &m, int &j, bool &active) {
+                                             long long count, Item &it) {
   constexpr int NPW = Lanes<S>::NPW;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long base = warp * NPW;
   if (base >= count) return false;
-  m = lane / NPW;
-  j = lane - m * NPW;
-  active = true;
-  if (m >= S) {
-    m = S - 1;
-    active = false;
+  it.m = lane / NPW;
+  it.j = lane - it.m * NPW;
+  it.active = true;
+  if (it.m >= S) {
+    it.m = S - 1;
+    it.active = false;
   }
-  long long i = base + j;
+  long long i = base + it.j;
   if (i >= count) {
     i = count - 1;
-    active = false;
+    it.active = false;
   }
-  const unsigned o = list ? __ldg(list + first + i) : (unsigned)(first + i);
+  it.li = first + i;
+  it.o = list ? __ldg(list + it.li) : (unsigned)it.li;
   const unsigned plane = (unsigned)g.plane;
-  const unsigned z = o / plane;
-  const unsigned r = o - z * plane;
+  const unsigned z = it.o / plane;
+  const unsigned r = it.o - z * plane;
   const unsigned y = r / (unsigned)g.NX;
-  nd.x = (int)(r - y * (unsigned)g.NX);
-  nd.y = (int)y;
-  nd.z = (int)z;
-  nd.o = (long long)o;
+  it.x = (int)(r - y * (unsigned)g.NX);
+  it.y = (int)y;
+  it.z = (int)z;
   return true;
 }
 
@@ -63,54 +72,45 @@ __device__ __forceinline__ double from_component(double v, int k, int j) {
   return __shfl_sync(0xffffffffu, v, k * Lanes<S>::NPW + j);
 }
 
-// pull streaming with bounce-back for ONE component (see pull<> in kernels.cuh)
-template <class L>
-__device__ __forceinline__ void pull1(const Grid &g, const double *__restrict__ fAm /* fA + m*Q*fstride */,
-                                      const NodeIdx &nd, uint32_t mask, double (&f)[L::Q]) {
-  const int xm = wrapc(nd.x - 1, g.NX, g.perx), xp = wrapc(nd.x + 1, g.NX, g.perx);
-  const int ym = wrapc(nd.y - 1, g.NY, g.pery), yp = wrapc(nd.y + 1, g.NY, g.pery);
-  const long long here = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
-  static_for<0, L::Q>([&](auto n_) {
-    constexpr int n = decltype(n_)::value;
-    constexpr int on = opp<L>(n);
-    const int sx = L::c(n, 0) == 0 ? nd.x : (L::c(n, 0) > 0 ? xm : xp);
-    const int sy = L::c(n, 1) == 0 ? nd.y : (L::c(n, 1) > 0 ? ym : yp);
-    const int sz = nd.z + 1 - L::c(n, 2);
-    const bool bounce = n != 0 && ((mask >> on) & 1u);
-    const long long src = bounce ? here + (long long)on * g.fstride
-                                 : ((long long)sz * g.plane + (long long)sy * g.NX + sx) + (long long)n * g.fstride;
-    f[n] = __ldg(fAm + src);
-  });
+// element offset from x to its periodic (or clamped) neighbour x + a
+__device__ __forceinline__ int wrap_delta(int v, int a, int N, int per) { return wrapc(v + a, N, per) - v; }
+
+// bulk value of the gradient normalisation W[d] = sum_e ffw(L_e) c_e,d^2 over all entries (reference order)
+template <class L, int ISO>
+TXG_HD constexpr double bulk_weight_sum(int d) {
+  double w = 0.;
+  for (int e = 0; e < L::FF::E; ++e)
+    if (L::FF::gate[e] <= ISO) {
+      const int c = L::FF::off[e][d];
+      if (c != 0) w = w + L::ffw(ISO, L::FF::L[e]) * (double)(c * c);
+    }
+  return w;
 }
 
-// FlowCalcForces for ONE component (see forces<> in kernels.cuh for the reference citations).
-// rho_m / psi_m: this lane's component at this node; psi_field = psi + m*rstride.
+// FlowCalcForces (lbm_flow.F90:760-808) for ONE component: fluid-solid, body, fluid-fluid, in the
+// reference's order.  psi_at: pointer to this component's psi at this node (rho array, ghosted in z).
+// The geometry-only factors come from the wall record: A[d] = sum_n w_n gw(mineral(X+c_n), m) c_n,d
+// (LBMAddFluidSolidForcesD*, lbm_forcing.F90:1326-1421, float literals 1./6. etc. folded in by
+// k_build_wallrec) and rW[d] = 1/weightsum_d (lbm_forcing.F90:946-953); bulk nodes use the
+// compile-time weight sum.  Neighbour densities are loaded unconditionally (solid nodes hold 0) and
+// masked afterwards, so that all loads of a lane are in flight together.
 template <class L, int S, int ISO>
-__device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const double *__restrict__ psi_field,
-                                        const uint8_t *__restrict__ cls, const uint32_t *__restrict__ ffmask,
-                                        const NodeIdx &nd, uint32_t mask, int m, int j, double rho_m, double psi_m,
-                                        double (&F)[L::D]) {
+__device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const double *__restrict__ psi_at,
+                                        const uint32_t *__restrict__ ffmask, const double *__restrict__ wallrec,
+                                        long long rec_stride, const Item &it, uint32_t mask, double rho_m,
+                                        double psi_m, double (&F)[L::D]) {
   constexpr int D = L::D;
+  const bool rec = (mask & MASK_WALLREC) != 0;
+  const int m = it.m;
 #pragma unroll
   for (int d = 0; d < D; ++d) F[d] = 0.;
 
-  if (p.fluidsolid && (mask & 0x7fffffffu)) {
-    const long long cbase = ((long long)(nd.z + g.Rz) * g.cny + (nd.y + g.R)) * g.cnx + (nd.x + g.R);
-    static_for<1, L::Q>([&](auto n_) {
-      constexpr int n = decltype(n_)::value;
-      if ((mask >> n) & 1u) {
-        const long long coff = ((long long)L::c(n, 2) * g.cny + L::c(n, 1)) * g.cnx + L::c(n, 0);
-        const int id = cls[cbase + coff];
-        if (id >= 1 && id <= p.nminerals) {
-          constexpr double w = L::fs_weight(n);
-          const double t = w * rho_m * __ldg(p.gw + (id - 1) * S + m);
-          static_for<0, D>([&](auto d_) {
-            constexpr int d = decltype(d_)::value;
-            if constexpr (L::c(n, d) != 0) F[d] = F[d] - t * (double)L::c(n, d);
-          });
-        }
-      }
-    });
+  if (p.fluidsolid) {
+    double A[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) A[d] = rec ? __ldg(wallrec + (long long)(m * D + d) * rec_stride + it.li) : 0.;
+#pragma unroll
+    for (int d = 0; d < D; ++d) F[d] = F[d] - rho_m * A[d];
   }
 
   if (p.body) {
@@ -122,20 +122,27 @@ __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const doub
     using FF = typename L::FF;
     constexpr int E = ff_entries<L>(ISO);
     constexpr int RAD = stencil_radius(ISO);
-    double G[D], W[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) G[d] = W[d] = 0.;
-    int xi[2 * RAD + 1], yi[2 * RAD + 1];
+    double rW[D];
+    static_for<0, D>([&](auto d_) {
+      constexpr int d = decltype(d_)::value;
+      constexpr double bulk = 1.0 / bulk_weight_sum<L, ISO>(d);
+      rW[d] = rec ? __ldg(wallrec + (long long)(S * D + d) * rec_stride + it.li) : bulk;
+    });
+    int dxo[2 * RAD + 1], dyo[2 * RAD + 1];
 #pragma unroll
     for (int a = -RAD; a <= RAD; ++a) {
-      xi[a + RAD] = wrapc(nd.x + a, g.NX, g.perx);
-      yi[a + RAD] = wrapc(nd.y + a, g.NY, g.pery);
+      dxo[a + RAD] = wrap_delta(it.x, a, g.NX, g.perx);
+      dyo[a + RAD] = wrap_delta(it.y, a, g.NY, g.pery) * g.NX;
     }
     uint32_t words[(E + 31) / 32];
     if constexpr (ISO != 4) {
 #pragma unroll
-      for (int w = 0; w < (E + 31) / 32; ++w) words[w] = __ldg(ffmask + (long long)w * g.nnodes + nd.o);
+      for (int w = 0; w < (E + 31) / 32; ++w) words[w] = __ldg(ffmask + (long long)w * g.nnodes + it.o);
     }
+    const int plane = (int)g.plane;
+    double G[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) G[d] = 0.;
     static_for<0, E>([&](auto e_) {
       constexpr int e = decltype(e_)::value;
       constexpr int dx = FF::off[e][0], dy = FF::off[e][1], dz = FF::off[e][2];
@@ -146,33 +153,22 @@ __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const doub
       } else {
         on = (words[e / 32] >> (e % 32)) & 1u;
       }
-      if (on) {
-        constexpr double wgt = L::ffw(ISO, FF::L[e]);
-        const long long nb = (long long)(nd.z + g.R + dz) * g.plane + (long long)yi[dy + RAD] * g.NX + xi[dx + RAD];
-        const double diff = __ldg(psi_field + nb) - psi_m;
-        if constexpr (dx != 0) {
-          G[0] = G[0] + ((double)dx * wgt) * diff;
-          W[0] = W[0] + wgt * (double)(dx * dx);
-        }
-        if constexpr (dy != 0) {
-          G[1] = G[1] + ((double)dy * wgt) * diff;
-          W[1] = W[1] + wgt * (double)(dy * dy);
-        }
-        if constexpr (D == 3 && dz != 0) {
-          G[D - 1] = G[D - 1] + ((double)dz * wgt) * diff;
-          W[D - 1] = W[D - 1] + wgt * (double)(dz * dz);
-        }
-      }
+      constexpr double wgt = L::ffw(ISO, FF::L[e]);
+      const int delta = dz * plane + dyo[dy + RAD] + dxo[dx + RAD];
+      const double v = __ldg(psi_at + delta);
+      const double diff = on ? v - psi_m : 0.;
+      if constexpr (dx != 0) G[0] = G[0] + ((double)dx * wgt) * diff;
+      if constexpr (dy != 0) G[1] = G[1] + ((double)dy * wgt) * diff;
+      if constexpr (D == 3 && dz != 0) G[D - 1] = G[D - 1] + ((double)dz * wgt) * diff;
     });
-    const double eps = (double)1.e-12f;  // default-real literal, lbm_forcing.F90:69
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      // gradient of this lane's component, normalised; every lane of the node sees the same W
-      const double q = W[d] > eps ? G[d] / W[d] : 0.;
+      // normalised gradient of this lane's component; rW = 0 where the reference skips the direction
+      const double q = G[d] * rW[d];
       double acc = 0.;
 #pragma unroll
-      for (int k = 0; k < S; ++k) acc += p.gf[m][k] * from_component<S>(q, k, j);
-      if (W[d] > eps) F[d] = F[d] - 6.0 * psi_m * acc;  // c_0 = 6 on both lattices
+      for (int k = 0; k < S; ++k) acc += p.gf[m][k] * from_component<S>(q, k, it.j);
+      F[d] = F[d] - 6.0 * psi_m * acc;  // c_0 = 6 on both lattices
     }
   }
 }
@@ -312,63 +308,65 @@ __device__ __forceinline__ void collide1(const Phys &p, int m, double rho, const
 
 // ================================================================== the two hot kernels
 
-// K1 moments: stream + bounce-back folded into the read, rho_m = sum_n f_n (ascending n); writes rho
-// (psi with an EOS).  Replaces DistributionStreamD*, DistributionBouncebackD*,
-// DistributionCalcDensityD* (lbm_distribution_function.F90:379-428,560-784) and EOSApply.
+// K1 moments: rho_m = sum_n f_n (ascending n) of the streamed populations; writes rho (psi with an
+// EOS).  Replaces DistributionCalcDensityD* (lbm_distribution_function.F90:379-428) and EOSApply;
+// streaming and bounce-back happened in the push of the previous collide.
 template <class L, int S>
 __global__ void __launch_bounds__(128) k_moments(Grid g, Phys p, const double *__restrict__ fA,
-                                                 double *__restrict__ rho, const uint32_t *__restrict__ nbmask,
-                                                 const uint32_t *__restrict__ list, long long first, long long count) {
-  NodeIdx nd;
-  int m, j;
-  bool active;
-  if (!item_of_lane<S>(g, list, first, count, nd, m, j, active)) return;
-  const uint32_t mask = __ldg(nbmask + nd.o);
-  if (mask >> 31) return;  // only reachable through the dense (list == nullptr) path
+                                                 double *__restrict__ rho, const uint32_t *__restrict__ list,
+                                                 long long first, long long count) {
+  Item it;
+  if (!item_of_lane<S>(g, list, first, count, it)) return;
+  const long long o = (long long)it.o + g.plane;  // f carries one ghost plane below
+  const double *src = fA + (long long)it.m * L::Q * g.fstride + o;
   double f[L::Q];
-  pull1<L>(g, fA + (long long)m * L::Q * g.fstride, nd, mask, f);
+#pragma unroll
+  for (int n = 0; n < L::Q; ++n) f[n] = __ldg(src + (long long)n * g.fstride);
   double a = 0.;
 #pragma unroll
   for (int n = 0; n < L::Q; ++n) a += f[n];
-  if (!active) return;
-  const long long o = (long long)m * g.rstride + (long long)(nd.z + g.R) * g.plane + (long long)nd.y * g.NX + nd.x;
-  rho[o] = p.eos ? eos_psi(p, m, a) : a;
+  if (!it.active) return;
+  rho[(long long)it.m * g.rstride + (long long)it.o + (long long)g.R * g.plane] = p.eos ? eos_psi(p, it.m, a) : a;
 }
 
-// K2 collide: pull again, forces from the rho stencil, momentum, common velocity, equilibrium,
-// prefactor, SRT/MRT relaxation, forcing term; writes the post-collision populations.
+// K2 collide + push: node populations, forces from the rho stencil, momentum, common velocity,
+// equilibrium, prefactor, SRT/MRT relaxation, forcing term; the post-collision populations are
+// streamed by the store (bounce-back folded in).
 // Replaces LBMAddFluidFluid/FluidSolid/BodyForcesD* (lbm_forcing.F90), DistributionCalcFluxD*
 // (lbm_distribution_function.F90:451-508), FlowUpdateUED* (lbm_flow.F90:494-574),
 // DiscretizationEquilf_*, FlowFiBarEqPrefactor, FlowCollisionD* (lbm_flow.F90:836-1029),
-// RelaxationCollide* (lbm_relaxation.F90:171-200).
+// RelaxationCollide* (lbm_relaxation.F90:171-200), DistributionStreamD*, DistributionBouncebackD*
+// (lbm_distribution_function.F90:560-784).
 template <class L, int S, bool MRT, int ISO>
 __global__ void __launch_bounds__(128, 3)
     k_collide(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ rho,
               const uint32_t *__restrict__ nbmask, const uint32_t *__restrict__ ffmask,
-              const uint8_t *__restrict__ cls, const uint32_t *__restrict__ list, long long first, long long count) {
-  NodeIdx nd;
-  int m, j;
-  bool active;
-  if (!item_of_lane<S>(g, list, first, count, nd, m, j, active)) return;
+              const double *__restrict__ wallrec, long long rec_stride, const uint32_t *__restrict__ list,
+              long long first, long long count) {
+  Item it;
+  if (!item_of_lane<S>(g, list, first, count, it)) return;
   constexpr int Q = L::Q, D = L::D;
-  const uint32_t mask = __ldg(nbmask + nd.o);
-  const bool solid = mask >> 31;  // dense path only; the lane keeps running for the shuffles
+  const long long o = (long long)it.o + g.plane;
+  const long long mo = (long long)it.m * Q * g.fstride + o;
   double f[Q];
-  pull1<L>(g, fA + (long long)m * Q * g.fstride, nd, solid ? 0u : mask, f);
+  {
+    const double *src = fA + mo;
+#pragma unroll
+    for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fstride);
+  }
+  const uint32_t mask = __ldg(nbmask + it.o);
+  const double *psi_at = rho + (long long)it.m * g.rstride + (long long)it.o + (long long)g.R * g.plane;
   double r = 0.;
 #pragma unroll
   for (int n = 0; n < Q; ++n) r += f[n];
-  if (solid) r = 1.;  // keeps the arithmetic finite; nothing is stored
-  const long long ro = (long long)(nd.z + g.R) * g.plane + (long long)nd.y * g.NX + nd.x;
-  const double psi_m = p.eos ? __ldg(rho + (long long)m * g.rstride + ro) : r;
+  const double psi_m = p.eos ? __ldg(psi_at) : r;
   double F[D];
-  forces1<L, S, ISO>(g, p, rho + (long long)m * g.rstride, cls, ffmask, nd, solid ? 0x7fffffffu : mask, m, j, r, psi_m,
-                     F);
+  forces1<L, S, ISO>(g, p, psi_at, ffmask, wallrec, rec_stride, it, mask, r, psi_m, F);
   // momentum j_m (DistributionCalcFluxD*) and the common velocity u' (FlowUpdateUED*)
   double up[D];
   {
     double num[D], den = 0.;
-    const double mmot = p.mmot[m];
+    const double mmot = p.mmot[it.m];
     double ue[D];
     static_for<0, D>([&](auto d_) {
       constexpr int d = decltype(d_)::value;
@@ -383,19 +381,142 @@ __global__ void __launch_bounds__(128, 3)
     const double rm = r * mmot;
 #pragma unroll
     for (int k = 0; k < S; ++k) {
-      den += from_component<S>(rm, k, j);
+      den += from_component<S>(rm, k, it.j);
 #pragma unroll
-      for (int d = 0; d < D; ++d) num[d] += from_component<S>(ue[d], k, j);
+      for (int d = 0; d < D; ++d) num[d] += from_component<S>(ue[d], k, it.j);
     }
+    const double rden = 1. / den;
 #pragma unroll
-    for (int d = 0; d < D; ++d) up[d] = num[d] / den;
+    for (int d = 0; d < D; ++d) up[d] = num[d] * rden;
   }
-  collide1<L, MRT>(p, m, r, F, up, f);
-  if (!active || solid) return;
-  const long long o = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
-  double *out = fB + (long long)m * Q * g.fstride + o;
+  collide1<L, MRT>(p, it.m, r, F, up, f);
+  if (!it.active) return;
+  // push: slot (n, X + c_n), or slot (opp(n), X) when X + c_n is solid
+  double *out = fB + mo;
+  const int dxm = wrap_delta(it.x, -1, g.NX, g.perx), dxp = wrap_delta(it.x, 1, g.NX, g.perx);
+  const int dym = wrap_delta(it.y, -1, g.NY, g.pery) * g.NX, dyp = wrap_delta(it.y, 1, g.NY, g.pery) * g.NX;
+  const int plane = (int)g.plane;
+  out[0] = f[0];
+  static_for<1, Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    constexpr int on = opp<L>(n);
+    const int delta = (L::c(n, 0) == 0 ? 0 : (L::c(n, 0) > 0 ? dxp : dxm)) +
+                      (L::c(n, 1) == 0 ? 0 : (L::c(n, 1) > 0 ? dyp : dym)) + L::c(n, 2) * plane;
+    const bool bounce = (mask >> n) & 1u;
+    double *dst = bounce ? out + (long long)on * g.fstride : out + (long long)n * g.fstride + delta;
+    *dst = f[n];
+  });
+}
+
+// Wall records (one thread per fluid-list entry with MASK_WALLREC): the geometry-only factors of the
+// fluid-solid force and of the gradient normalisation, evaluated once per walls upload.
+//   A[m][d]  = sum over lattice directions n (ascending) with a mineral neighbour of
+//              w_n * gw(mineral, m) * c_n,d, w_n the reference's default-real literals
+//              (lbm_forcing.F90:1355,1364,1406,1414; 0 < walls < 998 and a valid mineral id)
+//   rW[d]    = 1 / weightsum_d if weightsum_d > 1e-12 else 0   (lbm_forcing.F90:69,946-953)
+template <class L, int S, int ISO>
+__global__ void k_build_wallrec(Grid g, Phys p, const uint8_t *__restrict__ cls, const uint32_t *__restrict__ nbmask,
+                                const uint32_t *__restrict__ ffmask, const uint32_t *__restrict__ list,
+                                long long count, double *__restrict__ rec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  constexpr int D = L::D;
+  const unsigned o = list[i];
+  const uint32_t mask = nbmask[o];
+  if (!(mask & MASK_WALLREC)) return;
+  const unsigned plane = (unsigned)g.plane;
+  const int z = (int)(o / plane);
+  const unsigned rr = o - (unsigned)z * plane;
+  const int y = (int)(rr / (unsigned)g.NX);
+  const int x = (int)(rr - (unsigned)y * (unsigned)g.NX);
+  const long long cbase = ((long long)(z + g.Rz) * g.cny + (y + g.R)) * g.cnx + (x + g.R);
+  double A[S][D];
 #pragma unroll
-  for (int n = 0; n < Q; ++n) out[(long long)n * g.fstride] = f[n];
+  for (int m = 0; m < S; ++m)
+#pragma unroll
+    for (int d = 0; d < D; ++d) A[m][d] = 0.;
+  static_for<1, L::Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    if ((mask >> n) & 1u) {
+      const long long coff = ((long long)L::c(n, 2) * g.cny + L::c(n, 1)) * g.cnx + L::c(n, 0);
+      const int id = cls[cbase + coff];
+      if (id >= 1 && id <= p.nminerals) {
+        constexpr double w = L::fs_weight(n);
+#pragma unroll
+        for (int m = 0; m < S; ++m)
+          static_for<0, D>([&](auto d_) {
+            constexpr int d = decltype(d_)::value;
+            if constexpr (L::c(n, d) != 0) A[m][d] = A[m][d] + w * p.gw[(id - 1) * S + m] * (double)L::c(n, d);
+          });
+      }
+    }
+  });
+  using FF = typename L::FF;
+  constexpr int E = ff_entries<L>(ISO);
+  double W[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) W[d] = 0.;
+  static_for<0, E>([&](auto e_) {
+    constexpr int e = decltype(e_)::value;
+    constexpr int dx = FF::off[e][0], dy = FF::off[e][1], dz = FF::off[e][2];
+    bool on;
+    if constexpr (ISO == 4) {
+      constexpr int n = dir_of<L>(dx, dy, dz);
+      on = !((mask >> n) & 1u);
+    } else {
+      on = (ffmask[(long long)(e / 32) * g.nnodes + o] >> (e % 32)) & 1u;
+    }
+    if (on) {
+      constexpr double wgt = L::ffw(ISO, FF::L[e]);
+      if constexpr (dx != 0) W[0] = W[0] + wgt * (double)(dx * dx);
+      if constexpr (dy != 0) W[1] = W[1] + wgt * (double)(dy * dy);
+      if constexpr (D == 3 && dz != 0) W[D - 1] = W[D - 1] + wgt * (double)(dz * dz);
+    }
+  });
+  const double eps = (double)1.e-12f;  // default-real literal, lbm_forcing.F90:69
+#pragma unroll
+  for (int m = 0; m < S; ++m)
+#pragma unroll
+    for (int d = 0; d < D; ++d) rec[(long long)(m * D + d) * count + i] = A[m][d];
+#pragma unroll
+  for (int d = 0; d < D; ++d) rec[(long long)(S * D + d) * count + i] = W[d] > eps ? 1. / W[d] : 0.;
+}
+
+// Halo unpack (the receiving half of DistributionCommunicateFi, lbm_distribution_function.F90:309-334,
+// reduced to the populations that cross the face).  The pushes that left the neighbour slab through
+// its ghost plane arrive in `src`; population n of boundary-plane node Y is taken iff its source
+// Y - c_n is fluid -- otherwise slot (n, Y) already holds Y's own bounce-back value.
+//   up = 1: fills owned plane 0      with the directions c_z = +1 (from the slab below)
+//   up = 0: fills owned plane NZl-1  with the directions c_z = -1 (from the slab above)
+// src(m, n, r) = src[(m*Q + n) * src_stride + r] when !packed (a ghost plane of an f buffer), else
+// src[(m*NCROSS + k) * plane + r], k the rank of n among the crossing directions (NCCL staging).
+template <class L, int S>
+__global__ void k_halo_unpack(Grid g, double *__restrict__ f, const double *__restrict__ src, long long src_stride,
+                              int packed, const uint32_t *__restrict__ nbmask, int up) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= g.plane) return;
+  const int zo = up ? 0 : g.NZl - 1;
+  const uint32_t mask = nbmask[(long long)zo * g.plane + r];
+  if (mask >> 31) return;
+  const long long o = (long long)(zo + 1) * g.plane + r;
+  int k = 0;
+  static_for<1, L::Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    if constexpr (L::c(n, 2) != 0) {
+      if ((L::c(n, 2) > 0) == (up != 0)) {
+        constexpr int on = opp<L>(n);
+        if (!((mask >> on) & 1u)) {
+#pragma unroll
+          for (int m = 0; m < S; ++m) {
+            const double v = packed ? src[(long long)(m * L::NCROSS + k) * g.plane + r]
+                                    : src[(long long)(m * L::Q + n) * src_stride + r];
+            f[(long long)(m * L::Q + n) * g.fstride + o] = v;
+          }
+        }
+        ++k;
+      }
+    }
+  });
 }
 
 }  // namespace txg

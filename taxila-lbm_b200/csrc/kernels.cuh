@@ -1,15 +1,25 @@
 // kernels.cuh -- device code of the flow hot path (sm_100a).
 //
 // Storage (all fp64, one slab per GPU, x fastest):
-//   f    [S][Q][NZl+2 ][NY][NX]   populations in PULL form: slot (m,n,X) holds the post-collision
-//                                 value that leaves X along c_n; the value a node sees after
-//                                 streaming + bounce-back is pull(X,n) below.  One ghost z-plane
-//                                 each side (filled by the halo exchange).
+//   f    [S][Q][NZl+2 ][NY][NX]   populations in the reference's own sense: slot (m,n,X) is fi(m,n,X), the
+//                                 value node X holds AFTER streaming and bounce-back.  The collide kernel
+//                                 PUSHES: the post-collision value leaving X along c_n is stored into
+//                                 slot (n, X+c_n) of the other buffer, or -- when X+c_n is solid -- into
+//                                 slot (opp(n), X) (half-way bounce-back completed in the same step,
+//                                 SURVEY.md 8a-11).  Every read of f is therefore node-aligned and needs
+//                                 no mask.  One ghost z-plane each side receives the pushes that leave the
+//                                 slab; the halo exchange moves them into the neighbour's boundary plane.
+//                                 Slots of solid nodes are never written and stay 0.
 //   rho  [S][NZl+2R][NY][NX]      per-component density (psi when a non-ideal EOS is on), R ghost planes
 //   cls  [NZl+2Rz][NY+2R][NX+2R]  u8 node class incl. ghosts, straight from the host walls(rg..) array
-//   nbmask [NZl][NY][NX]          u32: bit n = neighbour X+c_n is solid, bit 31 = X itself is solid
+//   nbmask [NZl][NY][NX]          u32: bit n = neighbour X+c_n is solid, bit 30 = X has a wall record
+//                                 (some lattice neighbour solid or some gradient-stencil entry inactive),
+//                                 bit 31 = X itself is solid
 //   ffmask [NW][NZl][NY][NX]      u32 words: bit e = fluid-fluid stencil entry e is active at X
 //                                 (isotropy order > 4 only; order 4 re-uses nbmask)
+//   flist [nfluid]                ascending indices of the fluid nodes; the hot kernels put only these on lanes
+//   wallrec [S*D+D][nfluid]       per fluid-list entry with bit 30 set: A[m][d] = sum_n w_n gw(mineral(X+c_n),m) c_n,d
+//                                 (fluid-solid force = -rho_m A) and 1/W[d] of the gradient normalisation
 //
 // Reference loops each kernel replaces are cited at the kernel.
 #pragma once
@@ -72,29 +82,22 @@ __device__ __forceinline__ int wrapc(int v, int N, int per) {
   return v;
 }
 
-// ------------------------------------------------------------------ pull streaming with bounce-back
-// DistributionStreamD3/D2 + DistributionBouncebackD3/D2 (lbm_distribution_function.F90:560-784) in
-// pull form: f_n(X,t+1) = f*_n(X - c_n) if X - c_n is fluid, else f*_opp(n)(X)  (SURVEY.md 8a-11).
+// ------------------------------------------------------------------ populations of a node
+// fi(:,:,X) after DistributionStreamD*/DistributionBouncebackD* (lbm_distribution_function.F90:560-784):
+// with push storage simply the node's own slots.
 template <class L, int S>
-__device__ __forceinline__ void pull(const Grid &g, const double *__restrict__ fA, const NodeIdx &nd, uint32_t mask,
-                                     double (&f)[S][L::Q]) {
-  const int xm = wrapc(nd.x - 1, g.NX, g.perx), xp = wrapc(nd.x + 1, g.NX, g.perx);
-  const int ym = wrapc(nd.y - 1, g.NY, g.pery), yp = wrapc(nd.y + 1, g.NY, g.pery);
-  static_for<0, L::Q>([&](auto n_) {
-    constexpr int n = decltype(n_)::value;
-    constexpr int on = opp<L>(n);
-    // source node X - c_n
-    const int sx = L::c(n, 0) == 0 ? nd.x : (L::c(n, 0) > 0 ? xm : xp);
-    const int sy = L::c(n, 1) == 0 ? nd.y : (L::c(n, 1) > 0 ? ym : yp);
-    const int sz = nd.z + 1 - L::c(n, 2);  // +1: ghost plane offset
-    const bool bounce = n != 0 && ((mask >> on) & 1u);
-    const long long src_node = bounce ? ((long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x)
-                                      : ((long long)sz * g.plane + (long long)sy * g.NX + sx);
-    const int src_dir = bounce ? on : n;
+__device__ __forceinline__ void load_node(const Grid &g, const double *__restrict__ fA, const NodeIdx &nd,
+                                          double (&f)[S][L::Q]) {
+  const long long o = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
 #pragma unroll
-    for (int m = 0; m < S; ++m) f[m][n] = __ldg(fA + (long long)(m * L::Q + src_dir) * g.fstride + src_node);
-  });
+  for (int m = 0; m < S; ++m)
+#pragma unroll
+    for (int n = 0; n < L::Q; ++n) f[m][n] = __ldg(fA + (long long)(m * L::Q + n) * g.fstride + o);
 }
+
+constexpr uint32_t MASK_SOLID = 0x80000000u;    // the node itself is solid
+constexpr uint32_t MASK_WALLREC = 0x40000000u;  // the node has a wall record
+constexpr uint32_t MASK_DIRS = 0x3fffffffu;     // bit n: neighbour X + c_n is solid
 
 // ------------------------------------------------------------------ forces
 // FlowCalcForces (lbm_flow.F90:760-808): F = 0; fluid-solid (LBMAddFluidSolidForcesD*,
@@ -112,7 +115,7 @@ __device__ __forceinline__ void forces(const Grid &g, const Phys &p, const doubl
 #pragma unroll
     for (int d = 0; d < D; ++d) F[m][d] = 0.;
 
-  if (p.fluidsolid && (mask & 0x7fffffffu)) {
+  if (p.fluidsolid && (mask & MASK_DIRS)) {
     const long long cbase = ((long long)(nd.z + g.Rz) * g.cny + (nd.y + g.R)) * g.cnx + (nd.x + g.R);
     static_for<1, L::Q>([&](auto n_) {
       constexpr int n = decltype(n_)::value;
@@ -296,41 +299,6 @@ __device__ __forceinline__ void prefactor(double rho, const double (&F)[L::D], c
   });
 }
 
-// collision of one component (FlowCollisionD3/D2 lbm_flow.F90:960-1029 with
-// RelaxationCollideSRT/MRT lbm_relaxation.F90:171-200): f <- relax(f, (1-pref/2) feq) + pref feq
-template <class L, bool MRT>
-__device__ __forceinline__ void collide_component(const Phys &p, int m, double (&f)[L::Q], const double (&feq)[L::Q],
-                                                  const double (&pref)[L::Q]) {
-  constexpr int Q = L::Q;
-  if constexpr (!MRT) {
-    const double it = p.inv_tau[m];
-#pragma unroll
-    for (int n = 0; n < Q; ++n) {
-      const double fbar = (1. - .5 * pref[n]) * feq[n];
-      f[n] = f[n] - (f[n] - fbar) * it + pref[n] * feq[n];
-    }
-  } else {
-    double dfi[Q];
-#pragma unroll
-    for (int n = 0; n < Q; ++n) dfi[n] = f[n] - (1. - .5 * pref[n]) * feq[n];
-    static_for<0, Q>([&](auto r_) {
-      constexpr int r = decltype(r_)::value;
-      double mom = 0.;
-      static_for<0, Q>([&](auto i_) {
-        constexpr int i = decltype(i_)::value;
-        if constexpr (L::M(r, i) != 0) mom += (double)L::M(r, i) * dfi[i];
-      });
-      const double cr = p.mrt_rate[m][r] * mom;
-      static_for<0, Q>([&](auto i_) {
-        constexpr int i = decltype(i_)::value;
-        if constexpr (L::M(r, i) != 0) f[i] = f[i] - cr * (double)L::M(r, i);
-      });
-    });
-#pragma unroll
-    for (int n = 0; n < Q; ++n) f[n] = f[n] + pref[n] * feq[n];
-  }
-}
-
 __device__ __forceinline__ double eos_psi(const Phys &p, int m, double rho) {
   return p.eos_sc[m] ? p.eos_rho0[m] * (1. - exp(-rho / p.eos_rho0[m])) : rho;
 }
@@ -338,8 +306,7 @@ __device__ __forceinline__ double eos_psi(const Phys &p, int m, double rho) {
 // ================================================================== kernels
 
 // K3 fi_init (FlowFiInit lbm_flow.F90:923-934, FlowFeqBarD* :867-921): F from rho0, feq(rho0, u0),
-// f = (1 - prefactor/2) feq, written as NODE values (post-stream form) into fN; k_unstream then
-// converts to pull form.  u0 is [S][D][nnodes] or null (= 0).
+// f = (1 - prefactor/2) feq, written into the node's own slots.  u0 is [S][D][nnodes] or null (= 0).
 template <class L, int S, int ISO>
 __global__ void __launch_bounds__(128) k_fi_init(Grid g, Phys p, double *__restrict__ fN,
                                                  const double *__restrict__ rho, const double *__restrict__ rho_true,
@@ -369,56 +336,7 @@ __global__ void __launch_bounds__(128) k_fi_init(Grid g, Phys p, double *__restr
   }
 }
 
-// node values -> pull form: A_n(Y) = f_n(Y + c_n) if Y + c_n is fluid, else f_opp(n)(Y).
-// Exact inverse of pull(); used after fi_init and txg_set_fi.
-template <class L, int S>
-__global__ void __launch_bounds__(128) k_unstream(Grid g, const double *__restrict__ fN, double *__restrict__ fA,
-                                                  const uint32_t *__restrict__ nbmask, int z0, int nz) {
-  NodeIdx nd;
-  if (!node_of_thread(g, z0, nz, nd)) return;
-  const uint32_t mask = nbmask[nd.o];
-  if (mask >> 31) return;
-  const int xm = wrapc(nd.x - 1, g.NX, g.perx), xp = wrapc(nd.x + 1, g.NX, g.perx);
-  const int ym = wrapc(nd.y - 1, g.NY, g.pery), yp = wrapc(nd.y + 1, g.NY, g.pery);
-  const long long o = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
-  static_for<0, L::Q>([&](auto n_) {
-    constexpr int n = decltype(n_)::value;
-    const int tx = L::c(n, 0) == 0 ? nd.x : (L::c(n, 0) > 0 ? xp : xm);
-    const int ty = L::c(n, 1) == 0 ? nd.y : (L::c(n, 1) > 0 ? yp : ym);
-    const int tz = nd.z + 1 + L::c(n, 2);
-    const bool solid = n != 0 && ((mask >> n) & 1u);
-    const long long src = solid ? o : ((long long)tz * g.plane + (long long)ty * g.NX + tx);
-    const int sd = solid ? opp<L>(n) : n;
-#pragma unroll
-    for (int m = 0; m < S; ++m)
-      fA[(long long)(m * L::Q + n) * g.fstride + o] = fN[(long long)(m * L::Q + sd) * g.fstride + src];
-  });
-}
-
-// pull form -> node values (what the reference holds in fi after FlowBounceback); solid nodes 0.
-template <class L, int S>
-__global__ void __launch_bounds__(128) k_stream_out(Grid g, const double *__restrict__ fA, double *__restrict__ fN,
-                                                    const uint32_t *__restrict__ nbmask, int z0, int nz) {
-  NodeIdx nd;
-  if (!node_of_thread(g, z0, nz, nd)) return;
-  const uint32_t mask = nbmask[nd.o];
-  const long long o = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
-  double f[S][L::Q];
-  if (mask >> 31) {
-#pragma unroll
-    for (int m = 0; m < S; ++m)
-#pragma unroll
-      for (int n = 0; n < L::Q; ++n) f[m][n] = 0.;
-  } else {
-    pull<L, S>(g, fA, nd, mask, f);
-  }
-#pragma unroll
-  for (int m = 0; m < S; ++m)
-#pragma unroll
-    for (int n = 0; n < L::Q; ++n) fN[(long long)(m * L::Q + n) * g.fstride + o] = f[m][n];
-}
-
-// K6 state/diagnostics export: from the pull-form populations and the current rho field compute
+// K6 state/diagnostics export: from the populations and the current rho field compute
 // what the reference holds after FlowUpdateMoments (rho, forces, common velocity u') and what
 // FlowUpdateDiagnosticsD* (lbm_flow.F90:654-758) derives (rhot, prs, velt).  Any output may be null.
 template <class L, int S, int ISO>
@@ -453,7 +371,7 @@ __global__ void __launch_bounds__(128) k_export(Grid g, Phys p, const double *__
     return;
   }
   double f[S][Q], r[S], F[S][D], up[D];
-  pull<L, S>(g, fA, nd, mask, f);
+  load_node<L, S>(g, fA, nd, f);
   density<L, S>(f, r);
   forces<L, S, ISO>(g, p, rho, cls, ffmask, nd, mask, r, F);
   common_velocity<L, S>(p, f, r, F, up);
@@ -526,7 +444,7 @@ __global__ void k_build_masks(Grid g, const uint8_t *__restrict__ cls, uint32_t 
     if (c != 0) mask |= 1u << n;
     if (c >= 250 && c <= 252 && !(mask >> 31)) atomicAdd(specular, 1);
   });
-  nbmask[nd.o] = mask;
+  bool wallrec = (mask & MASK_DIRS) != 0;
   if constexpr (ISO != 4) {
     using FF = typename L::FF;
     constexpr int E = ff_entries<L>(ISO);
@@ -552,11 +470,16 @@ __global__ void k_build_masks(Grid g, const uint8_t *__restrict__ cls, uint32_t 
           any = any || all;
         }
       });
-      if (ok && any) words[e / 32] |= 1u << (e % 32);
+      if (ok && any)
+        words[e / 32] |= 1u << (e % 32);
+      else
+        wallrec = true;
     });
 #pragma unroll
     for (int w = 0; w < (E + 31) / 32; ++w) ffmask[(long long)w * g.nnodes + nd.o] = words[w];
   }
+  if (wallrec && !(mask >> 31)) mask |= MASK_WALLREC;
+  nbmask[nd.o] = mask;
 }
 
 }  // namespace txg

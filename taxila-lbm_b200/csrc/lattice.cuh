@@ -27,7 +27,8 @@ TXG_HD constexpr void static_for(F &&f) {
 
 struct D3Q19 {
   static constexpr int D = 3, Q = 19;
-  static constexpr int NAXIS = 6;  // directions 1..6 are the axis neighbours
+  static constexpr int NAXIS = 6;   // directions 1..6 are the axis neighbours
+  static constexpr int NCROSS = 5;  // directions with c_z = +1 (and as many with c_z = -1)
   using FF = FFStencilD3;
   TXG_HD static constexpr int c(int n, int d) {
     // lbm_discretization_d3q19.F90:163-168
@@ -91,6 +92,7 @@ struct D3Q19 {
 struct D2Q9 {
   static constexpr int D = 2, Q = 9;
   static constexpr int NAXIS = 4;
+  static constexpr int NCROSS = 0;
   using FF = FFStencilD2;
   TXG_HD static constexpr int c(int n, int d) {
     // lbm_discretization_d2q9.F90:99-100

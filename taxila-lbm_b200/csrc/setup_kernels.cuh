@@ -35,12 +35,19 @@ __global__ void k_classify(const double *__restrict__ walls, uint8_t *__restrict
 }
 
 // fluid-node list, pass 1: fluid nodes (nbmask bit 31 clear) per 256-slot chunk of each plane
-__global__ void k_count_fluid(const uint32_t *__restrict__ nbmask, long long plane, int bpp, unsigned *__restrict__ cnt) {
+// (and the number of fluid nodes that carry a wall record, bit 30, accumulated into *nrec)
+__global__ void k_count_fluid(const uint32_t *__restrict__ nbmask, long long plane, int bpp, unsigned *__restrict__ cnt,
+                              int *__restrict__ nrec) {
   const long long z = blockIdx.x / bpp;
   const long long r = (long long)(blockIdx.x % bpp) * 256 + threadIdx.x;
-  const bool fluid = r < plane && !(nbmask[z * plane + r] >> 31);
+  const uint32_t mask = r < plane ? nbmask[z * plane + r] : 0x80000000u;
+  const bool fluid = !(mask >> 31);
   const int n = __syncthreads_count(fluid);
-  if (threadIdx.x == 0) cnt[blockIdx.x] = (unsigned)n;
+  const int w = __syncthreads_count(fluid && (mask & 0x40000000u));
+  if (threadIdx.x == 0) {
+    cnt[blockIdx.x] = (unsigned)n;
+    if (w) atomicAdd(nrec, w);
+  }
 }
 
 // pass 2: off[chunk] = list position of the chunk's first fluid node; rank inside the chunk by ballot
