@@ -109,13 +109,14 @@ struct txg_flow {
   double *gw = nullptr;
   uint8_t *cls = nullptr;
   uint32_t *nbmask = nullptr, *ffmask = nullptr;
-  // ascending list of fluid node indices (nullptr: every node is fluid) and, per owned z-plane, the
-  // offset of its first entry; plane_off[NZl] = number of fluid nodes
-  uint32_t *flist = nullptr;
-  double *wallrec = nullptr;   // [S*D + D][nfluid], see kernels.cuh
-  double *halo_recv = nullptr; // NCCL staging: [2 faces][S][NCROSS][plane]
+  // sparse storage (kernels.cuh): node -> position map, position -> node list, per-position masks and
+  // wall records; plane_off[zz] = position of the first fluid node of extended plane zz (NZl+2Rz+1 entries)
+  uint32_t *P = nullptr, *list = nullptr, *lmask = nullptr;
+  double *wallrec = nullptr;    // [S*D + D][fs]
+  double *halo_recv = nullptr;  // NCCL staging: [2 faces][S][NCROSS][fluid nodes of the boundary plane]
+  size_t halo_recv_doubles = 0;
   std::vector<long long> plane_off;
-  long long nfluid = 0;
+  long long nstore = 0;
   int *counters = nullptr;  // [0] bad wall codes, [1] fluid nodes next to 900-902 walls
   double *staging = nullptr;
   size_t staging_bytes = 0;
@@ -286,8 +287,8 @@ static int validate(const txg_config *c) {
   if (c->stencil_size_rho < Rneed || c->stencil_size_rho > 3)
     TXG_FAIL(h, TXG_ERR_ARG_WRONG, "stencil_size_rho %d too small for isotropy order %d (needs %d)", c->stencil_size_rho,
              c->isotropy_order, Rneed);
-  if ((long long)c->NX * c->NY * (c->ndims == 3 ? c->zl : 1) >= (1ll << 32))
-    TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "slab of %d x %d x %d nodes exceeds the 32-bit node index of the fluid list", c->NX, c->NY, c->zl);
+  if ((long long)c->NX * c->NY * (c->ndims == 3 ? c->zl + 2 * c->stencil_size_rho : 1) >= (1ll << 31))
+    TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "slab of %d x %d x %d nodes exceeds the 31-bit node index of the fluid list", c->NX, c->NY, c->zl);
   if (c->NX <= 2 * c->stencil_size_rho || c->NY <= 2 * c->stencil_size_rho)
     TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "box too small for the stencil");
   if (c->nminerals < 1 || c->nminerals > TXG_MAX_MINERALS) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "nminerals %d out of range", c->nminerals);
@@ -343,7 +344,7 @@ extern "C" int txg_destroy(txg_handle h) {
   drain_timers(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
-                  h->nbmask, h->ffmask, h->flist, h->wallrec, h->halo_recv, h->counters, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
+                  h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->wallrec, h->halo_recv, h->counters, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -400,9 +401,11 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
   g.perx = cfg->periodic[0];
   g.pery = cfg->periodic[1];
   g.plane = (long long)g.NX * g.NY;
-  g.fstride = (long long)(g.NZl + 2) * g.plane;
-  g.rstride = (long long)(g.NZl + 2 * g.R) * g.plane;
   g.nnodes = (long long)g.NZl * g.plane;
+  g.nE = (long long)(g.NZl + 2 * g.Rz) * g.plane;
+  g.fs = 0;
+  g.own0 = g.own1 = 0;
+  g.P = g.list = nullptr;
   g.cnx = g.NX + 2 * g.R;
   g.cny = g.NY + 2 * g.R;
   auto body = [&]() -> int {
@@ -412,14 +415,7 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     TXG_CUDA(h, cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
     TXG_CUDA(h, cudaEventCreate(&h->ev_step0));
     TXG_CUDA(h, cudaEventCreate(&h->ev_step1));
-    const size_t fbytes = (size_t)h->S * h->Q * g.fstride * sizeof(double);
-    TXG_TRY(alloc_zero(h, (void **)&h->f[0], fbytes));
-    TXG_TRY(alloc_zero(h, (void **)&h->f[1], fbytes));
-    TXG_TRY(alloc_zero(h, (void **)&h->rho, (size_t)h->S * g.rstride * sizeof(double)));
-    if (cfg->use_nonideal_eos)
-      TXG_TRY(alloc_zero(h, (void **)&h->rho_true, (size_t)h->S * g.rstride * sizeof(double)));
-    else
-      h->rho_true = h->rho;
+    // the population / density arrays are sized by the fluid-node count: allocated in txg_set_walls
     TXG_TRY(alloc_zero(h, (void **)&h->cls, (size_t)(g.NZl + 2 * g.Rz) * g.cny * g.cnx));
     TXG_TRY(alloc_zero(h, (void **)&h->nbmask, (size_t)g.nnodes * sizeof(uint32_t)));
     if (h->ks.ff_words) TXG_TRY(alloc_zero(h, (void **)&h->ffmask, (size_t)h->ks.ff_words * g.nnodes * sizeof(uint32_t)));
@@ -470,7 +466,7 @@ extern "C" int txg_comm_init(txg_handle h, const unsigned char id_in[128]) {
 // lists (offset into the buffer of the plane to send / the ghost plane to fill).
 struct Chunk {
   long long send_off, recv_off;
-  long long count;
+  long long send_count, recv_count;
 };
 
 static int exchange(txg_flow *h, double *buf, const std::vector<Chunk> &to_up, const std::vector<Chunk> &to_down,
@@ -480,89 +476,105 @@ static int exchange(txg_flow *h, double *buf, const std::vector<Chunk> &to_up, c
   const int nr = h->cfg.nranks;
   if (nr == 1) {
     if (h->up < 0) return 0;  // not periodic in z: ghosts are never read
-    // periodic single rank: my own top plane is my bottom ghost and vice versa
-    for (const Chunk &c : to_up)
-      TXG_CUDA(h, cudaMemcpyAsync(buf + c.recv_off, buf + c.send_off, c.count * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    for (const Chunk &c : to_down)
-      TXG_CUDA(h, cudaMemcpyAsync(buf + c.recv_off, buf + c.send_off, c.count * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    // periodic single rank: my own top planes are my bottom ghost and vice versa
+    for (const std::vector<Chunk> *v : {&to_up, &to_down})
+      for (const Chunk &c : *v) {
+        if (c.send_count != c.recv_count) TXG_FAIL(h, TXG_ERR_ARG_WRONG, "periodic z: ghost planes do not mirror the boundary planes");
+        if (c.send_count)
+          TXG_CUDA(h, cudaMemcpyAsync(buf + c.recv_off, buf + c.send_off, c.send_count * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      }
     h->launches += (int64_t)(to_up.size() + to_down.size());
     return 0;
   }
   if (!h->comm) TXG_FAIL(h, TXG_ERR_ORDER, "nranks > 1 but txg_comm_init was not called");
   TXG_NCCL(h, g_nccl.GroupStart());
   for (const Chunk &c : to_up) {
-    if (h->up >= 0) TXG_NCCL(h, g_nccl.Send(buf + c.send_off, (size_t)c.count, ncclFloat64, h->up, h->comm, s));
-    if (h->down >= 0) TXG_NCCL(h, g_nccl.Recv(buf + c.recv_off, (size_t)c.count, ncclFloat64, h->down, h->comm, s));
+    if (h->up >= 0 && c.send_count) TXG_NCCL(h, g_nccl.Send(buf + c.send_off, (size_t)c.send_count, ncclFloat64, h->up, h->comm, s));
+    if (h->down >= 0 && c.recv_count) TXG_NCCL(h, g_nccl.Recv(buf + c.recv_off, (size_t)c.recv_count, ncclFloat64, h->down, h->comm, s));
   }
   for (const Chunk &c : to_down) {
-    if (h->down >= 0) TXG_NCCL(h, g_nccl.Send(buf + c.send_off, (size_t)c.count, ncclFloat64, h->down, h->comm, s));
-    if (h->up >= 0) TXG_NCCL(h, g_nccl.Recv(buf + c.recv_off, (size_t)c.count, ncclFloat64, h->up, h->comm, s));
+    if (h->down >= 0 && c.send_count) TXG_NCCL(h, g_nccl.Send(buf + c.send_off, (size_t)c.send_count, ncclFloat64, h->down, h->comm, s));
+    if (h->up >= 0 && c.recv_count) TXG_NCCL(h, g_nccl.Recv(buf + c.recv_off, (size_t)c.recv_count, ncclFloat64, h->up, h->comm, s));
   }
   TXG_NCCL(h, g_nccl.GroupEnd());
   return 0;
 }
 
-// Populations pushed across a z face sit in this slab's ghost plane; they belong in the
+// Populations pushed across a z face sit in this slab's ghost-plane positions; they belong in the
 // neighbour's boundary plane.  Single rank, periodic z: unpack straight from the own opposite
-// ghost plane.  Several ranks: send each ghost plane's crossing directions (one contiguous plane
-// per (m, n)), receive the neighbours' into the staging buffer, unpack from there.  The unpack is
-// masked (k_halo_unpack): a slot whose source node is solid keeps the bounce-back value its own
-// node wrote.
+// ghost plane.  Several ranks: send each ghost plane's crossing directions (one contiguous run of
+// positions per (m, n)), receive the neighbours' into the staging buffer, unpack from there.  The
+// unpack is masked (k_halo_unpack): a slot whose source node is solid keeps the bounce-back value
+// its own node wrote.
 static int exchange_f(txg_flow *h, double *buf, cudaStream_t s) {
   if (h->D != 3) return 0;
   const Grid &g = h->g;
-  const int nr = h->cfg.nranks;
-  const unsigned nb = blocks_for(g.plane, 256);
+  const int nr = h->cfg.nranks, Rz = g.Rz;
+  const std::vector<long long> &po = h->plane_off;
+  // extended planes: bottom ghost Rz-1, bottom owned Rz, top owned Rz+NZl-1, top ghost Rz+NZl
+  const long long gb0 = po[Rz - 1], ob0 = po[Rz], ob1 = po[Rz + 1];
+  const long long ot0 = po[Rz + g.NZl - 1], gt0 = po[Rz + g.NZl], gt1 = po[Rz + g.NZl + 1];
+  const long long nbot = ob1 - ob0, ntop = gt0 - ot0;  // fluid nodes of the boundary planes
   if (nr == 1) {
     if (h->up < 0) return 0;  // not periodic in z: the ghost planes are solid (class 255), nothing is pushed
-    // plane 0 (bottom) takes c_z = +1 pushes that left through the top ghost plane NZl+1, and vice versa
-    h->ks.halo_unpack<<<nb, 256, 0, s>>>(g, buf, buf + (long long)(g.NZl + 1) * g.plane, g.fstride, 0, h->nbmask, 1);
-    h->ks.halo_unpack<<<nb, 256, 0, s>>>(g, buf, buf, g.fstride, 0, h->nbmask, 0);
+    // the bottom plane takes the c_z = +1 pushes that left through the top ghost plane, and vice versa
+    if (gt1 - gt0 != nbot || ob0 - gb0 != ntop) TXG_FAIL(h, TXG_ERR_ARG_WRONG, "periodic z: ghost planes do not mirror the boundary planes");
+    if (nbot) h->ks.halo_unpack<<<blocks_for(nbot, 256), 256, 0, s>>>(g, buf, buf, gt0, 0, h->lmask, ob0, nbot, 1);
+    if (ntop) h->ks.halo_unpack<<<blocks_for(ntop, 256), 256, 0, s>>>(g, buf, buf, gb0, 0, h->lmask, ot0, ntop, 0);
     TXG_CUDA(h, cudaGetLastError());
     h->launches += 2;
     return 0;
   }
   if (!h->comm) TXG_FAIL(h, TXG_ERR_ORDER, "nranks > 1 but txg_comm_init was not called");
   const int NC = D3Q19::NCROSS;
-  const size_t face = (size_t)h->S * NC * g.plane;  // doubles per face
-  if (!h->halo_recv) TXG_CUDA(h, cudaMalloc((void **)&h->halo_recv, 2 * face * sizeof(double)));
-  double *from_down = h->halo_recv, *from_up = h->halo_recv + face;
+  const size_t need = (size_t)h->S * NC * (size_t)(nbot + ntop);
+  if (h->halo_recv_doubles < need) {
+    if (h->halo_recv) cudaFree(h->halo_recv);
+    h->halo_recv = nullptr;
+    TXG_CUDA(h, cudaMalloc((void **)&h->halo_recv, std::max<size_t>(need, 1) * sizeof(double)));
+    h->halo_recv_doubles = need;
+  }
+  double *from_down = h->halo_recv, *from_up = h->halo_recv + (size_t)h->S * NC * (size_t)nbot;
+  const long long nsend_up = gt1 - gt0, nsend_down = ob0 - gb0;  // fluid nodes of my ghost planes
   TXG_NCCL(h, g_nccl.GroupStart());
   for (int m = 0; m < h->S; ++m) {
     int ku = 0, kd = 0;
     for (int n = 1; n < h->Q; ++n) {
       const int cz = D3Q19::c(n, 2);
-      const long long blk = (long long)(m * h->Q + n) * g.fstride;
+      const long long blk = (long long)(m * h->Q + n) * g.fs;
       if (cz > 0) {  // my top ghost plane -> up; the same directions arrive from down
-        if (h->up >= 0) TXG_NCCL(h, g_nccl.Send(buf + blk + (long long)(g.NZl + 1) * g.plane, (size_t)g.plane, ncclFloat64, h->up, h->comm, s));
-        if (h->down >= 0) TXG_NCCL(h, g_nccl.Recv(from_down + (size_t)(m * NC + ku) * g.plane, (size_t)g.plane, ncclFloat64, h->down, h->comm, s));
+        if (h->up >= 0 && nsend_up) TXG_NCCL(h, g_nccl.Send(buf + blk + gt0, (size_t)nsend_up, ncclFloat64, h->up, h->comm, s));
+        if (h->down >= 0 && nbot) TXG_NCCL(h, g_nccl.Recv(from_down + (size_t)(m * NC + ku) * nbot, (size_t)nbot, ncclFloat64, h->down, h->comm, s));
         ++ku;
       } else if (cz < 0) {  // my bottom ghost plane -> down; the same directions arrive from up
-        if (h->down >= 0) TXG_NCCL(h, g_nccl.Send(buf + blk, (size_t)g.plane, ncclFloat64, h->down, h->comm, s));
-        if (h->up >= 0) TXG_NCCL(h, g_nccl.Recv(from_up + (size_t)(m * NC + kd) * g.plane, (size_t)g.plane, ncclFloat64, h->up, h->comm, s));
+        if (h->down >= 0 && nsend_down) TXG_NCCL(h, g_nccl.Send(buf + blk + gb0, (size_t)nsend_down, ncclFloat64, h->down, h->comm, s));
+        if (h->up >= 0 && ntop) TXG_NCCL(h, g_nccl.Recv(from_up + (size_t)(m * NC + kd) * ntop, (size_t)ntop, ncclFloat64, h->up, h->comm, s));
         ++kd;
       }
     }
   }
   TXG_NCCL(h, g_nccl.GroupEnd());
-  if (h->down >= 0) h->ks.halo_unpack<<<nb, 256, 0, s>>>(g, buf, from_down, 0, 1, h->nbmask, 1);
-  if (h->up >= 0) h->ks.halo_unpack<<<nb, 256, 0, s>>>(g, buf, from_up, 0, 1, h->nbmask, 0);
+  if (h->down >= 0 && nbot) h->ks.halo_unpack<<<blocks_for(nbot, 256), 256, 0, s>>>(g, buf, from_down, 0, 1, h->lmask, ob0, nbot, 1);
+  if (h->up >= 0 && ntop) h->ks.halo_unpack<<<blocks_for(ntop, 256), 256, 0, s>>>(g, buf, from_up, 0, 1, h->lmask, ot0, ntop, 0);
   TXG_CUDA(h, cudaGetLastError());
   h->launches += 2;
   return 0;
 }
 
+// rho (psi) halo: my top R owned planes fill the up neighbour's bottom ghost planes and vice versa;
+// both are contiguous runs of positions with matching fluid-node counts.
 static int exchange_rho(txg_flow *h, double *buf, cudaStream_t s) {
   if (h->D != 3) return 0;
   const Grid &g = h->g;
-  const int R = g.R;
+  const int Rz = g.Rz;
+  const std::vector<long long> &po = h->plane_off;
   std::vector<Chunk> upv, downv;
   for (int m = 0; m < h->S; ++m) {
-    const long long base = (long long)m * g.rstride;
-    // my top R owned planes [NZl, NZl+R) (ghosted index) -> neighbour's bottom ghost [0, R)
-    upv.push_back({base + (long long)g.NZl * g.plane, base, (long long)R * g.plane});
+    const long long base = (long long)m * g.fs;
+    // my top R owned planes [NZl, NZl+R) (extended index) -> neighbour's bottom ghost [0, R)
+    upv.push_back({base + po[g.NZl], base + po[0], po[g.NZl + Rz] - po[g.NZl], po[Rz] - po[0]});
     // my bottom R owned planes [R, 2R) -> neighbour's top ghost [NZl+R, NZl+2R)
-    downv.push_back({base + (long long)R * g.plane, base + (long long)(g.NZl + R) * g.plane, (long long)R * g.plane});
+    downv.push_back({base + po[Rz], base + po[g.NZl + Rz], po[2 * Rz] - po[Rz], po[g.NZl + 2 * Rz] - po[g.NZl + Rz]});
   }
   return exchange(h, buf, upv, downv, s);
 }
@@ -578,9 +590,9 @@ static int ensure_staging(txg_flow *h, size_t bytes) {
   return 0;
 }
 
-// host array [gz][gy][gx][K*S] (ghost width gw in x,y; gwz in z) -> device SoA
-static int import_field(txg_flow *h, const double *host, int gw, int gwz, int K, double *dst, long long dst_stride,
-                        long long dst_plane0) {
+// host array [gz][gy][gx][K*S] (ghost width gw in x,y; gwz in z) -> device SoA (dense over the owned
+// nodes, or position-indexed over the fluid nodes)
+static int import_field(txg_flow *h, const double *host, int gw, int gwz, int K, double *dst, int dense) {
   const Grid &g = h->g;
   const int dof = h->S * K;
   const size_t plane_elems = (size_t)(g.NX + 2 * gw) * (g.NY + 2 * gw) * dof;
@@ -591,16 +603,14 @@ static int import_field(txg_flow *h, const double *host, int gw, int gwz, int K,
     TXG_CUDA(h, cudaMemcpyAsync(h->staging, host + (size_t)(z0 + gwz) * plane_elems, plane_elems * 8 * nz,
                                 cudaMemcpyHostToDevice, h->s_main));
     const long long total = (long long)nz * g.plane * dof;
-    k_import_aos<<<blocks_for(total, 256), 256, 0, h->s_main>>>(h->staging, dst, g.NX, g.NY, gw, h->S, K, dst_stride,
-                                                                dst_plane0, z0, nz);
+    k_import_aos<<<blocks_for(total, 256), 256, 0, h->s_main>>>(g, h->staging, dst, gw, h->S, K, dense, z0, nz);
     TXG_CUDA(h, cudaGetLastError());
     TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
   }
   return 0;
 }
 
-static int export_field(txg_flow *h, double *host, int gw, int gwz, int K, int S, const double *src,
-                        long long src_stride, long long src_plane0) {
+static int export_field(txg_flow *h, double *host, int gw, int gwz, int K, int S, const double *src, int dense) {
   const Grid &g = h->g;
   const int dof = S * K;
   const size_t plane_elems = (size_t)(g.NX + 2 * gw) * (g.NY + 2 * gw) * dof;
@@ -612,8 +622,7 @@ static int export_field(txg_flow *h, double *host, int gw, int gwz, int K, int S
       TXG_CUDA(h, cudaMemcpyAsync(h->staging, host + (size_t)(z0 + gwz) * plane_elems, plane_elems * 8 * nz,
                                   cudaMemcpyHostToDevice, h->s_main));
     const long long total = (long long)nz * g.plane * dof;
-    k_export_aos<<<blocks_for(total, 256), 256, 0, h->s_main>>>(h->staging, src, g.NX, g.NY, gw, S, K, src_stride,
-                                                                src_plane0, z0, nz);
+    k_export_aos<<<blocks_for(total, 256), 256, 0, h->s_main>>>(g, h->staging, src, gw, S, K, dense, z0, nz);
     TXG_CUDA(h, cudaGetLastError());
     TXG_CUDA(h, cudaMemcpyAsync(host + (size_t)(z0 + gwz) * plane_elems, h->staging, plane_elems * 8 * nz,
                                 cudaMemcpyDeviceToHost, h->s_main));
@@ -622,26 +631,33 @@ static int export_field(txg_flow *h, double *host, int gw, int gwz, int K, int S
   return 0;
 }
 
-// ------------------------------------------------------------------ fluid-node list
-// Ascending indices of the fluid nodes of the slab, so that the hot kernels put only fluid nodes on
-// lanes.  Count per 256-slot chunk of each plane, scan the chunk counts on the host (NZl * plane/256
-// integers), then fill with a ballot rank inside each chunk.
-static int build_fluid_list(txg_flow *h) {
-  const Grid &g = h->g;
-  if (h->flist) {
-    cudaFree(h->flist);
-    h->flist = nullptr;
+// ------------------------------------------------------------------ sparse storage
+// Positions of the fluid nodes of the extended slab: count per 256-slot chunk of each plane, scan the
+// chunk counts on the host ((NZl+2Rz) * plane/256 integers), fill P and list with a ballot rank
+// inside each chunk.  Then size and allocate every position-indexed array.
+static int build_storage(txg_flow *h) {
+  Grid &g = h->g;
+  for (void **q : {(void **)&h->P, (void **)&h->list, (void **)&h->lmask, (void **)&h->wallrec, (void **)&h->f[0],
+                   (void **)&h->f[1], (void **)&h->rho, (void **)&h->f_old}) {
+    if (*q) cudaFree(*q);
+    *q = nullptr;
   }
+  if (h->rho_true && h->cfg.use_nonideal_eos) cudaFree(h->rho_true);
+  h->rho_true = nullptr;
+  h->have_old = false;
+  h->state_set = false;
+  g.P = g.list = nullptr;
+  const int nzE = g.NZl + 2 * g.Rz;
   const int bpp = (int)((g.plane + 255) / 256);  // chunks per plane
-  const long long nchunks = (long long)bpp * g.NZl;
+  const long long nchunks = (long long)bpp * nzE;
   unsigned *d_cnt = nullptr;
   TXG_CUDA(h, cudaMalloc((void **)&d_cnt, (size_t)nchunks * sizeof(unsigned)));
-  k_count_fluid<<<(unsigned)nchunks, 256, 0, h->s_main>>>(h->nbmask, g.plane, bpp, d_cnt, h->counters + 2);
+  k_count_fluid<<<(unsigned)nchunks, 256, 0, h->s_main>>>(g, h->cls, bpp, d_cnt);
   TXG_CUDA(h, cudaGetLastError());
   std::vector<unsigned> cnt((size_t)nchunks);
   TXG_CUDA(h, cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nchunks * sizeof(unsigned), cudaMemcpyDeviceToHost, h->s_main));
   TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
-  h->plane_off.assign((size_t)g.NZl + 1, 0);
+  h->plane_off.assign((size_t)nzE + 1, 0);
   long long run = 0;
   for (long long c = 0; c < nchunks; ++c) {
     if (c % bpp == 0) h->plane_off[(size_t)(c / bpp)] = run;
@@ -649,45 +665,58 @@ static int build_fluid_list(txg_flow *h) {
     cnt[(size_t)c] = (unsigned)run;
     run += k;
   }
-  h->plane_off[(size_t)g.NZl] = run;
-  h->nfluid = run;
-  if (h->wallrec) {
-    cudaFree(h->wallrec);
-    h->wallrec = nullptr;
-  }
-  int nrec = 0;
-  TXG_CUDA(h, cudaMemcpyAsync(&nrec, h->counters + 2, sizeof nrec, cudaMemcpyDeviceToHost, h->s_main));
-  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
-  if ((run == g.nnodes && nrec == 0) || run == 0) {  // nothing solid in reach (dense identity) or no fluid at all
-    cudaFree(d_cnt);
-    return 0;
-  }
-  TXG_CUDA(h, cudaMemcpyAsync(d_cnt, cnt.data(), (size_t)nchunks * sizeof(unsigned), cudaMemcpyHostToDevice, h->s_main));
-  TXG_CUDA(h, cudaMalloc((void **)&h->flist, (size_t)run * sizeof(uint32_t)));
-  k_fill_fluid<<<(unsigned)nchunks, 256, 0, h->s_main>>>(h->nbmask, g.plane, bpp, d_cnt, h->flist);
-  TXG_CUDA(h, cudaGetLastError());
-  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
-  cudaFree(d_cnt);
-  if (nrec) {
-    const size_t nk = (size_t)(h->S * h->D + h->D);
-    TXG_CUDA(h, cudaMalloc((void **)&h->wallrec, nk * (size_t)run * sizeof(double)));
-    TXG_CUDA(h, cudaMemsetAsync(h->wallrec, 0, nk * (size_t)run * sizeof(double), h->s_main));
-    h->ks.build_wallrec<<<blocks_for(run, 128), 128, 0, h->s_main>>>(g, h->p, h->cls, h->nbmask, h->ffmask, h->flist, run, h->wallrec);
+  h->plane_off[(size_t)nzE] = run;
+  h->nstore = run;
+  g.own0 = h->plane_off[(size_t)g.Rz];
+  g.own1 = h->plane_off[(size_t)(g.Rz + g.NZl)];
+  g.fs = ((run + 1 + 15) / 16) * 16;  // >= nstore + 1 (a solid neighbour maps to the next position), 128-byte rows
+  if (run != g.nE) {
+    TXG_CUDA(h, cudaMemcpyAsync(d_cnt, cnt.data(), (size_t)nchunks * sizeof(unsigned), cudaMemcpyHostToDevice, h->s_main));
+    TXG_CUDA(h, cudaMalloc((void **)&h->P, (size_t)(g.nE + 1) * sizeof(uint32_t)));
+    TXG_CUDA(h, cudaMalloc((void **)&h->list, (size_t)std::max<long long>(run, 1) * sizeof(uint32_t)));
+    k_fill_fluid<<<(unsigned)nchunks, 256, 0, h->s_main>>>(g, h->cls, bpp, d_cnt, h->P, h->list);
     TXG_CUDA(h, cudaGetLastError());
+    const uint32_t total = (uint32_t)run;
+    TXG_CUDA(h, cudaMemcpyAsync(h->P + g.nE, &total, sizeof total, cudaMemcpyHostToDevice, h->s_main));
+    TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+    g.P = h->P;
+    g.list = h->list;
+  }
+  cudaFree(d_cnt);
+  // position-indexed arrays
+  const size_t fbytes = (size_t)h->S * h->Q * g.fs * sizeof(double);
+  TXG_TRY(alloc_zero(h, (void **)&h->f[0], fbytes));
+  TXG_TRY(alloc_zero(h, (void **)&h->f[1], fbytes));
+  h->cur = 0;
+  TXG_TRY(alloc_zero(h, (void **)&h->rho, (size_t)h->S * g.fs * sizeof(double)));
+  if (h->cfg.use_nonideal_eos)
+    TXG_TRY(alloc_zero(h, (void **)&h->rho_true, (size_t)h->S * g.fs * sizeof(double)));
+  else
+    h->rho_true = h->rho;
+  TXG_TRY(alloc_zero(h, (void **)&h->lmask, (size_t)g.fs * sizeof(uint32_t)));
+  const long long nown = g.own1 - g.own0;
+  int nrec = 0;
+  if (nown) {
+    TXG_CUDA(h, cudaMemsetAsync(h->counters + 2, 0, sizeof(int), h->s_main));
+    k_gather_mask<<<blocks_for(nown, 256), 256, 0, h->s_main>>>(g, h->nbmask, h->list, h->lmask, h->counters + 2);
+    TXG_CUDA(h, cudaGetLastError());
+    TXG_CUDA(h, cudaMemcpyAsync(&nrec, h->counters + 2, sizeof nrec, cudaMemcpyDeviceToHost, h->s_main));
     TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
   }
+  if (nrec) {
+    const size_t nk = (size_t)(h->S * h->D + h->D);
+    TXG_TRY(alloc_zero(h, (void **)&h->wallrec, nk * (size_t)g.fs * sizeof(double)));
+    h->ks.build_wallrec<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->p, h->cls, h->lmask, h->ffmask, h->wallrec);
+    TXG_CUDA(h, cudaGetLastError());
+  }
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
   return 0;
 }
 
-// (first, count) of the list entries of owned planes [z0, z0 + nz)
+// (first, count) of the positions of owned planes [z0, z0 + nz)
 static inline void plane_range(const txg_flow *h, int z0, int nz, long long *first, long long *count) {
-  if (h->flist) {
-    *first = h->plane_off[(size_t)z0];
-    *count = h->plane_off[(size_t)(z0 + nz)] - *first;
-  } else {
-    *first = (long long)z0 * h->g.plane;
-    *count = h->nfluid ? (long long)nz * h->g.plane : 0;
-  }
+  *first = h->plane_off[(size_t)(h->g.Rz + z0)];
+  *count = h->plane_off[(size_t)(h->g.Rz + z0 + nz)] - *first;
 }
 
 // ------------------------------------------------------------------ walls
@@ -719,7 +748,7 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
              "%d fluid/wall contacts with free-slip codes 900-902 (WALL_NORMAL_X/Y/Z): specular walls are not "
              "implemented on the device yet",
              counters[1]);
-  TXG_TRY(build_fluid_list(h));
+  TXG_TRY(build_storage(h));
   h->walls_set = true;
   return 0;
 }
@@ -745,7 +774,7 @@ static int run_moments(txg_flow *h, int z0, int nz, cudaStream_t s) {
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
   ScopedKernel sk(h, "k_moments", s);
-  h->ks.moments<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, h->flist, first, count);
+  h->ks.moments<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, first, count);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -755,8 +784,8 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
   ScopedKernel sk(h, "k_collide", s);
-  h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->nbmask,
-                                                      h->ffmask, h->wallrec, h->nfluid, h->flist, first, count);
+  h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
+                                                      h->ffmask, h->wallrec, first, count);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -771,12 +800,13 @@ static int state_ready(txg_flow *h) {
 extern "C" int txg_set_rho_u(txg_handle h, const double *rho_rg, const double *u_g) {
   if (!h) return TXG_ERR_ARG_NULL;
   if (!rho_rg) TXG_FAIL(h, TXG_ERR_ARG_NULL, "txg_set_rho_u: null rho");
+  if (!h->walls_set) TXG_FAIL(h, TXG_ERR_ORDER, "txg_set_rho_u before txg_set_walls (the walls size the device storage)");
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
-  TXG_TRY(import_field(h, rho_rg, g.R, g.Rz, 1, h->rho_true, g.rstride, g.R));
+  TXG_TRY(import_field(h, rho_rg, g.R, g.Rz, 1, h->rho_true, 0));
   if (u_g) {
     if (!h->u0) TXG_CUDA(h, cudaMalloc((void **)&h->u0, (size_t)h->S * h->D * g.nnodes * sizeof(double)));
-    TXG_TRY(import_field(h, u_g, 1, h->D == 3 ? 1 : 0, h->D, h->u0, g.nnodes, 0));
+    TXG_TRY(import_field(h, u_g, 1, h->D == 3 ? 1 : 0, h->D, h->u0, 1));
   } else if (h->u0) {
     cudaFree(h->u0);
     h->u0 = nullptr;
@@ -790,16 +820,16 @@ extern "C" int txg_set_fi(txg_handle h, const double *fi_g) {
   if (!h->walls_set) TXG_FAIL(h, TXG_ERR_ORDER, "txg_set_fi before txg_set_walls");
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
-  TXG_TRY(import_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->f[h->cur], g.fstride, 1));
+  TXG_TRY(import_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->f[h->cur], 0));
   return state_ready(h);
 }
 
 // psi = EOS(rho) over the owned planes of rho_true -> rho (stencil field); identity without an EOS
 __global__ void k_eos_field(Grid g, Phys p, int S, const double *__restrict__ rho_true, double *__restrict__ psi) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.nnodes) return;
+  const long long pos = g.own0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= g.own1) return;
   for (int m = 0; m < S; ++m) {
-    const long long o = m * g.rstride + (long long)g.R * g.plane + i;
+    const long long o = m * g.fs + pos;
     psi[o] = eos_psi(p, m, rho_true[o]);
   }
 }
@@ -810,7 +840,7 @@ extern "C" int txg_fi_init(txg_handle h) {
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
   if (h->cfg.use_nonideal_eos) {
-    k_eos_field<<<blocks_for(g.nnodes, 256), 256, 0, h->s_main>>>(g, h->p, h->S, h->rho_true, h->rho);
+    k_eos_field<<<blocks_for(std::max<long long>(g.own1 - g.own0, 1), 256), 256, 0, h->s_main>>>(g, h->p, h->S, h->rho_true, h->rho);
     TXG_CUDA(h, cudaGetLastError());
     h->launches++;
   }
@@ -938,7 +968,7 @@ extern "C" int txg_get_fi(txg_handle h, double *fi_g) {
   if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "no state on the device yet");
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
-  return export_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->S, h->f[h->cur], g.fstride, 1);
+  return export_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->S, h->f[h->cur], 0);
 }
 
 extern "C" int txg_get_state(txg_handle h, double *rho_rg, double *u_g, double *forces_g) {
@@ -953,9 +983,9 @@ extern "C" int txg_get_state(txg_handle h, double *rho_rg, double *u_g, double *
   if (forces_g) TXG_TRY(ensure(h, &h->x_F, n * h->S * h->D));
   TXG_TRY(run_export(h, rho_rg ? h->x_rho : nullptr, u_g ? h->x_u : nullptr, forces_g ? h->x_F : nullptr, nullptr, nullptr, nullptr));
   const int gz1 = h->D == 3 ? 1 : 0;
-  if (rho_rg) TXG_TRY(export_field(h, rho_rg, g.R, g.Rz, 1, h->S, h->x_rho, g.nnodes, 0));
-  if (u_g) TXG_TRY(export_field(h, u_g, 1, gz1, h->D, h->S, h->x_u, g.nnodes, 0));
-  if (forces_g) TXG_TRY(export_field(h, forces_g, 1, gz1, h->D, h->S, h->x_F, g.nnodes, 0));
+  if (rho_rg) TXG_TRY(export_field(h, rho_rg, g.R, g.Rz, 1, h->S, h->x_rho, 1));
+  if (u_g) TXG_TRY(export_field(h, u_g, 1, gz1, h->D, h->S, h->x_u, 1));
+  if (forces_g) TXG_TRY(export_field(h, forces_g, 1, gz1, h->D, h->S, h->x_F, 1));
   return 0;
 }
 
@@ -973,7 +1003,7 @@ extern "C" int txg_get_diagnostics(txg_handle h, double *rhot, double *prs, doub
   if (rhot) TXG_CUDA(h, cudaMemcpyAsync(rhot, h->x_rhot, n * 8, cudaMemcpyDeviceToHost, h->s_main));
   if (prs) TXG_CUDA(h, cudaMemcpyAsync(prs, h->x_prs, n * 8, cudaMemcpyDeviceToHost, h->s_main));
   TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
-  if (velt) TXG_TRY(export_field(h, velt, 0, 0, h->D, 1, h->x_velt, g.nnodes, 0));
+  if (velt) TXG_TRY(export_field(h, velt, 0, 0, h->D, 1, h->x_velt, 1));
   return 0;
 }
 
@@ -983,16 +1013,17 @@ extern "C" int txg_delta_norm(txg_handle h, double *norm) {
   if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "no state on the device yet");
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
-  const long long n = (long long)h->S * h->Q * g.fstride;
+  const long long n = (long long)h->S * h->Q * g.fs;
   if (!h->f_old) {
     TXG_CUDA(h, cudaMalloc((void **)&h->f_old, (size_t)n * 8));
     TXG_CUDA(h, cudaMemsetAsync(h->f_old, 0, (size_t)n * 8, h->s_main));
   }
   TXG_CUDA(h, cudaMemsetAsync(h->norm_bits, 0, sizeof(unsigned long long), h->s_main));
-  // ghost planes hold pushes in transit: compare owned planes only, per (m,n) block
-  for (int b = 0; b < h->S * h->Q; ++b) {
-    const long long off = (long long)b * g.fstride + g.plane;
-    k_delta_norm<<<blocks_for(g.nnodes, 256), 256, 0, h->s_main>>>(h->f[h->cur] + off, h->f_old + off, g.nnodes, h->norm_bits);
+  // ghost-plane positions hold pushes in transit: compare the owned positions only, per (m,n) block
+  const long long nown = g.own1 - g.own0;
+  for (int b = 0; b < h->S * h->Q && nown; ++b) {
+    const long long off = (long long)b * g.fs + g.own0;
+    k_delta_norm<<<blocks_for(nown, 256), 256, 0, h->s_main>>>(h->f[h->cur] + off, h->f_old + off, nown, h->norm_bits);
   }
   TXG_CUDA(h, cudaGetLastError());
   h->launches += h->S * h->Q;

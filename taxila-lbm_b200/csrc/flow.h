@@ -11,19 +11,18 @@ namespace txg {
 // One set of kernel entry points per (lattice, S, MRT, ISO) combination; the instantiations are
 // spread over inst_*.cu so they compile in parallel.
 struct KernelSet {
-  // hot path: one lane per (fluid node, component); (list, first, count) select the entries
-  void (*moments)(Grid, Phys, const double *, double *, const uint32_t *, long long, long long);
+  // hot path: one lane per (fluid node, component); (first, count) select the positions
+  void (*moments)(Grid, Phys, const double *, double *, long long, long long);
   void (*collide)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
-                  const double *, long long, const uint32_t *, long long, long long);
-  void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, int);
+                  const double *, long long, long long);
+  void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, long long, long long, int);
   // set-up and export
   void (*fi_init)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
                   const uint32_t *, const uint8_t *, int, int);
   void (*export_state)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *,
                        const uint8_t *, double *, double *, double *, double *, double *, double *, double, int, int);
   void (*build_masks)(Grid, const uint8_t *, uint32_t *, uint32_t *, int *);
-  void (*build_wallrec)(Grid, Phys, const uint8_t *, const uint32_t *, const uint32_t *, const uint32_t *, long long,
-                        double *);
+  void (*build_wallrec)(Grid, Phys, const uint8_t *, const uint32_t *, const uint32_t *, double *);
   int npw;       // fluid nodes per warp of the hot kernels (32 / S)
   int ff_words;  // u32 words of ffmask per node (0 for isotropy order 4)
   const char *name;

@@ -8,10 +8,8 @@
 // reference.  Splitting by component halves the live register set (19 populations instead of 38):
 // the fp64 collision is otherwise register- and latency-bound on B200 long before HBM is.
 //
-// Only fluid nodes occupy lanes: `list` is the ascending list of fluid node indices of the slab
-// (built once per walls upload), so a porous medium does not waste fp64 issue slots on solid
-// voxels.  list == nullptr means "every node is fluid and none has a wall record": entry i is node
-// first + i.
+// Only fluid nodes exist in storage (kernels.cuh), so a porous medium wastes neither fp64 issue slots
+// nor DRAM sectors on solid voxels.  A launch covers the positions [first, first + count).
 #pragma once
 #include "kernels.cuh"
 
@@ -23,19 +21,16 @@ struct Lanes {
 };
 
 struct Item {
-  int x, y, z;       // owned coordinates
-  unsigned o;        // z*plane + y*NX + x
-  long long li;      // position in the fluid list (index of the wall record)
-  int m, j;          // component, node slot inside the warp
-  bool active;       // false: replayed item, stores nothing
+  long long pos;  // position in the fluid list
+  int m, j;       // component, node slot inside the warp
+  bool active;    // false: replayed item, stores nothing
 };
 
-// (node, component) of this lane.  Returns false if the whole warp is beyond the range.  Lanes past
+// (position, component) of this lane.  Returns false if the whole warp is beyond the range.  Lanes past
 // the end of the range (or the 32 - S*NPW spare lanes when S does not divide 32) replay a valid
 // item with active = false: they take part in the shuffles and store nothing.
 template <int S>
-__device__ __forceinline__ bool item_of_lane(const Grid &g, const uint32_t *__restrict__ list, long long first,
-                                             long long count, Item &it) {
+__device__ __forceinline__ bool item_of_lane(long long first, long long count, Item &it) {
   constexpr int NPW = Lanes<S>::NPW;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -53,16 +48,17 @@ __device__ __forceinline__ bool item_of_lane(const Grid &g, const uint32_t *__re
     i = count - 1;
     it.active = false;
   }
-  it.li = first + i;
-  it.o = list ? __ldg(list + it.li) : (unsigned)it.li;
-  const unsigned plane = (unsigned)g.plane;
-  const unsigned z = it.o / plane;
-  const unsigned r = it.o - z * plane;
-  const unsigned y = r / (unsigned)g.NX;
-  it.x = (int)(r - y * (unsigned)g.NX);
-  it.y = (int)y;
-  it.z = (int)z;
+  it.pos = first + i;
   return true;
+}
+
+// in-plane coordinates of extended node index oe
+__device__ __forceinline__ void xy_of(const Grid &g, unsigned oe, int &x, int &y) {
+  const unsigned plane = (unsigned)g.plane;
+  const unsigned r = oe % plane;
+  const unsigned yy = r / (unsigned)g.NX;
+  x = (int)(r - yy * (unsigned)g.NX);
+  y = (int)yy;
 }
 
 // value of `v` held by the lane of component k for the same node
@@ -88,17 +84,18 @@ TXG_HD constexpr double bulk_weight_sum(int d) {
 }
 
 // FlowCalcForces (lbm_flow.F90:760-808) for ONE component: fluid-solid, body, fluid-fluid, in the
-// reference's order.  psi_at: pointer to this component's psi at this node (rho array, ghosted in z).
+// reference's order.  psi_m: pointer to this component's psi array (position-indexed).
 // The geometry-only factors come from the wall record: A[d] = sum_n w_n gw(mineral(X+c_n), m) c_n,d
 // (LBMAddFluidSolidForcesD*, lbm_forcing.F90:1326-1421, float literals 1./6. etc. folded in by
 // k_build_wallrec) and rW[d] = 1/weightsum_d (lbm_forcing.F90:946-953); bulk nodes use the
-// compile-time weight sum.  Neighbour densities are loaded unconditionally (solid nodes hold 0) and
-// masked afterwards, so that all loads of a lane are in flight together.
+// compile-time weight sum.  Neighbour densities are loaded unconditionally (a solid neighbour's
+// position is that of the next fluid node -- some valid, finite value) and masked afterwards, so that
+// all loads of a lane are in flight together.  npos[n]: position of X + c_n (order 4 re-uses them).
 template <class L, int S, int ISO>
-__device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const double *__restrict__ psi_at,
+__device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const double *__restrict__ psi_field,
                                         const uint32_t *__restrict__ ffmask, const double *__restrict__ wallrec,
-                                        long long rec_stride, const Item &it, uint32_t mask, double rho_m,
-                                        double psi_m, double (&F)[L::D]) {
+                                        const Item &it, unsigned oe, int x, int y, uint32_t mask,
+                                        const unsigned (&npos)[L::Q], double rho_m, double psi_m, double (&F)[L::D]) {
   constexpr int D = L::D;
   const bool rec = (mask & MASK_WALLREC) != 0;
   const int m = it.m;
@@ -108,7 +105,7 @@ __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const doub
   if (p.fluidsolid) {
     double A[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) A[d] = rec ? __ldg(wallrec + (long long)(m * D + d) * rec_stride + it.li) : 0.;
+    for (int d = 0; d < D; ++d) A[d] = rec ? __ldg(wallrec + (long long)(m * D + d) * g.fs + it.pos) : 0.;
 #pragma unroll
     for (int d = 0; d < D; ++d) F[d] = F[d] - rho_m * A[d];
   }
@@ -126,18 +123,19 @@ __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const doub
     static_for<0, D>([&](auto d_) {
       constexpr int d = decltype(d_)::value;
       constexpr double bulk = 1.0 / bulk_weight_sum<L, ISO>(d);
-      rW[d] = rec ? __ldg(wallrec + (long long)(S * D + d) * rec_stride + it.li) : bulk;
+      rW[d] = rec ? __ldg(wallrec + (long long)(S * D + d) * g.fs + it.pos) : bulk;
     });
     int dxo[2 * RAD + 1], dyo[2 * RAD + 1];
-#pragma unroll
-    for (int a = -RAD; a <= RAD; ++a) {
-      dxo[a + RAD] = wrap_delta(it.x, a, g.NX, g.perx);
-      dyo[a + RAD] = wrap_delta(it.y, a, g.NY, g.pery) * g.NX;
-    }
     uint32_t words[(E + 31) / 32];
     if constexpr (ISO != 4) {
 #pragma unroll
-      for (int w = 0; w < (E + 31) / 32; ++w) words[w] = __ldg(ffmask + (long long)w * g.nnodes + it.o);
+      for (int a = -RAD; a <= RAD; ++a) {
+        dxo[a + RAD] = wrap_delta(x, a, g.NX, g.perx);
+        dyo[a + RAD] = wrap_delta(y, a, g.NY, g.pery) * g.NX;
+      }
+      const long long o = (long long)oe - (long long)g.Rz * g.plane;  // owned dense index
+#pragma unroll
+      for (int w = 0; w < (E + 31) / 32; ++w) words[w] = __ldg(ffmask + (long long)w * g.nnodes + o);
     }
     const int plane = (int)g.plane;
     double G[D];
@@ -147,15 +145,17 @@ __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const doub
       constexpr int e = decltype(e_)::value;
       constexpr int dx = FF::off[e][0], dy = FF::off[e][1], dz = FF::off[e][2];
       bool on;
+      long long np;
       if constexpr (ISO == 4) {
         constexpr int n = dir_of<L>(dx, dy, dz);
         on = !((mask >> n) & 1u);
+        np = npos[n];
       } else {
         on = (words[e / 32] >> (e % 32)) & 1u;
+        np = pos_of(g, (long long)oe + (dz * plane + dyo[dy + RAD] + dxo[dx + RAD]));
       }
       constexpr double wgt = L::ffw(ISO, FF::L[e]);
-      const int delta = dz * plane + dyo[dy + RAD] + dxo[dx + RAD];
-      const double v = __ldg(psi_at + delta);
+      const double v = __ldg(psi_field + np);
       const double diff = on ? v - psi_m : 0.;
       if constexpr (dx != 0) G[0] = G[0] + ((double)dx * wgt) * diff;
       if constexpr (dy != 0) G[1] = G[1] + ((double)dy * wgt) * diff;
@@ -306,27 +306,25 @@ __device__ __forceinline__ void collide1(const Phys &p, int m, double rho, const
   }
 }
 
-// ================================================================== the two hot kernels
+// ================================================================== the hot kernels
 
 // K1 moments: rho_m = sum_n f_n (ascending n) of the streamed populations; writes rho (psi with an
 // EOS).  Replaces DistributionCalcDensityD* (lbm_distribution_function.F90:379-428) and EOSApply;
 // streaming and bounce-back happened in the push of the previous collide.
 template <class L, int S>
 __global__ void __launch_bounds__(128) k_moments(Grid g, Phys p, const double *__restrict__ fA,
-                                                 double *__restrict__ rho, const uint32_t *__restrict__ list,
-                                                 long long first, long long count) {
+                                                 double *__restrict__ rho, long long first, long long count) {
   Item it;
-  if (!item_of_lane<S>(g, list, first, count, it)) return;
-  const long long o = (long long)it.o + g.plane;  // f carries one ghost plane below
-  const double *src = fA + (long long)it.m * L::Q * g.fstride + o;
+  if (!item_of_lane<S>(first, count, it)) return;
+  const double *src = fA + (long long)it.m * L::Q * g.fs + it.pos;
   double f[L::Q];
 #pragma unroll
-  for (int n = 0; n < L::Q; ++n) f[n] = __ldg(src + (long long)n * g.fstride);
+  for (int n = 0; n < L::Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
   double a = 0.;
 #pragma unroll
   for (int n = 0; n < L::Q; ++n) a += f[n];
   if (!it.active) return;
-  rho[(long long)it.m * g.rstride + (long long)it.o + (long long)g.R * g.plane] = p.eos ? eos_psi(p, it.m, a) : a;
+  rho[(long long)it.m * g.fs + it.pos] = p.eos ? eos_psi(p, it.m, a) : a;
 }
 
 // K2 collide + push: node populations, forces from the rho stencil, momentum, common velocity,
@@ -340,28 +338,43 @@ __global__ void __launch_bounds__(128) k_moments(Grid g, Phys p, const double *_
 template <class L, int S, bool MRT, int ISO>
 __global__ void __launch_bounds__(128, 3)
     k_collide(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ rho,
-              const uint32_t *__restrict__ nbmask, const uint32_t *__restrict__ ffmask,
-              const double *__restrict__ wallrec, long long rec_stride, const uint32_t *__restrict__ list,
-              long long first, long long count) {
+              const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ ffmask,
+              const double *__restrict__ wallrec, long long first, long long count) {
   Item it;
-  if (!item_of_lane<S>(g, list, first, count, it)) return;
+  if (!item_of_lane<S>(first, count, it)) return;
   constexpr int Q = L::Q, D = L::D;
-  const long long o = (long long)it.o + g.plane;
-  const long long mo = (long long)it.m * Q * g.fstride + o;
+  const long long mo = (long long)it.m * Q * g.fs + it.pos;
   double f[Q];
   {
     const double *src = fA + mo;
 #pragma unroll
-    for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fstride);
+    for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
   }
-  const uint32_t mask = __ldg(nbmask + it.o);
-  const double *psi_at = rho + (long long)it.m * g.rstride + (long long)it.o + (long long)g.R * g.plane;
+  const uint32_t mask = __ldg(lmask + it.pos);
+  const unsigned oe = g.list ? __ldg(g.list + it.pos) : (unsigned)it.pos;
+  int x, y;
+  xy_of(g, oe, x, y);
+  // positions of the lattice neighbours X + c_n
+  unsigned npos[Q];
+  {
+    const int dxm = wrap_delta(x, -1, g.NX, g.perx), dxp = wrap_delta(x, 1, g.NX, g.perx);
+    const int dym = wrap_delta(y, -1, g.NY, g.pery) * g.NX, dyp = wrap_delta(y, 1, g.NY, g.pery) * g.NX;
+    const int plane = (int)g.plane;
+    npos[0] = (unsigned)it.pos;
+    static_for<1, Q>([&](auto n_) {
+      constexpr int n = decltype(n_)::value;
+      const int delta = (L::c(n, 0) == 0 ? 0 : (L::c(n, 0) > 0 ? dxp : dxm)) +
+                        (L::c(n, 1) == 0 ? 0 : (L::c(n, 1) > 0 ? dyp : dym)) + L::c(n, 2) * plane;
+      npos[n] = g.P ? __ldg(g.P + ((long long)oe + delta)) : (unsigned)((long long)oe + delta);
+    });
+  }
+  const double *psi_field = rho + (long long)it.m * g.fs;
   double r = 0.;
 #pragma unroll
   for (int n = 0; n < Q; ++n) r += f[n];
-  const double psi_m = p.eos ? __ldg(psi_at) : r;
+  const double psi_m = p.eos ? __ldg(psi_field + it.pos) : r;
   double F[D];
-  forces1<L, S, ISO>(g, p, psi_at, ffmask, wallrec, rec_stride, it, mask, r, psi_m, F);
+  forces1<L, S, ISO>(g, p, psi_field, ffmask, wallrec, it, oe, x, y, mask, npos, r, psi_m, F);
   // momentum j_m (DistributionCalcFluxD*) and the common velocity u' (FlowUpdateUED*)
   double up[D];
   {
@@ -391,45 +404,38 @@ __global__ void __launch_bounds__(128, 3)
   }
   collide1<L, MRT>(p, it.m, r, F, up, f);
   if (!it.active) return;
-  // push: slot (n, X + c_n), or slot (opp(n), X) when X + c_n is solid
-  double *out = fB + mo;
-  const int dxm = wrap_delta(it.x, -1, g.NX, g.perx), dxp = wrap_delta(it.x, 1, g.NX, g.perx);
-  const int dym = wrap_delta(it.y, -1, g.NY, g.pery) * g.NX, dyp = wrap_delta(it.y, 1, g.NY, g.pery) * g.NX;
-  const int plane = (int)g.plane;
-  out[0] = f[0];
+  // push: slot (n, pos(X + c_n)), or slot (opp(n), pos(X)) when X + c_n is solid
+  double *out = fB + (long long)it.m * Q * g.fs;
+  out[it.pos] = f[0];
   static_for<1, Q>([&](auto n_) {
     constexpr int n = decltype(n_)::value;
     constexpr int on = opp<L>(n);
-    const int delta = (L::c(n, 0) == 0 ? 0 : (L::c(n, 0) > 0 ? dxp : dxm)) +
-                      (L::c(n, 1) == 0 ? 0 : (L::c(n, 1) > 0 ? dyp : dym)) + L::c(n, 2) * plane;
     const bool bounce = (mask >> n) & 1u;
-    double *dst = bounce ? out + (long long)on * g.fstride : out + (long long)n * g.fstride + delta;
+    double *dst = bounce ? out + (long long)on * g.fs + it.pos : out + (long long)n * g.fs + npos[n];
     *dst = f[n];
   });
 }
 
-// Wall records (one thread per fluid-list entry with MASK_WALLREC): the geometry-only factors of the
+// Wall records (one thread per owned position with MASK_WALLREC): the geometry-only factors of the
 // fluid-solid force and of the gradient normalisation, evaluated once per walls upload.
 //   A[m][d]  = sum over lattice directions n (ascending) with a mineral neighbour of
 //              w_n * gw(mineral, m) * c_n,d, w_n the reference's default-real literals
 //              (lbm_forcing.F90:1355,1364,1406,1414; 0 < walls < 998 and a valid mineral id)
 //   rW[d]    = 1 / weightsum_d if weightsum_d > 1e-12 else 0   (lbm_forcing.F90:69,946-953)
 template <class L, int S, int ISO>
-__global__ void k_build_wallrec(Grid g, Phys p, const uint8_t *__restrict__ cls, const uint32_t *__restrict__ nbmask,
-                                const uint32_t *__restrict__ ffmask, const uint32_t *__restrict__ list,
-                                long long count, double *__restrict__ rec) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+__global__ void k_build_wallrec(Grid g, Phys p, const uint8_t *__restrict__ cls, const uint32_t *__restrict__ lmask,
+                                const uint32_t *__restrict__ ffmask, double *__restrict__ rec) {
+  const long long pos = g.own0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= g.own1) return;
   constexpr int D = L::D;
-  const unsigned o = list[i];
-  const uint32_t mask = nbmask[o];
+  const uint32_t mask = lmask[pos];
   if (!(mask & MASK_WALLREC)) return;
-  const unsigned plane = (unsigned)g.plane;
-  const int z = (int)(o / plane);
-  const unsigned rr = o - (unsigned)z * plane;
-  const int y = (int)(rr / (unsigned)g.NX);
-  const int x = (int)(rr - (unsigned)y * (unsigned)g.NX);
-  const long long cbase = ((long long)(z + g.Rz) * g.cny + (y + g.R)) * g.cnx + (x + g.R);
+  const unsigned oe = g.list ? g.list[pos] : (unsigned)pos;
+  int x, y;
+  xy_of(g, oe, x, y);
+  const int zz = (int)(oe / (unsigned)g.plane);  // z + Rz
+  const long long o = (long long)oe - (long long)g.Rz * g.plane;
+  const long long cbase = ((long long)zz * g.cny + (y + g.R)) * g.cnx + (x + g.R);
   double A[S][D];
 #pragma unroll
   for (int m = 0; m < S; ++m)
@@ -477,28 +483,29 @@ __global__ void k_build_wallrec(Grid g, Phys p, const uint8_t *__restrict__ cls,
 #pragma unroll
   for (int m = 0; m < S; ++m)
 #pragma unroll
-    for (int d = 0; d < D; ++d) rec[(long long)(m * D + d) * count + i] = A[m][d];
+    for (int d = 0; d < D; ++d) rec[(long long)(m * D + d) * g.fs + pos] = A[m][d];
 #pragma unroll
-  for (int d = 0; d < D; ++d) rec[(long long)(S * D + d) * count + i] = W[d] > eps ? 1. / W[d] : 0.;
+  for (int d = 0; d < D; ++d) rec[(long long)(S * D + d) * g.fs + pos] = W[d] > eps ? 1. / W[d] : 0.;
 }
 
 // Halo unpack (the receiving half of DistributionCommunicateFi, lbm_distribution_function.F90:309-334,
 // reduced to the populations that cross the face).  The pushes that left the neighbour slab through
 // its ghost plane arrive in `src`; population n of boundary-plane node Y is taken iff its source
-// Y - c_n is fluid -- otherwise slot (n, Y) already holds Y's own bounce-back value.
-//   up = 1: fills owned plane 0      with the directions c_z = +1 (from the slab below)
-//   up = 0: fills owned plane NZl-1  with the directions c_z = -1 (from the slab above)
-// src(m, n, r) = src[(m*Q + n) * src_stride + r] when !packed (a ghost plane of an f buffer), else
-// src[(m*NCROSS + k) * plane + r], k the rank of n among the crossing directions (NCCL staging).
+// Y - c_n is fluid -- otherwise slot (n, Y) already holds Y's own bounce-back value.  The fluid nodes
+// of the sender's ghost plane are the fluid nodes of this boundary plane, in the same order.
+//   up = 1: fills the bottom owned plane with the directions c_z = +1 (from the slab below)
+//   up = 0: fills the top owned plane    with the directions c_z = -1 (from the slab above)
+// [first, first+count): positions of the boundary plane.  Entry i of direction n, component m is
+// src[(m*Q + n) * fs + src_first + i] when !packed (a ghost plane of an f buffer), else
+// src[(m*NCROSS + k) * count + i], k the rank of n among the crossing directions (NCCL staging).
 template <class L, int S>
-__global__ void k_halo_unpack(Grid g, double *__restrict__ f, const double *__restrict__ src, long long src_stride,
-                              int packed, const uint32_t *__restrict__ nbmask, int up) {
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= g.plane) return;
-  const int zo = up ? 0 : g.NZl - 1;
-  const uint32_t mask = nbmask[(long long)zo * g.plane + r];
-  if (mask >> 31) return;
-  const long long o = (long long)(zo + 1) * g.plane + r;
+__global__ void k_halo_unpack(Grid g, double *__restrict__ f, const double *__restrict__ src, long long src_first,
+                              int packed, const uint32_t *__restrict__ lmask, long long first, long long count,
+                              int up) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const long long pos = first + i;
+  const uint32_t mask = lmask[pos];
   int k = 0;
   static_for<1, L::Q>([&](auto n_) {
     constexpr int n = decltype(n_)::value;
@@ -508,9 +515,9 @@ __global__ void k_halo_unpack(Grid g, double *__restrict__ f, const double *__re
         if (!((mask >> on) & 1u)) {
 #pragma unroll
           for (int m = 0; m < S; ++m) {
-            const double v = packed ? src[(long long)(m * L::NCROSS + k) * g.plane + r]
-                                    : src[(long long)(m * L::Q + n) * src_stride + r];
-            f[(long long)(m * L::Q + n) * g.fstride + o] = v;
+            const double v = packed ? src[(long long)(m * L::NCROSS + k) * count + i]
+                                    : src[(long long)(m * L::Q + n) * g.fs + src_first + i];
+            f[(long long)(m * L::Q + n) * g.fs + pos] = v;
           }
         }
         ++k;

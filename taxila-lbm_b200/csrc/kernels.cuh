@@ -1,25 +1,28 @@
 // kernels.cuh -- device code of the flow hot path (sm_100a).
 //
-// Storage (all fp64, one slab per GPU, x fastest):
-//   f    [S][Q][NZl+2 ][NY][NX]   populations in the reference's own sense: slot (m,n,X) is fi(m,n,X), the
-//                                 value node X holds AFTER streaming and bounce-back.  The collide kernel
-//                                 PUSHES: the post-collision value leaving X along c_n is stored into
-//                                 slot (n, X+c_n) of the other buffer, or -- when X+c_n is solid -- into
-//                                 slot (opp(n), X) (half-way bounce-back completed in the same step,
-//                                 SURVEY.md 8a-11).  Every read of f is therefore node-aligned and needs
-//                                 no mask.  One ghost z-plane each side receives the pushes that leave the
-//                                 slab; the halo exchange moves them into the neighbour's boundary plane.
-//                                 Slots of solid nodes are never written and stay 0.
-//   rho  [S][NZl+2R][NY][NX]      per-component density (psi when a non-ideal EOS is on), R ghost planes
-//   cls  [NZl+2Rz][NY+2R][NX+2R]  u8 node class incl. ghosts, straight from the host walls(rg..) array
-//   nbmask [NZl][NY][NX]          u32: bit n = neighbour X+c_n is solid, bit 30 = X has a wall record
-//                                 (some lattice neighbour solid or some gradient-stencil entry inactive),
-//                                 bit 31 = X itself is solid
-//   ffmask [NW][NZl][NY][NX]      u32 words: bit e = fluid-fluid stencil entry e is active at X
-//                                 (isotropy order > 4 only; order 4 re-uses nbmask)
-//   flist [nfluid]                ascending indices of the fluid nodes; the hot kernels put only these on lanes
-//   wallrec [S*D+D][nfluid]       per fluid-list entry with bit 30 set: A[m][d] = sum_n w_n gw(mineral(X+c_n),m) c_n,d
-//                                 (fluid-solid force = -rho_m A) and 1/W[d] of the gradient normalisation
+// Storage (all fp64, one slab per GPU).  Only FLUID nodes are stored: every per-node array is indexed by
+// the node's position in the ascending list of fluid nodes of the extended slab (owned planes plus R
+// ghost planes each side in 3-D), so a porous medium costs neither memory nor partially used DRAM
+// sectors for its solid voxels, and every population read of a warp is one contiguous run.
+//   P     [nE+1]      u32   extended node index oe = (z+Rz)*plane + y*NX + x  ->  number of fluid nodes
+//                           before oe, i.e. the position of oe if it is fluid      (nullptr: identity)
+//   list  [nstore]    u32   position -> oe                                         (nullptr: identity)
+//   f     [S][Q][fs]        populations in the reference's own sense: slot (m,n,pos) is fi(m,n,X), the value
+//                           node X holds AFTER streaming and bounce-back.  The collide kernel PUSHES: the
+//                           post-collision value leaving X along c_n goes into slot (n, pos(X+c_n)) of the
+//                           other buffer, or -- when X+c_n is solid -- into slot (opp(n), pos(X)) (half-way
+//                           bounce-back completed in the same step).  Reads of f are
+//                           position-aligned and need no mask.  Pushes that leave the slab land in the
+//                           ghost-plane positions; the halo exchange moves them into the neighbour's
+//                           boundary plane.  fs = nstore rounded up (+ padding): the stride of every array.
+//   rho   [S][fs]           per-component density (psi when a non-ideal EOS is on); ghost planes by halo
+//   lmask [fs]        u32   per OWNED position: bit n = neighbour X+c_n is solid, bit 30 = X has a wall
+//                           record (some lattice neighbour solid or some gradient-stencil entry inactive)
+//   wallrec [S*D+D][fs]     per owned position with bit 30: A[m][d] = sum_n w_n gw(mineral(X+c_n),m) c_n,d
+//                           (fluid-solid force = -rho_m A) and 1/W[d] of the gradient normalisation
+//   cls   [NZl+2Rz][NY+2R][NX+2R]  u8 node class incl. ghosts, straight from the host walls(rg..) array
+//   nbmask [NZl][NY][NX]    u32 dense copy of the masks (bit 31 = solid) for the set-up / export kernels
+//   ffmask [NW][NZl][NY][NX] u32 words: bit e = fluid-fluid stencil entry e active (isotropy order > 4)
 //
 // Reference loops each kernel replaces are cited at the kernel.
 #pragma once
@@ -33,12 +36,20 @@ struct Grid {
   int NX, NY, NZl;  // owned slab
   int R, Rz;        // ghost width of rho/cls in x,y (R) and z (Rz = R in 3-D, 0 in 2-D)
   int perx, pery;   // periodic flags (non-periodic neighbours are class 255 and never dereferenced)
-  long long plane;    // NX*NY
-  long long fstride;  // (NZl+2)*plane     distance between (m,n) blocks of f
-  long long rstride;  // (NZl+2R)*plane    distance between components of rho
-  long long nnodes;   // NZl*plane
-  int cnx, cny;       // NX+2R, NY+2R
+  long long plane;   // NX*NY
+  long long nnodes;  // NZl*plane (owned nodes)
+  long long nE;      // (NZl+2Rz)*plane (extended slab)
+  long long fs;      // stride of every position-indexed array (>= nstore + 1)
+  long long own0, own1;  // positions of the owned fluid nodes: [own0, own1)
+  const uint32_t *P;     // [nE+1] extended node index -> position (nullptr: identity)
+  const uint32_t *list;  // [nstore] position -> extended node index (nullptr: identity)
+  int cnx, cny;      // NX+2R, NY+2R
 };
+
+// position of extended node index oe (for a solid node: the position of the next fluid node)
+__device__ __forceinline__ long long pos_of(const Grid &g, long long oe) {
+  return g.P ? (long long)__ldg(g.P + oe) : oe;
+}
 
 constexpr int MAXS = 3;  // instantiated component counts: 1..3
 
@@ -60,6 +71,8 @@ struct Phys {
 struct NodeIdx {
   int x, y, z;      // owned coordinates
   long long o;      // z*plane + y*NX + x  (nbmask / export index)
+  long long oe;     // (z+Rz)*plane + y*NX + x  (extended index)
+  long long pos;    // position in the fluid list (valid for fluid nodes)
 };
 
 __device__ __forceinline__ bool node_of_thread(const Grid &g, int z0, int nz, NodeIdx &nd) {
@@ -71,6 +84,8 @@ __device__ __forceinline__ bool node_of_thread(const Grid &g, int z0, int nz, No
   nd.x = r - nd.y * g.NX;
   nd.z = z0 + zz;
   nd.o = (long long)nd.z * g.plane + r;
+  nd.oe = nd.o + (long long)g.Rz * g.plane;
+  nd.pos = pos_of(g, nd.oe);
   return true;
 }
 
@@ -88,11 +103,10 @@ __device__ __forceinline__ int wrapc(int v, int N, int per) {
 template <class L, int S>
 __device__ __forceinline__ void load_node(const Grid &g, const double *__restrict__ fA, const NodeIdx &nd,
                                           double (&f)[S][L::Q]) {
-  const long long o = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
 #pragma unroll
   for (int m = 0; m < S; ++m)
 #pragma unroll
-    for (int n = 0; n < L::Q; ++n) f[m][n] = __ldg(fA + (long long)(m * L::Q + n) * g.fstride + o);
+    for (int n = 0; n < L::Q; ++n) f[m][n] = __ldg(fA + (long long)(m * L::Q + n) * g.fs + nd.pos);
 }
 
 constexpr uint32_t MASK_SOLID = 0x80000000u;    // the node itself is solid
@@ -166,7 +180,7 @@ __device__ __forceinline__ void forces(const Grid &g, const Phys &p, const doubl
     }
     double psi_here[S];
 #pragma unroll
-    for (int m = 0; m < S; ++m) psi_here[m] = p.eos ? psi[m * g.rstride + (long long)(nd.z + g.R) * g.plane + (long long)nd.y * g.NX + nd.x] : rho_here[m];
+    for (int m = 0; m < S; ++m) psi_here[m] = p.eos ? psi[m * g.fs + nd.pos] : rho_here[m];
 
     uint32_t words[(E + 31) / 32];
     if constexpr (ISO != 4) {
@@ -185,10 +199,10 @@ __device__ __forceinline__ void forces(const Grid &g, const Phys &p, const doubl
       }
       if (active) {
         constexpr double wgt = L::ffw(ISO, FF::L[e]);
-        const long long nb = (long long)(nd.z + g.R + dz) * g.plane + (long long)yi[dy + RAD] * g.NX + xi[dx + RAD];
+        const long long nb = pos_of(g, (long long)(nd.z + g.Rz + dz) * g.plane + (long long)yi[dy + RAD] * g.NX + xi[dx + RAD]);
         double diff[S];
 #pragma unroll
-        for (int m = 0; m < S; ++m) diff[m] = __ldg(psi + m * g.rstride + nb) - psi_here[m];
+        for (int m = 0; m < S; ++m) diff[m] = __ldg(psi + m * g.fs + nb) - psi_here[m];
         if constexpr (dx != 0) {
 #pragma unroll
           for (int m = 0; m < S; ++m) G[0][m] = G[0][m] + ((double)dx * wgt) * diff[m];
@@ -319,11 +333,9 @@ __global__ void __launch_bounds__(128) k_fi_init(Grid g, Phys p, double *__restr
   if (mask >> 31) return;
   constexpr int Q = L::Q, D = L::D;
   double r[S], F[S][D];
-  const long long ro = (long long)(nd.z + g.R) * g.plane + (long long)nd.y * g.NX + nd.x;
 #pragma unroll
-  for (int m = 0; m < S; ++m) r[m] = rho_true[m * g.rstride + ro];
+  for (int m = 0; m < S; ++m) r[m] = rho_true[m * g.fs + nd.pos];
   forces<L, S, ISO>(g, p, rho, cls, ffmask, nd, mask, r, F);
-  const long long o = (long long)(nd.z + 1) * g.plane + (long long)nd.y * g.NX + nd.x;
 #pragma unroll
   for (int m = 0; m < S; ++m) {
     double u[D], feq[Q], pref[Q];
@@ -332,7 +344,7 @@ __global__ void __launch_bounds__(128) k_fi_init(Grid g, Phys p, double *__restr
     equilibrium<L>(r[m], p.d_k[m], u, feq);
     prefactor<L>(r[m], F[m], u, pref);
 #pragma unroll
-    for (int n = 0; n < Q; ++n) fN[(long long)(m * Q + n) * g.fstride + o] = (1. - 0.5 * pref[n]) * feq[n];
+    for (int n = 0; n < Q; ++n) fN[(long long)(m * Q + n) * g.fs + nd.pos] = (1. - 0.5 * pref[n]) * feq[n];
   }
 }
 

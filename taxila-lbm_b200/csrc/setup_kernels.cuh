@@ -34,74 +34,113 @@ __global__ void k_classify(const double *__restrict__ walls, uint8_t *__restrict
   cls[i] = c;
 }
 
-// fluid-node list, pass 1: fluid nodes (nbmask bit 31 clear) per 256-slot chunk of each plane
-// (and the number of fluid nodes that carry a wall record, bit 30, accumulated into *nrec)
-__global__ void k_count_fluid(const uint32_t *__restrict__ nbmask, long long plane, int bpp, unsigned *__restrict__ cnt,
-                              int *__restrict__ nrec) {
-  const long long z = blockIdx.x / bpp;
+// fluid-node list over the EXTENDED slab (owned planes + Rz ghost planes each side), from the classes.
+// pass 1: fluid nodes per 256-slot chunk of each extended plane
+__device__ __forceinline__ bool ext_fluid(const Grid &g, const uint8_t *__restrict__ cls, long long zz, long long r) {
+  const int y = (int)(r / g.NX), x = (int)(r - (long long)y * g.NX);
+  return cls[((long long)zz * g.cny + (y + g.R)) * g.cnx + (x + g.R)] == 0;
+}
+__global__ void k_count_fluid(Grid g, const uint8_t *__restrict__ cls, int bpp, unsigned *__restrict__ cnt) {
+  const long long zz = blockIdx.x / bpp;
   const long long r = (long long)(blockIdx.x % bpp) * 256 + threadIdx.x;
-  const uint32_t mask = r < plane ? nbmask[z * plane + r] : 0x80000000u;
-  const bool fluid = !(mask >> 31);
+  const bool fluid = r < g.plane && ext_fluid(g, cls, zz, r);
   const int n = __syncthreads_count(fluid);
-  const int w = __syncthreads_count(fluid && (mask & 0x40000000u));
-  if (threadIdx.x == 0) {
-    cnt[blockIdx.x] = (unsigned)n;
-    if (w) atomicAdd(nrec, w);
-  }
+  if (threadIdx.x == 0) cnt[blockIdx.x] = (unsigned)n;
 }
 
-// pass 2: off[chunk] = list position of the chunk's first fluid node; rank inside the chunk by ballot
-__global__ void k_fill_fluid(const uint32_t *__restrict__ nbmask, long long plane, int bpp,
-                             const unsigned *__restrict__ off, uint32_t *__restrict__ list) {
+// pass 2: off[chunk] = position of the chunk's first fluid node; rank inside the chunk by ballot.
+// Writes P[oe] for every node (fluid or not) and list[P[oe]] = oe for the fluid ones.
+__global__ void k_fill_fluid(Grid g, const uint8_t *__restrict__ cls, int bpp, const unsigned *__restrict__ off,
+                             uint32_t *__restrict__ P, uint32_t *__restrict__ list) {
   __shared__ unsigned warp_cnt[8];
-  const long long z = blockIdx.x / bpp;
+  const long long zz = blockIdx.x / bpp;
   const long long r = (long long)(blockIdx.x % bpp) * 256 + threadIdx.x;
-  const bool fluid = r < plane && !(nbmask[z * plane + r] >> 31);
+  const bool in = r < g.plane;
+  const bool fluid = in && ext_fluid(g, cls, zz, r);
   const unsigned b = __ballot_sync(0xffffffffu, fluid);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) warp_cnt[w] = __popc(b);
   __syncthreads();
   unsigned base = off[blockIdx.x];
   for (int k = 0; k < w; ++k) base += warp_cnt[k];
-  if (fluid) list[base + __popc(b & ((1u << lane) - 1u))] = (uint32_t)(z * plane + r);
+  const unsigned pos = base + __popc(b & ((1u << lane) - 1u));
+  if (in) {
+    const long long oe = zz * g.plane + r;
+    P[oe] = pos;
+    if (fluid) list[pos] = (uint32_t)oe;
+  }
 }
 
-// host AoS (ghosted, dof = K*S with index k*S+m) -> device SoA [(m*K+k)][z][y][x] and back.
-// The staging buffer holds the nzl ghosted (in x,y) z-planes of owned planes [zl0, zl0+nzl); only owned
-// nodes are touched.
-__global__ void k_import_aos(const double *__restrict__ src, double *__restrict__ dst, int NX, int NY, int gw,
-                             int S, int K, long long dst_stride, long long dst_plane0, int zl0, int nzl) {
-  // one thread per (zl, y, x, c)
+// per-position copy of the dense masks of the owned nodes; counts the wall records
+__global__ void k_gather_mask(Grid g, const uint32_t *__restrict__ nbmask, const uint32_t *__restrict__ list,
+                              uint32_t *__restrict__ lmask, int *__restrict__ nrec) {
+  const long long pos = g.own0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool rec = false;
+  if (pos < g.own1) {
+    const long long oe = list ? (long long)list[pos] : pos;
+    const uint32_t m = nbmask[oe - (long long)g.Rz * g.plane];
+    lmask[pos] = m;
+    rec = (m & 0x40000000u) != 0;
+  }
+  const int w = __syncthreads_count(rec);
+  if (threadIdx.x == 0 && w) atomicAdd(nrec, w);
+}
+
+// host AoS (ghosted, dof = K*S with index k*S+m) <-> device SoA block (m*K+k).  The staging buffer
+// holds the nzl ghosted (in x,y) z-planes of owned planes [zl0, zl0+nzl); only owned nodes are touched.
+// dense = 1: the device array is [S*K][nnodes] over the owned nodes; dense = 0: position-indexed
+// [S*K][fs] holding fluid nodes only (solid nodes are skipped on import and exported as 0).
+__global__ void k_import_aos(Grid g, const double *__restrict__ src, double *__restrict__ dst, int gw, int S, int K,
+                             int dense, int zl0, int nzl) {
   const int dof = S * K;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)nzl * NY * NX * dof;
+  long long total = (long long)nzl * g.plane * dof;
   if (idx >= total) return;
   int c = (int)(idx % dof);
   long long node = idx / dof;
-  int x = (int)(node % NX);
-  int y = (int)((node / NX) % NY);
-  int zz = (int)(node / ((long long)NX * NY));
-  const int gnx = NX + 2 * gw, gny = NY + 2 * gw;
-  long long s = (((long long)zz * gny + (y + gw)) * gnx + (x + gw)) * dof + c;
+  int x = (int)(node % g.NX);
+  int y = (int)((node / g.NX) % g.NY);
+  int zz = (int)(node / g.plane);
+  const int gnx = g.NX + 2 * gw, gny = g.NY + 2 * gw;
+  const double v = src[(((long long)zz * gny + (y + gw)) * gnx + (x + gw)) * dof + c];
   int m = c % S, k = c / S;
-  dst[(long long)(m * K + k) * dst_stride + (dst_plane0 + zl0 + zz) * ((long long)NX * NY) + (long long)y * NX + x] = src[s];
+  const long long o = (long long)(zl0 + zz) * g.plane + (long long)y * g.NX + x;
+  if (dense) {
+    dst[(long long)(m * K + k) * g.nnodes + o] = v;
+  } else {
+    const long long oe = o + (long long)g.Rz * g.plane;
+    if (!g.P)
+      dst[(long long)(m * K + k) * g.fs + oe] = v;
+    else if (g.P[oe + 1] != g.P[oe])
+      dst[(long long)(m * K + k) * g.fs + g.P[oe]] = v;
+  }
 }
 
-__global__ void k_export_aos(double *__restrict__ dst, const double *__restrict__ src, int NX, int NY, int gw, int S,
-                             int K, long long src_stride, long long src_plane0, int zl0, int nzl) {
+__global__ void k_export_aos(Grid g, double *__restrict__ dst, const double *__restrict__ src, int gw, int S, int K,
+                             int dense, int zl0, int nzl) {
   const int dof = S * K;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)nzl * NY * NX * dof;
+  long long total = (long long)nzl * g.plane * dof;
   if (idx >= total) return;
   int c = (int)(idx % dof);
   long long node = idx / dof;
-  int x = (int)(node % NX);
-  int y = (int)((node / NX) % NY);
-  int zz = (int)(node / ((long long)NX * NY));
-  const int gnx = NX + 2 * gw, gny = NY + 2 * gw;
-  long long d = (((long long)zz * gny + (y + gw)) * gnx + (x + gw)) * dof + c;
+  int x = (int)(node % g.NX);
+  int y = (int)((node / g.NX) % g.NY);
+  int zz = (int)(node / g.plane);
+  const int gnx = g.NX + 2 * gw, gny = g.NY + 2 * gw;
   int m = c % S, k = c / S;
-  dst[d] = src[(long long)(m * K + k) * src_stride + (src_plane0 + zl0 + zz) * ((long long)NX * NY) + (long long)y * NX + x];
+  const long long o = (long long)(zl0 + zz) * g.plane + (long long)y * g.NX + x;
+  double v = 0.;
+  if (dense) {
+    v = src[(long long)(m * K + k) * g.nnodes + o];
+  } else {
+    const long long oe = o + (long long)g.Rz * g.plane;
+    if (!g.P)
+      v = src[(long long)(m * K + k) * g.fs + oe];
+    else if (g.P[oe + 1] != g.P[oe])
+      v = src[(long long)(m * K + k) * g.fs + g.P[oe]];
+  }
+  dst[(((long long)zz * gny + (y + gw)) * gnx + (x + gw)) * dof + c] = v;
 }
 
 // max |(old - cur)/cur| over a range, then old = cur  (DistributionCalcDeltaNorm,
