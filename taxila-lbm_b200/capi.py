@@ -9,7 +9,10 @@ from pathlib import Path
 
 from .config import TxgConfig
 
-LIB_PATH = Path(__file__).resolve().parent / "libtaxila_gpu.so"
+import os
+
+# TAXILA_GPU_LIB selects another build of the same library (kernel-tuning experiments)
+LIB_PATH = Path(os.environ.get("TAXILA_GPU_LIB") or Path(__file__).resolve().parent / "libtaxila_gpu.so")
 
 _dp = C.POINTER(C.c_double)
 _h = C.c_void_p

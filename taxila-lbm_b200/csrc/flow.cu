@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -98,6 +99,8 @@ struct txg_flow {
   Phys p;
   KernelSet ks;
   int device = 0;
+  int num_sms = 0;
+  bool use_pipe = true;  // TXG_NO_PIPE=1 in the environment selects the plain collide kernel
   int S = 0, Q = 0, D = 0, R = 1;
   cudaStream_t s_main = nullptr, s_comm = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_step0 = nullptr, ev_step1 = nullptr;
@@ -111,7 +114,7 @@ struct txg_flow {
   uint32_t *nbmask = nullptr, *ffmask = nullptr;
   // sparse storage (kernels.cuh): node -> position map, position -> node list, per-position masks and
   // wall records; plane_off[zz] = position of the first fluid node of extended plane zz (NZl+2Rz+1 entries)
-  uint32_t *P = nullptr, *list = nullptr, *lmask = nullptr;
+  uint32_t *P = nullptr, *list = nullptr, *lmask = nullptr, *nbr = nullptr;
   double *wallrec = nullptr;    // [S*D + D][fs]
   double *halo_recv = nullptr;  // NCCL staging: [2 faces][S][NCROSS][fluid nodes of the boundary plane]
   size_t halo_recv_doubles = 0;
@@ -344,7 +347,7 @@ extern "C" int txg_destroy(txg_handle h) {
   drain_timers(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
-                  h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->wallrec, h->halo_recv, h->counters, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
+                  h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->wallrec, h->halo_recv, h->counters, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -392,6 +395,21 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     return fail(TXG_ERR_LIB);
   }
   if ((rc = select_kernels(h))) return fail(rc);
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+      h->err = "cudaGetDeviceProperties failed";
+      return fail(TXG_ERR_LIB);
+    }
+    h->num_sms = prop.multiProcessorCount;
+    const char *np = getenv("TXG_NO_PIPE");
+    h->use_pipe = !(np && np[0] == '1');
+    if (h->ks.collide_pipe &&
+        cudaFuncSetAttribute((const void *)h->ks.collide_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, h->ks.pipe_smem) != cudaSuccess) {
+      h->err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the pipelined collide kernel";
+      return fail(TXG_ERR_LIB);
+    }
+  }
   Grid &g = h->g;
   g.NX = cfg->NX;
   g.NY = cfg->NY;
@@ -637,7 +655,7 @@ static int export_field(txg_flow *h, double *host, int gw, int gwz, int K, int S
 // inside each chunk.  Then size and allocate every position-indexed array.
 static int build_storage(txg_flow *h) {
   Grid &g = h->g;
-  for (void **q : {(void **)&h->P, (void **)&h->list, (void **)&h->lmask, (void **)&h->wallrec, (void **)&h->f[0],
+  for (void **q : {(void **)&h->P, (void **)&h->list, (void **)&h->lmask, (void **)&h->nbr, (void **)&h->wallrec, (void **)&h->f[0],
                    (void **)&h->f[1], (void **)&h->rho, (void **)&h->f_old}) {
     if (*q) cudaFree(*q);
     *q = nullptr;
@@ -670,6 +688,10 @@ static int build_storage(txg_flow *h) {
   g.own0 = h->plane_off[(size_t)g.Rz];
   g.own1 = h->plane_off[(size_t)(g.Rz + g.NZl)];
   g.fs = ((run + 1 + 15) / 16) * 16;  // >= nstore + 1 (a solid neighbour maps to the next position), 128-byte rows
+  if ((long long)h->Q * g.fs >= (1ll << 32)) {
+    cudaFree(d_cnt);
+    TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "%lld fluid nodes in the slab: the %d populations of one component exceed the 32-bit element index; use more z-slabs", run, h->Q);
+  }
   if (run != g.nE) {
     TXG_CUDA(h, cudaMemcpyAsync(d_cnt, cnt.data(), (size_t)nchunks * sizeof(unsigned), cudaMemcpyHostToDevice, h->s_main));
     TXG_CUDA(h, cudaMalloc((void **)&h->P, (size_t)(g.nE + 1) * sizeof(uint32_t)));
@@ -696,7 +718,10 @@ static int build_storage(txg_flow *h) {
   TXG_TRY(alloc_zero(h, (void **)&h->lmask, (size_t)g.fs * sizeof(uint32_t)));
   const long long nown = g.own1 - g.own0;
   int nrec = 0;
+  TXG_TRY(alloc_zero(h, (void **)&h->nbr, (size_t)(h->Q - 1) * g.fs * sizeof(uint32_t)));
   if (nown) {
+    h->ks.build_nbr<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->nbr);
+    TXG_CUDA(h, cudaGetLastError());
     TXG_CUDA(h, cudaMemsetAsync(h->counters + 2, 0, sizeof(int), h->s_main));
     k_gather_mask<<<blocks_for(nown, 256), 256, 0, h->s_main>>>(g, h->nbmask, h->list, h->lmask, h->counters + 2);
     TXG_CUDA(h, cudaGetLastError());
@@ -784,8 +809,17 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
   ScopedKernel sk(h, "k_collide", s);
+  if (h->ks.collide_pipe && h->use_pipe) {
+    // persistent warps: 3 blocks of 4 warps per SM, each warp strides over the items
+    const long long nitems = (count + h->ks.npw - 1) / h->ks.npw;
+    const unsigned blocks = (unsigned)std::min<long long>((nitems + PIPE_WARPS - 1) / PIPE_WARPS, (long long)h->num_sms * 3);
+    h->ks.collide_pipe<<<blocks, 32 * PIPE_WARPS, h->ks.pipe_smem, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
+                                                                      h->nbr, h->wallrec, first, count);
+    TXG_CUDA(h, cudaGetLastError());
+    return 0;
+  }
   h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
-                                                      h->ffmask, h->wallrec, first, count);
+                                                      h->nbr, h->ffmask, h->wallrec, first, count);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }

@@ -4,7 +4,7 @@
 
 #include <cstdint>
 
-#include "hot_kernels.cuh"
+#include "pipe_kernel.cuh"
 
 namespace txg {
 
@@ -14,7 +14,12 @@ struct KernelSet {
   // hot path: one lane per (fluid node, component); (first, count) select the positions
   void (*moments)(Grid, Phys, const double *, double *, long long, long long);
   void (*collide)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
-                  const double *, long long, long long);
+                  const uint32_t *, const double *, long long, long long);
+  void (*build_nbr)(Grid, uint32_t *);
+  // software-pipelined persistent variant of collide (isotropy order 4 only, else nullptr)
+  void (*collide_pipe)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
+                       const double *, long long, long long);
+  int pipe_smem;  // dynamic shared memory per block of collide_pipe
   void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, long long, long long, int);
   // set-up and export
   void (*fi_init)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
@@ -38,6 +43,14 @@ KernelSet make_kernel_set(const char *name) {
   k.export_state = k_export<L, S, ISO>;
   k.build_masks = k_build_masks<L, ISO>;
   k.build_wallrec = k_build_wallrec<L, S, ISO>;
+  k.build_nbr = k_build_nbr<L>;
+  if constexpr (ISO == 4) {
+    k.collide_pipe = k_collide_pipe<L, S, MRT>;
+    k.pipe_smem = (int)(PIPE_WARPS * sizeof(PipeStage<L>));
+  } else {
+    k.collide_pipe = nullptr;
+    k.pipe_smem = 0;
+  }
   k.npw = Lanes<S>::NPW;
   k.ff_words = ISO == 4 ? 0 : ff_words<L>(ISO);
   k.name = name;

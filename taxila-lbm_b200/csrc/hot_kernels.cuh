@@ -335,11 +335,15 @@ __global__ void __launch_bounds__(128) k_moments(Grid g, Phys p, const double *_
 // DiscretizationEquilf_*, FlowFiBarEqPrefactor, FlowCollisionD* (lbm_flow.F90:836-1029),
 // RelaxationCollide* (lbm_relaxation.F90:171-200), DistributionStreamD*, DistributionBouncebackD*
 // (lbm_distribution_function.F90:560-784).
+#ifndef TXG_COLLIDE_MIN_BLOCKS
+#define TXG_COLLIDE_MIN_BLOCKS 4
+#endif
 template <class L, int S, bool MRT, int ISO>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
     k_collide(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ rho,
-              const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ ffmask,
-              const double *__restrict__ wallrec, long long first, long long count) {
+              const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr,
+              const uint32_t *__restrict__ ffmask, const double *__restrict__ wallrec, long long first,
+              long long count) {
   Item it;
   if (!item_of_lane<S>(first, count, it)) return;
   constexpr int Q = L::Q, D = L::D;
@@ -351,22 +355,16 @@ __global__ void __launch_bounds__(128, 3)
     for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
   }
   const uint32_t mask = __ldg(lmask + it.pos);
-  const unsigned oe = g.list ? __ldg(g.list + it.pos) : (unsigned)it.pos;
-  int x, y;
-  xy_of(g, oe, x, y);
-  // positions of the lattice neighbours X + c_n
+  // positions of the lattice neighbours X + c_n (adjacency table, built once per walls upload)
   unsigned npos[Q];
-  {
-    const int dxm = wrap_delta(x, -1, g.NX, g.perx), dxp = wrap_delta(x, 1, g.NX, g.perx);
-    const int dym = wrap_delta(y, -1, g.NY, g.pery) * g.NX, dyp = wrap_delta(y, 1, g.NY, g.pery) * g.NX;
-    const int plane = (int)g.plane;
-    npos[0] = (unsigned)it.pos;
-    static_for<1, Q>([&](auto n_) {
-      constexpr int n = decltype(n_)::value;
-      const int delta = (L::c(n, 0) == 0 ? 0 : (L::c(n, 0) > 0 ? dxp : dxm)) +
-                        (L::c(n, 1) == 0 ? 0 : (L::c(n, 1) > 0 ? dyp : dym)) + L::c(n, 2) * plane;
-      npos[n] = g.P ? __ldg(g.P + ((long long)oe + delta)) : (unsigned)((long long)oe + delta);
-    });
+  npos[0] = (unsigned)it.pos;
+#pragma unroll
+  for (int n = 1; n < Q; ++n) npos[n] = __ldg(nbr + (long long)(n - 1) * g.fs + it.pos);
+  unsigned oe = 0;
+  int x = 0, y = 0;
+  if constexpr (ISO != 4) {  // wider stencils look their extra neighbours up through P
+    oe = g.list ? __ldg(g.list + it.pos) : (unsigned)it.pos;
+    xy_of(g, oe, x, y);
   }
   const double *psi_field = rho + (long long)it.m * g.fs;
   double r = 0.;
@@ -405,14 +403,37 @@ __global__ void __launch_bounds__(128, 3)
   collide1<L, MRT>(p, it.m, r, F, up, f);
   if (!it.active) return;
   // push: slot (n, pos(X + c_n)), or slot (opp(n), pos(X)) when X + c_n is solid
+  // (element indices inside one component's Q*fs block fit 32 bits: checked in txg_set_walls)
   double *out = fB + (long long)it.m * Q * g.fs;
-  out[it.pos] = f[0];
+  const unsigned fs = (unsigned)g.fs, here = (unsigned)it.pos;
+  out[here] = f[0];
   static_for<1, Q>([&](auto n_) {
     constexpr int n = decltype(n_)::value;
     constexpr int on = opp<L>(n);
     const bool bounce = (mask >> n) & 1u;
-    double *dst = bounce ? out + (long long)on * g.fs + it.pos : out + (long long)n * g.fs + npos[n];
-    *dst = f[n];
+    const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + npos[n];
+    out[e] = f[n];
+  });
+}
+
+// Adjacency table (one thread per owned position): nbr[(n-1)*fs + pos] = position of X + c_n, with
+// the periodic wrap in x and y applied.  For a solid or out-of-domain neighbour the entry is some
+// valid position that the mask bit keeps from being used.
+template <class L>
+__global__ void k_build_nbr(Grid g, uint32_t *__restrict__ nbr) {
+  const long long pos = g.own0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= g.own1) return;
+  const unsigned oe = g.list ? g.list[pos] : (unsigned)pos;
+  int x, y;
+  xy_of(g, oe, x, y);
+  const int dxm = wrap_delta(x, -1, g.NX, g.perx), dxp = wrap_delta(x, 1, g.NX, g.perx);
+  const int dym = wrap_delta(y, -1, g.NY, g.pery) * g.NX, dyp = wrap_delta(y, 1, g.NY, g.pery) * g.NX;
+  const int plane = (int)g.plane;
+  static_for<1, L::Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    const int delta = (L::c(n, 0) == 0 ? 0 : (L::c(n, 0) > 0 ? dxp : dxm)) +
+                      (L::c(n, 1) == 0 ? 0 : (L::c(n, 1) > 0 ? dyp : dym)) + L::c(n, 2) * plane;
+    nbr[(long long)(n - 1) * g.fs + pos] = (uint32_t)pos_of(g, (long long)oe + delta);
   });
 }
 
