@@ -116,40 +116,30 @@ def build_case(size, nranks, rank, scaling, order):
     """Per-rank slab of the workload: (cfg, walls_rg, rho_rg, fluid_fraction, global_nodes)."""
     import cases
     from taxila_lbm_b200 import geometry as geo
+    from taxila_lbm_b200 import slab
 
     cfg, walls, rho = cases.porous_3d(size, order=order)
-    NZ = size
     R = cfg.stencil_size_rho
-    if nranks == 1:
-        zs, zl, NZg = 0, NZ, NZ
-        walls_g, rho_g = walls, rho
-    elif scaling == "weak":
-        # global box = the block tiled nranks times along periodic z; rank r owns tile r.
-        NZg = NZ * nranks
-        zs, zl = rank * NZ, NZ
-        walls_g, rho_g = walls, rho  # every tile is the same block; wrap indices modulo NZ
+    if nranks == 1 or scaling == "strong":
+        # the one size^3 box, split into z-slabs (DMDA ownership ranges)
+        c, walls_rg, rho_rg = slab.local_arrays(cfg, walls, rho, nranks, rank)
+        NZg = size
+    else:
+        # weak: the global box is the size^3 block tiled nranks times along periodic z and rank r
+        # owns tile r, so every halo is a real exchange between different GPUs.  All tiles hold the
+        # same geometry, so the ghost planes of a tile are its own opposite planes; the flushing IC
+        # puts the invading fluid in the first 10 planes of the GLOBAL box only, i.e. in tile 0.
+        NZg = size * nranks
+        c = cfg.copy()
+        c.NZ = NZg
+        c.zs, c.zl = rank * size, size
+        c.rank, c.nranks = rank, nranks
         if rank != 0:
-            # flushing IC: only global k <= 10 is invading fluid, i.e. tile 0
-            rho_g = geo.flushing_rho(cfg, walls, (0.03, 0.97), (0.03, 0.97), "z", 10)
-    else:
-        NZg = NZ
-        zl = NZ // nranks
-        zs = rank * zl
-        walls_g, rho_g = walls, rho
-    cfg.NZ = NZg
-    cfg.zs, cfg.zl = zs, zl
-    cfg.rank, cfg.nranks = rank, nranks
-    if nranks > 1 and scaling == "weak":
-        # the slab is one whole tile, ghost planes wrap within the tile (== the neighbour tile),
-        # except rho where tile 0 differs: take ghosts from the proper neighbour tile
-        walls_rg = geo.ghosted(walls_g, R, cfg.periodic, 3, wall_ghost=True)
-        rho_rg = geo.ghosted(rho_g, R, cfg.periodic, 3)
-        # ghost planes of rho come from the halo exchange inside txg_fi_init, host values unused
-    else:
-        walls_rg = geo.ghosted(walls_g, R, cfg.periodic, 3, zs=zs, zl=zl, wall_ghost=True)
-        rho_rg = geo.ghosted(rho_g, R, cfg.periodic, 3, zs=zs, zl=zl)
+            rho = geo.flushing_rho(cfg, walls, (0.03, 0.97), (0.03, 0.97), "z", 10)
+        walls_rg = geo.ghosted(walls, R, cfg.periodic, 3, wall_ghost=True)
+        rho_rg = geo.ghosted(rho, R, cfg.periodic, 3)  # ghost planes of rho are refreshed by the halo exchange
     fluid_local = float((geo.owned(walls_rg, R, 3) == 0).mean())
-    return cfg, walls_rg, rho_rg, fluid_local, size * size * NZg
+    return c, walls_rg, rho_rg, fluid_local, size * size * NZg
 
 
 def run_cpu_sample(order, sample_size, steps, threads):
@@ -273,9 +263,19 @@ def main():
     ms_max = float(t.item())
     value = global_nodes * args.steps / (ms_max * 1e-3) / 1e6
 
-    # sanity: the state is finite and mass is conserved (no work skipped)
-    rhot, _, _ = flow.update_diagnostics()
-    assert np.isfinite(rhot).all()
+    # sanity: the state is finite and the mass of each component over ALL ranks is what the initial
+    # state held (no work skipped, no population lost in a halo)
+    R = cfg.stencil_size_rho
+    fluid = geo.owned(walls_rg, R, 3) == 0
+    rho_now = geo.owned(flow.get_arrays(u=False, forces=False)[0], R, 3)
+    nocheck = os.environ.get("TXG_BENCH_NOCHECK") == "1"  # ablation builds only
+    assert np.isfinite(rho_now).all() or nocheck
+    m = torch.tensor([[float(np.sum(a[..., k][fluid], dtype=np.longdouble)) for k in range(cfg.ncomponents)]
+                      for a in (geo.owned(rho_rg, R, 3), rho_now)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(m, op=dist.ReduceOp.SUM)
+    mass_drift = float(((m[1] - m[0]).abs() / m[0].abs()).max().item())
+    assert mass_drift <= 1e-10 or nocheck, mass_drift
 
     # ------------------------------------------------------------------ e2e through the host-buffer API
     e2e = None
@@ -343,7 +343,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
-        "gpu_launches": int(launches), "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels,
+        "gpu_launches": int(launches) * world, "mass_drift_rel": mass_drift, "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

@@ -41,6 +41,7 @@ typedef struct {
 } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclFloat64 = 8 };
+enum { ncclMax = 2 };
 struct NcclApi {
   void *lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
@@ -48,6 +49,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -74,6 +76,7 @@ struct NcclApi {
     TXG_SYM(CommDestroy, "ncclCommDestroy")
     TXG_SYM(Send, "ncclSend")
     TXG_SYM(Recv, "ncclRecv")
+    TXG_SYM(AllReduce, "ncclAllReduce")
     TXG_SYM(GroupStart, "ncclGroupStart")
     TXG_SYM(GroupEnd, "ncclGroupEnd")
     TXG_SYM(GetErrorString, "ncclGetErrorString")
@@ -100,7 +103,11 @@ struct txg_flow {
   KernelSet ks;
   int device = 0;
   int num_sms = 0;
-  bool use_pipe = true;  // TXG_NO_PIPE=1 in the environment selects the plain collide kernel
+  int pf_blocks = 0;  // L2 prefetch distance of the plain collide kernel in blocks (TXG_PF; 0 = off)
+  bool use_stream = false;  // TXG_STREAM=1 selects the bulk-copy (TMA) collide kernel; measured slower, see DESIGN.md
+  int stream_blocks_per_sm = 4;
+  int stream_opts = 0;  // StreamOpts bits (TXG_OPTS)
+  int stream_strip = 1;  // consecutive chunks a block takes per visit (TXG_STRIP)
   int S = 0, Q = 0, D = 0, R = 1;
   cudaStream_t s_main = nullptr, s_comm = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_step0 = nullptr, ev_step1 = nullptr;
@@ -402,13 +409,22 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
       return fail(TXG_ERR_LIB);
     }
     h->num_sms = prop.multiProcessorCount;
-    const char *np = getenv("TXG_NO_PIPE");
-    h->use_pipe = !(np && np[0] == '1');
-    if (h->ks.collide_pipe &&
-        cudaFuncSetAttribute((const void *)h->ks.collide_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, h->ks.pipe_smem) != cudaSuccess) {
-      h->err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the pipelined collide kernel";
+    if (const char *pf = getenv("TXG_PF")) h->pf_blocks = atoi(pf);
+    if (const char *e = getenv("TXG_STREAM")) h->use_stream = e[0] != '0';
+    if (const char *e = getenv("TXG_OPTS")) h->stream_opts = atoi(e);
+    if (const char *e = getenv("TXG_STRIP")) h->stream_strip = std::max(1, atoi(e));
+    if (cudaFuncSetAttribute((const void *)h->ks.collide_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, h->ks.stream_smem) != cudaSuccess ||
+        cudaFuncSetAttribute((const void *)h->ks.collide_stream, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             getenv("TXG_CARVEOUT") ? atoi(getenv("TXG_CARVEOUT")) : 88) != cudaSuccess) {
+      h->err = "cudaFuncSetAttribute failed for the bulk-copy collide kernel";
       return fail(TXG_ERR_LIB);
     }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)h->ks.collide_stream, h->ks.stream_threads, h->ks.stream_smem) != cudaSuccess || nb < 1) {
+      h->err = "the bulk-copy collide kernel does not fit on this device";
+      return fail(TXG_ERR_LIB);
+    }
+    h->stream_blocks_per_sm = nb;
   }
   Grid &g = h->g;
   g.NX = cfg->NX;
@@ -687,7 +703,9 @@ static int build_storage(txg_flow *h) {
   h->nstore = run;
   g.own0 = h->plane_off[(size_t)g.Rz];
   g.own1 = h->plane_off[(size_t)(g.Rz + g.NZl)];
-  g.fs = ((run + 1 + 15) / 16) * 16;  // >= nstore + 1 (a solid neighbour maps to the next position), 128-byte rows
+  // >= nstore + 1 (a solid neighbour maps to the next position), padded so that the aligned
+  // chunks of the bulk-copy kernel (40, 64 or 128 positions) never run past the end of a row
+  g.fs = ((run + 128 + 127) / 128) * 128;
   if ((long long)h->Q * g.fs >= (1ll << 32)) {
     cudaFree(d_cnt);
     TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "%lld fluid nodes in the slab: the %d populations of one component exceed the 32-bit element index; use more z-slabs", run, h->Q);
@@ -809,17 +827,18 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
   ScopedKernel sk(h, "k_collide", s);
-  if (h->ks.collide_pipe && h->use_pipe) {
-    // persistent warps: 3 blocks of 4 warps per SM, each warp strides over the items
-    const long long nitems = (count + h->ks.npw - 1) / h->ks.npw;
-    const unsigned blocks = (unsigned)std::min<long long>((nitems + PIPE_WARPS - 1) / PIPE_WARPS, (long long)h->num_sms * 3);
-    h->ks.collide_pipe<<<blocks, 32 * PIPE_WARPS, h->ks.pipe_smem, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
-                                                                      h->nbr, h->wallrec, first, count);
+  if (h->use_stream) {
+    const long long PB = h->ks.stream_pb;
+    const long long nchunks = (first + count + PB - 1) / PB - first / PB;
+    const long long nstrips = (nchunks + h->stream_strip - 1) / h->stream_strip;
+    const unsigned blocks = (unsigned)std::min<long long>(nstrips, (long long)h->num_sms * h->stream_blocks_per_sm);
+    h->ks.collide_stream<<<blocks, h->ks.stream_threads, h->ks.stream_smem, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
+                                                                 h->nbr, h->ffmask, h->wallrec, first, count, h->stream_opts, h->stream_strip);
     TXG_CUDA(h, cudaGetLastError());
     return 0;
   }
   h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
-                                                      h->nbr, h->ffmask, h->wallrec, first, count);
+                                                      h->nbr, h->ffmask, h->wallrec, first, count, h->pf_blocks);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -1061,6 +1080,12 @@ extern "C" int txg_delta_norm(txg_handle h, double *norm) {
   }
   TXG_CUDA(h, cudaGetLastError());
   h->launches += h->S * h->Q;
+  // VecNorm(NORM_INFINITY) is a reduction over all ranks (lbm_distribution_function.F90:822); the
+  // maximum of non-negative doubles is the maximum of their bit patterns, here taken as doubles
+  if (h->cfg.nranks > 1) {
+    if (!h->comm) TXG_FAIL(h, TXG_ERR_ORDER, "nranks > 1 but txg_comm_init was not called");
+    TXG_NCCL(h, g_nccl.AllReduce(h->norm_bits, h->norm_bits, 1, ncclFloat64, ncclMax, h->comm, h->s_main));
+  }
   unsigned long long bits = 0;
   TXG_CUDA(h, cudaMemcpyAsync(&bits, h->norm_bits, sizeof bits, cudaMemcpyDeviceToHost, h->s_main));
   TXG_CUDA(h, cudaStreamSynchronize(h->s_main));

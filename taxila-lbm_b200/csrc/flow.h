@@ -4,7 +4,7 @@
 
 #include <cstdint>
 
-#include "pipe_kernel.cuh"
+#include "stream_kernel.cuh"
 
 namespace txg {
 
@@ -14,12 +14,13 @@ struct KernelSet {
   // hot path: one lane per (fluid node, component); (first, count) select the positions
   void (*moments)(Grid, Phys, const double *, double *, long long, long long);
   void (*collide)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
-                  const uint32_t *, const double *, long long, long long);
+                  const uint32_t *, const double *, long long, long long, int);
+  // the same step fed by bulk asynchronous copies (stream_kernel.cuh): persistent blocks
+  void (*collide_stream)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
+                         const uint32_t *, const double *, long long, long long, int, int);
+  int stream_smem;  // dynamic shared memory per block of collide_stream
+  int stream_threads, stream_pb;  // block size and positions per chunk of collide_stream
   void (*build_nbr)(Grid, uint32_t *);
-  // software-pipelined persistent variant of collide (isotropy order 4 only, else nullptr)
-  void (*collide_pipe)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
-                       const double *, long long, long long);
-  int pipe_smem;  // dynamic shared memory per block of collide_pipe
   void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, long long, long long, int);
   // set-up and export
   void (*fi_init)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
@@ -38,19 +39,16 @@ KernelSet make_kernel_set(const char *name) {
   KernelSet k;
   k.moments = k_moments<L, S>;
   k.collide = k_collide<L, S, MRT, ISO>;
+  k.collide_stream = k_collide_stream<L, S, MRT, ISO>;
+  k.stream_smem = (int)sizeof(StreamSmem<L, S>) + 128;
+  k.stream_threads = STREAM_THREADS;
+  k.stream_pb = StreamStage<L, S>::PB;
   k.halo_unpack = k_halo_unpack<L, S>;
   k.fi_init = k_fi_init<L, S, ISO>;
   k.export_state = k_export<L, S, ISO>;
   k.build_masks = k_build_masks<L, ISO>;
   k.build_wallrec = k_build_wallrec<L, S, ISO>;
   k.build_nbr = k_build_nbr<L>;
-  if constexpr (ISO == 4) {
-    k.collide_pipe = k_collide_pipe<L, S, MRT>;
-    k.pipe_smem = (int)(PIPE_WARPS * sizeof(PipeStage<L>));
-  } else {
-    k.collide_pipe = nullptr;
-    k.pipe_smem = 0;
-  }
   k.npw = Lanes<S>::NPW;
   k.ff_words = ISO == 4 ? 0 : ff_words<L>(ISO);
   k.name = name;

@@ -155,7 +155,11 @@ __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const doub
         np = pos_of(g, (long long)oe + (dz * plane + dyo[dy + RAD] + dxo[dx + RAD]));
       }
       constexpr double wgt = L::ffw(ISO, FF::L[e]);
+#if TXG_ABL == 3
+      const double v = psi_m * (double)(np & 3);
+#else
       const double v = __ldg(psi_field + np);
+#endif
       const double diff = on ? v - psi_m : 0.;
       if constexpr (dx != 0) G[0] = G[0] + ((double)dx * wgt) * diff;
       if constexpr (dy != 0) G[1] = G[1] + ((double)dy * wgt) * diff;
@@ -306,6 +310,39 @@ __device__ __forceinline__ void collide1(const Phys &p, int m, double rho, const
   }
 }
 
+// momentum j_m = sum_n f_n c_n of this lane's component (DistributionCalcFluxD*,
+// lbm_distribution_function.F90:451-508) and the common velocity u' shared by all components
+// (FlowUpdateUED*, lbm_flow.F90:494-574); the component sums run in ascending component order
+// over the lanes that hold the same node.
+template <class L, int S>
+__device__ __forceinline__ void common_velocity1(const Phys &p, const Item &it, const double (&f)[L::Q], double r,
+                                                 const double (&F)[L::D], double (&up)[L::D]) {
+  constexpr int Q = L::Q, D = L::D;
+  double num[D], den = 0.;
+  const double mmot = p.mmot[it.m];
+  double ue[D];
+  static_for<0, D>([&](auto d_) {
+    constexpr int d = decltype(d_)::value;
+    double a = 0.;
+    static_for<0, Q>([&](auto n_) {
+      constexpr int n = decltype(n_)::value;
+      if constexpr (L::c(n, d) != 0) a += f[n] * (double)L::c(n, d);
+    });
+    ue[d] = (a + .5 * F[d]) * mmot;
+    num[d] = 0.;
+  });
+  const double rm = r * mmot;
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    den += from_component<S>(rm, k, it.j);
+#pragma unroll
+    for (int d = 0; d < D; ++d) num[d] += from_component<S>(ue[d], k, it.j);
+  }
+  const double rden = 1. / den;
+#pragma unroll
+  for (int d = 0; d < D; ++d) up[d] = num[d] * rden;
+}
+
 // ================================================================== the hot kernels
 
 // K1 moments: rho_m = sum_n f_n (ascending n) of the streamed populations; writes rho (psi with an
@@ -327,6 +364,40 @@ __global__ void __launch_bounds__(128) k_moments(Grid g, Phys p, const double *_
   rho[(long long)it.m * g.fs + it.pos] = p.eos ? eos_psi(p, it.m, a) : a;
 }
 
+// L2 prefetch of the rows a block of 128 lanes (4 warps x NPW positions) reads at the start of
+// k_collide: S*Q population rows, Q-1 adjacency rows and the mask row of positions
+// [first + blk*PB, first + (blk+1)*PB), PB = 4*NPW.  One 128-byte line per lane and round.
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+template <class L, int S>
+__device__ __forceinline__ void prefetch_block_rows(const Grid &g, const double *__restrict__ fA,
+                                                    const uint32_t *__restrict__ lmask,
+                                                    const uint32_t *__restrict__ nbr,
+                                                    const double *__restrict__ wallrec, long long first,
+                                                    long long count, long long blk) {
+  constexpr int Q = L::Q, PB = 4 * Lanes<S>::NPW;
+  constexpr int FL = (PB * 8 + 127) / 128, NL = (PB * 4 + 127) / 128;  // lines per row
+  constexpr int NF = S * Q * FL, NN = (Q - 1) * NL, NW = (S * L::D + L::D) * FL;
+  const int total = NF + NN + NL + (wallrec ? NW : 0);
+  const long long p0 = blk * PB;
+  if (p0 >= count) return;
+  const long long pos = first + p0;
+  for (int t = threadIdx.x; t < total; t += 128) {
+    if (t < NF) {
+      const int row = t / FL, seg = t - row * FL;
+      prefetch_l2(fA + (long long)row * g.fs + pos + seg * 16);
+    } else if (t < NF + NN) {
+      const int u = t - NF, row = u / NL, seg = u - row * NL;
+      prefetch_l2(nbr + (long long)row * g.fs + pos + seg * 32);
+    } else if (t < NF + NN + NL) {
+      prefetch_l2(lmask + pos + (t - NF - NN) * 32);
+    } else {
+      const int u = t - NF - NN - NL, row = u / FL, seg = u - row * FL;
+      prefetch_l2(wallrec + (long long)row * g.fs + pos + seg * 16);
+    }
+  }
+}
+
 // K2 collide + push: node populations, forces from the rho stencil, momentum, common velocity,
 // equilibrium, prefactor, SRT/MRT relaxation, forcing term; the post-collision populations are
 // streamed by the store (bounce-back folded in).
@@ -335,18 +406,35 @@ __global__ void __launch_bounds__(128) k_moments(Grid g, Phys p, const double *_
 // DiscretizationEquilf_*, FlowFiBarEqPrefactor, FlowCollisionD* (lbm_flow.F90:836-1029),
 // RelaxationCollide* (lbm_relaxation.F90:171-200), DistributionStreamD*, DistributionBouncebackD*
 // (lbm_distribution_function.F90:560-784).
+#ifndef TXG_ABL
+#define TXG_ABL 0
+#endif
 #ifndef TXG_COLLIDE_MIN_BLOCKS
 #define TXG_COLLIDE_MIN_BLOCKS 4
 #endif
+// `pf_blocks` > 0: every block first asks L2 for the rows (populations, adjacency, mask) of the block
+// pf_blocks further on -- about one wave of resident blocks ahead -- so that the demand loads of
+// that block find their lines on chip.  The collision needs ~126 registers per lane, which caps the
+// SM at 16 warps; without the prefetch the bytes those few warps keep in flight bound the kernel
+// (Little's law), not HBM.
 template <class L, int S, bool MRT, int ISO>
 __global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
     k_collide(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ rho,
               const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr,
               const uint32_t *__restrict__ ffmask, const double *__restrict__ wallrec, long long first,
-              long long count) {
+              long long count, int pf_blocks) {
+  constexpr int Q = L::Q, D = L::D;
+  if (pf_blocks > 0) prefetch_block_rows<L, S>(g, fA, lmask, nbr, wallrec, first, count, (long long)blockIdx.x + pf_blocks);
   Item it;
   if (!item_of_lane<S>(first, count, it)) return;
-  constexpr int Q = L::Q, D = L::D;
+  // adjacency row and mask first: the second round of loads (neighbour densities, wall record)
+  // hangs on them, the populations are not needed until the arithmetic starts
+  const uint32_t mask = __ldg(lmask + it.pos);
+  // positions of the lattice neighbours X + c_n (adjacency table, built once per walls upload)
+  unsigned npos[Q];
+  npos[0] = (unsigned)it.pos;
+#pragma unroll
+  for (int n = 1; n < Q; ++n) npos[n] = __ldg(nbr + (long long)(n - 1) * g.fs + it.pos);
   const long long mo = (long long)it.m * Q * g.fs + it.pos;
   double f[Q];
   {
@@ -354,12 +442,6 @@ __global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
 #pragma unroll
     for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
   }
-  const uint32_t mask = __ldg(lmask + it.pos);
-  // positions of the lattice neighbours X + c_n (adjacency table, built once per walls upload)
-  unsigned npos[Q];
-  npos[0] = (unsigned)it.pos;
-#pragma unroll
-  for (int n = 1; n < Q; ++n) npos[n] = __ldg(nbr + (long long)(n - 1) * g.fs + it.pos);
   unsigned oe = 0;
   int x = 0, y = 0;
   if constexpr (ISO != 4) {  // wider stencils look their extra neighbours up through P
@@ -373,35 +455,23 @@ __global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
   const double psi_m = p.eos ? __ldg(psi_field + it.pos) : r;
   double F[D];
   forces1<L, S, ISO>(g, p, psi_field, ffmask, wallrec, it, oe, x, y, mask, npos, r, psi_m, F);
-  // momentum j_m (DistributionCalcFluxD*) and the common velocity u' (FlowUpdateUED*)
   double up[D];
-  {
-    double num[D], den = 0.;
-    const double mmot = p.mmot[it.m];
-    double ue[D];
-    static_for<0, D>([&](auto d_) {
-      constexpr int d = decltype(d_)::value;
-      double a = 0.;
-      static_for<0, Q>([&](auto n_) {
-        constexpr int n = decltype(n_)::value;
-        if constexpr (L::c(n, d) != 0) a += f[n] * (double)L::c(n, d);
-      });
-      ue[d] = (a + .5 * F[d]) * mmot;
-      num[d] = 0.;
-    });
-    const double rm = r * mmot;
-#pragma unroll
-    for (int k = 0; k < S; ++k) {
-      den += from_component<S>(rm, k, it.j);
-#pragma unroll
-      for (int d = 0; d < D; ++d) num[d] += from_component<S>(ue[d], k, it.j);
-    }
-    const double rden = 1. / den;
-#pragma unroll
-    for (int d = 0; d < D; ++d) up[d] = num[d] * rden;
-  }
+  common_velocity1<L, S>(p, it, f, r, F, up);
+#if TXG_ABL != 2 && TXG_ABL != 5
   collide1<L, MRT>(p, it.m, r, F, up, f);
+#else
+  f[0] += up[0] + up[D - 1];
+#endif
   if (!it.active) return;
+#if TXG_ABL == 1
+  {
+    double acc = 0.;
+#pragma unroll
+    for (int n = 0; n < Q; ++n) acc += f[n];
+    if (acc == 1.2345e300) fB[it.pos] = acc;
+    return;
+  }
+#endif
   // push: slot (n, pos(X + c_n)), or slot (opp(n), pos(X)) when X + c_n is solid
   // (element indices inside one component's Q*fs block fit 32 bits: checked in txg_set_walls)
   double *out = fB + (long long)it.m * Q * g.fs;
@@ -411,7 +481,11 @@ __global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
     constexpr int n = decltype(n_)::value;
     constexpr int on = opp<L>(n);
     const bool bounce = (mask >> n) & 1u;
+#if TXG_ABL == 4 || TXG_ABL == 5
+    const unsigned e = (unsigned)n * fs + here + ((bounce && npos[n] == 0xffffffffu) ? 1u : 0u);
+#else
     const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + npos[n];
+#endif
     out[e] = f[n];
   });
 }
