@@ -103,11 +103,6 @@ struct txg_flow {
   KernelSet ks;
   int device = 0;
   int num_sms = 0;
-  int pf_blocks = 0;  // L2 prefetch distance of the plain collide kernel in blocks (TXG_PF; 0 = off)
-  bool use_stream = false;  // TXG_STREAM=1 selects the bulk-copy (TMA) collide kernel; measured slower, see DESIGN.md
-  int stream_blocks_per_sm = 4;
-  int stream_opts = 0;  // StreamOpts bits (TXG_OPTS)
-  int stream_strip = 1;  // consecutive chunks a block takes per visit (TXG_STRIP)
   int S = 0, Q = 0, D = 0, R = 1;
   cudaStream_t s_main = nullptr, s_comm = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_step0 = nullptr, ev_step1 = nullptr;
@@ -123,6 +118,7 @@ struct txg_flow {
   // wall records; plane_off[zz] = position of the first fluid node of extended plane zz (NZl+2Rz+1 entries)
   uint32_t *P = nullptr, *list = nullptr, *lmask = nullptr, *nbr = nullptr;
   double *wallrec = nullptr;    // [S*D + D][fs]
+  double *Fbuf = nullptr;       // [S*D][fs] forces of the current step (k_forces -> k_collide)
   double *halo_recv = nullptr;  // NCCL staging: [2 faces][S][NCROSS][fluid nodes of the boundary plane]
   size_t halo_recv_doubles = 0;
   std::vector<long long> plane_off;
@@ -354,7 +350,7 @@ extern "C" int txg_destroy(txg_handle h) {
   drain_timers(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
-                  h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->wallrec, h->halo_recv, h->counters, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
+                  h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -364,6 +360,7 @@ extern "C" int txg_destroy(txg_handle h) {
   if (h->ev_step1) cudaEventDestroy(h->ev_step1);
   if (h->s_main) cudaStreamDestroy(h->s_main);
   if (h->s_comm) cudaStreamDestroy(h->s_comm);
+
   delete h;
   return 0;
 }
@@ -409,22 +406,6 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
       return fail(TXG_ERR_LIB);
     }
     h->num_sms = prop.multiProcessorCount;
-    if (const char *pf = getenv("TXG_PF")) h->pf_blocks = atoi(pf);
-    if (const char *e = getenv("TXG_STREAM")) h->use_stream = e[0] != '0';
-    if (const char *e = getenv("TXG_OPTS")) h->stream_opts = atoi(e);
-    if (const char *e = getenv("TXG_STRIP")) h->stream_strip = std::max(1, atoi(e));
-    if (cudaFuncSetAttribute((const void *)h->ks.collide_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, h->ks.stream_smem) != cudaSuccess ||
-        cudaFuncSetAttribute((const void *)h->ks.collide_stream, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             getenv("TXG_CARVEOUT") ? atoi(getenv("TXG_CARVEOUT")) : 88) != cudaSuccess) {
-      h->err = "cudaFuncSetAttribute failed for the bulk-copy collide kernel";
-      return fail(TXG_ERR_LIB);
-    }
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)h->ks.collide_stream, h->ks.stream_threads, h->ks.stream_smem) != cudaSuccess || nb < 1) {
-      h->err = "the bulk-copy collide kernel does not fit on this device";
-      return fail(TXG_ERR_LIB);
-    }
-    h->stream_blocks_per_sm = nb;
   }
   Grid &g = h->g;
   g.NX = cfg->NX;
@@ -445,6 +426,7 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
   auto body = [&]() -> int {
     TXG_CUDA(h, cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
     TXG_CUDA(h, cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking));
+
     TXG_CUDA(h, cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     TXG_CUDA(h, cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
     TXG_CUDA(h, cudaEventCreate(&h->ev_step0));
@@ -671,7 +653,7 @@ static int export_field(txg_flow *h, double *host, int gw, int gwz, int K, int S
 // inside each chunk.  Then size and allocate every position-indexed array.
 static int build_storage(txg_flow *h) {
   Grid &g = h->g;
-  for (void **q : {(void **)&h->P, (void **)&h->list, (void **)&h->lmask, (void **)&h->nbr, (void **)&h->wallrec, (void **)&h->f[0],
+  for (void **q : {(void **)&h->P, (void **)&h->list, (void **)&h->lmask, (void **)&h->nbr, (void **)&h->wallrec, (void **)&h->Fbuf, (void **)&h->f[0],
                    (void **)&h->f[1], (void **)&h->rho, (void **)&h->f_old}) {
     if (*q) cudaFree(*q);
     *q = nullptr;
@@ -733,10 +715,11 @@ static int build_storage(txg_flow *h) {
     TXG_TRY(alloc_zero(h, (void **)&h->rho_true, (size_t)h->S * g.fs * sizeof(double)));
   else
     h->rho_true = h->rho;
+  TXG_TRY(alloc_zero(h, (void **)&h->Fbuf, (size_t)h->S * h->D * g.fs * sizeof(double)));
   TXG_TRY(alloc_zero(h, (void **)&h->lmask, (size_t)g.fs * sizeof(uint32_t)));
   const long long nown = g.own1 - g.own0;
   int nrec = 0;
-  TXG_TRY(alloc_zero(h, (void **)&h->nbr, (size_t)(h->Q - 1) * g.fs * sizeof(uint32_t)));
+  TXG_TRY(alloc_zero(h, (void **)&h->nbr, (size_t)h->ks.ncen * g.fs * sizeof(uint32_t)));
   if (nown) {
     h->ks.build_nbr<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->nbr);
     TXG_CUDA(h, cudaGetLastError());
@@ -817,7 +800,18 @@ static int run_moments(txg_flow *h, int z0, int nz, cudaStream_t s) {
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
   ScopedKernel sk(h, "k_moments", s);
-  h->ks.moments<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, first, count);
+  h->ks.moments<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, h->rho_true, first, count);
+  TXG_CUDA(h, cudaGetLastError());
+  return 0;
+}
+static int run_forces(txg_flow *h, int z0, int nz, cudaStream_t s) {
+  if (nz <= 0) return 0;
+  long long first, count;
+  plane_range(h, z0, nz, &first, &count);
+  if (count == 0) return 0;
+  ScopedKernel sk(h, "k_forces", s);
+  h->ks.forces<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->rho, h->rho_true, h->lmask, h->nbr, h->ffmask, h->wallrec,
+                                                     h->Fbuf, first, count);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -827,18 +821,8 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
   ScopedKernel sk(h, "k_collide", s);
-  if (h->use_stream) {
-    const long long PB = h->ks.stream_pb;
-    const long long nchunks = (first + count + PB - 1) / PB - first / PB;
-    const long long nstrips = (nchunks + h->stream_strip - 1) / h->stream_strip;
-    const unsigned blocks = (unsigned)std::min<long long>(nstrips, (long long)h->num_sms * h->stream_blocks_per_sm);
-    h->ks.collide_stream<<<blocks, h->ks.stream_threads, h->ks.stream_smem, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
-                                                                 h->nbr, h->ffmask, h->wallrec, first, count, h->stream_opts, h->stream_strip);
-    TXG_CUDA(h, cudaGetLastError());
-    return 0;
-  }
-  h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
-                                                      h->nbr, h->ffmask, h->wallrec, first, count, h->pf_blocks);
+  h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->Fbuf, h->lmask, h->nbr,
+                                                      first, count);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -909,9 +893,9 @@ extern "C" int txg_fi_init(txg_handle h) {
 
 // ------------------------------------------------------------------ the step
 // One reference time step = collide, communicate fi, stream, bounce-back, density, forces, flux,
-// common velocity (lbm.F90:286-361).  On the device: K1 moments (density) with the rho halo, then K2
-// (forces + momentum + velocity + collision + push-streaming with bounce-back) with the halo of the
-// pushed populations.  Boundary planes run first so that their halos travel on the communication
+// common velocity (lbm.F90:286-361).  On the device: K1 moments (density) with the rho halo, K2a
+// forces (every gather of the step), then K2b (momentum + velocity + collision + push-streaming with
+// bounce-back) with the halo of the pushed populations.  Boundary planes run first so that their halos travel on the communication
 // stream while the interior computes.
 static int one_step(txg_flow *h) {
   const Grid &g = h->g;
@@ -920,13 +904,16 @@ static int one_step(txg_flow *h) {
   if (!split) {
     TXG_TRY(run_moments(h, 0, g.NZl, sm));
     TXG_TRY(exchange_rho(h, h->rho, sm));
+    TXG_TRY(run_forces(h, 0, g.NZl, sm));
     TXG_TRY(run_collide(h, 0, g.NZl, sm));
     TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sm));
     h->cur ^= 1;
     return 0;
   }
   const int R = g.R;
-  // K1: bottom and top R planes, then their halo on the comm stream, interior meanwhile
+  // K1: bottom and top R planes, then their halo on the comm stream; interior K1 and the interior
+  // forces (which need no halo) meanwhile.  (Running K1 and the forces of different sub-slabs on two
+  // streams was tried and gains nothing: a later grid only gets SMs at the tail of an earlier one.)
   TXG_TRY(run_moments(h, 0, R, sm));
   TXG_TRY(run_moments(h, g.NZl - R, R, sm));
   TXG_CUDA(h, cudaEventRecord(h->ev_a, sm));
@@ -934,8 +921,12 @@ static int one_step(txg_flow *h) {
   TXG_TRY(exchange_rho(h, h->rho, sc));
   TXG_CUDA(h, cudaEventRecord(h->ev_b, sc));
   TXG_TRY(run_moments(h, R, g.NZl - 2 * R, sm));
+  TXG_TRY(run_forces(h, R, g.NZl - 2 * R, sm));
   TXG_CUDA(h, cudaStreamWaitEvent(sm, h->ev_b, 0));
-  // K2: boundary planes (they need the rho halo), halo of the new populations, interior meanwhile
+  // boundary planes: forces (they need the rho halo), collide, halo of the new populations on the
+  // comm stream; interior collide meanwhile
+  TXG_TRY(run_forces(h, 0, R, sm));
+  TXG_TRY(run_forces(h, g.NZl - R, R, sm));
   TXG_TRY(run_collide(h, 0, 1, sm));
   TXG_TRY(run_collide(h, g.NZl - 1, 1, sm));
   TXG_CUDA(h, cudaEventRecord(h->ev_a, sm));

@@ -4,7 +4,7 @@
 
 #include <cstdint>
 
-#include "stream_kernel.cuh"
+#include "hot_kernels.cuh"
 
 namespace txg {
 
@@ -12,14 +12,11 @@ namespace txg {
 // spread over inst_*.cu so they compile in parallel.
 struct KernelSet {
   // hot path: one lane per (fluid node, component); (first, count) select the positions
-  void (*moments)(Grid, Phys, const double *, double *, long long, long long);
-  void (*collide)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
-                  const uint32_t *, const double *, long long, long long, int);
-  // the same step fed by bulk asynchronous copies (stream_kernel.cuh): persistent blocks
-  void (*collide_stream)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
-                         const uint32_t *, const double *, long long, long long, int, int);
-  int stream_smem;  // dynamic shared memory per block of collide_stream
-  int stream_threads, stream_pb;  // block size and positions per chunk of collide_stream
+  void (*moments)(Grid, Phys, const double *, double *, double *, long long, long long);
+  void (*forces)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *, const uint32_t *,
+                 const double *, double *, long long, long long);
+  void (*collide)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *, long long,
+                  long long);
   void (*build_nbr)(Grid, uint32_t *);
   void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, long long, long long, int);
   // set-up and export
@@ -30,6 +27,7 @@ struct KernelSet {
   void (*build_masks)(Grid, const uint8_t *, uint32_t *, uint32_t *, int *);
   void (*build_wallrec)(Grid, Phys, const uint8_t *, const uint32_t *, const uint32_t *, double *);
   int npw;       // fluid nodes per warp of the hot kernels (32 / S)
+  int ncen;      // rows of the adjacency table (centre directions)
   int ff_words;  // u32 words of ffmask per node (0 for isotropy order 4)
   const char *name;
 };
@@ -38,11 +36,8 @@ template <class L, int S, bool MRT, int ISO>
 KernelSet make_kernel_set(const char *name) {
   KernelSet k;
   k.moments = k_moments<L, S>;
-  k.collide = k_collide<L, S, MRT, ISO>;
-  k.collide_stream = k_collide_stream<L, S, MRT, ISO>;
-  k.stream_smem = (int)sizeof(StreamSmem<L, S>) + 128;
-  k.stream_threads = STREAM_THREADS;
-  k.stream_pb = StreamStage<L, S>::PB;
+  k.forces = k_forces<L, S, ISO>;
+  k.collide = k_collide<L, S, MRT>;
   k.halo_unpack = k_halo_unpack<L, S>;
   k.fi_init = k_fi_init<L, S, ISO>;
   k.export_state = k_export<L, S, ISO>;
@@ -50,6 +45,7 @@ KernelSet make_kernel_set(const char *name) {
   k.build_wallrec = k_build_wallrec<L, S, ISO>;
   k.build_nbr = k_build_nbr<L>;
   k.npw = Lanes<S>::NPW;
+  k.ncen = num_centres<L>();
   k.ff_words = ISO == 4 ? 0 : ff_words<L>(ISO);
   k.name = name;
   return k;

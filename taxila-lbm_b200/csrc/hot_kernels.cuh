@@ -13,6 +13,10 @@
 #pragma once
 #include "kernels.cuh"
 
+#ifndef TXG_ABL
+#define TXG_ABL 0  // ablation builds (tools/): 1 no stores, 2 no collision arithmetic, 3 no density gather, 4 node-aligned stores, 5 = 2 + 4
+#endif
+
 namespace txg {
 
 template <int S>
@@ -30,9 +34,8 @@ struct Item {
 // the end of the range (or the 32 - S*NPW spare lanes when S does not divide 32) replay a valid
 // item with active = false: they take part in the shuffles and store nothing.
 template <int S>
-__device__ __forceinline__ bool item_of_lane(long long first, long long count, Item &it) {
+__device__ __forceinline__ bool item_of_lane(long long first, long long count, long long warp, Item &it) {
   constexpr int NPW = Lanes<S>::NPW;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long base = warp * NPW;
   if (base >= count) return false;
@@ -50,6 +53,10 @@ __device__ __forceinline__ bool item_of_lane(long long first, long long count, I
   }
   it.pos = first + i;
   return true;
+}
+template <int S>
+__device__ __forceinline__ bool item_of_lane(long long first, long long count, Item &it) {
+  return item_of_lane<S>(first, count, ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, it);
 }
 
 // in-plane coordinates of extended node index oe
@@ -91,23 +98,121 @@ TXG_HD constexpr double bulk_weight_sum(int d) {
 // compile-time weight sum.  Neighbour densities are loaded unconditionally (a solid neighbour's
 // position is that of the next fluid node -- some valid, finite value) and masked afterwards, so that
 // all loads of a lane are in flight together.  npos[n]: position of X + c_n (order 4 re-uses them).
+// Adjacency of a fluid node.  Positions run along x, so P(x+1,y',z') = P(x,y',z') + fluid(x,y',z') for any
+// row (P of a solid node = position of the next fluid node): the table holds the position of X + c for
+// the NCEN centre directions (c_x = 0) only, and the c_x = +-1 neighbours follow from those and the
+// mask bits.  Nodes on a periodic x face (mask bits 28/29) look their wrapped neighbours up through
+// the node -> position map instead.  For a solid neighbour the result is some valid position that
+// the mask bit keeps from being used.
+template <class L>
+struct Adjacency {
+  static constexpr int NCEN = num_centres<L>();
+  unsigned cen[NCEN > 0 ? NCEN : 1];
+  unsigned here;
+  uint32_t mask;
+
+  __device__ __forceinline__ void load(const Grid &g, const uint32_t *__restrict__ nbr, long long pos) {
+    here = (unsigned)pos;
+#pragma unroll
+    for (int k = 0; k < NCEN; ++k) cen[k] = __ldg(nbr + (long long)k * g.fs + pos);
+  }
+
+  // the same row out of the shared-memory columns of this thread (k_collide)
+  __device__ __forceinline__ void load_staged(const uint32_t (*col)[128], long long pos) {
+    here = (unsigned)pos;
+#pragma unroll
+    for (int k = 0; k < NCEN; ++k) cen[k] = col[k][threadIdx.x];
+    mask = col[NCEN][threadIdx.x];
+  }
+
+  // wrapped neighbour of a node on a periodic x face (rare path: two dependent loads).  Takes the
+  // grid fields by value: a reference would force a local copy of the kernel parameter.
+  template <int n>
+  __device__ __forceinline__ static unsigned wrapped(const uint32_t *__restrict__ list, const uint32_t *__restrict__ P,
+                                                  int NX, int NY, int pery, unsigned here) {
+    const unsigned oe = list ? __ldg(list + here) : here;
+    const unsigned plane = (unsigned)(NX * NY);
+    const unsigned r = oe % plane;
+    const int y = (int)(r / (unsigned)NX), x = (int)(r - (unsigned)y * (unsigned)NX);
+    const int delta = wrap_delta(x, L::c(n, 0), NX, 1) + wrap_delta(y, L::c(n, 1), NY, pery) * NX +
+                      L::c(n, 2) * (int)plane;
+    const long long t = (long long)oe + delta;
+    return P ? __ldg(P + t) : (unsigned)t;
+  }
+
+  // position of X + c_n
+  template <int n>
+  __device__ __forceinline__ unsigned at(const Grid &g) const {
+    constexpr int cx = L::c(n, 0);
+    if constexpr (n == 0) return here;
+    if constexpr (cx == 0) return cen[centre_rank<L>(n)];
+    constexpr int nc = dir_of<L>(0, L::c(n, 1), L::c(n, 2));  // centre of the row of X + c_n (0: own row)
+    unsigned base = here, centre_solid = 0u;
+    if constexpr (nc != 0) {
+      base = cen[centre_rank<L>(nc)];
+      centre_solid = (mask >> nc) & 1u;
+    }
+    unsigned v;
+    if constexpr (cx > 0)
+      v = base + 1u - centre_solid;
+    else
+      v = base - 1u + ((mask >> n) & 1u);
+    if (mask & (cx > 0 ? MASK_XHI : MASK_XLO)) v = wrapped<n>(g.list, g.P, g.NX, g.NY, g.pery, here);
+    return v;
+  }
+};
+
+// Second-round operands of a node, loaded by the caller as soon as the adjacency row and the mask
+// have arrived and before the populations are touched (so that one wait covers both rounds):
+//   A[d], rW[d]: the wall record (0 / bulk weight for a node without one);  vn[n]: psi(X + c_n) for the
+//   order-4 stencil, whose offsets are the lattice directions (wider stencils load inside forces1).
+template <class L>
+struct Round2 {
+  double A[L::D], rW[L::D], vn[L::Q];
+};
+
 template <class L, int S, int ISO>
-__device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const double *__restrict__ psi_field,
-                                        const uint32_t *__restrict__ ffmask, const double *__restrict__ wallrec,
-                                        const Item &it, unsigned oe, int x, int y, uint32_t mask,
-                                        const unsigned (&npos)[L::Q], double rho_m, double psi_m, double (&F)[L::D]) {
+__device__ __forceinline__ void load_round2(const Grid &g, const Phys &p, const double *__restrict__ psi_field,
+                                            const double *__restrict__ wallrec, const Item &it, uint32_t mask,
+                                            const unsigned (&npos)[L::Q], Round2<L> &r2) {
   constexpr int D = L::D;
   const bool rec = (mask & MASK_WALLREC) != 0;
+  if (p.fluidsolid) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) r2.A[d] = rec ? __ldg(wallrec + (long long)(it.m * D + d) * g.fs + it.pos) : 0.;
+  }
+  if (p.fluidfluid) {
+    static_for<0, D>([&](auto d_) {
+      constexpr int d = decltype(d_)::value;
+      constexpr double bulk = 1.0 / bulk_weight_sum<L, ISO>(d);
+      r2.rW[d] = rec ? __ldg(wallrec + (long long)(S * D + d) * g.fs + it.pos) : bulk;
+    });
+    if constexpr (ISO == 4) {
+#pragma unroll
+      for (int n = 1; n < L::Q; ++n) {
+#if TXG_ABL == 3
+        r2.vn[n] = (double)(npos[n] & 3u);
+#else
+        r2.vn[n] = __ldg(psi_field + npos[n]);
+#endif
+      }
+    }
+  }
+}
+
+template <class L, int S, int ISO>
+__device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const double *__restrict__ psi_field,
+                                        const uint32_t *__restrict__ ffmask, const Round2<L> &r2,
+                                        const Item &it, unsigned oe, int x, int y, uint32_t mask,
+                                        double rho_m, double psi_m, double (&F)[L::D]) {
+  constexpr int D = L::D;
   const int m = it.m;
 #pragma unroll
   for (int d = 0; d < D; ++d) F[d] = 0.;
 
   if (p.fluidsolid) {
-    double A[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) A[d] = rec ? __ldg(wallrec + (long long)(m * D + d) * g.fs + it.pos) : 0.;
-#pragma unroll
-    for (int d = 0; d < D; ++d) F[d] = F[d] - rho_m * A[d];
+    for (int d = 0; d < D; ++d) F[d] = F[d] - rho_m * r2.A[d];
   }
 
   if (p.body) {
@@ -119,12 +224,6 @@ __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const doub
     using FF = typename L::FF;
     constexpr int E = ff_entries<L>(ISO);
     constexpr int RAD = stencil_radius(ISO);
-    double rW[D];
-    static_for<0, D>([&](auto d_) {
-      constexpr int d = decltype(d_)::value;
-      constexpr double bulk = 1.0 / bulk_weight_sum<L, ISO>(d);
-      rW[d] = rec ? __ldg(wallrec + (long long)(S * D + d) * g.fs + it.pos) : bulk;
-    });
     int dxo[2 * RAD + 1], dyo[2 * RAD + 1];
     uint32_t words[(E + 31) / 32];
     if constexpr (ISO != 4) {
@@ -145,21 +244,16 @@ __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const doub
       constexpr int e = decltype(e_)::value;
       constexpr int dx = FF::off[e][0], dy = FF::off[e][1], dz = FF::off[e][2];
       bool on;
-      long long np;
+      double v;
       if constexpr (ISO == 4) {
         constexpr int n = dir_of<L>(dx, dy, dz);
         on = !((mask >> n) & 1u);
-        np = npos[n];
+        v = r2.vn[n];
       } else {
         on = (words[e / 32] >> (e % 32)) & 1u;
-        np = pos_of(g, (long long)oe + (dz * plane + dyo[dy + RAD] + dxo[dx + RAD]));
+        v = __ldg(psi_field + pos_of(g, (long long)oe + (dz * plane + dyo[dy + RAD] + dxo[dx + RAD])));
       }
       constexpr double wgt = L::ffw(ISO, FF::L[e]);
-#if TXG_ABL == 3
-      const double v = psi_m * (double)(np & 3);
-#else
-      const double v = __ldg(psi_field + np);
-#endif
       const double diff = on ? v - psi_m : 0.;
       if constexpr (dx != 0) G[0] = G[0] + ((double)dx * wgt) * diff;
       if constexpr (dy != 0) G[1] = G[1] + ((double)dy * wgt) * diff;
@@ -168,7 +262,7 @@ __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const doub
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       // normalised gradient of this lane's component; rW = 0 where the reference skips the direction
-      const double q = G[d] * rW[d];
+      const double q = G[d] * r2.rW[d];
       double acc = 0.;
 #pragma unroll
       for (int k = 0; k < S; ++k) acc += p.gf[m][k] * from_component<S>(q, k, it.j);
@@ -350,7 +444,8 @@ __device__ __forceinline__ void common_velocity1(const Phys &p, const Item &it, 
 // streaming and bounce-back happened in the push of the previous collide.
 template <class L, int S>
 __global__ void __launch_bounds__(128) k_moments(Grid g, Phys p, const double *__restrict__ fA,
-                                                 double *__restrict__ rho, long long first, long long count) {
+                                                 double *__restrict__ rho, double *__restrict__ rho_true,
+                                                 long long first, long long count) {
   Item it;
   if (!item_of_lane<S>(first, count, it)) return;
   const double *src = fA + (long long)it.m * L::Q * g.fs + it.pos;
@@ -361,100 +456,103 @@ __global__ void __launch_bounds__(128) k_moments(Grid g, Phys p, const double *_
 #pragma unroll
   for (int n = 0; n < L::Q; ++n) a += f[n];
   if (!it.active) return;
-  rho[(long long)it.m * g.fs + it.pos] = p.eos ? eos_psi(p, it.m, a) : a;
-}
-
-// L2 prefetch of the rows a block of 128 lanes (4 warps x NPW positions) reads at the start of
-// k_collide: S*Q population rows, Q-1 adjacency rows and the mask row of positions
-// [first + blk*PB, first + (blk+1)*PB), PB = 4*NPW.  One 128-byte line per lane and round.
-__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-
-template <class L, int S>
-__device__ __forceinline__ void prefetch_block_rows(const Grid &g, const double *__restrict__ fA,
-                                                    const uint32_t *__restrict__ lmask,
-                                                    const uint32_t *__restrict__ nbr,
-                                                    const double *__restrict__ wallrec, long long first,
-                                                    long long count, long long blk) {
-  constexpr int Q = L::Q, PB = 4 * Lanes<S>::NPW;
-  constexpr int FL = (PB * 8 + 127) / 128, NL = (PB * 4 + 127) / 128;  // lines per row
-  constexpr int NF = S * Q * FL, NN = (Q - 1) * NL, NW = (S * L::D + L::D) * FL;
-  const int total = NF + NN + NL + (wallrec ? NW : 0);
-  const long long p0 = blk * PB;
-  if (p0 >= count) return;
-  const long long pos = first + p0;
-  for (int t = threadIdx.x; t < total; t += 128) {
-    if (t < NF) {
-      const int row = t / FL, seg = t - row * FL;
-      prefetch_l2(fA + (long long)row * g.fs + pos + seg * 16);
-    } else if (t < NF + NN) {
-      const int u = t - NF, row = u / NL, seg = u - row * NL;
-      prefetch_l2(nbr + (long long)row * g.fs + pos + seg * 32);
-    } else if (t < NF + NN + NL) {
-      prefetch_l2(lmask + pos + (t - NF - NN) * 32);
-    } else {
-      const int u = t - NF - NN - NL, row = u / FL, seg = u - row * FL;
-      prefetch_l2(wallrec + (long long)row * g.fs + pos + seg * 16);
-    }
+  // with a non-ideal EOS the stencil field is psi(rho) and the density proper is kept beside it
+  // (rho_true == rho otherwise)
+  if (p.eos) {
+    rho_true[(long long)it.m * g.fs + it.pos] = a;
+    a = eos_psi(p, it.m, a);
   }
+  rho[(long long)it.m * g.fs + it.pos] = a;
 }
 
-// K2 collide + push: node populations, forces from the rho stencil, momentum, common velocity,
-// equilibrium, prefactor, SRT/MRT relaxation, forcing term; the post-collision populations are
-// streamed by the store (bounce-back folded in).
-// Replaces LBMAddFluidFluid/FluidSolid/BodyForcesD* (lbm_forcing.F90), DistributionCalcFluxD*
-// (lbm_distribution_function.F90:451-508), FlowUpdateUED* (lbm_flow.F90:494-574),
-// DiscretizationEquilf_*, FlowFiBarEqPrefactor, FlowCollisionD* (lbm_flow.F90:836-1029),
-// RelaxationCollide* (lbm_relaxation.F90:171-200), DistributionStreamD*, DistributionBouncebackD*
-// (lbm_distribution_function.F90:560-784).
-#ifndef TXG_ABL
-#define TXG_ABL 0
-#endif
-#ifndef TXG_COLLIDE_MIN_BLOCKS
-#define TXG_COLLIDE_MIN_BLOCKS 4
-#endif
-// `pf_blocks` > 0: every block first asks L2 for the rows (populations, adjacency, mask) of the block
-// pf_blocks further on -- about one wave of resident blocks ahead -- so that the demand loads of
-// that block find their lines on chip.  The collision needs ~126 registers per lane, which caps the
-// SM at 16 warps; without the prefetch the bytes those few warps keep in flight bound the kernel
-// (Little's law), not HBM.
-template <class L, int S, bool MRT, int ISO>
-__global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
-    k_collide(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ rho,
-              const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr,
-              const uint32_t *__restrict__ ffmask, const double *__restrict__ wallrec, long long first,
-              long long count, int pf_blocks) {
+// asynchronous 4-byte copy global -> shared (LDGSTS): no register holds the value in flight
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// K2a forces: F_m(X) of FlowCalcForces (lbm_flow.F90:760-808) for every fluid node, written to
+// Fbuf[(m*D + d)*fs + pos].  All data-dependent gathers of the step live here -- the neighbour
+// densities (18 for the order-4 stencil, up to 92 for order 8) and the wall record -- in a kernel that
+// needs few registers and runs at full occupancy; inside the register-heavy collide kernel the same
+// gathers cost 3.5 ms per step against 1.4 ms here (tools/membench/layoutbench.cu, 512^3 porous).
+// Replaces LBMAddFluidSolidForcesD*, LBMAddBodyForcesD*, LBMAddFluidFluidForcesD* (lbm_forcing.F90).
+template <class L, int S, int ISO>
+__global__ void __launch_bounds__(128, 8) k_forces(Grid g, Phys p, const double *__restrict__ rho,
+                                                const double *__restrict__ rho_true, const uint32_t *__restrict__ lmask,
+                                                const uint32_t *__restrict__ nbr, const uint32_t *__restrict__ ffmask,
+                                                const double *__restrict__ wallrec, double *__restrict__ Fbuf,
+                                                long long first, long long count) {
   constexpr int Q = L::Q, D = L::D;
-  if (pf_blocks > 0) prefetch_block_rows<L, S>(g, fA, lmask, nbr, wallrec, first, count, (long long)blockIdx.x + pf_blocks);
   Item it;
   if (!item_of_lane<S>(first, count, it)) return;
-  // adjacency row and mask first: the second round of loads (neighbour densities, wall record)
-  // hangs on them, the populations are not needed until the arithmetic starts
-  const uint32_t mask = __ldg(lmask + it.pos);
-  // positions of the lattice neighbours X + c_n (adjacency table, built once per walls upload)
+  Adjacency<L> adj;
+  adj.mask = __ldg(lmask + it.pos);
+  adj.load(g, nbr, it.pos);
+  const uint32_t mask = adj.mask;
+  const double *psi_field = rho + (long long)it.m * g.fs;
+  const double psi_m = __ldg(psi_field + it.pos);
+  // density proper (differs from psi only with a non-ideal EOS)
+  const double r = p.eos ? __ldg(rho_true + (long long)it.m * g.fs + it.pos) : psi_m;
   unsigned npos[Q];
-  npos[0] = (unsigned)it.pos;
-#pragma unroll
-  for (int n = 1; n < Q; ++n) npos[n] = __ldg(nbr + (long long)(n - 1) * g.fs + it.pos);
-  const long long mo = (long long)it.m * Q * g.fs + it.pos;
-  double f[Q];
-  {
-    const double *src = fA + mo;
-#pragma unroll
-    for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
-  }
+  static_for<0, Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    npos[n] = adj.template at<n>(g);
+  });
   unsigned oe = 0;
   int x = 0, y = 0;
   if constexpr (ISO != 4) {  // wider stencils look their extra neighbours up through P
     oe = g.list ? __ldg(g.list + it.pos) : (unsigned)it.pos;
     xy_of(g, oe, x, y);
   }
-  const double *psi_field = rho + (long long)it.m * g.fs;
+  Round2<L> r2;
+  load_round2<L, S, ISO>(g, p, psi_field, wallrec, it, mask, npos, r2);
+  double F[D];
+  forces1<L, S, ISO>(g, p, psi_field, ffmask, r2, it, oe, x, y, mask, r, psi_m, F);
+  if (!it.active) return;
+#pragma unroll
+  for (int d = 0; d < D; ++d) Fbuf[(long long)(it.m * D + d) * g.fs + it.pos] = F[d];
+}
+
+// K2b collide + push: node populations and forces in, momentum, common velocity, equilibrium,
+// prefactor, SRT/MRT relaxation, forcing term; the post-collision populations are streamed by the
+// store (bounce-back folded in).  Every load address follows from the position alone.
+// Replaces DistributionCalcFluxD* (lbm_distribution_function.F90:451-508), FlowUpdateUED*
+// (lbm_flow.F90:494-574), DiscretizationEquilf_*, FlowFiBarEqPrefactor, FlowCollisionD*
+// (lbm_flow.F90:836-1029), RelaxationCollide* (lbm_relaxation.F90:171-200), DistributionStreamD*,
+// DistributionBouncebackD* (lbm_distribution_function.F90:560-784).
+#ifndef TXG_COLLIDE_MIN_BLOCKS
+#define TXG_COLLIDE_MIN_BLOCKS 4
+#endif
+template <class L, int S, bool MRT>
+__global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
+    k_collide(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ Fbuf,
+              const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr, long long first, long long count) {
+  constexpr int Q = L::Q, D = L::D, NCEN = num_centres<L>();
+  // The adjacency row and the mask are needed by the push only.  They travel into shared memory
+  // asynchronously (no register is tied up while the collision runs, and their round trip hides
+  // behind the population loads and the arithmetic); column threadIdx.x belongs to this lane alone.
+  __shared__ uint32_t adj_col[NCEN + 1][128];
+  Item it;
+  if (!item_of_lane<S>(first, count, it)) return;
+#pragma unroll
+  for (int k = 0; k < NCEN; ++k) cp_async4(&adj_col[k][threadIdx.x], nbr + (long long)k * g.fs + it.pos);
+  cp_async4(&adj_col[NCEN][threadIdx.x], lmask + it.pos);
+  cp_async_commit();
+  double f[Q];
+  {
+    const double *src = fA + (long long)it.m * Q * g.fs + it.pos;
+#pragma unroll
+    for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
+  }
+  double F[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) F[d] = __ldg(Fbuf + (long long)(it.m * D + d) * g.fs + it.pos);
   double r = 0.;
 #pragma unroll
   for (int n = 0; n < Q; ++n) r += f[n];
-  const double psi_m = p.eos ? __ldg(psi_field + it.pos) : r;
-  double F[D];
-  forces1<L, S, ISO>(g, p, psi_field, ffmask, wallrec, it, oe, x, y, mask, npos, r, psi_m, F);
   double up[D];
   common_velocity1<L, S>(p, it, f, r, F, up);
 #if TXG_ABL != 2 && TXG_ABL != 5
@@ -474,6 +572,10 @@ __global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
 #endif
   // push: slot (n, pos(X + c_n)), or slot (opp(n), pos(X)) when X + c_n is solid
   // (element indices inside one component's Q*fs block fit 32 bits: checked in txg_set_walls)
+  cp_async_wait_all();
+  Adjacency<L> adj;
+  adj.load_staged(adj_col, it.pos);
+  const uint32_t mask = adj.mask;
   double *out = fB + (long long)it.m * Q * g.fs;
   const unsigned fs = (unsigned)g.fs, here = (unsigned)it.pos;
   out[here] = f[0];
@@ -482,17 +584,17 @@ __global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
     constexpr int on = opp<L>(n);
     const bool bounce = (mask >> n) & 1u;
 #if TXG_ABL == 4 || TXG_ABL == 5
-    const unsigned e = (unsigned)n * fs + here + ((bounce && npos[n] == 0xffffffffu) ? 1u : 0u);
+    const unsigned e = (unsigned)n * fs + here + ((bounce && adj.cen[0] == 0xffffffffu) ? 1u : 0u);
 #else
-    const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + npos[n];
+    const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + adj.template at<n>(g);
 #endif
     out[e] = f[n];
   });
 }
 
-// Adjacency table (one thread per owned position): nbr[(n-1)*fs + pos] = position of X + c_n, with
-// the periodic wrap in x and y applied.  For a solid or out-of-domain neighbour the entry is some
-// valid position that the mask bit keeps from being used.
+// Adjacency table (one thread per owned position): nbr[k*fs + pos] = position of X + c_n for the k-th
+// centre direction (c_x = 0), with the periodic wrap in y applied.  For a solid or out-of-domain
+// neighbour the entry is the position of the next fluid node (see Adjacency).
 template <class L>
 __global__ void k_build_nbr(Grid g, uint32_t *__restrict__ nbr) {
   const long long pos = g.own0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -500,14 +602,15 @@ __global__ void k_build_nbr(Grid g, uint32_t *__restrict__ nbr) {
   const unsigned oe = g.list ? g.list[pos] : (unsigned)pos;
   int x, y;
   xy_of(g, oe, x, y);
-  const int dxm = wrap_delta(x, -1, g.NX, g.perx), dxp = wrap_delta(x, 1, g.NX, g.perx);
   const int dym = wrap_delta(y, -1, g.NY, g.pery) * g.NX, dyp = wrap_delta(y, 1, g.NY, g.pery) * g.NX;
   const int plane = (int)g.plane;
   static_for<1, L::Q>([&](auto n_) {
     constexpr int n = decltype(n_)::value;
-    const int delta = (L::c(n, 0) == 0 ? 0 : (L::c(n, 0) > 0 ? dxp : dxm)) +
-                      (L::c(n, 1) == 0 ? 0 : (L::c(n, 1) > 0 ? dyp : dym)) + L::c(n, 2) * plane;
-    nbr[(long long)(n - 1) * g.fs + pos] = (uint32_t)pos_of(g, (long long)oe + delta);
+    constexpr int k = centre_rank<L>(n);
+    if constexpr (k >= 0) {
+      const int delta = (L::c(n, 1) == 0 ? 0 : (L::c(n, 1) > 0 ? dyp : dym)) + L::c(n, 2) * plane;
+      nbr[(long long)k * g.fs + pos] = (uint32_t)pos_of(g, (long long)oe + delta);
+    }
   });
 }
 

@@ -17,7 +17,9 @@
 //                           boundary plane.  fs = nstore rounded up (+ padding): the stride of every array.
 //   rho   [S][fs]           per-component density (psi when a non-ideal EOS is on); ghost planes by halo
 //   lmask [fs]        u32   per OWNED position: bit n = neighbour X+c_n is solid, bit 30 = X has a wall
-//                           record (some lattice neighbour solid or some gradient-stencil entry inactive)
+//                           record (some lattice neighbour solid or some gradient-stencil entry inactive),
+//                           bits 28/29 = X sits on the periodic x = 0 / x = NX-1 face
+//   nbr   [NCEN][fs]  u32   per OWNED position: position of X + c_n for the centre directions (c_x = 0)
 //   wallrec [S*D+D][fs]     per owned position with bit 30: A[m][d] = sum_n w_n gw(mineral(X+c_n),m) c_n,d
 //                           (fluid-solid force = -rho_m A) and 1/W[d] of the gradient normalisation
 //   cls   [NZl+2Rz][NY+2R][NX+2R]  u8 node class incl. ghosts, straight from the host walls(rg..) array
@@ -111,7 +113,9 @@ __device__ __forceinline__ void load_node(const Grid &g, const double *__restric
 
 constexpr uint32_t MASK_SOLID = 0x80000000u;    // the node itself is solid
 constexpr uint32_t MASK_WALLREC = 0x40000000u;  // the node has a wall record
-constexpr uint32_t MASK_DIRS = 0x3fffffffu;     // bit n: neighbour X + c_n is solid
+constexpr uint32_t MASK_XLO = 0x10000000u;      // x = 0 and x periodic: the -x neighbours wrap
+constexpr uint32_t MASK_XHI = 0x20000000u;      // x = NX-1 and x periodic: the +x neighbours wrap
+constexpr uint32_t MASK_DIRS = 0x07ffffffu;     // bit n: neighbour X + c_n is solid
 
 // ------------------------------------------------------------------ forces
 // FlowCalcForces (lbm_flow.F90:760-808): F = 0; fluid-solid (LBMAddFluidSolidForcesD*,
@@ -491,6 +495,8 @@ __global__ void k_build_masks(Grid g, const uint8_t *__restrict__ cls, uint32_t 
     for (int w = 0; w < (E + 31) / 32; ++w) ffmask[(long long)w * g.nnodes + nd.o] = words[w];
   }
   if (wallrec && !(mask >> 31)) mask |= MASK_WALLREC;
+  if (g.perx && nd.x == 0) mask |= MASK_XLO;
+  if (g.perx && nd.x == g.NX - 1) mask |= MASK_XHI;
   nbmask[nd.o] = mask;
 }
 

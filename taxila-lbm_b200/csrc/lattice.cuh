@@ -150,6 +150,25 @@ template <class L>
 TXG_HD constexpr int opp(int n) {
   return dir_of<L>(-L::c(n, 0), -L::c(n, 1), -L::c(n, 2));
 }
+// Centre directions: the lattice directions with c_x = 0 (n >= 1).  The adjacency table stores the
+// position of X + c_n for these only; the c_x = +-1 neighbours follow from them and the mask bits,
+// because positions run along x (hot_kernels.cuh, Adjacency).
+template <class L>
+TXG_HD constexpr int num_centres() {
+  int k = 0;
+  for (int n = 1; n < L::Q; ++n)
+    if (L::c(n, 0) == 0) ++k;
+  return k;
+}
+// rank of direction n among the centre directions, or -1
+template <class L>
+TXG_HD constexpr int centre_rank(int n) {
+  if (n < 1 || L::c(n, 0) != 0) return -1;
+  int k = 0;
+  for (int i = 1; i < n; ++i)
+    if (L::c(i, 0) == 0) ++k;
+  return k;
+}
 // number of fluid-fluid stencil entries used at a given isotropy order
 template <class L>
 TXG_HD constexpr int ff_entries(int order) {
