@@ -40,8 +40,9 @@ import numpy as np  # noqa: E402
 METRIC = "MLUPS"
 B_ALG_FLUID = 641.0  # 16*S*Q + 16*S + 1 for D3Q19, S=2
 B_ALG_SOLID = 1.0
-B_K2_FLUID = 625.0  # collide kernel: 16*S*Q + 8*S + 1
-B_K1_FLUID = 321.0  # moments kernel: 8*S*Q + 8*S + 1
+B_K2_FLUID = 693.0  # collide kernel: 16*S*Q (f in, f out) + 8*S*D (forces) + 32 (adjacency) + 4 (mask) + 1
+B_K1_FLUID = 320.0  # moments kernel: 8*S*Q + 8*S
+B_KF_FLUID = 101.0  # forces kernel: 8*S (own rho; gathers are L2 reuse) + 8*S*D (F out) + 32 + 4 + 1
 
 
 def measured_peak():
@@ -330,6 +331,12 @@ def main():
                      "frac_of_hbm_peak": step_bytes * args.steps / (ms_max * 1e-3) / 1e9 / world / peak,
                      "mflups": value * fluid_frac}
     kernels = {k: {"ms": v[0], "launches": v[1]} for k, v in ktimes.items()}
+    # per-kernel achieved algorithmic GB/s (the launches of one step add up to the slab)
+    for name, b in (("k_moments", B_K1_FLUID), ("k_forces", B_KF_FLUID), ("k_collide", B_K2_FLUID)):
+        if name in kernels and kernels[name]["ms"] > 0:
+            by = nodes_local * fluid_frac * b * args.steps
+            kernels[name]["algorithmic_gbs"] = by / (kernels[name]["ms"] * 1e-3) / 1e9
+            kernels[name]["frac_of_peak"] = kernels[name]["algorithmic_gbs"] / peak
 
     cpu = None
     if not args.no_cpu:

@@ -14,7 +14,7 @@
  *
  * Parity pinning: tests/test_oracle_golden.py checks this oracle against the
  * reference's shipped golden vector tests/bubble_2D/reference_solution/fi001.dat
- * (committed copy: tests/golden/bubble_2D_fi001.f64be) -- D2Q9/SRT/iso-4 directly,
+ * (committed copy: tests/golden/bubble_2D_fi001.dat) -- D2Q9/SRT/iso-4 directly,
  * the MRT tables through MRT(all rates 1) == SRT, and the D3Q19 tables through a
  * z-invariant extrusion projected onto the same golden.  D3Q19 MRT with general
  * rates, iso-8/10, walls, minerals and body force have no golden in the
