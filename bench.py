@@ -40,9 +40,12 @@ import numpy as np  # noqa: E402
 METRIC = "MLUPS"
 B_ALG_FLUID = 641.0  # 16*S*Q + 16*S + 1 for D3Q19, S=2
 B_ALG_SOLID = 1.0
-B_K2_FLUID = 693.0  # collide kernel: 16*S*Q (f in, f out) + 8*S*D (forces) + 32 (adjacency) + 4 (mask) + 1
+# algorithmic bytes per fluid node of each hot kernel (each datum once; the adjacency tables of the sparse
+# storage are NOT counted: they are overhead of this implementation and show up in `traffic`)
+B_K2_FLUID = 625.0  # fused forces+collide kernel: 16*S*Q (f in, f out) + 8*S (rho) + 1 (node class)   [SURVEY 8d]
+B_K2B_FLUID = 657.0  # split collide kernel: 16*S*Q + 8*S*D (forces in) + 1
 B_K1_FLUID = 320.0  # moments kernel: 8*S*Q + 8*S
-B_KF_FLUID = 101.0  # forces kernel: 8*S (own rho; gathers are L2 reuse) + 8*S*D (F out) + 32 + 4 + 1
+B_KF_FLUID = 65.0   # split forces kernel: 8*S (rho) + 8*S*D (F out) + 1
 
 
 def measured_peak():
@@ -312,19 +315,28 @@ def main():
     # ------------------------------------------------------------------ roofline of the dominant kernel
     peak, peak_src = measured_peak()
     nodes_local = args.size ** 2 * cfg.zl
-    kc_ms, kc_n = ktimes.get("k_collide", (0.0, 0))
-    km_ms, km_n = ktimes.get("k_moments", (0.0, 0))
+    # dominant kernel: the fused forces+collide kernel (order-4 stencil) or the split collide kernel
+    dom, dom_bytes = ("k_step_fused", B_K2_FLUID) if ktimes.get("k_step_fused", (0.0, 0))[1] else ("k_collide", B_K2B_FLUID)
+    kc_ms, kc_n = ktimes.get(dom, (0.0, 0))
     roofline = None
     if kc_n:
         # per-launch algorithmic bytes: launches may cover sub-ranges of the slab (boundary/interior
         # split); bytes of all launches of one step add up to the slab
-        per_step_bytes = nodes_local * (fluid_frac * B_K2_FLUID + (1 - fluid_frac) * B_ALG_SOLID)
-        steps_timed = args.steps
-        achieved = per_step_bytes * steps_timed / (kc_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_collide", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "bytes_per_fluid_node": B_K2_FLUID, "avg_launch_ms": kc_ms / kc_n,
-                    "share_of_step": kc_ms / (ms_max if ms_max else 1.0)}
+        per_step_bytes = nodes_local * (fluid_frac * dom_bytes + (1 - fluid_frac) * B_ALG_SOLID)
+        achieved = per_step_bytes * args.steps / (kc_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tj = ROOT / "profiles" / "traffic.json"
+        if tj.exists():
+            try:
+                t = json.loads(tj.read_text()).get(dom)
+                if t and t.get("size") == args.size and t.get("order") == args.order and world == 1:
+                    traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
+            except Exception:
+                pass
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "bytes_per_fluid_node": dom_bytes, "bytes_per_launch": per_step_bytes * args.steps / kc_n,
+                    "avg_launch_ms": kc_ms / kc_n, "share_of_step": kc_ms / (ms_max if ms_max else 1.0)}
     step_bytes = global_nodes * (fluid_frac * B_ALG_FLUID + (1 - fluid_frac) * B_ALG_SOLID)
     step_roofline = {"bytes_per_lup_fluid": B_ALG_FLUID, "fluid_fraction": fluid_frac,
                      "achieved_gbs_per_gpu": step_bytes * args.steps / (ms_max * 1e-3) / 1e9 / world,
@@ -332,7 +344,7 @@ def main():
                      "mflups": value * fluid_frac}
     kernels = {k: {"ms": v[0], "launches": v[1]} for k, v in ktimes.items()}
     # per-kernel achieved algorithmic GB/s (the launches of one step add up to the slab)
-    for name, b in (("k_moments", B_K1_FLUID), ("k_forces", B_KF_FLUID), ("k_collide", B_K2_FLUID)):
+    for name, b in (("k_moments", B_K1_FLUID), ("k_forces", B_KF_FLUID), ("k_collide", B_K2B_FLUID), ("k_step_fused", B_K2_FLUID)):
         if name in kernels and kernels[name]["ms"] > 0:
             by = nodes_local * fluid_frac * b * args.steps
             kernels[name]["algorithmic_gbs"] = by / (kernels[name]["ms"] * 1e-3) / 1e9

@@ -117,6 +117,8 @@ struct txg_flow {
   // sparse storage (kernels.cuh): node -> position map, position -> node list, per-position masks and
   // wall records; plane_off[zz] = position of the first fluid node of extended plane zz (NZl+2Rz+1 entries)
   uint32_t *P = nullptr, *list = nullptr, *lmask = nullptr, *nbr = nullptr;
+  uint32_t *nbr_all = nullptr;  // [Q-1][fs] every lattice neighbour: the fused path; nbr (centres only) and Fbuf: the split path
+  bool fused = false;           // forces + collide in one kernel (order-4 stencil; TXG_SPLIT=1 forces the split path)
   double *wallrec = nullptr;    // [S*D + D][fs]
   double *Fbuf = nullptr;       // [S*D][fs] forces of the current step (k_forces -> k_collide)
   double *halo_recv = nullptr;  // NCCL staging: [2 faces][S][NCROSS][fluid nodes of the boundary plane]
@@ -350,7 +352,7 @@ extern "C" int txg_destroy(txg_handle h) {
   drain_timers(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
-                  h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
+                  h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->nbr_all, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -406,6 +408,8 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
       return fail(TXG_ERR_LIB);
     }
     h->num_sms = prop.multiProcessorCount;
+    const char *sp = getenv("TXG_SPLIT");
+    h->fused = h->ks.step_fused != nullptr && !(sp && sp[0] == '1');
   }
   Grid &g = h->g;
   g.NX = cfg->NX;
@@ -653,7 +657,7 @@ static int export_field(txg_flow *h, double *host, int gw, int gwz, int K, int S
 // inside each chunk.  Then size and allocate every position-indexed array.
 static int build_storage(txg_flow *h) {
   Grid &g = h->g;
-  for (void **q : {(void **)&h->P, (void **)&h->list, (void **)&h->lmask, (void **)&h->nbr, (void **)&h->wallrec, (void **)&h->Fbuf, (void **)&h->f[0],
+  for (void **q : {(void **)&h->P, (void **)&h->list, (void **)&h->lmask, (void **)&h->nbr, (void **)&h->nbr_all, (void **)&h->wallrec, (void **)&h->Fbuf, (void **)&h->f[0],
                    (void **)&h->f[1], (void **)&h->rho, (void **)&h->f_old}) {
     if (*q) cudaFree(*q);
     *q = nullptr;
@@ -715,13 +719,19 @@ static int build_storage(txg_flow *h) {
     TXG_TRY(alloc_zero(h, (void **)&h->rho_true, (size_t)h->S * g.fs * sizeof(double)));
   else
     h->rho_true = h->rho;
-  TXG_TRY(alloc_zero(h, (void **)&h->Fbuf, (size_t)h->S * h->D * g.fs * sizeof(double)));
+  if (!h->fused) TXG_TRY(alloc_zero(h, (void **)&h->Fbuf, (size_t)h->S * h->D * g.fs * sizeof(double)));
   TXG_TRY(alloc_zero(h, (void **)&h->lmask, (size_t)g.fs * sizeof(uint32_t)));
   const long long nown = g.own1 - g.own0;
   int nrec = 0;
-  TXG_TRY(alloc_zero(h, (void **)&h->nbr, (size_t)h->ks.ncen * g.fs * sizeof(uint32_t)));
+  if (h->fused)
+    TXG_TRY(alloc_zero(h, (void **)&h->nbr_all, (size_t)(h->Q - 1) * g.fs * sizeof(uint32_t)));
+  else
+    TXG_TRY(alloc_zero(h, (void **)&h->nbr, (size_t)h->ks.ncen * g.fs * sizeof(uint32_t)));
   if (nown) {
-    h->ks.build_nbr<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->nbr);
+    if (h->fused)
+      h->ks.build_nbr_all<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->nbr_all);
+    else
+      h->ks.build_nbr<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->nbr);
     TXG_CUDA(h, cudaGetLastError());
     TXG_CUDA(h, cudaMemsetAsync(h->counters + 2, 0, sizeof(int), h->s_main));
     k_gather_mask<<<blocks_for(nown, 256), 256, 0, h->s_main>>>(g, h->nbmask, h->list, h->lmask, h->counters + 2);
@@ -809,6 +819,7 @@ static int run_forces(txg_flow *h, int z0, int nz, cudaStream_t s) {
   long long first, count;
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
+  if (h->fused) return 0;  // the collide launch forms the forces itself
   ScopedKernel sk(h, "k_forces", s);
   h->ks.forces<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->rho, h->rho_true, h->lmask, h->nbr, h->ffmask, h->wallrec,
                                                      h->Fbuf, first, count);
@@ -820,6 +831,13 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   long long first, count;
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
+  if (h->fused) {
+    ScopedKernel sk(h, "k_step_fused", s);
+    h->ks.step_fused<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask, h->nbr_all,
+                                                           h->wallrec, first, count);
+    TXG_CUDA(h, cudaGetLastError());
+    return 0;
+  }
   ScopedKernel sk(h, "k_collide", s);
   h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->Fbuf, h->lmask, h->nbr,
                                                       first, count);

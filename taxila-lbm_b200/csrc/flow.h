@@ -4,7 +4,7 @@
 
 #include <cstdint>
 
-#include "hot_kernels.cuh"
+#include "fused_kernel.cuh"
 
 namespace txg {
 
@@ -17,6 +17,10 @@ struct KernelSet {
                  const double *, double *, long long, long long);
   void (*collide)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *, long long,
                   long long);
+  // forces + collide in one kernel (order-4 stencil only; nullptr otherwise), fed by the full adjacency table
+  void (*step_fused)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
+                     const double *, long long, long long);
+  void (*build_nbr_all)(Grid, uint32_t *);
   void (*build_nbr)(Grid, uint32_t *);
   void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, long long, long long, int);
   // set-up and export
@@ -44,6 +48,11 @@ KernelSet make_kernel_set(const char *name) {
   k.build_masks = k_build_masks<L, ISO>;
   k.build_wallrec = k_build_wallrec<L, S, ISO>;
   k.build_nbr = k_build_nbr<L>;
+  k.build_nbr_all = k_build_nbr_all<L>;
+  if constexpr (ISO == 4)
+    k.step_fused = k_step_fused<L, S, MRT>;
+  else
+    k.step_fused = nullptr;
   k.npw = Lanes<S>::NPW;
   k.ncen = num_centres<L>();
   k.ff_words = ISO == 4 ? 0 : ff_words<L>(ISO);

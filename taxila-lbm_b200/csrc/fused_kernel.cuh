@@ -1,0 +1,182 @@
+// fused_kernel.cuh -- the one-kernel form of forces + collision + push (K2) for the order-4 stencil.
+//
+// With the order-4 Shan-Chen stencil the 18 gathered densities are the lattice neighbours the push needs
+// anyway, and folding the forces into the collide kernel measures ~0.9 ms per step faster at 512^3 than
+// the split k_forces + k_collide pair (11.4 ms against 3.1 + 9.3 ms; profiles/), although the gathers
+// are individually more expensive inside the 126-register kernel.  Wider stencils (92 gathers at order
+// 8) always take the split path.  Neighbour positions come from the full adjacency table nbr_all
+// ((Q-1) entries per node); the split path's compact centre table is not used here.
+#pragma once
+#include "hot_kernels.cuh"
+
+namespace txg {
+
+// FlowCalcForces (lbm_flow.F90:760-808) for ONE component: fluid-solid, body, fluid-fluid, in the
+// reference's order.  psi_m: pointer to this component's psi array (position-indexed).
+// The geometry-only factors come from the wall record: A[d] = sum_n w_n gw(mineral(X+c_n), m) c_n,d
+// (LBMAddFluidSolidForcesD*, lbm_forcing.F90:1326-1421, float literals 1./6. etc. folded in by
+// k_build_wallrec) and rW[d] = 1/weightsum_d (lbm_forcing.F90:946-953); bulk nodes use the
+// compile-time weight sum.  Neighbour densities are loaded unconditionally (a solid neighbour's
+// position is that of the next fluid node -- some valid, finite value) and masked afterwards, so that
+// all loads of a lane are in flight together.  npos[n]: position of X + c_n (order 4 re-uses them).
+template <class L, int S, int ISO>
+__device__ __forceinline__ void forces1_inline(const Grid &g, const Phys &p, const double *__restrict__ psi_field,
+                                        const uint32_t *__restrict__ ffmask, const double *__restrict__ wallrec,
+                                        const Item &it, unsigned oe, int x, int y, uint32_t mask,
+                                        const unsigned (&npos)[L::Q], double rho_m, double psi_m, double (&F)[L::D]) {
+  constexpr int D = L::D;
+  const bool rec = (mask & MASK_WALLREC) != 0;
+  const int m = it.m;
+#pragma unroll
+  for (int d = 0; d < D; ++d) F[d] = 0.;
+
+  if (p.fluidsolid) {
+    double A[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) A[d] = rec ? __ldg(wallrec + (long long)(m * D + d) * g.fs + it.pos) : 0.;
+#pragma unroll
+    for (int d = 0; d < D; ++d) F[d] = F[d] - rho_m * A[d];
+  }
+
+  if (p.body) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) F[d] = F[d] + p.gvt[d] * p.mm[m] * rho_m;
+  }
+
+  if (p.fluidfluid) {
+    using FF = typename L::FF;
+    constexpr int E = ff_entries<L>(ISO);
+    constexpr int RAD = stencil_radius(ISO);
+    double rW[D];
+    static_for<0, D>([&](auto d_) {
+      constexpr int d = decltype(d_)::value;
+      constexpr double bulk = 1.0 / bulk_weight_sum<L, ISO>(d);
+      rW[d] = rec ? __ldg(wallrec + (long long)(S * D + d) * g.fs + it.pos) : bulk;
+    });
+    int dxo[2 * RAD + 1], dyo[2 * RAD + 1];
+    uint32_t words[(E + 31) / 32];
+    if constexpr (ISO != 4) {
+#pragma unroll
+      for (int a = -RAD; a <= RAD; ++a) {
+        dxo[a + RAD] = wrap_delta(x, a, g.NX, g.perx);
+        dyo[a + RAD] = wrap_delta(y, a, g.NY, g.pery) * g.NX;
+      }
+      const long long o = (long long)oe - (long long)g.Rz * g.plane;  // owned dense index
+#pragma unroll
+      for (int w = 0; w < (E + 31) / 32; ++w) words[w] = __ldg(ffmask + (long long)w * g.nnodes + o);
+    }
+    const int plane = (int)g.plane;
+    double G[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) G[d] = 0.;
+    static_for<0, E>([&](auto e_) {
+      constexpr int e = decltype(e_)::value;
+      constexpr int dx = FF::off[e][0], dy = FF::off[e][1], dz = FF::off[e][2];
+      bool on;
+      long long np;
+      if constexpr (ISO == 4) {
+        constexpr int n = dir_of<L>(dx, dy, dz);
+        on = !((mask >> n) & 1u);
+        np = npos[n];
+      } else {
+        on = (words[e / 32] >> (e % 32)) & 1u;
+        np = pos_of(g, (long long)oe + (dz * plane + dyo[dy + RAD] + dxo[dx + RAD]));
+      }
+      constexpr double wgt = L::ffw(ISO, FF::L[e]);
+      const double v = __ldg(psi_field + np);
+      const double diff = on ? v - psi_m : 0.;
+      if constexpr (dx != 0) G[0] = G[0] + ((double)dx * wgt) * diff;
+      if constexpr (dy != 0) G[1] = G[1] + ((double)dy * wgt) * diff;
+      if constexpr (D == 3 && dz != 0) G[D - 1] = G[D - 1] + ((double)dz * wgt) * diff;
+    });
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      // normalised gradient of this lane's component; rW = 0 where the reference skips the direction
+      const double q = G[d] * rW[d];
+      double acc = 0.;
+#pragma unroll
+      for (int k = 0; k < S; ++k) acc += p.gf[m][k] * from_component<S>(q, k, it.j);
+      F[d] = F[d] - 6.0 * psi_m * acc;  // c_0 = 6 on both lattices
+    }
+  }
+}
+
+// K2 forces + collide + push: node populations, forces from the rho stencil, momentum, common velocity,
+// equilibrium, prefactor, SRT/MRT relaxation, forcing term; the post-collision populations are
+// streamed by the store (bounce-back folded in).
+// Replaces LBMAddFluidFluid/FluidSolid/BodyForcesD* (lbm_forcing.F90), DistributionCalcFluxD*
+// (lbm_distribution_function.F90:451-508), FlowUpdateUED* (lbm_flow.F90:494-574),
+// DiscretizationEquilf_*, FlowFiBarEqPrefactor, FlowCollisionD* (lbm_flow.F90:836-1029),
+// RelaxationCollide* (lbm_relaxation.F90:171-200), DistributionStreamD*, DistributionBouncebackD*
+// (lbm_distribution_function.F90:560-784).
+// (order-4 stencil only: its offsets are the lattice directions, so the gathers re-use npos)
+template <class L, int S, bool MRT>
+__global__ void __launch_bounds__(128, 4)
+    k_step_fused(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ rho,
+                 const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr_all,
+                 const double *__restrict__ wallrec, long long first, long long count) {
+  constexpr int Q = L::Q, D = L::D, ISO = 4;
+  Item it;
+  if (!item_of_lane<S>(first, count, it)) return;
+  // adjacency row and mask first: the second round of loads (neighbour densities, wall record)
+  // hangs on them, the populations are not needed until the arithmetic starts
+  const uint32_t mask = __ldg(lmask + it.pos);
+  // positions of the lattice neighbours X + c_n (adjacency table, built once per walls upload)
+  unsigned npos[Q];
+  npos[0] = (unsigned)it.pos;
+#pragma unroll
+  for (int n = 1; n < Q; ++n) npos[n] = __ldg(nbr_all + (long long)(n - 1) * g.fs + it.pos);
+  const long long mo = (long long)it.m * Q * g.fs + it.pos;
+  double f[Q];
+  {
+    const double *src = fA + mo;
+#pragma unroll
+    for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
+  }
+  const double *psi_field = rho + (long long)it.m * g.fs;
+  double r = 0.;
+#pragma unroll
+  for (int n = 0; n < Q; ++n) r += f[n];
+  const double psi_m = p.eos ? __ldg(psi_field + it.pos) : r;
+  double F[D];
+  forces1_inline<L, S, ISO>(g, p, psi_field, nullptr, wallrec, it, 0u, 0, 0, mask, npos, r, psi_m, F);
+  double up[D];
+  common_velocity1<L, S>(p, it, f, r, F, up);
+  collide1<L, MRT>(p, it.m, r, F, up, f);
+  if (!it.active) return;
+  // push: slot (n, pos(X + c_n)), or slot (opp(n), pos(X)) when X + c_n is solid
+  // (element indices inside one component's Q*fs block fit 32 bits: checked in txg_set_walls)
+  double *out = fB + (long long)it.m * Q * g.fs;
+  const unsigned fs = (unsigned)g.fs, here = (unsigned)it.pos;
+  out[here] = f[0];
+  static_for<1, Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    constexpr int on = opp<L>(n);
+    const bool bounce = (mask >> n) & 1u;
+    const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + npos[n];
+    out[e] = f[n];
+  });
+}
+
+// Adjacency table (one thread per owned position): nbr[(n-1)*fs + pos] = position of X + c_n, with
+// the periodic wrap in x and y applied.  For a solid or out-of-domain neighbour the entry is some
+// valid position that the mask bit keeps from being used.
+template <class L>
+__global__ void k_build_nbr_all(Grid g, uint32_t *__restrict__ nbr) {
+  const long long pos = g.own0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= g.own1) return;
+  const unsigned oe = g.list ? g.list[pos] : (unsigned)pos;
+  int x, y;
+  xy_of(g, oe, x, y);
+  const int dxm = wrap_delta(x, -1, g.NX, g.perx), dxp = wrap_delta(x, 1, g.NX, g.perx);
+  const int dym = wrap_delta(y, -1, g.NY, g.pery) * g.NX, dyp = wrap_delta(y, 1, g.NY, g.pery) * g.NX;
+  const int plane = (int)g.plane;
+  static_for<1, L::Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    const int delta = (L::c(n, 0) == 0 ? 0 : (L::c(n, 0) > 0 ? dxp : dxm)) +
+                      (L::c(n, 1) == 0 ? 0 : (L::c(n, 1) > 0 ? dyp : dym)) + L::c(n, 2) * plane;
+    nbr[(long long)(n - 1) * g.fs + pos] = (uint32_t)pos_of(g, (long long)oe + delta);
+  });
+}
+
+}  // namespace txg
