@@ -118,6 +118,7 @@ struct txg_flow {
   // wall records; plane_off[zz] = position of the first fluid node of extended plane zz (NZl+2Rz+1 entries)
   uint32_t *P = nullptr, *list = nullptr, *lmask = nullptr, *nbr = nullptr;
   uint32_t *nbr_all = nullptr;  // [Q-1][fs] every lattice neighbour: the fused path; nbr (centres only) and Fbuf: the split path
+  int pf_blocks = 0;            // L2 prefetch distance of the fused kernel in blocks (TXG_PF)
   bool fused = false;           // forces + collide in one kernel (order-4 stencil; TXG_SPLIT=1 forces the split path)
   double *wallrec = nullptr;    // [S*D + D][fs]
   double *Fbuf = nullptr;       // [S*D][fs] forces of the current step (k_forces -> k_collide)
@@ -408,6 +409,8 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
       return fail(TXG_ERR_LIB);
     }
     h->num_sms = prop.multiProcessorCount;
+    h->pf_blocks = 2 * h->num_sms;  // measured best at 512^3 (0: 11.21 ms, 296: 10.92, 592: 11.15, 888: 11.99)
+    if (const char *pf = getenv("TXG_PF")) h->pf_blocks = atoi(pf);
     const char *sp = getenv("TXG_SPLIT");
     h->fused = h->ks.step_fused != nullptr && !(sp && sp[0] == '1');
   }
@@ -834,7 +837,7 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   if (h->fused) {
     ScopedKernel sk(h, "k_step_fused", s);
     h->ks.step_fused<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask, h->nbr_all,
-                                                           h->wallrec, first, count);
+                                                           h->wallrec, first, count, h->pf_blocks);
     TXG_CUDA(h, cudaGetLastError());
     return 0;
   }

@@ -19,7 +19,7 @@ struct KernelSet {
                   long long);
   // forces + collide in one kernel (order-4 stencil only; nullptr otherwise), fed by the full adjacency table
   void (*step_fused)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
-                     const double *, long long, long long);
+                     const double *, long long, long long, int);
   void (*build_nbr_all)(Grid, uint32_t *);
   void (*build_nbr)(Grid, uint32_t *);
   void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, long long, long long, int);

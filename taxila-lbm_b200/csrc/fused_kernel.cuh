@@ -101,6 +101,40 @@ __device__ __forceinline__ void forces1_inline(const Grid &g, const Phys &p, con
   }
 }
 
+// L2 prefetch of the rows a block of 128 lanes (4 warps x NPW positions) reads at the start of
+// k_step_fused: S*Q population rows, Q-1 adjacency rows and the mask row of positions
+// [first + blk*PB, first + (blk+1)*PB), PB = 4*NPW.  One 128-byte line per lane and round.
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+template <class L, int S>
+__device__ __forceinline__ void prefetch_block_rows(const Grid &g, const double *__restrict__ fA,
+                                                    const uint32_t *__restrict__ lmask,
+                                                    const uint32_t *__restrict__ nbr,
+                                                    const double *__restrict__ wallrec, long long first,
+                                                    long long count, long long blk) {
+  constexpr int Q = L::Q, PB = 4 * Lanes<S>::NPW;
+  constexpr int FL = (PB * 8 + 127) / 128, NL = (PB * 4 + 127) / 128;  // lines per row
+  constexpr int NF = S * Q * FL, NN = (Q - 1) * NL, NW = (S * L::D + L::D) * FL;
+  const int total = NF + NN + NL + (wallrec ? NW : 0);
+  const long long p0 = blk * PB;
+  if (p0 >= count) return;
+  const long long pos = first + p0;
+  for (int t = threadIdx.x; t < total; t += 128) {
+    if (t < NF) {
+      const int row = t / FL, seg = t - row * FL;
+      prefetch_l2(fA + (long long)row * g.fs + pos + seg * 16);
+    } else if (t < NF + NN) {
+      const int u = t - NF, row = u / NL, seg = u - row * NL;
+      prefetch_l2(nbr + (long long)row * g.fs + pos + seg * 32);
+    } else if (t < NF + NN + NL) {
+      prefetch_l2(lmask + pos + (t - NF - NN) * 32);
+    } else {
+      const int u = t - NF - NN - NL, row = u / FL, seg = u - row * FL;
+      prefetch_l2(wallrec + (long long)row * g.fs + pos + seg * 16);
+    }
+  }
+}
+
 // K2 forces + collide + push: node populations, forces from the rho stencil, momentum, common velocity,
 // equilibrium, prefactor, SRT/MRT relaxation, forcing term; the post-collision populations are
 // streamed by the store (bounce-back folded in).
@@ -114,8 +148,11 @@ template <class L, int S, bool MRT>
 __global__ void __launch_bounds__(128, 4)
     k_step_fused(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ rho,
                  const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr_all,
-                 const double *__restrict__ wallrec, long long first, long long count) {
+                 const double *__restrict__ wallrec, long long first, long long count, int pf_blocks) {
   constexpr int Q = L::Q, D = L::D, ISO = 4;
+  // pf_blocks > 0: first ask L2 for the rows (populations, adjacency, mask, wall record) of the block
+  // pf_blocks further on -- about one wave of resident blocks ahead -- so that its demand loads hit L2
+  if (pf_blocks > 0) prefetch_block_rows<L, S>(g, fA, lmask, nbr_all, wallrec, first, count, (long long)blockIdx.x + pf_blocks);
   Item it;
   if (!item_of_lane<S>(first, count, it)) return;
   // adjacency row and mask first: the second round of loads (neighbour densities, wall record)

@@ -165,10 +165,19 @@ class Flow:
         self._check(self.lib.txg_get_state(self.h, _dp(r), _dp(uu), _dp(ff)))
         return r, uu, ff
 
-    def update_diagnostics(self):
-        """FlowUpdateDiagnostics: (rhot[z,y,x], prs[z,y,x], velt[z,y,x,d]) owned only."""
+    def shape_diagnostics(self):
         n = (self.NZl, self.NY, self.NX)
-        rhot, prs, velt = np.zeros(n), np.zeros(n), np.zeros(n + (self.D,))
+        return n, n, n + (self.D,)
+
+    def update_diagnostics(self, out=None):
+        """FlowUpdateDiagnostics: (rhot[z,y,x], prs[z,y,x], velt[z,y,x,d]) owned only.  `out`: the caller's
+        own (rhot, prs, velt) arrays -- the reference writes into its existing Vecs; page-locked
+        arrays make the device-to-host copy run at the full PCIe rate."""
+        if out is None:
+            out = tuple(np.zeros(sh) for sh in self.shape_diagnostics())
+        rhot, prs, velt = out
+        for a, sh, nm in zip(out, self.shape_diagnostics(), ("rhot", "prs", "velt")):
+            self._expect(a, sh, nm)
         self._check(self.lib.txg_get_diagnostics(self.h, _dp(rhot), _dp(prs), _dp(velt)))
         return rhot, prs, velt
 

@@ -94,6 +94,22 @@ def test_porous_mrt_minerals_body(order):
     compare(*cases.porous_3d(40, order=order, rmin=4.0, rmax=9.0), steps=100)
 
 
+def test_porous_split_path_order4(monkeypatch):
+    """The order-4 stencil through the split k_forces + k_collide pair (the default is the fused kernel)."""
+    monkeypatch.setenv("TXG_SPLIT", "1")
+    compare(*cases.porous_3d(40, order=4, rmin=4.0, rmax=9.0), steps=100)
+
+
+def test_bubble_2d_split_path(monkeypatch):
+    monkeypatch.setenv("TXG_SPLIT", "1")
+    compare(*cases.bubble_2d(), steps=100)
+
+
+def test_porous_1000_steps():
+    """The parity bar of SURVEY.md 8d: fields within 1e-10 of the oracle after 1000 steps (C4 recipe, 48^3 crop)."""
+    compare(*cases.porous_3d(48, order=4, rmin=4.0, rmax=9.0), steps=1000)
+
+
 def test_porous_srt_nonperiodic_box():
     """Closed box: every face non-periodic -> 999 ghosts, bounce-back off the ghost layer."""
     compare(*cases.porous_3d(32, mrt=False, rmin=4.0, rmax=8.0, periodic=(0, 0, 0)), steps=60)
