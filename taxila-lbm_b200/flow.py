@@ -181,6 +181,49 @@ class Flow:
         self._check(self.lib.txg_get_diagnostics(self.h, _dp(rhot), _dp(prs), _dp(velt)))
         return rhot, prs, velt
 
+    def output_diagnostics(self, prefix, counter, fi=True, rho=True, velt=True, rhot=True, prs=True):
+        """FlowUpdateDiagnostics + FlowOutputDiagnostics (lbm_flow.F90:576-601, called from LBMOutput,
+        lbm.F90:424-438): <prefix>{fi,rho,u,rhot,prs}NNN.dat as PETSc binary Vecs in DMDA natural ordering
+        (petsc_io.py), so src/testing/check_solution.py and petsc2tec.py read them unchanged.  The velocity
+        file is named `u` like the reference's (it holds velt).  With several ranks every rank writes its
+        z-slab -- one contiguous byte range of the natural ordering -- into the same file; returns the paths."""
+        import os
+
+        from . import geometry as geo
+        from . import petsc_io
+
+        D, S = self.D, self.S
+        NZg = self.cfg.NZ if D == 3 else 1
+        plane = self.NY * self.NX
+        zs = self.cfg.zs if D == 3 else 0
+        fields = {}
+        if fi:
+            fields["fi"] = geo.owned(self.get_fi(), 1, D)
+        if rho:
+            fields["rho"] = geo.owned(self.get_arrays(u=False, forces=False)[0], self.R, D)
+        if velt or rhot or prs:
+            rt, pr, vt = self.update_diagnostics()
+            if velt:
+                fields["u"] = vt
+            if rhot:
+                fields["rhot"] = rt
+            if prs:
+                fields["prs"] = pr
+        paths = []
+        for name, a in fields.items():
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            dof = a.size // (self.NZl * plane)
+            path = petsc_io.output_name(prefix, name, counter)
+            fd = os.open(path, os.O_RDWR | os.O_CREAT, 0o644)
+            try:
+                if self.cfg.rank == 0:
+                    os.pwrite(fd, np.array([petsc_io.VEC_CLASSID, NZg * plane * dof], dtype=">i4").tobytes(), 0)
+                os.pwrite(fd, a.astype(">f8").tobytes(), 8 + zs * plane * dof * 8)
+            finally:
+                os.close(fd)
+            paths.append(path)
+        return paths
+
     def node_class(self):
         out = np.zeros(self.shape_walls(), dtype=np.uint8)
         self._check(self.lib.txg_get_node_class(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8))))

@@ -226,3 +226,30 @@ def test_mass_conservation_large_porous():
     assert np.all(np.abs(m1 - m0) <= 1e-12 * np.abs(m0)), (m0, m1)
     assert np.all(r[~fluid] == 0)
     assert np.isfinite(r).all()
+
+
+def test_output_files_match_reference_golden(tmp_path):
+    """LBMOutput through the device path: fi001.dat of the shipped bubble_2D case, compared the way the
+    reference's `make test` does (src/testing/check_solution.py: max |a - b| < eps = 1e-5) and at round-off."""
+    from pathlib import Path
+
+    from taxila_lbm_b200 import petsc_io
+
+    cfg, walls, rho = cases.bubble_2d()
+    flow = gpu_util.make_flow(cfg, walls, rho)
+    flow.step(100)
+    paths = flow.output_diagnostics(str(tmp_path) + "/", 1)
+    names = sorted(Path(q).name for q in paths)
+    assert names == ["fi001.dat", "prs001.dat", "rho001.dat", "rhot001.dat", "u001.dat"]
+    got = petsc_io.read_vec(tmp_path / "fi001.dat")
+    ref = petsc_io.read_vec(Path(__file__).resolve().parent / "golden" / "bubble_2D_fi001.dat")
+    assert got.size == ref.size
+    assert np.abs(got - ref).max() < 1e-5
+    assert np.abs(got - ref).max() <= 1e-12
+    # rho file = sum over directions of the fi file; rhot = sum over components (mm = 1)
+    fi = got.reshape(128, 128, 9, 2)
+    r = petsc_io.read_vec(tmp_path / "rho001.dat").reshape(128, 128, 2)
+    assert np.abs(r - fi.sum(axis=2)).max() <= 1e-13
+    rt = petsc_io.read_vec(tmp_path / "rhot001.dat").reshape(128, 128)
+    assert np.abs(rt - r.sum(axis=2)).max() <= 1e-13
+    flow.close()
