@@ -180,6 +180,16 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
 
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, extension build chatter) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -213,7 +223,7 @@ def main():
             "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ CUDA arm
@@ -375,7 +385,7 @@ def main():
         "gpu_launches": int(launches) * world, "mass_drift_rel": mass_drift, "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
