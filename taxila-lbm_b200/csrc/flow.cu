@@ -877,7 +877,6 @@ extern "C" int txg_set_fi(txg_handle h, const double *fi_g) {
   if (!fi_g) TXG_FAIL(h, TXG_ERR_ARG_NULL, "txg_set_fi: null fi");
   if (!h->walls_set) TXG_FAIL(h, TXG_ERR_ORDER, "txg_set_fi before txg_set_walls");
   TXG_CUDA(h, cudaSetDevice(h->device));
-  const Grid &g = h->g;
   TXG_TRY(import_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->f[h->cur], 0));
   return state_ready(h);
 }
@@ -1032,7 +1031,6 @@ extern "C" int txg_get_fi(txg_handle h, double *fi_g) {
   if (!fi_g) TXG_FAIL(h, TXG_ERR_ARG_NULL, "null array");
   if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "no state on the device yet");
   TXG_CUDA(h, cudaSetDevice(h->device));
-  const Grid &g = h->g;
   return export_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->S, h->f[h->cur], 0);
 }
 
