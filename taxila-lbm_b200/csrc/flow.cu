@@ -836,8 +836,11 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   if (count == 0) return 0;
   if (h->fused) {
     ScopedKernel sk(h, "k_step_fused", s);
-    h->ks.step_fused<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask, h->nbr_all,
-                                                           h->wallrec, first, count, h->pf_blocks);
+    const int wpb = h->ks.fused_threads / 32;  // warps per block
+    const long long warps = (count + h->ks.npw - 1) / h->ks.npw;
+    h->ks.step_fused<<<(unsigned)((warps + wpb - 1) / wpb), h->ks.fused_threads, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask, h->nbr_all,
+                                                           h->wallrec, first, count,
+                                                           h->ks.fused_threads == 128 ? h->pf_blocks : 0);
     TXG_CUDA(h, cudaGetLastError());
     return 0;
   }
@@ -902,7 +905,15 @@ extern "C" int txg_fi_init(txg_handle h) {
     h->launches++;
   }
   TXG_TRY(exchange_rho(h, h->rho, h->s_main));
-  {
+  if (h->fused) {
+    const long long nown = g.own1 - g.own0;
+    if (nown) {
+      ScopedKernel sk(h, "k_fi_init_fused", h->s_main);
+      h->ks.fi_init_fused<<<hot_blocks(h, nown), 128, 0, h->s_main>>>(g, h->p, h->f[h->cur], h->rho, h->rho_true, h->u0, h->lmask,
+                                                                      h->nbr_all, h->wallrec, g.own0, nown);
+      TXG_CUDA(h, cudaGetLastError());
+    }
+  } else {
     ScopedKernel sk(h, "k_fi_init", h->s_main);
     h->ks.fi_init<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->p, h->f[h->cur], h->rho, h->rho_true, h->u0,
                                                                      h->nbmask, h->ffmask, h->cls, 0, g.NZl);

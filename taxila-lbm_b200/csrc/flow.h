@@ -20,6 +20,8 @@ struct KernelSet {
   // forces + collide in one kernel (order-4 stencil only; nullptr otherwise), fed by the full adjacency table
   void (*step_fused)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
                      const double *, long long, long long, int);
+  void (*fi_init_fused)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
+                        const uint32_t *, const double *, long long, long long);
   void (*build_nbr_all)(Grid, uint32_t *);
   void (*build_nbr)(Grid, uint32_t *);
   void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, long long, long long, int);
@@ -30,6 +32,7 @@ struct KernelSet {
                        const uint8_t *, double *, double *, double *, double *, double *, double *, double, int, int);
   void (*build_masks)(Grid, const uint8_t *, uint32_t *, uint32_t *, int *);
   void (*build_wallrec)(Grid, Phys, const uint8_t *, const uint32_t *, const uint32_t *, double *);
+  int fused_threads;  // block size of step_fused
   int npw;       // fluid nodes per warp of the hot kernels (32 / S)
   int ncen;      // rows of the adjacency table (centre directions)
   int ff_words;  // u32 words of ffmask per node (0 for isotropy order 4)
@@ -49,10 +52,14 @@ KernelSet make_kernel_set(const char *name) {
   k.build_wallrec = k_build_wallrec<L, S, ISO>;
   k.build_nbr = k_build_nbr<L>;
   k.build_nbr_all = k_build_nbr_all<L>;
-  if constexpr (ISO == 4)
+  if constexpr (ISO == 4) {
     k.step_fused = k_step_fused<L, S, MRT>;
-  else
+    k.fi_init_fused = k_fi_init_fused<L, S>;
+  } else {
     k.step_fused = nullptr;
+    k.fi_init_fused = nullptr;
+  }
+  k.fused_threads = TXG_FUSED_THREADS;
   k.npw = Lanes<S>::NPW;
   k.ncen = num_centres<L>();
   k.ff_words = ISO == 4 ? 0 : ff_words<L>(ISO);

@@ -145,7 +145,10 @@ __device__ __forceinline__ void prefetch_block_rows(const Grid &g, const double 
 // (lbm_distribution_function.F90:560-784).
 // (order-4 stencil only: its offsets are the lattice directions, so the gathers re-use npos)
 template <class L, int S, bool MRT>
-__global__ void __launch_bounds__(128, 4)
+#ifndef TXG_FUSED_THREADS
+#define TXG_FUSED_THREADS 128
+#endif
+__global__ void __launch_bounds__(TXG_FUSED_THREADS, 512 / TXG_FUSED_THREADS)
     k_step_fused(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ rho,
                  const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr_all,
                  const double *__restrict__ wallrec, long long first, long long count, int pf_blocks) {
@@ -193,6 +196,47 @@ __global__ void __launch_bounds__(128, 4)
     const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + npos[n];
     out[e] = f[n];
   });
+}
+
+// FlowFiInit for the fused path (FlowFiInit lbm_flow.F90:923-934, FlowFeqBarD* :867-921), one lane per
+// (fluid node, component) like the step kernel: F from rho0 through the same forces routine, then
+// f = (1 - prefactor/2) feq(rho0, u0) into the node's own slots.  u0 is [S][D][nnodes] (dense) or null.
+// (The generic k_fi_init walks the dense box and looks every neighbour up through P: 55 ms at 512^3
+// against one step's 14 ms; this one streams.)
+template <class L, int S>
+__global__ void __launch_bounds__(128, 4)
+    k_fi_init_fused(Grid g, Phys p, double *__restrict__ fN, const double *__restrict__ psi,
+                    const double *__restrict__ rho_true, const double *__restrict__ u0,
+                    const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr_all,
+                    const double *__restrict__ wallrec, long long first, long long count) {
+  constexpr int Q = L::Q, D = L::D;
+  Item it;
+  if (!item_of_lane<S>(first, count, it)) return;
+  const uint32_t mask = __ldg(lmask + it.pos);
+  unsigned npos[Q];
+  npos[0] = (unsigned)it.pos;
+#pragma unroll
+  for (int n = 1; n < Q; ++n) npos[n] = __ldg(nbr_all + (long long)(n - 1) * g.fs + it.pos);
+  const double *psi_field = psi + (long long)it.m * g.fs;
+  const double r = __ldg(rho_true + (long long)it.m * g.fs + it.pos);
+  const double psi_m = __ldg(psi_field + it.pos);
+  double F[D];
+  forces1_inline<L, S, 4>(g, p, psi_field, nullptr, wallrec, it, 0u, 0, 0, mask, npos, r, psi_m, F);
+  double u[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) u[d] = 0.;
+  if (u0) {
+    const long long o = (g.list ? (long long)__ldg(g.list + it.pos) : it.pos) - (long long)g.Rz * g.plane;
+#pragma unroll
+    for (int d = 0; d < D; ++d) u[d] = __ldg(u0 + (long long)(it.m * D + d) * g.nnodes + o);
+  }
+  double feq[Q], pref[Q];
+  equilibrium<L>(r, p.d_k[it.m], u, feq);
+  prefactor<L>(r, F, u, pref);
+  if (!it.active) return;
+  double *dst = fN + (long long)it.m * Q * g.fs + it.pos;
+#pragma unroll
+  for (int n = 0; n < Q; ++n) dst[(long long)n * g.fs] = (1. - 0.5 * pref[n]) * feq[n];
 }
 
 // Adjacency table (one thread per owned position): nbr[(n-1)*fs + pos] = position of X + c_n, with

@@ -110,6 +110,46 @@ def test_porous_1000_steps():
     compare(*cases.porous_3d(48, order=4, rmin=4.0, rmax=9.0), steps=1000)
 
 
+@pytest.mark.parametrize("split", [False, True])
+def test_porous_shan_chen_eos(monkeypatch, split):
+    """-flow_use_nonideal_eos with EOS_SC psi = rho0 (1 - exp(-rho / rho0)) (lbm_eos.F90:183-229): psi
+    replaces rho in the fluid-fluid stencil only; fused and split kernels."""
+    if split:
+        monkeypatch.setenv("TXG_SPLIT", "1")
+    cfg, walls, rho = cases.porous_3d(32, order=4, rmin=4.0, rmax=8.0)
+    cfg.use_nonideal_eos = 1
+    for m in range(2):
+        cfg.eos_type[m] = tc.EOS_SC
+        cfg.eos_rho0[m] = 0.8 + 0.3 * m
+    compare(cfg, walls, rho, steps=60)
+
+
+def test_three_components_mrt():
+    """S = 3: 10 nodes x 3 components per warp (two spare lanes), 3 x 3 coupling matrix, minerals."""
+    cfg = tc.default_config(3, 3, 24, 24, 24)
+    for d in range(3):
+        cfg.periodic[d] = 1
+    cfg.relaxation_mode = tc.RELAXATION_MODE_MRT
+    for m in range(3):
+        cfg.s_e[m], cfg.s_e2[m], cfg.s_q[m], cfg.s_pi[m], cfg.s_m[m] = 1.19, 1.4, 1.2, 1.4, 1.98
+        cfg.mm[m] = 1.0 + 0.25 * m
+        for k in range(3):
+            if k != m:
+                cfg.gf[m][k] = 0.05 + 0.01 * (m + k)
+    cfg.nminerals = 2
+    for k in range(2):
+        for m in range(3):
+            cfg.gw[k][m] = 0.01 * (k + 1) * (m - 1)
+    cfg.body_forces = 1
+    cfg.gvt[2] = 1e-5
+    tc.finalize_flags(cfg)
+    walls = geo.porous_spheres(24, 24, 24, seed=11, rmin=3.0, rmax=6.0, solid_fraction=0.4, nminerals=2)
+    rng = np.random.default_rng(5)
+    rho = 0.2 + 0.6 * rng.random((24, 24, 24, 3))
+    rho[walls != 0] = 0.0
+    compare(cfg, walls, rho, steps=50)
+
+
 def test_porous_srt_nonperiodic_box():
     """Closed box: every face non-periodic -> 999 ghosts, bounce-back off the ghost layer."""
     compare(*cases.porous_3d(32, mrt=False, rmin=4.0, rmax=8.0, periodic=(0, 0, 0)), steps=60)
