@@ -126,6 +126,7 @@ struct txg_flow {
   size_t halo_recv_doubles = 0;
   std::vector<long long> plane_off;
   long long nstore = 0;
+  long long alloc_nstore = -1;  // fluid-node count the position-indexed arrays are allocated for
   int *counters = nullptr;  // [0] bad wall codes, [1] fluid nodes next to 900-902 walls
   double *staging = nullptr;
   size_t staging_bytes = 0;
@@ -658,8 +659,10 @@ static int export_field(txg_flow *h, double *host, int gw, int gwz, int K, int S
 // Positions of the fluid nodes of the extended slab: count per 256-slot chunk of each plane, scan the
 // chunk counts on the host ((NZl+2Rz) * plane/256 integers), fill P and list with a ballot rank
 // inside each chunk.  Then size and allocate every position-indexed array.
-static int build_storage(txg_flow *h) {
-  Grid &g = h->g;
+// device arrays sized by the fluid-node count: freed and re-allocated only when that count changes (a
+// second walls upload with the same geometry -- the reference calls WallsSetValues once, a driver that
+// re-initialises a run does not pay for 40 GB of cudaFree / cudaMalloc)
+static void free_storage(txg_flow *h) {
   for (void **q : {(void **)&h->P, (void **)&h->list, (void **)&h->lmask, (void **)&h->nbr, (void **)&h->nbr_all, (void **)&h->wallrec, (void **)&h->Fbuf, (void **)&h->f[0],
                    (void **)&h->f[1], (void **)&h->rho, (void **)&h->f_old}) {
     if (*q) cudaFree(*q);
@@ -667,6 +670,17 @@ static int build_storage(txg_flow *h) {
   }
   if (h->rho_true && h->cfg.use_nonideal_eos) cudaFree(h->rho_true);
   h->rho_true = nullptr;
+  h->alloc_nstore = -1;
+}
+// zeroed array of `bytes`: the existing allocation when the storage is being re-used
+static int fresh_zero(txg_flow *h, void **p, size_t bytes) {
+  if (!*p) TXG_CUDA(h, cudaMalloc(p, bytes));
+  TXG_CUDA(h, cudaMemsetAsync(*p, 0, bytes, h->s_main));
+  return 0;
+}
+
+static int build_storage(txg_flow *h) {
+  Grid &g = h->g;
   h->have_old = false;
   h->state_set = false;
   g.P = g.list = nullptr;
@@ -699,10 +713,14 @@ static int build_storage(txg_flow *h) {
     cudaFree(d_cnt);
     TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "%lld fluid nodes in the slab: the %d populations of one component exceed the 32-bit element index; use more z-slabs", run, h->Q);
   }
+  if (h->alloc_nstore != run) {
+    free_storage(h);
+    h->alloc_nstore = run;
+  }
   if (run != g.nE) {
     TXG_CUDA(h, cudaMemcpyAsync(d_cnt, cnt.data(), (size_t)nchunks * sizeof(unsigned), cudaMemcpyHostToDevice, h->s_main));
-    TXG_CUDA(h, cudaMalloc((void **)&h->P, (size_t)(g.nE + 1) * sizeof(uint32_t)));
-    TXG_CUDA(h, cudaMalloc((void **)&h->list, (size_t)std::max<long long>(run, 1) * sizeof(uint32_t)));
+    if (!h->P) TXG_CUDA(h, cudaMalloc((void **)&h->P, (size_t)(g.nE + 1) * sizeof(uint32_t)));
+    if (!h->list) TXG_CUDA(h, cudaMalloc((void **)&h->list, (size_t)std::max<long long>(run, 1) * sizeof(uint32_t)));
     k_fill_fluid<<<(unsigned)nchunks, 256, 0, h->s_main>>>(g, h->cls, bpp, d_cnt, h->P, h->list);
     TXG_CUDA(h, cudaGetLastError());
     const uint32_t total = (uint32_t)run;
@@ -714,22 +732,24 @@ static int build_storage(txg_flow *h) {
   cudaFree(d_cnt);
   // position-indexed arrays
   const size_t fbytes = (size_t)h->S * h->Q * g.fs * sizeof(double);
-  TXG_TRY(alloc_zero(h, (void **)&h->f[0], fbytes));
-  TXG_TRY(alloc_zero(h, (void **)&h->f[1], fbytes));
+  TXG_TRY(fresh_zero(h, (void **)&h->f[0], fbytes));
+  TXG_TRY(fresh_zero(h, (void **)&h->f[1], fbytes));
   h->cur = 0;
-  TXG_TRY(alloc_zero(h, (void **)&h->rho, (size_t)h->S * g.fs * sizeof(double)));
-  if (h->cfg.use_nonideal_eos)
-    TXG_TRY(alloc_zero(h, (void **)&h->rho_true, (size_t)h->S * g.fs * sizeof(double)));
-  else
+  TXG_TRY(fresh_zero(h, (void **)&h->rho, (size_t)h->S * g.fs * sizeof(double)));
+  if (h->cfg.use_nonideal_eos) {
+    if (h->rho_true == h->rho) h->rho_true = nullptr;
+    TXG_TRY(fresh_zero(h, (void **)&h->rho_true, (size_t)h->S * g.fs * sizeof(double)));
+  } else {
     h->rho_true = h->rho;
-  if (!h->fused) TXG_TRY(alloc_zero(h, (void **)&h->Fbuf, (size_t)h->S * h->D * g.fs * sizeof(double)));
-  TXG_TRY(alloc_zero(h, (void **)&h->lmask, (size_t)g.fs * sizeof(uint32_t)));
+  }
+  if (!h->fused) TXG_TRY(fresh_zero(h, (void **)&h->Fbuf, (size_t)h->S * h->D * g.fs * sizeof(double)));
+  TXG_TRY(fresh_zero(h, (void **)&h->lmask, (size_t)g.fs * sizeof(uint32_t)));
   const long long nown = g.own1 - g.own0;
   int nrec = 0;
   if (h->fused)
-    TXG_TRY(alloc_zero(h, (void **)&h->nbr_all, (size_t)(h->Q - 1) * g.fs * sizeof(uint32_t)));
+    TXG_TRY(fresh_zero(h, (void **)&h->nbr_all, (size_t)(h->Q - 1) * g.fs * sizeof(uint32_t)));
   else
-    TXG_TRY(alloc_zero(h, (void **)&h->nbr, (size_t)h->ks.ncen * g.fs * sizeof(uint32_t)));
+    TXG_TRY(fresh_zero(h, (void **)&h->nbr, (size_t)h->ks.ncen * g.fs * sizeof(uint32_t)));
   if (nown) {
     if (h->fused)
       h->ks.build_nbr_all<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->nbr_all);
@@ -744,7 +764,7 @@ static int build_storage(txg_flow *h) {
   }
   if (nrec) {
     const size_t nk = (size_t)(h->S * h->D + h->D);
-    TXG_TRY(alloc_zero(h, (void **)&h->wallrec, nk * (size_t)g.fs * sizeof(double)));
+    TXG_TRY(fresh_zero(h, (void **)&h->wallrec, nk * (size_t)g.fs * sizeof(double)));
     h->ks.build_wallrec<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->p, h->cls, h->lmask, h->ffmask, h->wallrec);
     TXG_CUDA(h, cudaGetLastError());
   }
