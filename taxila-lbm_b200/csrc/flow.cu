@@ -507,7 +507,7 @@ static int exchange(txg_flow *h, double *buf, const std::vector<Chunk> &to_up, c
         if (c.send_count)
           TXG_CUDA(h, cudaMemcpyAsync(buf + c.recv_off, buf + c.send_off, c.send_count * sizeof(double), cudaMemcpyDeviceToDevice, s));
       }
-    h->launches += (int64_t)(to_up.size() + to_down.size());
+    // (device-to-device copies, not kernels: not counted in `launches`)
     return 0;
   }
   if (!h->comm) TXG_FAIL(h, TXG_ERR_ORDER, "nranks > 1 but txg_comm_init was not called");
