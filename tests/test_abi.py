@@ -54,3 +54,37 @@ def test_product_never_imports_the_oracle():
         assert "oracle" not in f.read_text().lower(), f
     for f in (ROOT / "taxila-lbm_b200" / "csrc").glob("*.cu*"):
         assert "taxila_oracle" not in f.read_text(), f
+
+
+def _c_config_fields():
+    text = (ROOT / "include" / "taxila_gpu.h").read_text()
+    body = text[text.index("typedef struct txg_config {") + len("typedef struct txg_config {"):text.index("} txg_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        m = re.match(r"\s*(?:int32_t|double)\s+(.*)$", decl.strip(), flags=re.S)
+        if m:
+            for part in m.group(1).split(","):
+                names.append(re.match(r"\s*(\w+)", part).group(1))
+    return names
+
+
+def _f90_config_fields():
+    text = (ROOT / "shim" / "lbm_gpu_binding.F90").read_text()
+    body = text[text.index("type, bind(C), public :: txg_config"):text.index("end type txg_config")]
+    names = []
+    for line in body.splitlines()[1:]:
+        line = line.split("!")[0]
+        if "::" in line:
+            for part in re.split(r",(?![^()]*\))", line.split("::")[1]):
+                names.append(re.match(r"\s*(\w+)", part).group(1))
+    return names
+
+
+def test_fortran_binding_mirrors_the_header():
+    """shim/lbm_gpu_binding.F90 (not compilable in this image): same struct fields in the same order, and one
+    bind(C) interface per exported function."""
+    assert _f90_config_fields() == _c_config_fields()
+    text = (ROOT / "shim" / "lbm_gpu_binding.F90").read_text()
+    bound = sorted(set(re.findall(r'bind\(C, name="(txg_\w+)"\)', text)))
+    assert bound == declared_symbols()
