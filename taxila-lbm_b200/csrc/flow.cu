@@ -410,7 +410,8 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
       return fail(TXG_ERR_LIB);
     }
     h->num_sms = prop.multiProcessorCount;
-    h->pf_blocks = 2 * h->num_sms;  // measured best at 512^3 (0: 11.21 ms, 296: 10.92, 592: 11.15, 888: 11.99)
+    // measured at 512^3 porous, k_step_fused ms: 0: 11.21, 148: 10.83, 222: 10.84, 296: 10.89, 444: 11.01, 592: 11.15, 888: 11.99
+    h->pf_blocks = h->num_sms;
     if (const char *pf = getenv("TXG_PF")) h->pf_blocks = atoi(pf);
     const char *sp = getenv("TXG_SPLIT");
     h->fused = h->ks.step_fused != nullptr && !(sp && sp[0] == '1');
