@@ -61,6 +61,19 @@ extern "C" {
 #define TXG_WALL_NORMAL_Y 901.0
 #define TXG_WALL_NORMAL_Z 902.0
 #define TXG_WALL_GHOST 999.0
+/* bc%flags values (lbm_definitions.h:29-35) and boundary numbers (:45-50, here 0-based) */
+#define TXG_BC_NULL 0
+#define TXG_BC_PERIODIC 1
+#define TXG_BC_REFLECTING 2
+#define TXG_BC_DIRICHLET 3
+#define TXG_BC_NEUMANN 4
+#define TXG_BC_VELOCITY 5
+#define TXG_BOUNDARY_XM 0
+#define TXG_BOUNDARY_XP 1
+#define TXG_BOUNDARY_YM 2
+#define TXG_BOUNDARY_YP 3
+#define TXG_BOUNDARY_ZM 4
+#define TXG_BOUNDARY_ZP 5
 /* device node classes (u8) the wall codes are mapped to, one-to-one */
 #define TXG_CLASS_PORE 0u          /* 1..100 = mineral id, unchanged */
 #define TXG_CLASS_NORMAL_X 250u
@@ -94,7 +107,7 @@ typedef struct txg_config {
   int32_t use_nonideal_eos; /* flow%use_nonideal_eos, lbm_options.F90:142           */
   int32_t eos_type[TXG_NMAX_COMPONENTS]; /* TXG_EOS_*; only DENSITY and SC on device */
   int32_t rank, nranks;     /* position in the z-slab ring                          */
-  int32_t reserved_i[6];
+  int32_t bc_flags[6];      /* bc%flags(BOUNDARY_XM..ZP), lbm_bc.F90:36: TXG_BC_*; 0 = none  */
   /* per component m (relaxation_type, component_type) */
   double tau[TXG_NMAX_COMPONENTS];   /* SRT; s_c = 1/tau (lbm_relaxation.F90:133)   */
   double s_c[TXG_NMAX_COMPONENTS];   /* MRT rates, lbm_relaxation.F90:134-149       */
@@ -143,6 +156,18 @@ TXG_API int txg_comm_init(txg_handle h, const unsigned char id[128]);
  * walls(rg..) array of doubles.  Classified into u8 node classes on the device. */
 TXG_API int txg_set_walls(txg_handle h, const double *walls_rg);
 
+/* BCSetValues result (lbm_bc.F90:215-228; filled by the user's initialize_bcs or by
+ * FlowSetUpBCsD2/D3, lbm_flow.F90:1311-1956): the face array of boundary
+ * `boundary` (TXG_BOUNDARY_*), this rank's part, in the reference's own layout
+ *   xm/xp_vals(nbcs, ys:ye[, zs:ze])  ym/yp_vals(nbcs, xs:xe[, zs:ze])  zm/zp_vals(nbcs, xs:xe, ys:ye)
+ * with nbcs = ndims * ncomponents (lbm_flow.F90:245) viewed by the node routines
+ * as (S, ndims): densities in (m,1) for BC_DIRICHLET, momentum (m,d) for BC_NEUMANN,
+ * velocity (1,d) for BC_VELOCITY (lbm_bc.F90:1273-1333,1533-1593,1793-1865).
+ * Only faces whose bc_flags entry is DIRICHLET / NEUMANN / VELOCITY read values.
+ * May be called again at any time (the outlet updates of FlowApplyBCs,
+ * lbm_flow.F90:1958-1991, stay on the host and re-upload). */
+TXG_API int txg_set_bc_values(txg_handle h, int boundary, const double *vals);
+
 /* LBMInitializeState result (lbm.F90:444-453): host rho(S,rg..) and u(S,ndims,g..)
  * as filled by the user's initialize_state.  u may be NULL (= 0, what every
  * shipped initialize_state sets). */
@@ -160,8 +185,10 @@ TXG_API int txg_fi_init(txg_handle h);
 TXG_API int txg_update_moments(txg_handle h);
 
 /* LBMRun2 inner body (lbm.F90:286-361), nsteps times: FlowCollision,
- * DistributionCommunicateFi, FlowStream, FlowBounceback, FlowApplyBCs (periodic /
- * bounce-back faces), FlowUpdateFlux.  Asynchronous on the handle's streams. */
+ * DistributionCommunicateFi, FlowStream (BCPreStream + stream), FlowBounceback
+ * (plain and free-slip 900-902 walls), FlowApplyBCs (FlowCalcRhoForces, BCApply,
+ * BCUpdateRho for the faces flagged in bc_flags), FlowUpdateFlux.  Asynchronous on
+ * the handle's streams. */
 TXG_API int txg_step(txg_handle h, int nsteps);
 
 /* The six reference procedures individually, for a shim that keeps LBMRun2's

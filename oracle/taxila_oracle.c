@@ -71,6 +71,9 @@ typedef struct txo_state {
   double *fi_old; /* DistributionCalcDeltaNorm */
   int have_old;
   int threads; /* 1 = literal serial order everywhere */
+  /* external boundary conditions (bc_type, lbm_bc.F90:32-48): flags in cfg.bc_flags */
+  double *bc_vals[6]; /* face arrays xm,xp,ym,yp,zm,zp: [t2][t1][nbcs], nbcs = D*S */
+  int prestream;      /* 1 (default): BCPreStream runs as in the reference; 0: skipped (test of its effect) */
 } txo_state;
 
 /* ---------------------------------------------------------------- indexing */
@@ -265,6 +268,7 @@ txo_state *txo_create(const txg_config *cfg) {
   s->walls = (double *)calloc(nrg, sizeof(double));
   s->fi_old = NULL;
   s->threads = 1;
+  s->prestream = 1;
   return s;
 }
 
@@ -279,6 +283,7 @@ void txo_destroy(txo_state *s) {
   free(s->forces);
   free(s->walls);
   free(s->fi_old);
+  for (int b = 0; b < 6; ++b) free(s->bc_vals[b]);
   free(s);
 }
 
@@ -723,19 +728,293 @@ void txo_update_moments(txo_state *s) {
   update_ue(s);
 }
 
+/* ---------------------------------------------------------------- external boundary conditions
+ * lbm_bc.F90.  A face is addressed by its boundary number b = 0..5 (XM, XP, YM, YP, ZM, ZP;
+ * lbm_definitions.h:45-50 minus one).  The node routines are written for one boundary and rotated
+ * onto the others through DiscSetLocalDirections (lbm_discretization_d3q19.F90:566-714,
+ * lbm_discretization_d2q9.F90:372-434); the only thing they take from the rotation is
+ * ci(directions(local_normal), cardinals(CARDINAL_NORMAL)), which is the INWARD normal sign on
+ * every boundary of both lattices (local_normal = UP / SOUTH, :81 / :67), and the set of
+ * tangential axes, each of which is treated independently. */
+typedef struct {
+  int axis, sign, coord; /* normal axis, inward sign, index of the face plane */
+  int t1, t2, n1, n2;    /* tangential axes (t1 fastest in the face array) and their extents */
+} txo_face;
+
+static txo_face face_of(const txo_state *s, int b) {
+  const int N[3] = {s->NX, s->NY, s->NZ};
+  txo_face f;
+  f.axis = b / 2;
+  f.sign = (b % 2 == 0) ? 1 : -1;
+  f.coord = (b % 2 == 0) ? 0 : N[f.axis] - 1;
+  f.t1 = f.axis == 0 ? 1 : 0;
+  f.t2 = f.axis == 2 ? 1 : 2;
+  f.n1 = N[f.t1];
+  f.n2 = s->D == 3 ? N[f.t2] : 1;
+  return f;
+}
+static inline void face_node(const txo_face *f, int a, int b, int ijk[3]) {
+  ijk[f->axis] = f->coord;
+  ijk[f->t1] = a;
+  ijk[f->t2] = b;
+}
+static inline int bc_active(const txo_state *s, int b) {
+  const int fl = s->cfg.bc_flags[b];
+  return b < 2 * s->D && (fl == TXG_BC_DIRICHLET || fl == TXG_BC_NEUMANN || fl == TXG_BC_VELOCITY);
+}
+
+/* BCSetValues (lbm_bc.F90:215-228): the face array of one boundary in the reference's layout */
+void txo_set_bc_values(txo_state *s, int b, const double *vals) {
+  const txo_face f = face_of(s, b);
+  const size_t n = (size_t)f.n1 * f.n2 * s->D * s->S;
+  free(s->bc_vals[b]);
+  s->bc_vals[b] = (double *)malloc(n * sizeof(double));
+  memcpy(s->bc_vals[b], vals, n * sizeof(double));
+}
+void txo_set_prestream(txo_state *s, int on) { s->prestream = on; }
+
+/* BCPreStream -> BCPreStream_D2/D3, lbm_bc.F90:613-779: on a Dirichlet / Neumann / velocity face every
+ * population with a component along the inward normal is copied from the face node X into X - c_n (a
+ * ghost node), so that the stream brings it back.  No wall test, whole owned face. */
+static void bc_prestream(txo_state *s) {
+  for (int b = 0; b < 2 * s->D; ++b) {
+    if (!bc_active(s, b)) continue;
+    const txo_face f = face_of(s, b);
+    for (int n = 1; n < s->Q; ++n) {
+      if (s->ci[n][f.axis] * f.sign <= 0) continue;
+      for (int bb = 0; bb < f.n2; ++bb)
+        for (int a = 0; a < f.n1; ++a) {
+          int x[3] = {0, 0, 0};
+          face_node(&f, a, bb, x);
+          for (int m = 0; m < s->S; ++m)
+            FI(s, m, n, x[0] - s->ci[n][0], x[1] - s->ci[n][1], x[2] - s->ci[n][2]) = FI(s, m, n, x[0], x[1], x[2]);
+        }
+    }
+  }
+}
+
+/* BCApplyDirichletToRho -> _D2/_D3, lbm_bc.F90:252-434 */
+static void bc_dirichlet_to_rho(txo_state *s) {
+  const int nbcs = s->D * s->S;
+  for (int b = 0; b < 2 * s->D; ++b) {
+    if (s->cfg.bc_flags[b] != TXG_BC_DIRICHLET) continue;
+    const txo_face f = face_of(s, b);
+    for (int bb = 0; bb < f.n2; ++bb)
+      for (int a = 0; a < f.n1; ++a) {
+        int x[3] = {0, 0, 0};
+        face_node(&f, a, bb, x);
+        if (WALLS(s, x[0], x[1], x[2]) != 0.) continue;
+        const double *v = s->bc_vals[b] + ((size_t)bb * f.n1 + a) * nbcs;
+        for (int m = 0; m < s->S; ++m) RHO(s, m, x[0], x[1], x[2]) = v[m];
+      }
+  }
+}
+
+/* BCUpdateRho -> _D2/_D3, lbm_bc.F90:436-611: rho = sum(fi(m,:)) on the fluid nodes of every
+ * Dirichlet / Neumann / velocity face */
+static void bc_update_rho(txo_state *s) {
+  for (int b = 0; b < 2 * s->D; ++b) {
+    if (!bc_active(s, b)) continue;
+    const txo_face f = face_of(s, b);
+    for (int bb = 0; bb < f.n2; ++bb)
+      for (int a = 0; a < f.n1; ++a) {
+        int x[3] = {0, 0, 0};
+        face_node(&f, a, bb, x);
+        if (WALLS(s, x[0], x[1], x[2]) != 0.) continue;
+        for (int m = 0; m < s->S; ++m) {
+          double acc = 0.;
+          for (int n = 0; n < s->Q; ++n) acc += FI(s, m, n, x[0], x[1], x[2]);
+          RHO(s, m, x[0], x[1], x[2]) = acc;
+        }
+      }
+  }
+}
+
+/* "incoming": c_n has a component along the inward normal
+ * (ci(local_normal, normal) * ci(n, normal) .eq. 1, lbm_bc.F90:1300) */
+static inline int incoming(const txo_state *s, const txo_face *f, int n) { return f->sign * s->ci[n][f->axis] == 1; }
+
+/* the shared tail of the three node routines: fi(m,n) += w_n sum_d c_n,d Q_d on the incoming directions */
+static void bc_distribute(const txo_state *s, const txo_face *f, double *fi_m /* stride S */, const double Q[3]) {
+  for (int n = 1; n < s->Q; ++n)
+    if (incoming(s, f, n)) {
+      double acc = 0.;
+      for (int d = 0; d < s->D; ++d) acc += s->ci[n][d] * Q[d];
+      fi_m[(size_t)n * s->S] = fi_m[(size_t)n * s->S] + s->weights[n] * acc;
+    }
+}
+static double bc_sum_fi(const txo_state *s, const double *fi_m) {
+  double acc = 0.;
+  for (int n = 0; n < s->Q; ++n) acc += fi_m[(size_t)n * s->S];
+  return acc;
+}
+
+/* BCApplyDirichletNode, lbm_bc.F90:1273-1333.  pvals(m,1) = v[m]. */
+static void bc_dirichlet_node(const txo_state *s, const txo_face *f, double *fi, const double *v) {
+  const int D = s->D, S = s->S, N = f->axis;
+  for (int m = 0; m < S; ++m) {
+    double *fm = fi + m;
+    double Q[3] = {0., 0., 0.}, weightsum[3] = {0., 0., 0.}, momentum[3] = {0., 0., 0.};
+    for (int n = 1; n < s->Q; ++n)
+      if (incoming(s, f, n)) weightsum[N] = weightsum[N] + s->weights[n];
+    Q[N] = f->sign * (v[m] - bc_sum_fi(s, fm)) / weightsum[N];
+    for (int p = 0; p < D; ++p) {
+      if (p == N) continue;
+      for (int n = 1; n < s->Q; ++n) {
+        momentum[p] = momentum[p] + fm[(size_t)n * S] * s->ci[n][p];
+        if (incoming(s, f, n) && s->ci[n][p] != 0) weightsum[p] = weightsum[p] + s->weights[n];
+      }
+      Q[p] = -momentum[p] / weightsum[p];
+    }
+    bc_distribute(s, f, fm, Q);
+  }
+}
+
+/* BCApplyNeumannNode, lbm_bc.F90:1533-1593.  mvals(m,p) = v[p*S + m]. */
+static void bc_neumann_node(const txo_state *s, const txo_face *f, double *fi, const double *frc, const double *v) {
+  const int D = s->D, S = s->S;
+  for (int m = 0; m < S; ++m) {
+    double *fm = fi + m;
+    double Q[3] = {0., 0., 0.}, weightsum[3] = {0., 0., 0.}, momentum[3] = {0., 0., 0.};
+    for (int p = 0; p < D; ++p) {
+      for (int n = 1; n < s->Q; ++n) {
+        momentum[p] = momentum[p] + fm[(size_t)n * S] * s->ci[n][p];
+        if (incoming(s, f, n) && s->ci[n][p] != 0) weightsum[p] = weightsum[p] + s->weights[n];
+      }
+      Q[p] = (v[p * S + m] - frc[p * S + m] / 2. - momentum[p]) / weightsum[p];
+    }
+    bc_distribute(s, f, fm, Q);
+  }
+}
+
+/* BCApplyVelocityNode, lbm_bc.F90:1793-1865.  uvals(1,p) = v[p*S]: every component takes the
+ * velocity row of the first one. */
+static void bc_velocity_node(const txo_state *s, const txo_face *f, double *fi, const double *frc, const double *v) {
+  const int D = s->D, S = s->S, N = f->axis;
+  for (int m = 0; m < S; ++m) {
+    double *fm = fi + m;
+    double Q[3] = {0., 0., 0.}, weightsum[3] = {0., 0., 0.}, momentum[3] = {0., 0., 0.};
+    for (int n = 1; n < s->Q; ++n) {
+      momentum[N] = momentum[N] + fm[(size_t)n * S] * s->ci[n][N];
+      if (incoming(s, f, n)) weightsum[N] = weightsum[N] + s->weights[n];
+    }
+    const double uN = v[N * S];
+    Q[N] = (bc_sum_fi(s, fm) * uN - momentum[N] - frc[N * S + m] / 2.) / (1. - f->sign * uN) / weightsum[N];
+    const double rho = bc_sum_fi(s, fm) + weightsum[N] * Q[N] * f->sign;
+    for (int p = 0; p < D; ++p) {
+      if (p == N) continue;
+      for (int n = 1; n < s->Q; ++n) {
+        momentum[p] = momentum[p] + fm[(size_t)n * S] * s->ci[n][p];
+        if (incoming(s, f, n) && s->ci[n][p] != 0) weightsum[p] = weightsum[p] + s->weights[n];
+      }
+      Q[p] = (rho * v[p * S] - frc[p * S + m] / 2. - momentum[p]) / weightsum[p];
+    }
+    bc_distribute(s, f, fm, Q);
+  }
+}
+
+/* BCApplyReflectingD3/D2, lbm_bc.F90:825-1073: fi(:,n) = fi(:,p) for every incoming n and every p
+ * (ascending, assignments in sequence) that passes the face's own test.  The tests are restated
+ * face by face because two of them are not the mirror rule: XM in 3-D compares ci(n,X) with
+ * -ci(p,Z) (:849), and XM in 2-D reads ci(p,Z_DIRECTION) of a two-column array (:1001, out of
+ * bounds in the reference -> rejected by txo_bc_supported). */
+static int reflecting_match(const txo_state *s, int b, int n, int p) {
+  const int(*c)[3] = s->ci;
+  if (s->D == 3) switch (b) {
+      case 0: return c[n][1] == c[p][1] && c[n][2] == c[p][2] && c[n][0] == -c[p][2];
+      case 1: return c[n][1] == c[p][1] && c[n][2] == c[p][2] && c[n][0] == -c[p][0];
+      case 2:
+      case 3: return c[n][0] == c[p][0] && c[n][2] == c[p][2] && c[n][1] == -c[p][1];
+      default: return c[n][0] == c[p][0] && c[n][1] == c[p][1] && c[n][2] == -c[p][2];
+    }
+  switch (b) {
+    case 1: return c[n][1] == c[p][1] && c[n][0] == -c[p][0];
+    case 2:
+    case 3: return c[n][0] == c[p][0] && c[n][1] == -c[p][1];
+    default: return 0;
+  }
+}
+int txo_bc_supported(const txo_state *s) {
+  return !(s->D == 2 && s->cfg.bc_flags[TXG_BOUNDARY_XM] == TXG_BC_REFLECTING);
+}
+/* the (n <- p) assignment list of one reflecting face, in execution order; returns the count */
+int txo_reflecting_pairs(const txo_state *s, int b, int *n_out, int *p_out) {
+  const txo_face f = face_of(s, b);
+  int k = 0;
+  for (int n = 1; n < s->Q; ++n) {
+    if (f.sign * s->ci[n][f.axis] <= 0) continue;
+    for (int p = 1; p < s->Q; ++p)
+      if (reflecting_match(s, b, n, p)) {
+        n_out[k] = n;
+        p_out[k] = p;
+        ++k;
+      }
+  }
+  return k;
+}
+
+/* BCApply, lbm_bc.F90:781-807: every BC type once, in the order of its first face; inside a type
+ * the faces in the order XM, XP, YM, YP, ZM, ZP (BCApplyDirichletD3 etc.). */
+static void bc_apply(txo_state *s) {
+  int done[16] = {0};
+  done[TXG_BC_PERIODIC] = 1;
+  done[TXG_BC_NULL] = 1; /* select case has no branch for BC_NULL */
+  const int nbcs = s->D * s->S, SD = s->S * s->D, SQ = s->S * s->Q;
+  for (int side = 0; side < 6; ++side) {
+    const int type = side < 2 * s->D ? s->cfg.bc_flags[side] : TXG_BC_NULL;
+    if (type < 0 || type > 15 || done[type]) continue;
+    done[type] = 1;
+    for (int b = 0; b < 2 * s->D; ++b) {
+      if (s->cfg.bc_flags[b] != type) continue;
+      const txo_face f = face_of(s, b);
+      int rn[64], rp[64], nr = 0;
+      if (type == TXG_BC_REFLECTING) nr = txo_reflecting_pairs(s, b, rn, rp);
+      for (int bb = 0; bb < f.n2; ++bb)
+        for (int a = 0; a < f.n1; ++a) {
+          int x[3] = {0, 0, 0};
+          face_node(&f, a, bb, x);
+          if (WALLS(s, x[0], x[1], x[2]) != 0.) continue;
+          double *fi = &FI(s, 0, 0, x[0], x[1], x[2]);
+          const double *frc = s->forces + gnode(s, x[0], x[1], x[2]) * (size_t)SD;
+          const double *v = s->bc_vals[b] ? s->bc_vals[b] + ((size_t)bb * f.n1 + a) * nbcs : NULL;
+          (void)SQ;
+          if (type == TXG_BC_REFLECTING) {
+            for (int e = 0; e < nr; ++e)
+              for (int m = 0; m < s->S; ++m) fi[(size_t)rn[e] * s->S + m] = fi[(size_t)rp[e] * s->S + m];
+          } else if (type == TXG_BC_DIRICHLET) {
+            bc_dirichlet_node(s, &f, fi, v);
+          } else if (type == TXG_BC_NEUMANN) {
+            bc_neumann_node(s, &f, fi, frc, v);
+          } else if (type == TXG_BC_VELOCITY) {
+            bc_velocity_node(s, &f, fi, frc, v);
+          }
+        }
+    }
+  }
+}
+
 /* ---------------------------------------------------------------- time step
- * LBMRun2 body, lbm.F90:286-361, for periodic / bounce-back faces:
- * FlowCollision; DistributionCommunicateFi; FlowStream; FlowBounceback;
- * FlowApplyBCs (= FlowCalcRhoForces, lbm_flow.F90:445-456,1958-1991);
+ * LBMRun2 body, lbm.F90:286-361:
+ * FlowCollision; DistributionCommunicateFi; FlowStream (= BCPreStream + DistributionStream,
+ * lbm_flow.F90:810-814); FlowBounceback; FlowApplyBCs (lbm_flow.F90:1958-1991 = FlowCalcRhoForces
+ * [density, BCApplyDirichletToRho, forces; :445-456], BCApply, BCUpdateRho; the outlet value updates
+ * at its top are host-side set-up of the face arrays and not part of this restatement);
  * FlowUpdateFlux (:458-464). */
+static void apply_bcs(txo_state *s) {
+  calc_density(s);
+  bc_dirichlet_to_rho(s);
+  calc_forces(s);
+  bc_apply(s);
+  bc_update_rho(s);
+}
 void txo_step(txo_state *s, int nsteps) {
   for (int it = 0; it < nsteps; ++it) {
     flow_collision(s);
     communicate_fi(s);
+    if (s->prestream) bc_prestream(s);
     stream(s);
     bounceback(s);
-    calc_density(s);
-    calc_forces(s);
+    apply_bcs(s);
     calc_flux_into(s, s->flux);
     update_ue(s);
   }
@@ -744,12 +1023,12 @@ void txo_step(txo_state *s, int nsteps) {
 /* the phases individually, for white-box tests */
 void txo_phase_collision(txo_state *s) { flow_collision(s); }
 void txo_phase_communicate_fi(txo_state *s) { communicate_fi(s); }
-void txo_phase_stream(txo_state *s) { stream(s); }
-void txo_phase_bounceback(txo_state *s) { bounceback(s); }
-void txo_phase_apply_bcs(txo_state *s) {
-  calc_density(s);
-  calc_forces(s);
+void txo_phase_stream(txo_state *s) {
+  if (s->prestream) bc_prestream(s);
+  stream(s);
 }
+void txo_phase_bounceback(txo_state *s) { bounceback(s); }
+void txo_phase_apply_bcs(txo_state *s) { apply_bcs(s); }
 void txo_phase_update_flux(txo_state *s) {
   calc_flux_into(s, s->flux);
   update_ue(s);

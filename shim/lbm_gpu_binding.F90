@@ -41,7 +41,7 @@ module LBM_GPU_Binding_module
      integer(c_int32_t) :: use_nonideal_eos
      integer(c_int32_t) :: eos_type(TXG_NMAX_COMPONENTS)
      integer(c_int32_t) :: rank, nranks
-     integer(c_int32_t) :: reserved_i(6)
+     integer(c_int32_t) :: bc_flags(6)
      real(c_double) :: tau(TXG_NMAX_COMPONENTS)
      real(c_double) :: s_c(TXG_NMAX_COMPONENTS)
      real(c_double) :: s_e(TXG_NMAX_COMPONENTS)
@@ -60,6 +60,7 @@ module LBM_GPU_Binding_module
   end type txg_config
 
   public :: txg_config_defaults, txg_create, txg_destroy, txg_last_error, txg_nccl_unique_id, txg_comm_init
+  public :: txg_set_bc_values
   public :: txg_set_walls, txg_set_rho_u, txg_set_fi, txg_fi_init, txg_update_moments, txg_step
   public :: txg_collision, txg_communicate_fi, txg_stream, txg_bounceback, txg_apply_bcs, txg_update_flux
   public :: txg_get_fi, txg_get_state, txg_get_diagnostics, txg_get_node_class, txg_delta_norm, txg_synchronize
@@ -112,6 +113,14 @@ module LBM_GPU_Binding_module
        type(c_ptr), value :: h
        real(c_double), intent(in) :: walls_rg(*)
      end function txg_set_walls
+
+     ! BCSetValues result (lbm_bc.F90:215-228): bc%xm_a .. bc%zp_a of one boundary (0-based: BOUNDARY_XM-1 ..)
+     integer(c_int) function txg_set_bc_values(h, boundary, vals) bind(C, name="txg_set_bc_values")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: boundary
+       real(c_double), intent(in) :: vals(*)
+     end function txg_set_bc_values
 
      ! LBMInitializeState result (lbm.F90:444-453); u_g may be c_null_ptr (= 0)
      integer(c_int) function txg_set_rho_u(h, rho_rg, u_g) bind(C, name="txg_set_rho_u")

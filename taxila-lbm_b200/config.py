@@ -25,6 +25,9 @@ RELAXATION_MODE_SRT = 0
 RELAXATION_MODE_MRT = 1
 EOS_NULL, EOS_DENSITY, EOS_SC, EOS_PR, EOS_THERMO = 0, 1, 2, 3, 4
 
+BC_NULL, BC_PERIODIC, BC_REFLECTING, BC_DIRICHLET, BC_NEUMANN, BC_VELOCITY = 0, 1, 2, 3, 4, 5
+BOUNDARY_XM, BOUNDARY_XP, BOUNDARY_YM, BOUNDARY_YP, BOUNDARY_ZM, BOUNDARY_ZP = range(6)
+
 WALL_PORESPACE = 0.0
 WALL_NONREACTIVE = 800.0
 WALL_NORMAL_X = 900.0
@@ -56,7 +59,7 @@ class TxgConfig(C.Structure):
         ("eos_type", C.c_int32 * NMAX_COMPONENTS),
         ("rank", C.c_int32),
         ("nranks", C.c_int32),
-        ("reserved_i", C.c_int32 * 6),
+        ("bc_flags", C.c_int32 * 6),
         ("tau", C.c_double * NMAX_COMPONENTS),
         ("s_c", C.c_double * NMAX_COMPONENTS),
         ("s_e", C.c_double * NMAX_COMPONENTS),

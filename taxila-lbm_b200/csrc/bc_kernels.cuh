@@ -1,0 +1,136 @@
+// bc_kernels.cuh -- surface kernels of the flow step: external face boundary conditions
+// (lbm_bc.F90) and the free-slip (WALL_NORMAL_X/Y/Z = 900-902) part of DistributionBouncebackD*.
+//
+// These run over O(N^(2/3)) face nodes once per step, next to hot kernels that move ~600 B for every
+// node of the box: they are written for clarity (run-time lattice tables, one thread per face node,
+// all components in a loop) and follow the reference's evaluation order statement by statement.
+#pragma once
+#include "kernels.cuh"
+#include "specular_table.h"
+
+namespace txg {
+
+// One face of the box in the numbering of lbm_definitions.h:45-50 (0-based: XM, XP, YM, YP, ZM, ZP).
+// The node routines of lbm_bc.F90 are written for one boundary and rotated onto the others with
+// DiscSetLocalDirections (lbm_discretization_d3q19.F90:566-714, lbm_discretization_d2q9.F90:372-434);
+// all they take from the rotation is ci(directions(local_normal), normal axis) -- the inward normal
+// sign on every boundary -- and the set of tangential axes, each handled independently.
+struct FaceDesc {
+  int axis, sign, coord;  // normal axis, inward sign, coordinate of the face plane (owned, local in z)
+  int t1, t2, n1, n2;     // tangential axes (t1 fastest in the face array) and their local extents
+  int type;               // TXG_BC_* (lbm_definitions.h:29-35)
+  int npairs;             // BC_REFLECTING: (n <- p) assignments in execution order
+  int pair_n[32], pair_p[32];
+};
+
+// (owned dense index, position) of face entry idx; false for a solid node or past the end
+__device__ __forceinline__ bool face_node(const Grid &g, const FaceDesc &fd, const uint32_t *__restrict__ nbmask,
+                                          long long idx, long long &pos) {
+  if (idx >= (long long)fd.n1 * fd.n2) return false;
+  int x[3] = {0, 0, 0};
+  x[fd.axis] = fd.coord;
+  x[fd.t1] = (int)(idx % fd.n1);
+  x[fd.t2] = (int)(idx / fd.n1);
+  const long long o = (long long)x[2] * g.plane + (long long)x[1] * g.NX + x[0];
+  if (nbmask[o] >> 31) return false;
+  pos = pos_of(g, o + (long long)g.Rz * g.plane);
+  return true;
+}
+
+// BCApplyDirichletToRho -> _D2/_D3 (lbm_bc.F90:252-434): rho(m, face node) = vals(m) on the fluid
+// nodes of a Dirichlet face, before the density halo and the forces.
+__global__ void k_bc_dirichlet_rho(Grid g, Phys p, int S, FaceDesc fd, const double *__restrict__ vals, int nbcs,
+                                   double *__restrict__ rho, double *__restrict__ rho_true,
+                                   const uint32_t *__restrict__ nbmask) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long pos;
+  if (!face_node(g, fd, nbmask, idx, pos)) return;
+  for (int m = 0; m < S; ++m) {
+    const double v = vals[idx * nbcs + m];
+    if (p.eos) {
+      rho_true[(long long)m * g.fs + pos] = v;
+      rho[(long long)m * g.fs + pos] = eos_psi(p, m, v);
+    } else {
+      rho[(long long)m * g.fs + pos] = v;
+    }
+  }
+}
+
+// BCApply -> BCApply{Reflecting,Dirichlet,Neumann,Velocity}D* -> ...Node (lbm_bc.F90:781-1865) on one
+// face.  f: the populations after streaming and bounce-back (the incoming directions of a face node
+// hold what the bounce-back off the 999 ghost layer put there); F: forces of FlowCalcRhoForces.
+// vals(nbcs) of a node is viewed as (S, ndims): pvals(m,1), mvals(m,d), uvals(1,d).
+__global__ void k_bc_apply(Grid g, LatticeTab lt, int S, FaceDesc fd, const double *__restrict__ vals,
+                           double *__restrict__ f, const double *__restrict__ Fbuf,
+                           const uint32_t *__restrict__ nbmask) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long pos;
+  if (!face_node(g, fd, nbmask, idx, pos)) return;
+  const int Q = lt.Q, D = lt.D, N = fd.axis;
+  const int nbcs = S * D;
+  const double *v = vals ? vals + idx * nbcs : nullptr;
+  for (int m = 0; m < S; ++m) {
+    double *fm = f + (long long)m * Q * g.fs + pos;
+    double fi[19];
+    for (int n = 0; n < Q; ++n) fi[n] = fm[(long long)n * g.fs];
+    if (fd.type == 2) {  // BC_REFLECTING (lbm_bc.F90:825-1073)
+      for (int e = 0; e < fd.npairs; ++e) fi[fd.pair_n[e]] = fi[fd.pair_p[e]];
+      for (int e = 0; e < fd.npairs; ++e) fm[(long long)fd.pair_n[e] * g.fs] = fi[fd.pair_n[e]];
+      continue;
+    }
+    double Qc[3] = {0., 0., 0.}, weightsum[3] = {0., 0., 0.}, momentum[3] = {0., 0., 0.};
+    double sumf = 0.;
+    for (int n = 0; n < Q; ++n) sumf += fi[n];
+    // weightsum(d): incoming directions with a component along d; momentum(d) = sum_n fi(n) c_n,d
+    for (int d = 0; d < D; ++d)
+      for (int n = 1; n < Q; ++n) {
+        momentum[d] = momentum[d] + fi[n] * (double)lt.c[n][d];
+        if (fd.sign * lt.c[n][N] == 1 && lt.c[n][d] != 0) weightsum[d] = weightsum[d] + lt.w[n];
+      }
+    double Fm[3] = {0., 0., 0.};
+    for (int d = 0; d < D; ++d) Fm[d] = Fbuf[(long long)(m * D + d) * g.fs + pos];
+    if (fd.type == 3) {  // BC_DIRICHLET: BCApplyDirichletNode (lbm_bc.F90:1273-1333)
+      Qc[N] = (double)fd.sign * (v[m] - sumf) / weightsum[N];
+      for (int d = 0; d < D; ++d)
+        if (d != N) Qc[d] = -momentum[d] / weightsum[d];
+    } else if (fd.type == 4) {  // BC_NEUMANN: BCApplyNeumannNode (:1533-1593)
+      for (int d = 0; d < D; ++d) Qc[d] = (v[d * S + m] - Fm[d] / 2. - momentum[d]) / weightsum[d];
+    } else {  // BC_VELOCITY: BCApplyVelocityNode (:1793-1865); every component takes uvals(1,:)
+      const double uN = v[N * S];
+      Qc[N] = (sumf * uN - momentum[N] - Fm[N] / 2.) / (1. - (double)fd.sign * uN) / weightsum[N];
+      const double rho = sumf + weightsum[N] * Qc[N] * (double)fd.sign;
+      for (int d = 0; d < D; ++d)
+        if (d != N) Qc[d] = (rho * v[d * S] - Fm[d] / 2. - momentum[d]) / weightsum[d];
+    }
+    for (int n = 1; n < Q; ++n)
+      if (fd.sign * lt.c[n][N] == 1) {
+        double acc = 0.;
+        for (int d = 0; d < D; ++d) acc += (double)lt.c[n][d] * Qc[d];
+        fm[(long long)n * g.fs] = fi[n] + lt.w[n] * acc;
+      }
+  }
+}
+
+// Free-slip walls.  After the push (which treats every solid neighbour as a plain bounce-back wall) and
+// the z halo, the slots listed in the table are rewritten: dst <- value currently in src (or 0).  The
+// table is built on the host from the geometry alone (specular_table.h); gather and scatter
+// are separate launches because a slot can be both a source and a destination.
+__global__ void k_specular_gather(const double *__restrict__ f, const uint32_t *__restrict__ src,
+                                  double *__restrict__ tmp, long long n, int S, long long comp_stride) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * S) return;
+  const long long e = idx % n;
+  const int m = (int)(idx / n);
+  const uint32_t s = src[e];
+  tmp[idx] = s == SPEC_ZERO ? 0. : f[(long long)m * comp_stride + s];
+}
+__global__ void k_specular_scatter(double *__restrict__ f, const uint32_t *__restrict__ dst,
+                                   const double *__restrict__ tmp, long long n, int S, long long comp_stride) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * S) return;
+  const long long e = idx % n;
+  const int m = (int)(idx / n);
+  f[(long long)m * comp_stride + dst[e]] = tmp[idx];
+}
+
+}  // namespace txg

@@ -17,6 +17,7 @@
 #include "../../include/taxila_gpu.h"
 #include "flow.h"
 #include "setup_kernels.cuh"
+#include "bc_kernels.cuh"
 
 using namespace txg;
 
@@ -136,6 +137,19 @@ struct txg_flow {
   // exported copies (lazily allocated)
   double *x_rho = nullptr, *x_u = nullptr, *x_F = nullptr, *x_rhot = nullptr, *x_prs = nullptr, *x_velt = nullptr;
   bool walls_set = false, state_set = false, rho_current = false;
+  // external face BCs (lbm_bc.F90): bc_mode = some face is REFLECTING / DIRICHLET / NEUMANN / VELOCITY.
+  // The step then runs in the reference's own order (collide first, FlowApplyBCs last) on the split
+  // kernels, and Fbuf holds the forces of FlowCalcRhoForces between steps.
+  bool bc_mode = false, forces_current = false;
+  LatticeTab lt;
+  FaceDesc faces[6];
+  bool face_here[6] = {false, false, false, false, false, false};  // this rank holds the face
+  std::vector<int> bc_order;                                       // faces in BCApply's execution order
+  double *bc_vals[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // free-slip walls (900-902): slots rewritten after every push (bc_kernels.cuh)
+  uint32_t *spec_dst = nullptr, *spec_src = nullptr;
+  double *spec_tmp = nullptr;
+  long long spec_n = 0;
   int phase = 0;  // position in the six-procedure sequence of LBMRun2
   // multi-GPU
   ncclComm_t comm = nullptr;
@@ -307,12 +321,99 @@ static int validate(const txg_config *c) {
   if (c->zs < 0 || c->zl < 1 || c->zs + c->zl > c->NZ) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "invalid z-slab [%d, %d) of %d", c->zs, c->zs + c->zl, c->NZ);
   if (c->nranks == 1 && (c->zs != 0 || c->zl != c->NZ)) TXG_FAIL(h, TXG_ERR_ARG_WRONG, "a single rank must own the whole box");
   if (c->nranks > 1 && c->zl < c->stencil_size_rho) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "z-slab thinner than the stencil");
+  for (int b = 0; b < 6; ++b) {
+    const int fl = c->bc_flags[b];
+    if (fl < TXG_BC_NULL || fl > TXG_BC_VELOCITY)
+      TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "bc_flags[%d] = %d is not one of BC_NULL .. BC_VELOCITY (lbm_definitions.h:29-35)", b, fl);
+    if (b >= 2 * c->ndims && fl != TXG_BC_NULL && fl != TXG_BC_PERIODIC) TXG_FAIL(h, TXG_ERR_ARG_WRONG, "bc_flags[%d] set on a 2-D box", b);
+    if (fl >= TXG_BC_REFLECTING && b < 2 * c->ndims && c->periodic[b / 2])
+      TXG_FAIL(h, TXG_ERR_ARG_WRONG, "Multiple BCs provided for boundary %d: periodic and bc_flags = %d (lbm_flow.F90:1069-1071)", b, fl);
+  }
+  if (d2 && c->bc_flags[TXG_BOUNDARY_XM] == TXG_BC_REFLECTING)
+    TXG_FAIL(h, TXG_ERR_SUP, "BC_REFLECTING on the 2-D xm boundary indexes ci(p,Z_DIRECTION) out of bounds in the reference (lbm_bc.F90:1001): undefined there, refused here");
   for (int m = 0; m < c->ncomponents; ++m) {
     if (!(c->tau[m] > 0.) || !(c->mm[m] > 0.)) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "component %d: tau and mm must be positive", m + 1);
     if (c->use_nonideal_eos && c->eos_type[m] != TXG_EOS_DENSITY && c->eos_type[m] != TXG_EOS_SC)
       TXG_FAIL(h, TXG_ERR_SUP, "component %d: only EOS_DENSITY and EOS_SC are implemented on the device", m + 1);
   }
   return 0;
+}
+
+// ------------------------------------------------------------------ external face BCs: set-up
+// lattice tables for the run-time surface kernels
+template <class L>
+static void fill_lattice_tab(LatticeTab &lt) {
+  lt.Q = L::Q;
+  lt.D = L::D;
+  for (int n = 0; n < 19; ++n) {
+    for (int d = 0; d < 3; ++d) lt.c[n][d] = (n < L::Q && d < L::D) ? L::c(n, d) : 0;
+    lt.w[n] = n < L::Q ? L::w(n) : 0.;
+  }
+}
+
+// BCApplyReflectingD3/D2 (lbm_bc.F90:825-1073): the test each face applies to (n, p), restated face by
+// face -- xm in 3-D compares ci(n,X) with -ci(p,Z) (:849), which is what runs in the reference.
+static bool reflecting_match(const LatticeTab &lt, int b, int n, int p) {
+  const int(*c)[3] = lt.c;
+  if (lt.D == 3) switch (b) {
+      case 0: return c[n][1] == c[p][1] && c[n][2] == c[p][2] && c[n][0] == -c[p][2];
+      case 1: return c[n][1] == c[p][1] && c[n][2] == c[p][2] && c[n][0] == -c[p][0];
+      case 2:
+      case 3: return c[n][0] == c[p][0] && c[n][2] == c[p][2] && c[n][1] == -c[p][1];
+      default: return c[n][0] == c[p][0] && c[n][1] == c[p][1] && c[n][2] == -c[p][2];
+    }
+  switch (b) {
+    case 1: return c[n][1] == c[p][1] && c[n][0] == -c[p][0];
+    case 2:
+    case 3: return c[n][0] == c[p][0] && c[n][1] == -c[p][1];
+    default: return false;  // xm in 2-D is refused in validate()
+  }
+}
+
+static void setup_faces(txg_flow *h) {
+  const txg_config &c = h->cfg;
+  if (c.discretization == TXG_D3Q19_DISCRETIZATION)
+    fill_lattice_tab<D3Q19>(h->lt);
+  else
+    fill_lattice_tab<D2Q9>(h->lt);
+  const int D = h->D;
+  const int NZl = D == 3 ? c.zl : 1;
+  const int N[3] = {c.NX, c.NY, NZl};
+  for (int b = 0; b < 2 * D; ++b) {
+    FaceDesc &f = h->faces[b];
+    memset(&f, 0, sizeof f);
+    f.axis = b / 2;
+    f.sign = (b % 2 == 0) ? 1 : -1;
+    f.coord = (b % 2 == 0) ? 0 : N[f.axis] - 1;
+    f.t1 = f.axis == 0 ? 1 : 0;
+    f.t2 = f.axis == 2 ? 1 : 2;
+    f.n1 = N[f.t1];
+    f.n2 = D == 3 ? N[f.t2] : 1;
+    f.type = c.bc_flags[b];
+    // x and y faces exist on every z-slab; zm on the first, zp on the last (info%zs.eq.1, info%ze.eq.NZ)
+    h->face_here[b] = f.axis < 2 || (b == TXG_BOUNDARY_ZM ? c.zs == 0 : c.zs + c.zl == c.NZ);
+    if (f.type == TXG_BC_REFLECTING)
+      for (int n = 1; n < h->lt.Q; ++n) {
+        if (f.sign * h->lt.c[n][f.axis] <= 0) continue;
+        for (int p = 1; p < h->lt.Q; ++p)
+          if (reflecting_match(h->lt, b, n, p) && f.npairs < 32) {
+            f.pair_n[f.npairs] = n;
+            f.pair_p[f.npairs] = p;
+            ++f.npairs;
+          }
+      }
+  }
+  // BCApply (lbm_bc.F90:781-807): every BC type once, in the order of its first face; inside a type
+  // the faces in the order xm, xp, ym, yp, zm, zp
+  bool done[16] = {false};
+  done[TXG_BC_NULL] = done[TXG_BC_PERIODIC] = true;
+  for (int side = 0; side < 2 * D; ++side) {
+    const int type = c.bc_flags[side];
+    if (done[type]) continue;
+    done[type] = true;
+    for (int b = 0; b < 2 * D; ++b)
+      if (c.bc_flags[b] == type) h->bc_order.push_back(b);
+  }
 }
 
 extern "C" int txg_config_defaults(txg_config *c) {
@@ -355,7 +456,8 @@ extern "C" int txg_destroy(txg_handle h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
                   h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->nbr_all, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
-                  h->x_rhot, h->x_prs, h->x_velt};
+                  h->x_rhot, h->x_prs, h->x_velt, h->spec_dst, h->spec_src, h->spec_tmp, h->bc_vals[0], h->bc_vals[1],
+                  h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5]};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -414,7 +516,9 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     h->pf_blocks = h->num_sms;
     if (const char *pf = getenv("TXG_PF")) h->pf_blocks = atoi(pf);
     const char *sp = getenv("TXG_SPLIT");
-    h->fused = h->ks.step_fused != nullptr && !(sp && sp[0] == '1');
+    for (int b = 0; b < 2 * cfg->ndims; ++b) h->bc_mode = h->bc_mode || cfg->bc_flags[b] >= TXG_BC_REFLECTING;
+    // face BCs act between the forces and the collision: they need the split kernels and the force buffer
+    h->fused = h->ks.step_fused != nullptr && !(sp && sp[0] == '1') && !h->bc_mode;
   }
   Grid &g = h->g;
   g.NX = cfg->NX;
@@ -456,6 +560,7 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
   };
   if ((rc = body())) return fail(rc);
   fill_phys(h);
+  setup_faces(h);
   // z neighbours of the slab ring
   const int nr = cfg->nranks, r = cfg->rank;
   if (cfg->ndims == 3) {
@@ -779,6 +884,63 @@ static inline void plane_range(const txg_flow *h, int z0, int nz, long long *fir
   *count = h->plane_off[(size_t)(h->g.Rz + z0 + nz)] - *first;
 }
 
+// ------------------------------------------------------------------ free-slip walls (900-902)
+// The slots the mirrors rewrite after every push (specular_table.h has the derivation), rebuilt at every
+// walls upload.  Restrictions, each refused with PETSC_ERR_SUP and none silently different from the
+// reference: one rank only (source and target of a reflection may sit in different z-slabs), and every
+// population reflected off a free-slip wall must land on a fluid node.
+static int build_specular(txg_flow *h, int contacts) {
+  for (void **q : {(void **)&h->spec_dst, (void **)&h->spec_src, (void **)&h->spec_tmp}) {
+    if (*q) cudaFree(*q);
+    *q = nullptr;
+  }
+  h->spec_n = 0;
+  if (!contacts) return 0;
+  const Grid &g = h->g;
+  if (h->cfg.nranks != 1)
+    TXG_FAIL(h, TXG_ERR_SUP, "%d fluid/wall contacts with free-slip codes 900-902 (WALL_NORMAL_X/Y/Z): free-slip walls run on one rank only", contacts);
+  const long long ncls = (long long)(g.NZl + 2 * g.Rz) * g.cny * g.cnx;
+  std::vector<uint8_t> cls((size_t)ncls);
+  TXG_CUDA(h, cudaMemcpy(cls.data(), h->cls, (size_t)ncls, cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> P;
+  if (g.P) {
+    P.resize((size_t)g.nE + 1);
+    TXG_CUDA(h, cudaMemcpy(P.data(), g.P, P.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  const int per[3] = {g.perx, g.pery, h->D == 3 ? h->cfg.periodic[2] : 0};
+  SpecularTable t;
+  build_specular_table(h->lt, g.NX, g.NY, g.NZl, g.R, g.Rz, per, cls.data(), g.P ? P.data() : nullptr, g.fs, t);
+  if (t.parked)
+    TXG_FAIL(h, TXG_ERR_SUP,
+             "free-slip walls (900-902): %lld reflected populations would land on a solid node (walls meeting in a corner, "
+             "or an obstacle touching the wall); the reference parks them in wall-node storage, which the device does not have",
+             t.parked);
+  h->spec_n = (long long)t.dst.size();
+  if (!h->spec_n) return 0;
+  TXG_CUDA(h, cudaMalloc((void **)&h->spec_dst, t.dst.size() * sizeof(uint32_t)));
+  TXG_CUDA(h, cudaMalloc((void **)&h->spec_src, t.src.size() * sizeof(uint32_t)));
+  TXG_CUDA(h, cudaMalloc((void **)&h->spec_tmp, t.dst.size() * h->S * sizeof(double)));
+  TXG_CUDA(h, cudaMemcpy(h->spec_dst, t.dst.data(), t.dst.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  TXG_CUDA(h, cudaMemcpy(h->spec_src, t.src.data(), t.src.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// rewrite the free-slip slots of a freshly pushed buffer (after the z halo)
+static int apply_specular(txg_flow *h, double *f, cudaStream_t s) {
+  if (!h->spec_n) return 0;
+  const long long n = h->spec_n * h->S, stride = (long long)h->Q * h->g.fs;
+  {
+    ScopedKernel sk(h, "k_specular_gather", s);
+    k_specular_gather<<<blocks_for(n, 256), 256, 0, s>>>(f, h->spec_src, h->spec_tmp, h->spec_n, h->S, stride);
+  }
+  {
+    ScopedKernel sk(h, "k_specular_scatter", s);
+    k_specular_scatter<<<blocks_for(n, 256), 256, 0, s>>>(f, h->spec_dst, h->spec_tmp, h->spec_n, h->S, stride);
+  }
+  TXG_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ walls
 extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   if (!h) return TXG_ERR_ARG_NULL;
@@ -803,12 +965,8 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   TXG_CUDA(h, cudaMemcpyAsync(counters, h->counters, sizeof counters, cudaMemcpyDeviceToHost, h->s_main));
   TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
   if (counters[0]) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "walls array holds %d negative or NaN codes", counters[0]);
-  if (counters[1])
-    TXG_FAIL(h, TXG_ERR_SUP,
-             "%d fluid/wall contacts with free-slip codes 900-902 (WALL_NORMAL_X/Y/Z): specular walls are not "
-             "implemented on the device yet",
-             counters[1]);
   TXG_TRY(build_storage(h));
+  TXG_TRY(build_specular(h, counters[1]));
   h->walls_set = true;
   return 0;
 }
@@ -876,6 +1034,7 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
 static int state_ready(txg_flow *h) {
   h->state_set = true;
   h->rho_current = false;
+  h->forces_current = false;
   return 0;
 }
 
@@ -959,6 +1118,7 @@ static int one_step(txg_flow *h) {
     TXG_TRY(run_forces(h, 0, g.NZl, sm));
     TXG_TRY(run_collide(h, 0, g.NZl, sm));
     TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sm));
+    TXG_TRY(apply_specular(h, h->f[h->cur ^ 1], sm));
     h->cur ^= 1;
     return 0;
   }
@@ -991,6 +1151,76 @@ static int one_step(txg_flow *h) {
   return 0;
 }
 
+// ------------------------------------------------------------------ the step with external face BCs
+// FlowCalcRhoForces (lbm_flow.F90:445-456): density, BCApplyDirichletToRho, density halo, forces -> Fbuf.
+// `dirichlet` = false is FlowUpdateMoments (:466-478), which forms the same moments without the override.
+static int bc_moments_forces(txg_flow *h, bool dirichlet) {
+  const Grid &g = h->g;
+  cudaStream_t sm = h->s_main;
+  TXG_TRY(run_moments(h, 0, g.NZl, sm));
+  if (dirichlet)
+    for (int b = 0; b < 2 * h->D; ++b) {
+      const FaceDesc &fd = h->faces[b];
+      if (fd.type != TXG_BC_DIRICHLET || !h->face_here[b]) continue;
+      if (!h->bc_vals[b]) TXG_FAIL(h, TXG_ERR_ORDER, "boundary %d is BC_DIRICHLET but txg_set_bc_values was not called for it", b);
+      ScopedKernel sk(h, "k_bc_dirichlet_rho", sm);
+      k_bc_dirichlet_rho<<<blocks_for((long long)fd.n1 * fd.n2, 128), 128, 0, sm>>>(g, h->p, h->S, fd, h->bc_vals[b], h->S * h->D, h->rho,
+                                                                                  h->rho_true, h->nbmask);
+      TXG_CUDA(h, cudaGetLastError());
+    }
+  TXG_TRY(exchange_rho(h, h->rho, sm));
+  TXG_TRY(run_forces(h, 0, g.NZl, sm));
+  h->forces_current = true;
+  return 0;
+}
+
+// BCApply (lbm_bc.F90:781-807) on the populations of f[cur]; BCUpdateRho (:436-611) needs no launch:
+// every consumer of the density of a face node (collision, export) sums the populations itself.
+static int bc_apply(txg_flow *h) {
+  const Grid &g = h->g;
+  cudaStream_t sm = h->s_main;
+  for (int b : h->bc_order) {
+    const FaceDesc &fd = h->faces[b];
+    if (!h->face_here[b]) continue;
+    if (fd.type != TXG_BC_REFLECTING && !h->bc_vals[b])
+      TXG_FAIL(h, TXG_ERR_ORDER, "boundary %d has bc_flags = %d but txg_set_bc_values was not called for it", b, fd.type);
+    ScopedKernel sk(h, "k_bc_apply", sm);
+    k_bc_apply<<<blocks_for((long long)fd.n1 * fd.n2, 128), 128, 0, sm>>>(g, h->lt, h->S, fd, h->bc_vals[b], h->f[h->cur], h->Fbuf, h->nbmask);
+    TXG_CUDA(h, cudaGetLastError());
+  }
+  return 0;
+}
+
+// One time step in the reference's own order (lbm.F90:286-361): FlowCollision + communicate + stream +
+// bounce-back (k_collide with the z halo and the free-slip slots), then FlowApplyBCs.  Fbuf carries the
+// forces from one step's FlowApplyBCs to the next step's collision, as flow%forces does.
+static int one_step_bc(txg_flow *h) {
+  const Grid &g = h->g;
+  cudaStream_t sm = h->s_main;
+  TXG_TRY(run_collide(h, 0, g.NZl, sm));
+  TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sm));
+  TXG_TRY(apply_specular(h, h->f[h->cur ^ 1], sm));
+  h->cur ^= 1;
+  TXG_TRY(bc_moments_forces(h, true));
+  TXG_TRY(bc_apply(h));
+  return 0;
+}
+
+// BCSetValues (lbm_bc.F90:215-228)
+extern "C" int txg_set_bc_values(txg_handle h, int boundary, const double *vals) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (boundary < 0 || boundary >= 2 * h->D) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "boundary %d out of range", boundary);
+  if (!h->face_here[boundary]) return 0;  // a z face of another slab
+  if (!vals) TXG_FAIL(h, TXG_ERR_ARG_NULL, "txg_set_bc_values: null array");
+  TXG_CUDA(h, cudaSetDevice(h->device));
+  const FaceDesc &fd = h->faces[boundary];
+  const size_t bytes = (size_t)fd.n1 * fd.n2 * h->S * h->D * sizeof(double);
+  if (!h->bc_vals[boundary]) TXG_CUDA(h, cudaMalloc((void **)&h->bc_vals[boundary], bytes));
+  TXG_CUDA(h, cudaMemcpyAsync(h->bc_vals[boundary], vals, bytes, cudaMemcpyHostToDevice, h->s_main));
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  return 0;
+}
+
 extern "C" int txg_step(txg_handle h, int nsteps) {
   if (!h) return TXG_ERR_ARG_NULL;
   if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "txg_step before txg_fi_init / txg_set_fi");
@@ -998,7 +1228,12 @@ extern "C" int txg_step(txg_handle h, int nsteps) {
   TXG_CUDA(h, cudaSetDevice(h->device));
   const int64_t l0 = h->launches;
   TXG_CUDA(h, cudaEventRecord(h->ev_step0, h->s_main));
-  for (int i = 0; i < nsteps; ++i) TXG_TRY(one_step(h));
+  if (h->bc_mode) {
+    if (nsteps > 0 && !h->forces_current) TXG_TRY(bc_moments_forces(h, false));  // FlowUpdateMoments of LBMInit2 (lbm.F90:238)
+    for (int i = 0; i < nsteps; ++i) TXG_TRY(one_step_bc(h));
+  } else {
+    for (int i = 0; i < nsteps; ++i) TXG_TRY(one_step(h));
+  }
   TXG_CUDA(h, cudaEventRecord(h->ev_step1, h->s_main));
   h->last_launches = h->launches - l0;
   h->rho_current = false;
@@ -1027,6 +1262,7 @@ extern "C" int txg_update_flux(txg_handle h) {
 // ------------------------------------------------------------------ state out
 // refresh rho (+halo) from the current populations
 static int refresh_rho(txg_flow *h) {
+  if (h->bc_mode) return h->forces_current ? 0 : bc_moments_forces(h, false);  // exports read f and Fbuf
   if (h->rho_current) return 0;
   TXG_TRY(run_moments(h, 0, h->g.NZl, h->s_main));
   TXG_TRY(exchange_rho(h, h->rho, h->s_main));
@@ -1039,6 +1275,7 @@ extern "C" int txg_update_moments(txg_handle h) {
   if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "txg_update_moments before txg_fi_init / txg_set_fi");
   TXG_CUDA(h, cudaSetDevice(h->device));
   h->rho_current = false;
+  if (h->bc_mode) return bc_moments_forces(h, false);
   return refresh_rho(h);
 }
 
@@ -1046,7 +1283,7 @@ static int run_export(txg_flow *h, double *rho_o, double *u_o, double *F_o, doub
   const Grid &g = h->g;
   ScopedKernel sk(h, "k_export", h->s_main);
   h->ks.export_state<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->p, h->f[h->cur], h->rho, h->nbmask, h->ffmask, h->cls,
-                                                                        rho_o, u_o, F_o, rhot, prs, velt,
+                                                                        h->bc_mode ? h->Fbuf : nullptr, rho_o, u_o, F_o, rhot, prs, velt,
                                                                         h->cfg.null_pressure, 0, g.NZl);
   TXG_CUDA(h, cudaGetLastError());
   return 0;

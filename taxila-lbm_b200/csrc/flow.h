@@ -29,7 +29,8 @@ struct KernelSet {
   void (*fi_init)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
                   const uint32_t *, const uint8_t *, int, int);
   void (*export_state)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *,
-                       const uint8_t *, double *, double *, double *, double *, double *, double *, double, int, int);
+                       const uint8_t *, const double *, double *, double *, double *, double *, double *, double *,
+                       double, int, int);
   void (*build_masks)(Grid, const uint8_t *, uint32_t *, uint32_t *, int *);
   void (*build_wallrec)(Grid, Phys, const uint8_t *, const uint32_t *, const uint32_t *, double *);
   int fused_threads;  // block size of step_fused

@@ -355,10 +355,12 @@ __global__ void __launch_bounds__(128) k_fi_init(Grid g, Phys p, double *__restr
 // K6 state/diagnostics export: from the populations and the current rho field compute
 // what the reference holds after FlowUpdateMoments (rho, forces, common velocity u') and what
 // FlowUpdateDiagnosticsD* (lbm_flow.F90:654-758) derives (rhot, prs, velt).  Any output may be null.
+// Fsrc != null: the forces are read from the step's force buffer instead of being re-formed.
 template <class L, int S, int ISO>
 __global__ void __launch_bounds__(128) k_export(Grid g, Phys p, const double *__restrict__ fA,
                                                 const double *__restrict__ rho, const uint32_t *__restrict__ nbmask,
                                                 const uint32_t *__restrict__ ffmask, const uint8_t *__restrict__ cls,
+                                                const double *__restrict__ Fsrc /*[S*D][fs] or null*/,
                                                 double *__restrict__ rho_out /*[S][nnodes]*/,
                                                 double *__restrict__ u_out /*[S][D][nnodes]*/,
                                                 double *__restrict__ F_out /*[S][D][nnodes]*/,
@@ -389,7 +391,16 @@ __global__ void __launch_bounds__(128) k_export(Grid g, Phys p, const double *__
   double f[S][Q], r[S], F[S][D], up[D];
   load_node<L, S>(g, fA, nd, f);
   density<L, S>(f, r);
-  forces<L, S, ISO>(g, p, rho, cls, ffmask, nd, mask, r, F);
+  if (Fsrc) {
+    // with external face BCs the forces of the step are the ones FlowCalcRhoForces formed BEFORE
+    // BCApply / BCUpdateRho changed the face nodes (lbm_flow.F90:1958-1991): take the stored ones
+#pragma unroll
+    for (int m = 0; m < S; ++m)
+#pragma unroll
+      for (int d = 0; d < D; ++d) F[m][d] = __ldg(Fsrc + (long long)(m * D + d) * g.fs + nd.pos);
+  } else {
+    forces<L, S, ISO>(g, p, rho, cls, ffmask, nd, mask, r, F);
+  }
   common_velocity<L, S>(p, f, r, F, up);
 #pragma unroll
   for (int m = 0; m < S; ++m) {

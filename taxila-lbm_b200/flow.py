@@ -103,6 +103,21 @@ class Flow:
         self._expect(w, self.shape_walls(), "walls")
         self._check(self.lib.txg_set_walls(self.h, _dp(w)))
 
+    def shape_bc(self, boundary):
+        """Local face array of boundary 0..5 (xm, xp, ym, yp, zm, zp) in the reference's layout
+        (lbm_bc.F90:1100-1106): xm/xp (zl, NY, nbcs), ym/yp (zl, NX, nbcs), zm/zp (NY, NX, nbcs),
+        nbcs = ndims * ncomponents viewed as (ndims, S) in C order."""
+        n = {0: (self.NZl, self.NY), 1: (self.NZl, self.NX), 2: (self.NY, self.NX)}[boundary // 2]
+        if self.D == 2:
+            n = n[1:]
+        return n + (self.D, self.S)
+
+    def bc_set_values(self, boundary, vals):
+        """BCSetValues (lbm_bc.F90:215-228) for one face."""
+        v = _c(vals)
+        self._expect(v, self.shape_bc(boundary), "bc values of boundary %d" % boundary)
+        self._check(self.lib.txg_set_bc_values(self.h, int(boundary), _dp(v)))
+
     def initialize_state(self, rho_rg, u_g=None):
         r = _c(rho_rg)
         self._expect(r, self.shape_rho(), "rho")

@@ -55,11 +55,18 @@ def lib():
             "txo_get_forces": [dp],
             "txo_diagnostics": [dp, dp, dp],
             "txo_delta_norm": [],
+            "txo_set_bc_values": [C.c_int, dp],
+            "txo_set_prestream": [C.c_int],
         }.items():
             fn = getattr(L, name)
             fn.argtypes = [C.c_void_p] + args
             if name != "txo_delta_norm":
                 fn.restype = None
+        L.txo_bc_supported.argtypes = [C.c_void_p]
+        L.txo_bc_supported.restype = C.c_int
+        ip = C.POINTER(C.c_int)
+        L.txo_reflecting_pairs.argtypes = [C.c_void_p, C.c_int, ip, ip]
+        L.txo_reflecting_pairs.restype = C.c_int
         L.txo_get_lattice.argtypes = [C.c_void_p, C.POINTER(C.c_int), dp, C.POINTER(C.c_int), dp, dp, dp]
         L.txo_get_lattice.restype = None
         _lib = L
@@ -112,6 +119,26 @@ class Oracle:
         out = np.empty((self.NZ + 2 * rz, self.NY + 2 * R, self.NX + 2 * R))
         self.L.txo_get_walls_rg(self.h, _dp(out))
         return out
+
+    def shape_bc(self, boundary):
+        n = {0: (self.NZ, self.NY), 1: (self.NZ, self.NX), 2: (self.NY, self.NX)}[boundary // 2]
+        if self.D == 2:
+            n = n[1:]
+        return n + (self.D, self.S)
+
+    def set_bc_values(self, boundary, vals):
+        v = np.ascontiguousarray(vals, dtype=np.float64).reshape(self.shape_bc(boundary))
+        self.L.txo_set_bc_values(self.h, int(boundary), _dp(v))
+
+    def set_prestream(self, on):
+        self.L.txo_set_prestream(self.h, int(on))
+
+    def reflecting_pairs(self, boundary):
+        n = np.zeros(64, dtype=np.int32)
+        p = np.zeros(64, dtype=np.int32)
+        ip = C.POINTER(C.c_int)
+        k = self.L.txo_reflecting_pairs(self.h, int(boundary), n.ctypes.data_as(ip), p.ctypes.data_as(ip))
+        return list(zip(n[:k].tolist(), p[:k].tolist()))
 
     def set_rho(self, rho):
         r = np.ascontiguousarray(rho, dtype=np.float64).reshape(self.nodes + (self.S,))
