@@ -18,9 +18,7 @@ namespace txg {
 struct FaceDesc {
   int axis, sign, coord;  // normal axis, inward sign, coordinate of the face plane (owned, local in z)
   int t1, t2, n1, n2;     // tangential axes (t1 fastest in the face array) and their local extents
-  int type;               // TXG_BC_* (lbm_definitions.h:29-35)
-  int npairs;             // BC_REFLECTING: (n <- p) assignments in execution order
-  int pair_n[32], pair_p[32];
+  int type;               // TXG_BC_DIRICHLET / NEUMANN / VELOCITY (lbm_definitions.h:32-34)
 };
 
 // (owned dense index, position) of face entry idx; false for a solid node or past the end
@@ -56,7 +54,7 @@ __global__ void k_bc_dirichlet_rho(Grid g, Phys p, int S, FaceDesc fd, const dou
   }
 }
 
-// BCApply -> BCApply{Reflecting,Dirichlet,Neumann,Velocity}D* -> ...Node (lbm_bc.F90:781-1865) on one
+// BCApply -> BCApply{Dirichlet,Neumann,Velocity}D* -> ...Node (lbm_bc.F90:781-807,1075-1865) on one
 // face.  f: the populations after streaming and bounce-back (the incoming directions of a face node
 // hold what the bounce-back off the 999 ghost layer put there); F: forces of FlowCalcRhoForces.
 // vals(nbcs) of a node is viewed as (S, ndims): pvals(m,1), mvals(m,d), uvals(1,d).
@@ -68,16 +66,11 @@ __global__ void k_bc_apply(Grid g, LatticeTab lt, int S, FaceDesc fd, const doub
   if (!face_node(g, fd, nbmask, idx, pos)) return;
   const int Q = lt.Q, D = lt.D, N = fd.axis;
   const int nbcs = S * D;
-  const double *v = vals ? vals + idx * nbcs : nullptr;
+  const double *v = vals + idx * nbcs;
   for (int m = 0; m < S; ++m) {
     double *fm = f + (long long)m * Q * g.fs + pos;
     double fi[19];
     for (int n = 0; n < Q; ++n) fi[n] = fm[(long long)n * g.fs];
-    if (fd.type == 2) {  // BC_REFLECTING (lbm_bc.F90:825-1073)
-      for (int e = 0; e < fd.npairs; ++e) fi[fd.pair_n[e]] = fi[fd.pair_p[e]];
-      for (int e = 0; e < fd.npairs; ++e) fm[(long long)fd.pair_n[e] * g.fs] = fi[fd.pair_n[e]];
-      continue;
-    }
     double Qc[3] = {0., 0., 0.}, weightsum[3] = {0., 0., 0.}, momentum[3] = {0., 0., 0.};
     double sumf = 0.;
     for (int n = 0; n < Q; ++n) sumf += fi[n];

@@ -137,7 +137,7 @@ struct txg_flow {
   // exported copies (lazily allocated)
   double *x_rho = nullptr, *x_u = nullptr, *x_F = nullptr, *x_rhot = nullptr, *x_prs = nullptr, *x_velt = nullptr;
   bool walls_set = false, state_set = false, rho_current = false;
-  // external face BCs (lbm_bc.F90): bc_mode = some face is REFLECTING / DIRICHLET / NEUMANN / VELOCITY.
+  // external face BCs (lbm_bc.F90): bc_mode = some face is DIRICHLET / NEUMANN / VELOCITY.
   // The step then runs in the reference's own order (collide first, FlowApplyBCs last) on the split
   // kernels, and Fbuf holds the forces of FlowCalcRhoForces between steps.
   bool bc_mode = false, forces_current = false;
@@ -329,8 +329,13 @@ static int validate(const txg_config *c) {
     if (fl >= TXG_BC_REFLECTING && b < 2 * c->ndims && c->periodic[b / 2])
       TXG_FAIL(h, TXG_ERR_ARG_WRONG, "Multiple BCs provided for boundary %d: periodic and bc_flags = %d (lbm_flow.F90:1069-1071)", b, fl);
   }
-  if (d2 && c->bc_flags[TXG_BOUNDARY_XM] == TXG_BC_REFLECTING)
-    TXG_FAIL(h, TXG_ERR_SUP, "BC_REFLECTING on the 2-D xm boundary indexes ci(p,Z_DIRECTION) out of bounds in the reference (lbm_bc.F90:1001): undefined there, refused here");
+  for (int b = 0; b < 2 * c->ndims; ++b)
+    if (c->bc_flags[b] == TXG_BC_REFLECTING)
+      TXG_FAIL(h, TXG_ERR_SUP,
+               "BC_REFLECTING (boundary %d) is not built on the device: BCUpdateRho skips reflecting faces (lbm_bc.F90:443-445), so the "
+               "reference collides their nodes with the density from BEFORE BCApply rewrote the populations -- a stored per-node density "
+               "the collide kernel does not take -- and its xm tests index the wrong axis (lbm_bc.F90:849, :1001)",
+               b);
   for (int m = 0; m < c->ncomponents; ++m) {
     if (!(c->tau[m] > 0.) || !(c->mm[m] > 0.)) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "component %d: tau and mm must be positive", m + 1);
     if (c->use_nonideal_eos && c->eos_type[m] != TXG_EOS_DENSITY && c->eos_type[m] != TXG_EOS_SC)
@@ -348,25 +353,6 @@ static void fill_lattice_tab(LatticeTab &lt) {
   for (int n = 0; n < 19; ++n) {
     for (int d = 0; d < 3; ++d) lt.c[n][d] = (n < L::Q && d < L::D) ? L::c(n, d) : 0;
     lt.w[n] = n < L::Q ? L::w(n) : 0.;
-  }
-}
-
-// BCApplyReflectingD3/D2 (lbm_bc.F90:825-1073): the test each face applies to (n, p), restated face by
-// face -- xm in 3-D compares ci(n,X) with -ci(p,Z) (:849), which is what runs in the reference.
-static bool reflecting_match(const LatticeTab &lt, int b, int n, int p) {
-  const int(*c)[3] = lt.c;
-  if (lt.D == 3) switch (b) {
-      case 0: return c[n][1] == c[p][1] && c[n][2] == c[p][2] && c[n][0] == -c[p][2];
-      case 1: return c[n][1] == c[p][1] && c[n][2] == c[p][2] && c[n][0] == -c[p][0];
-      case 2:
-      case 3: return c[n][0] == c[p][0] && c[n][2] == c[p][2] && c[n][1] == -c[p][1];
-      default: return c[n][0] == c[p][0] && c[n][1] == c[p][1] && c[n][2] == -c[p][2];
-    }
-  switch (b) {
-    case 1: return c[n][1] == c[p][1] && c[n][0] == -c[p][0];
-    case 2:
-    case 3: return c[n][0] == c[p][0] && c[n][1] == -c[p][1];
-    default: return false;  // xm in 2-D is refused in validate()
   }
 }
 
@@ -392,16 +378,6 @@ static void setup_faces(txg_flow *h) {
     f.type = c.bc_flags[b];
     // x and y faces exist on every z-slab; zm on the first, zp on the last (info%zs.eq.1, info%ze.eq.NZ)
     h->face_here[b] = f.axis < 2 || (b == TXG_BOUNDARY_ZM ? c.zs == 0 : c.zs + c.zl == c.NZ);
-    if (f.type == TXG_BC_REFLECTING)
-      for (int n = 1; n < h->lt.Q; ++n) {
-        if (f.sign * h->lt.c[n][f.axis] <= 0) continue;
-        for (int p = 1; p < h->lt.Q; ++p)
-          if (reflecting_match(h->lt, b, n, p) && f.npairs < 32) {
-            f.pair_n[f.npairs] = n;
-            f.pair_p[f.npairs] = p;
-            ++f.npairs;
-          }
-      }
   }
   // BCApply (lbm_bc.F90:781-807): every BC type once, in the order of its first face; inside a type
   // the faces in the order xm, xp, ym, yp, zm, zp
@@ -1182,7 +1158,7 @@ static int bc_apply(txg_flow *h) {
   for (int b : h->bc_order) {
     const FaceDesc &fd = h->faces[b];
     if (!h->face_here[b]) continue;
-    if (fd.type != TXG_BC_REFLECTING && !h->bc_vals[b])
+    if (!h->bc_vals[b])
       TXG_FAIL(h, TXG_ERR_ORDER, "boundary %d has bc_flags = %d but txg_set_bc_values was not called for it", b, fd.type);
     ScopedKernel sk(h, "k_bc_apply", sm);
     k_bc_apply<<<blocks_for((long long)fd.n1 * fd.n2, 128), 128, 0, sm>>>(g, h->lt, h->S, fd, h->bc_vals[b], h->f[h->cur], h->Fbuf, h->nbmask);

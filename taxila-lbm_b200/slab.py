@@ -49,6 +49,19 @@ def local_arrays(cfg, walls, rho, nranks, rank):
     return c, walls_rg, rho_rg
 
 
+def local_bc_values(cfg, bcs, nranks, rank):
+    """This rank's face arrays (BCSetUp, lbm_bc.F90:127-213: xm..yp hold the rank's own zs:ze range, zm lives on
+    the rank with zs == 1 and zp on the one with ze == NZ) cut from the global ones {boundary: array}."""
+    zs, zl = slab_range(cfg.NZ, nranks, rank)
+    out = {}
+    for b, v in bcs.items():
+        if b < 4:
+            out[b] = np.ascontiguousarray(v[zs:zs + zl])
+        elif (b == 4 and zs == 0) or (b == 5 and zs + zl == cfg.NZ):
+            out[b] = v
+    return out
+
+
 def assemble(parts):
     """Global natural-order array from the per-rank owned arrays (rank order == z order)."""
     return np.concatenate(parts, axis=0)

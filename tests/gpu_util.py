@@ -37,3 +37,17 @@ def mass(rho, fluid):
     """Per-component total mass over fluid nodes, accumulated in extended precision (a plain
     float64 axis-sum over ~1e6 values is itself only good to ~1e-11)."""
     return np.array([np.sum(rho[..., m][fluid], dtype=np.longdouble) for m in range(rho.shape[-1])], dtype=np.float64)
+
+
+def make_flow_bc(cfg, walls, rho, bcs, device=0):
+    """make_flow with face arrays (BCSetValues) uploaded before FlowFiInit."""
+    D = cfg.ndims
+    R = cfg.stencil_size_rho
+    flow = tx.Flow(cfg, device=device)
+    flow.walls_set_values(geo.ghosted(walls, R, cfg.periodic, D, wall_ghost=True))
+    for b, v in bcs.items():
+        flow.bc_set_values(b, v)
+    flow.initialize_state(geo.ghosted(rho, R, cfg.periodic, D))
+    flow.fi_init()
+    flow.update_moments()
+    return flow

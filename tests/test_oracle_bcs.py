@@ -140,3 +140,18 @@ def test_reflecting_pairs_restated_literally():
     pairs = o.reflecting_pairs(0)
     assert [tuple(ci[n]) for n, _ in pairs] == [(1, 0, -1)] * 3
     assert tuple(ci[pairs[-1][1]]) == (1, 0, -1) and tuple(ci[pairs[-2][1]]) == (-1, 0, -1)
+
+
+def test_reflecting_face_keeps_a_stale_density():
+    """BCUpdateRho (lbm_bc.F90:436-456) runs for Dirichlet / Neumann / velocity faces only: after BCApplyReflecting has
+    rewritten the incoming populations of a reflecting face, dist%rho there is still the sum from before, and the
+    next collision uses it.  (Why the device path refuses BC_REFLECTING instead of summing the populations.)"""
+    cfg, walls, rho, bcs = cases.drainage_3d(N=12, NZ=12, inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET, x_bc=tc.BC_REFLECTING)
+    o = cases.run_oracle_bc(cfg, walls, rho, bcs, 5)
+    fi, r, mom = _moments(o, cfg)
+    stored = o.rho()
+    interior = (walls == 0)
+    interior[:, :, 0] = interior[:, :, -1] = False
+    assert np.abs(stored - r)[interior].max() < 1e-15
+    xp = (walls == 0)[:, :, -1]
+    assert np.abs(stored - r)[:, :, -1][xp].max() > 1e-6

@@ -45,6 +45,25 @@ def test_local_arrays_reassemble():
     assert np.array_equal(slab.assemble(parts_r), rho)
 
 
+def test_local_bc_values_follow_the_slabs():
+    """Face arrays per rank as BCSetUp sizes them (lbm_bc.F90:127-213)."""
+    from taxila_lbm_b200 import config as tc
+
+    cfg, walls, rho, bcs = cases.drainage_3d(N=8, NZ=11, x_bc=tc.BC_NEUMANN)
+    rng = np.random.default_rng(0)
+    bcs = {b: rng.uniform(size=v.shape) for b, v in bcs.items()}
+    parts = {b: [] for b in bcs}
+    for r in range(3):
+        zs, zl = slab.slab_range(cfg.NZ, 3, r)
+        loc = slab.local_bc_values(cfg, bcs, 3, r)
+        assert (tc.BOUNDARY_ZM in loc) == (r == 0) and (tc.BOUNDARY_ZP in loc) == (r == 2)
+        for b in (tc.BOUNDARY_XM, tc.BOUNDARY_XP):
+            assert loc[b].shape == (zl, cfg.NY, 3, 2)
+            parts[b].append(loc[b])
+    for b in (tc.BOUNDARY_XM, tc.BOUNDARY_XP):
+        assert np.array_equal(np.concatenate(parts[b], axis=0), bcs[b])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
