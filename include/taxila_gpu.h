@@ -105,7 +105,7 @@ typedef struct txg_config {
   int32_t fluidsolid_forces;/* options%flow_fluidsolid_forces, lbm_walls.F90:117-125*/
   int32_t body_forces;      /* flow%body_forces (-gvt given), lbm_flow.F90:226-231  */
   int32_t use_nonideal_eos; /* flow%use_nonideal_eos, lbm_options.F90:142           */
-  int32_t eos_type[TXG_NMAX_COMPONENTS]; /* TXG_EOS_*; only DENSITY and SC on device */
+  int32_t eos_type[TXG_NMAX_COMPONENTS]; /* TXG_EOS_DENSITY | SC | PR | THERMO (lbm_eos.F90:104-141)      */
   int32_t rank, nranks;     /* position in the z-slab ring                          */
   int32_t bc_flags[6];      /* bc%flags(BOUNDARY_XM..ZP), lbm_bc.F90:36: TXG_BC_*; 0 = none  */
   /* per component m (relaxation_type, component_type) */
@@ -119,11 +119,19 @@ typedef struct txg_config {
   double s_m[TXG_NMAX_COMPONENTS];
   double mm[TXG_NMAX_COMPONENTS];    /* molecular mass; d_k = 1 - 2/(3 mm)          */
   double gf[TXG_NMAX_COMPONENTS][TXG_NMAX_COMPONENTS]; /* gf[m][m'] = option -g_<m+1><m'+1> */
-  double eos_rho0[TXG_NMAX_COMPONENTS];                /* EOS_SC rho0               */
+  double eos_rho0[TXG_NMAX_COMPONENTS];                /* EOS_SC / EOS_THERMO rho0 (lbm_eos.F90:212,247) */
   double gw[TXG_MAX_MINERALS][TXG_NMAX_COMPONENTS];    /* gw[mineral-1][m]          */
   double gvt[3];                     /* body acceleration, lbm_flow.F90:226-231     */
   double null_pressure;              /* flow%null_pressure, written to prs on walls */
   double reserved_d[8];
+  /* eos_type fields of EOSSetFromOptions_Thermo / _PR (lbm_eos.F90:236-320), per component */
+  double eos_psi0[TXG_NMAX_COMPONENTS];     /* EOS_THERMO psi0                                   */
+  double eos_pr_a[TXG_NMAX_COMPONENTS];     /* EOS_PR a (default 2/49), b (2/21), R (1)          */
+  double eos_pr_b[TXG_NMAX_COMPONENTS];
+  double eos_pr_R[TXG_NMAX_COMPONENTS];
+  double eos_pr_T[TXG_NMAX_COMPONENTS];     /* temperature and critical temperature as set up by */
+  double eos_pr_Tc[TXG_NMAX_COMPONENTS];    /* EOSSetFromOptions_PR (:287-309)                   */
+  double eos_pr_omega[TXG_NMAX_COMPONENTS]; /* acentric factor (default: the default-real 0.344) */
 } txg_config;
 
 typedef struct txg_flow *txg_handle;

@@ -73,6 +73,7 @@ typedef struct txo_state {
   int threads; /* 1 = literal serial order everywhere */
   /* external boundary conditions (bc_type, lbm_bc.F90:32-48): flags in cfg.bc_flags */
   double *bc_vals[6]; /* face arrays xm,xp,ym,yp,zm,zp: [t2][t1][nbcs], nbcs = D*S */
+  int eos_bad;        /* EOS_PR: values whose inner square root went negative so far */
   int prestream;      /* 1 (default): BCPreStream runs as in the reference; 0: skipped (test of its effect) */
 } txo_state;
 
@@ -583,17 +584,40 @@ static void update_ue(txo_state *s) {
 }
 
 /* ---------------------------------------------------------------- forces */
-/* EOSApply_Rho / EOSApply_SC, lbm_eos.F90:183-229 (whole ghosted array) */
-static void eos_apply(txo_state *s) {
+/* EOSApply -> EOSApply_Rho / _SC / _Thermo / _PR, lbm_eos.F90:149-349 (whole ghosted array, component by
+ * component; g_mm = gf(m,m), lbm_flow.F90:799).  0.37464, 1.54226, 0.26992 are default-real literals in
+ * EOSApply_PR (:331): their single-precision values enter the double arithmetic.  Returns the number of
+ * values whose inner square root went negative (the reference stops with LBMError at the first, :337-341). */
+static int eos_apply(txo_state *s) {
   const size_t nrg = (size_t)s->rgnx * s->rgny * s->rgnz;
+  int bad = 0;
   for (int m = 0; m < s->S; ++m) {
     const int type = s->cfg.eos_type[m];
-    const double rho0 = s->cfg.eos_rho0[m];
-    for (size_t a = 0; a < nrg; ++a) {
-      const double r = s->rho[a * s->S + m];
-      s->psi[a * s->S + m] = type == TXG_EOS_SC ? rho0 * (1. - exp(-r / rho0)) : r;
+    const double rho0 = s->cfg.eos_rho0[m], psi0 = s->cfg.eos_psi0[m];
+    const double a = s->cfg.eos_pr_a[m], b = s->cfg.eos_pr_b[m], R = s->cfg.eos_pr_R[m], T = s->cfg.eos_pr_T[m];
+    const double omega = s->cfg.eos_pr_omega[m], g_mm = s->cfg.gf[m][m];
+    double alpha = 1. + ((double)0.37464f + (double)1.54226f * omega - (double)0.26992f * (omega * omega)) *
+                            (1. - sqrt(T / s->cfg.eos_pr_Tc[m]));
+    alpha = alpha * alpha;
+    for (size_t i = 0; i < nrg; ++i) {
+      const double r = s->rho[i * s->S + m];
+      double psi = r;
+      if (type == TXG_EOS_SC) {
+        psi = rho0 * (1. - exp(-r / rho0));
+      } else if (type == TXG_EOS_THERMO) {
+        psi = psi0 * exp(-rho0 / r);
+      } else if (type == TXG_EOS_PR) {
+        const double tmp =
+            2. * (r * R * T / (1. - b * r) - (a * alpha * (r * r)) / (1. + 2. * b * r - (b * r) * (b * r)) - r / 3.) /
+            (s->c_0 * g_mm);
+        if (tmp < 0) ++bad;
+        psi = sqrt(tmp);
+      }
+      s->psi[i * s->S + m] = psi;
     }
   }
+  s->eos_bad += bad;
+  return bad;
 }
 
 /* LBMAddFluidSolidForcesD3/D2, lbm_forcing.F90:1326-1421 (+ the neighbour gather
@@ -772,6 +796,7 @@ void txo_set_bc_values(txo_state *s, int b, const double *vals) {
   memcpy(s->bc_vals[b], vals, n * sizeof(double));
 }
 void txo_set_prestream(txo_state *s, int on) { s->prestream = on; }
+int txo_eos_bad(const txo_state *s) { return s->eos_bad; }
 
 /* BCPreStream -> BCPreStream_D2/D3, lbm_bc.F90:613-779: on a Dirichlet / Neumann / velocity face every
  * population with a component along the inward normal is copied from the face node X into X - c_n (a

@@ -57,6 +57,13 @@ module LBM_GPU_Binding_module
      real(c_double) :: gvt(3)
      real(c_double) :: null_pressure
      real(c_double) :: reserved_d(8)
+     real(c_double) :: eos_psi0(TXG_NMAX_COMPONENTS)
+     real(c_double) :: eos_pr_a(TXG_NMAX_COMPONENTS)
+     real(c_double) :: eos_pr_b(TXG_NMAX_COMPONENTS)
+     real(c_double) :: eos_pr_R(TXG_NMAX_COMPONENTS)
+     real(c_double) :: eos_pr_T(TXG_NMAX_COMPONENTS)
+     real(c_double) :: eos_pr_Tc(TXG_NMAX_COMPONENTS)
+     real(c_double) :: eos_pr_omega(TXG_NMAX_COMPONENTS)
   end type txg_config
 
   public :: txg_config_defaults, txg_create, txg_destroy, txg_last_error, txg_nccl_unique_id, txg_comm_init

@@ -75,6 +75,13 @@ class TxgConfig(C.Structure):
         ("gvt", C.c_double * 3),
         ("null_pressure", C.c_double),
         ("reserved_d", C.c_double * 8),
+        ("eos_psi0", C.c_double * NMAX_COMPONENTS),
+        ("eos_pr_a", C.c_double * NMAX_COMPONENTS),
+        ("eos_pr_b", C.c_double * NMAX_COMPONENTS),
+        ("eos_pr_R", C.c_double * NMAX_COMPONENTS),
+        ("eos_pr_T", C.c_double * NMAX_COMPONENTS),
+        ("eos_pr_Tc", C.c_double * NMAX_COMPONENTS),
+        ("eos_pr_omega", C.c_double * NMAX_COMPONENTS),
     ]
 
     def copy(self):
@@ -117,8 +124,25 @@ def default_config(ndims=3, ncomponents=2, NX=1, NY=1, NZ=1):
         c.mm[m] = 1.0
         c.eos_rho0[m] = 1.0
         c.eos_type[m] = EOS_DENSITY
+        set_eos_pr(c, m)
+        c.eos_psi0[m] = 1.0
     c.null_pressure = 0.0
     return c
+
+
+def set_eos_pr(c, m, a=2.0 / 49.0, b=2.0 / 21.0, R=1.0, T=None, reduced_T=None, omega=None):
+    """EOSSetFromOptions_PR (lbm_eos.F90:272-320).  0.0778, 0.45724, 0.9 and 0.344 are default-real
+    literals there: their single-precision values enter the double arithmetic."""
+    import numpy as np
+
+    f32 = lambda v: float(np.float32(v))  # noqa: E731
+    c.eos_pr_a[m], c.eos_pr_b[m], c.eos_pr_R[m] = a, b, R
+    Tc = a / b * f32(0.0778) / f32(0.45724) / R
+    c.eos_pr_Tc[m] = Tc
+    if T is None:
+        T = (f32(0.9) if reduced_T is None else reduced_T) * Tc
+    c.eos_pr_T[m] = T
+    c.eos_pr_omega[m] = f32(0.344) if omega is None else omega
 
 
 def finalize_flags(c):

@@ -280,8 +280,20 @@ static void fill_phys(txg_flow *h) {
     p.d_k[m] = 1. - 2. / (3. * c.mm[m]);  // lbm_component.F90:158
     p.mmot[m] = c.mm[m] * s_c;            // lbm_flow.F90:519-521
     for (int k = 0; k < h->S; ++k) p.gf[m][k] = c.gf[m][k];
+    p.eos_kind[m] = c.use_nonideal_eos ? c.eos_type[m] : TXG_EOS_DENSITY;
     p.eos_rho0[m] = c.eos_rho0[m];
-    p.eos_sc[m] = c.use_nonideal_eos && c.eos_type[m] == TXG_EOS_SC;
+    p.eos_psi0[m] = c.eos_psi0[m];
+    p.pr_a[m] = c.eos_pr_a[m];
+    p.pr_b[m] = c.eos_pr_b[m];
+    p.pr_R[m] = c.eos_pr_R[m];
+    p.pr_T[m] = c.eos_pr_T[m];
+    {  // alpha of EOSApply_PR (lbm_eos.F90:331-332); 0.37464, 1.54226, 0.26992 are default-real literals there
+      const double om = c.eos_pr_omega[m];
+      const double k = (double)0.37464f + (double)1.54226f * om - (double)0.26992f * (om * om);
+      const double t = 1. + k * (1. - sqrt(c.eos_pr_T[m] / c.eos_pr_Tc[m]));
+      p.pr_alpha[m] = t * t;
+    }
+    p.pr_c0g[m] = 6.0 * c.gf[m][m];  // dist%disc%c_0 * g_mm (lbm_flow.F90:799)
   }
   for (int d = 0; d < 3; ++d) p.gvt[d] = c.gvt[d];
   p.nminerals = c.nminerals;
@@ -290,6 +302,7 @@ static void fill_phys(txg_flow *h) {
   p.body = c.body_forces;
   p.eos = c.use_nonideal_eos;
   p.gw = h->gw;
+  p.eos_bad = h->counters + 3;
 }
 
 static int validate(const txg_config *c) {
@@ -338,8 +351,10 @@ static int validate(const txg_config *c) {
                b);
   for (int m = 0; m < c->ncomponents; ++m) {
     if (!(c->tau[m] > 0.) || !(c->mm[m] > 0.)) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "component %d: tau and mm must be positive", m + 1);
-    if (c->use_nonideal_eos && c->eos_type[m] != TXG_EOS_DENSITY && c->eos_type[m] != TXG_EOS_SC)
-      TXG_FAIL(h, TXG_ERR_SUP, "component %d: only EOS_DENSITY and EOS_SC are implemented on the device", m + 1);
+    if (c->use_nonideal_eos && (c->eos_type[m] < TXG_EOS_DENSITY || c->eos_type[m] > TXG_EOS_THERMO))
+      TXG_FAIL(h, 1, "Invalid EOS type");  // lbm_eos.F90:167
+    if (c->use_nonideal_eos && c->eos_type[m] == TXG_EOS_PR && !(c->eos_pr_Tc[m] > 0.))
+      TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "component %d: EOS_PR needs eos_pr_Tc > 0 (EOSSetFromOptions_PR, lbm_eos.F90:287)", m + 1);
   }
   return 0;
 }
@@ -411,7 +426,15 @@ extern "C" int txg_config_defaults(txg_config *c) {
     c->tau[m] = c->s_c[m] = c->s_e[m] = c->s_e2[m] = c->s_q[m] = c->s_nu[m] = c->s_pi[m] = c->s_m[m] = 1.0;
     c->mm[m] = 1.0;
     c->eos_rho0[m] = 1.0;
+    c->eos_psi0[m] = 1.0;
     c->eos_type[m] = TXG_EOS_DENSITY;
+    // EOSSetFromOptions_PR defaults (lbm_eos.F90:282-316); 0.0778, 0.45724, 0.9, 0.344 are default-real literals
+    c->eos_pr_a[m] = 2.0 / 49.;
+    c->eos_pr_b[m] = 2.0 / 21.;
+    c->eos_pr_R[m] = 1.0;
+    c->eos_pr_Tc[m] = c->eos_pr_a[m] / c->eos_pr_b[m] * (double)0.0778f / (double)0.45724f / c->eos_pr_R[m];
+    c->eos_pr_T[m] = (double)0.9f * c->eos_pr_Tc[m];
+    c->eos_pr_omega[m] = (double)0.344f;
   }
   return 0;
 }
@@ -1235,6 +1258,8 @@ extern "C" int txg_update_flux(txg_handle h) {
   return txg_step(h, 1);
 }
 
+static int check_eos(txg_flow *h);
+
 // ------------------------------------------------------------------ state out
 // refresh rho (+halo) from the current populations
 static int refresh_rho(txg_flow *h) {
@@ -1276,6 +1301,7 @@ extern "C" int txg_get_fi(txg_handle h, double *fi_g) {
   if (!fi_g) TXG_FAIL(h, TXG_ERR_ARG_NULL, "null array");
   if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "no state on the device yet");
   TXG_CUDA(h, cudaSetDevice(h->device));
+  TXG_TRY(check_eos(h));
   return export_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->S, h->f[h->cur], 0);
 }
 
@@ -1285,6 +1311,7 @@ extern "C" int txg_get_state(txg_handle h, double *rho_rg, double *u_g, double *
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
   TXG_TRY(refresh_rho(h));
+  TXG_TRY(check_eos(h));
   const size_t n = (size_t)g.nnodes;
   if (rho_rg) TXG_TRY(ensure(h, &h->x_rho, n * h->S));
   if (u_g) TXG_TRY(ensure(h, &h->x_u, n * h->S * h->D));
@@ -1351,12 +1378,25 @@ extern "C" int txg_delta_norm(txg_handle h, double *norm) {
   return 0;
 }
 
+// EOSApply_PR stops the run when its inner square root goes negative (lbm_eos.F90:337-341); the device
+// kernels count such values and the next synchronising call reports them
+static int check_eos(txg_flow *h) {
+  bool pr = false;
+  for (int m = 0; m < h->S; ++m) pr = pr || (h->cfg.use_nonideal_eos && h->cfg.eos_type[m] == TXG_EOS_PR);
+  if (!pr) return 0;
+  int bad = 0;
+  TXG_CUDA(h, cudaMemcpyAsync(&bad, h->counters + 3, sizeof bad, cudaMemcpyDeviceToHost, h->s_main));
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  if (bad) TXG_FAIL(h, TXG_ERR_ORDER, "PR EOS inner sqrt went negative (%d values)", bad);  // ierr = 58 in the reference
+  return 0;
+}
+
 extern "C" int txg_synchronize(txg_handle h) {
   if (!h) return TXG_ERR_ARG_NULL;
   TXG_CUDA(h, cudaSetDevice(h->device));
   TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
   TXG_CUDA(h, cudaStreamSynchronize(h->s_comm));
-  return 0;
+  return check_eos(h);
 }
 
 // ------------------------------------------------------------------ measurement hooks

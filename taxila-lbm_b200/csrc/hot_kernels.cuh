@@ -443,7 +443,7 @@ __device__ __forceinline__ void common_velocity1(const Phys &p, const Item &it, 
 // EOS).  Replaces DistributionCalcDensityD* (lbm_distribution_function.F90:379-428) and EOSApply;
 // streaming and bounce-back happened in the push of the previous collide.
 template <class L, int S>
-__global__ void __launch_bounds__(128) k_moments(Grid g, Phys p, const double *__restrict__ fA,
+__global__ void __launch_bounds__(128, 16) k_moments(Grid g, Phys p, const double *__restrict__ fA,
                                                  double *__restrict__ rho, double *__restrict__ rho_true,
                                                  long long first, long long count) {
   Item it;

@@ -61,8 +61,12 @@ struct Phys {
   double mrt_rate[MAXS][19];   // MRT: s_r / ||M_r||^2 per moment row
   double mm[MAXS], d_k[MAXS], mmot[MAXS];
   double gf[MAXS][MAXS];
-  double eos_rho0[MAXS];
-  int eos_sc[MAXS];            // 1: psi = rho0 (1 - exp(-rho/rho0)); 0: psi = rho
+  // EOSApply (lbm_eos.F90:149-349), active when eos != 0.  eos_kind: TXG_EOS_DENSITY 1 (psi = rho), SC 2, PR 3,
+  // THERMO 4.  SC / THERMO: eos_rho0, eos_psi0.  PR: a, b, R, T, alpha (host, :331-332) and c0g = c_0 * g_mm.
+  int eos_kind[MAXS];
+  double eos_rho0[MAXS], eos_psi0[MAXS];
+  double pr_a[MAXS], pr_b[MAXS], pr_R[MAXS], pr_T[MAXS], pr_alpha[MAXS], pr_c0g[MAXS];
+  int *eos_bad;                // device counter: PR inner square root went negative (lbm_eos.F90:337-341)
   double gvt[3];
   int nminerals;
   int fluidfluid, fluidsolid, body, eos;
@@ -317,8 +321,20 @@ __device__ __forceinline__ void prefactor(double rho, const double (&F)[L::D], c
   });
 }
 
+// EOSApply_Rho / _SC / _Thermo / _PR (lbm_eos.F90:183-349) for one value
 __device__ __forceinline__ double eos_psi(const Phys &p, int m, double rho) {
-  return p.eos_sc[m] ? p.eos_rho0[m] * (1. - exp(-rho / p.eos_rho0[m])) : rho;
+  const int kind = p.eos_kind[m];
+  if (kind == 2) return p.eos_rho0[m] * (1. - exp(-rho / p.eos_rho0[m]));
+  if (kind == 4) return p.eos_psi0[m] * exp(-p.eos_rho0[m] / rho);
+  if (kind == 3) {
+    const double b = p.pr_b[m];
+    const double tmp = 2. * (rho * p.pr_R[m] * p.pr_T[m] / (1. - b * rho) -
+                             (p.pr_a[m] * p.pr_alpha[m] * (rho * rho)) / (1. + 2. * b * rho - (b * rho) * (b * rho)) - rho / 3.) /
+                       p.pr_c0g[m];
+    if (tmp < 0.) atomicAdd(p.eos_bad, 1);  // "PR EOS inner sqrt went negative": reported at the next synchronising call
+    return sqrt(tmp);
+  }
+  return rho;
 }
 
 // ================================================================== kernels

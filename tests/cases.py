@@ -197,3 +197,24 @@ def run_oracle_bc(cfg, walls, rho, bcs, steps, prestream=True):
     o.update_moments()
     o.step(steps)
     return o
+
+
+def eos_pr_thermo_3d(N=32):
+    """-flow_use_nonideal_eos with a Peng-Robinson component (self-attraction g_11 < 0, T = 0.95 T_c) and a
+    Shan-Chen '94 "thermo" component psi = psi0 exp(-rho0 / rho) (lbm_eos.F90:231-349), smooth initial state,
+    C4's walls, minerals and body force."""
+    cfg, walls, rho = porous_3d(N, order=4, rmin=N / 8.0, rmax=N / 4.0)
+    cfg.use_nonideal_eos = 1
+    cfg.eos_type[0] = tc.EOS_PR
+    cfg.gf[0][0] = -0.5
+    cfg.gf[0][1] = cfg.gf[1][0] = 0.05
+    tc.set_eos_pr(cfg, 0, reduced_T=0.95)
+    cfg.eos_type[1] = tc.EOS_THERMO
+    cfg.eos_psi0[1], cfg.eos_rho0[1] = 1.2, 0.4
+    tc.finalize_flags(cfg)
+    zz, yy, xx = np.mgrid[0:N, 0:N, 0:N]
+    rho = np.zeros((N, N, N, 2))
+    rho[..., 0] = 0.8 + 0.1 * np.sin(2 * np.pi * xx / N) * np.cos(2 * np.pi * zz / N)
+    rho[..., 1] = 0.5 + 0.1 * np.cos(2 * np.pi * yy / N)
+    rho[walls != 0] = 0
+    return cfg, walls, rho

@@ -62,6 +62,8 @@ def lib():
             fn.argtypes = [C.c_void_p] + args
             if name != "txo_delta_norm":
                 fn.restype = None
+        L.txo_eos_bad.argtypes = [C.c_void_p]
+        L.txo_eos_bad.restype = C.c_int
         L.txo_bc_supported.argtypes = [C.c_void_p]
         L.txo_bc_supported.restype = C.c_int
         ip = C.POINTER(C.c_int)
@@ -129,6 +131,9 @@ class Oracle:
     def set_bc_values(self, boundary, vals):
         v = np.ascontiguousarray(vals, dtype=np.float64).reshape(self.shape_bc(boundary))
         self.L.txo_set_bc_values(self.h, int(boundary), _dp(v))
+
+    def eos_bad(self):
+        return self.L.txo_eos_bad(self.h)
 
     def set_prestream(self, on):
         self.L.txo_set_prestream(self.h, int(on))

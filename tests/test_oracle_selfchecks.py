@@ -87,3 +87,26 @@ def test_planar_specular_walls_conserve_mass():
     assert np.ptp(ux_slip) <= 1e-10
     assert abs(ux_slip.mean() - 200 * 1e-4) <= 2e-4
     assert ux_noslip.mean() < 0.8 * ux_slip.mean() and np.ptp(ux_noslip) > 1e-3
+
+
+def test_eos_variants_against_their_formulas():
+    """EOSApply_SC / _Thermo / _PR (lbm_eos.F90:183-349) as the pressure term of FlowUpdateDiagnostics
+    shows them: prs = rhot/3 + (c_0/2) sum_m psi_m sum_m' g_mm' psi_m' (lbm_flow.F90:654-758)."""
+    import cases
+
+    cfg, walls, rho = cases.eos_pr_thermo_3d(12)
+    o = cases.run_oracle(cfg, walls, rho, 0)
+    assert o.eos_bad() == 0
+    r = o.rho()
+    fluid = walls == 0
+    f32 = lambda v: float(np.float32(v))  # noqa: E731
+    om, T, Tc = cfg.eos_pr_omega[0], cfg.eos_pr_T[0], cfg.eos_pr_Tc[0]
+    assert abs(Tc - (2 / 49) / (2 / 21) * f32(0.0778) / f32(0.45724)) < 1e-17 and abs(T - 0.95 * Tc) < 1e-17
+    alpha = (1 + (f32(0.37464) + f32(1.54226) * om - f32(0.26992) * om ** 2) * (1 - np.sqrt(T / Tc))) ** 2
+    a, b, g = cfg.eos_pr_a[0], cfg.eos_pr_b[0], cfg.gf[0][0]
+    r0, r1 = r[..., 0][fluid], r[..., 1][fluid]
+    psi0 = np.sqrt(2 * (r0 * T / (1 - b * r0) - a * alpha * r0 ** 2 / (1 + 2 * b * r0 - (b * r0) ** 2) - r0 / 3) / (6 * g))
+    psi1 = cfg.eos_psi0[1] * np.exp(-cfg.eos_rho0[1] / r1)
+    want = (r0 + r1) / 3 + 3 * (psi0 * (g * psi0 + cfg.gf[0][1] * psi1) + psi1 * (cfg.gf[1][0] * psi0 + cfg.gf[1][1] * psi1))
+    prs = o.diagnostics()[1][fluid]
+    assert np.abs(prs - want).max() <= 1e-13 * np.abs(want).max()
