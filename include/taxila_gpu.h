@@ -176,6 +176,16 @@ TXG_API int txg_set_walls(txg_handle h, const double *walls_rg);
  * lbm_flow.F90:1958-1991, stay on the host and re-upload). */
 TXG_API int txg_set_bc_values(txg_handle h, int boundary, const double *vals);
 
+/* flow%bc_flags(boundary) = BC_PRESSURE_OUTLET with flow%bc_data(1,boundary) = pressure
+ * (FlowParseBC, lbm_flow.F90:1170-1189).  The face must be BC_DIRICHLET in bc_flags and its array
+ * uploaded with txg_set_bc_values.  With two components every step then starts FlowApplyBCs the way the
+ * reference does (FlowUpdateBCPressureOutlet + FlowUpdateDensityFromPressure, lbm_flow.F90:1993-2263):
+ * the face densities are re-derived on the device from the pressure and the phase fraction of the node one
+ * step inside.  Fails like the reference for a non-ideal EOS or g_11 /= 0 (:2000-2005) and for more than
+ * two components (:2260).  The flux-outlet update (FlowUpdateBCFluxOutlet, :2265-2497) tests for
+ * BC_PRESSURE_OUTLET faces only, so a BC_FLUX_OUTLET face keeps its constant BC_NEUMANN values: nothing to call. */
+TXG_API int txg_set_bc_pressure_outlet(txg_handle h, int boundary, double pressure);
+
 /* LBMInitializeState result (lbm.F90:444-453): host rho(S,rg..) and u(S,ndims,g..)
  * as filled by the user's initialize_state.  u may be NULL (= 0, what every
  * shipped initialize_state sets). */

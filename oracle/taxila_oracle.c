@@ -73,6 +73,8 @@ typedef struct txo_state {
   int threads; /* 1 = literal serial order everywhere */
   /* external boundary conditions (bc_type, lbm_bc.F90:32-48): flags in cfg.bc_flags */
   double *bc_vals[6]; /* face arrays xm,xp,ym,yp,zm,zp: [t2][t1][nbcs], nbcs = D*S */
+  int bc_pressure_outlet[6];   /* flow%bc_flags(b) .eq. BC_PRESSURE_OUTLET (lbm_flow.F90:1170-1189) */
+  double bc_outlet_pressure[6]; /* flow%bc_data(1,b) of such a face */
   int eos_bad;        /* EOS_PR: values whose inner square root went negative so far */
   int prestream;      /* 1 (default): BCPreStream runs as in the reference; 0: skipped (test of its effect) */
 } txo_state;
@@ -796,6 +798,10 @@ void txo_set_bc_values(txo_state *s, int b, const double *vals) {
   memcpy(s->bc_vals[b], vals, n * sizeof(double));
 }
 void txo_set_prestream(txo_state *s, int on) { s->prestream = on; }
+void txo_set_bc_pressure_outlet(txo_state *s, int b, double pressure) {
+  s->bc_pressure_outlet[b] = 1;
+  s->bc_outlet_pressure[b] = pressure;
+}
 int txo_eos_bad(const txo_state *s) { return s->eos_bad; }
 
 /* BCPreStream -> BCPreStream_D2/D3, lbm_bc.F90:613-779: on a Dirichlet / Neumann / velocity face every
@@ -851,6 +857,54 @@ static void bc_update_rho(txo_state *s) {
           for (int n = 0; n < s->Q; ++n) acc += FI(s, m, n, x[0], x[1], x[2]);
           RHO(s, m, x[0], x[1], x[2]) = acc;
         }
+      }
+  }
+}
+
+/* FlowUpdateDensityFromPressure, lbm_flow.F90:2235-2263 (components(2)%gf(1) = gf[1][0]) */
+static void density_from_pressure(const txo_state *s, double pressure, double rho1frac, double *rho /* stride 1, S entries */) {
+  const double eps = 1.e-10;
+  if (s->S == 1) {
+    rho[0] = pressure * 3.;
+  } else {
+    if (rho1frac < eps) {
+      rho[0] = 0.;
+      rho[1] = pressure * 3.;
+    } else if (rho1frac > 1 - eps) {
+      rho[0] = pressure * 3.;
+      rho[1] = 0.;
+    } else {
+      const double alpha = 1. / (1. / rho1frac - 1.);
+      const double g21 = s->cfg.gf[1][0];
+      rho[0] = (-(1. + alpha) / 3. + sqrt((1. + alpha) / 3. * (1. + alpha) / 3. + 4. * s->c_0 * g21 * alpha * pressure)) /
+               (2 * s->c_0 * g21);
+      rho[1] = rho[0] / alpha;
+    }
+  }
+}
+
+/* FlowUpdateBCPressureOutlet -> D2/D3, lbm_flow.F90:1993-2233, called at the top of FlowApplyBCs (:1965-1972,
+ * only when ncomponents /= 1): on every fluid node of a pressure-outlet face the Dirichlet densities are
+ * re-derived from the face's pressure and the phase fraction rho_1 / sum(rho) of the node one step inside
+ * (of the node itself when that one is solid), read from dist%rho as the previous step left it. */
+static void bc_pressure_outlet_update(txo_state *s) {
+  if (s->S == 1) return;
+  const int nbcs = s->D * s->S;
+  for (int b = 0; b < 2 * s->D; ++b) {
+    if (!s->bc_pressure_outlet[b]) continue;
+    const txo_face f = face_of(s, b);
+    for (int bb = 0; bb < f.n2; ++bb)
+      for (int a = 0; a < f.n1; ++a) {
+        int x[3] = {0, 0, 0};
+        face_node(&f, a, bb, x);
+        if (WALLS(s, x[0], x[1], x[2]) != 0.) continue;
+        int y[3] = {x[0], x[1], x[2]};
+        y[f.axis] += f.sign;
+        if (WALLS(s, y[0], y[1], y[2]) != 0.) y[f.axis] = x[f.axis];
+        double sum = 0.;
+        for (int m = 0; m < s->S; ++m) sum += RHO(s, m, y[0], y[1], y[2]);
+        const double rho1frac = RHO(s, 0, y[0], y[1], y[2]) / sum;
+        density_from_pressure(s, s->bc_outlet_pressure[b], rho1frac, s->bc_vals[b] + ((size_t)bb * f.n1 + a) * nbcs);
       }
   }
 }
@@ -1026,6 +1080,7 @@ static void bc_apply(txo_state *s) {
  * at its top are host-side set-up of the face arrays and not part of this restatement);
  * FlowUpdateFlux (:458-464). */
 static void apply_bcs(txo_state *s) {
+  bc_pressure_outlet_update(s);
   calc_density(s);
   bc_dirichlet_to_rho(s);
   calc_forces(s);

@@ -67,7 +67,7 @@ module LBM_GPU_Binding_module
   end type txg_config
 
   public :: txg_config_defaults, txg_create, txg_destroy, txg_last_error, txg_nccl_unique_id, txg_comm_init
-  public :: txg_set_bc_values
+  public :: txg_set_bc_values, txg_set_bc_pressure_outlet
   public :: txg_set_walls, txg_set_rho_u, txg_set_fi, txg_fi_init, txg_update_moments, txg_step
   public :: txg_collision, txg_communicate_fi, txg_stream, txg_bounceback, txg_apply_bcs, txg_update_flux
   public :: txg_get_fi, txg_get_state, txg_get_diagnostics, txg_get_node_class, txg_delta_norm, txg_synchronize
@@ -128,6 +128,14 @@ module LBM_GPU_Binding_module
        integer(c_int), value :: boundary
        real(c_double), intent(in) :: vals(*)
      end function txg_set_bc_values
+
+     ! flow%bc_flags(boundary) = BC_PRESSURE_OUTLET, flow%bc_data(1,boundary) = pressure (lbm_flow.F90:1170-1189)
+     integer(c_int) function txg_set_bc_pressure_outlet(h, boundary, pressure) bind(C, name="txg_set_bc_pressure_outlet")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: boundary
+       real(c_double), value :: pressure
+     end function txg_set_bc_pressure_outlet
 
      ! LBMInitializeState result (lbm.F90:444-453); u_g may be c_null_ptr (= 0)
      integer(c_int) function txg_set_rho_u(h, rho_rg, u_g) bind(C, name="txg_set_rho_u")

@@ -27,6 +27,7 @@ PROTOTYPES = {
     "txg_comm_init": (C.c_int, [_h, C.POINTER(C.c_ubyte)]),
     "txg_set_walls": (C.c_int, [_h, _dp]),
     "txg_set_bc_values": (C.c_int, [_h, C.c_int, _dp]),
+    "txg_set_bc_pressure_outlet": (C.c_int, [_h, C.c_int, C.c_double]),
     "txg_set_rho_u": (C.c_int, [_h, _dp, _dp]),
     "txg_set_fi": (C.c_int, [_h, _dp]),
     "txg_fi_init": (C.c_int, [_h]),

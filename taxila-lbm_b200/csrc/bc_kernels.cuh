@@ -54,6 +54,47 @@ __global__ void k_bc_dirichlet_rho(Grid g, Phys p, int S, FaceDesc fd, const dou
   }
 }
 
+// FlowUpdateBCPressureOutletD2/D3 + FlowUpdateDensityFromPressure (lbm_flow.F90:1993-2263) on one face, two
+// components: the Dirichlet densities of every fluid face node are re-derived from the face's pressure and
+// the phase fraction rho_1 / sum(rho) of the node one step inside (of the node itself when that one is
+// solid).  The reference reads dist%rho as the previous step left it, which is the sum of the populations
+// of that state everywhere (DistributionCalcDensity, BCUpdateRho): f is the buffer BEFORE this step's collide.
+__global__ void k_bc_pressure_outlet(Grid g, int Q, FaceDesc fd, double *__restrict__ vals, int nbcs,
+                                     const double *__restrict__ f, const uint32_t *__restrict__ nbmask,
+                                     double pressure, double g21) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long pos;
+  if (!face_node(g, fd, nbmask, idx, pos)) return;
+  int x[3] = {0, 0, 0};
+  x[fd.axis] = fd.coord + fd.sign;
+  x[fd.t1] = (int)(idx % fd.n1);
+  x[fd.t2] = (int)(idx / fd.n1);
+  const long long o = (long long)x[2] * g.plane + (long long)x[1] * g.NX + x[0];
+  if (!(nbmask[o] >> 31)) pos = pos_of(g, o + (long long)g.Rz * g.plane);
+  double rho[2];
+  for (int m = 0; m < 2; ++m) {
+    double a = 0.;
+    for (int n = 0; n < Q; ++n) a += f[(long long)(m * Q + n) * g.fs + pos];
+    rho[m] = a;
+  }
+  const double rho1frac = rho[0] / (rho[0] + rho[1]);
+  const double eps = 1.e-10;
+  double r0, r1;
+  if (rho1frac < eps) {
+    r0 = 0.;
+    r1 = pressure * 3.;
+  } else if (rho1frac > 1 - eps) {
+    r0 = pressure * 3.;
+    r1 = 0.;
+  } else {
+    const double alpha = 1. / (1. / rho1frac - 1.);
+    r0 = (-(1. + alpha) / 3. + sqrt((1. + alpha) / 3. * (1. + alpha) / 3. + 4. * 6.0 * g21 * alpha * pressure)) / (2 * 6.0 * g21);
+    r1 = r0 / alpha;
+  }
+  vals[idx * nbcs + 0] = r0;
+  vals[idx * nbcs + 1] = r1;
+}
+
 // BCApply -> BCApply{Dirichlet,Neumann,Velocity}D* -> ...Node (lbm_bc.F90:781-807,1075-1865) on one
 // face.  f: the populations after streaming and bounce-back (the incoming directions of a face node
 // hold what the bounce-back off the 999 ghost layer put there); F: forces of FlowCalcRhoForces.

@@ -146,6 +146,8 @@ struct txg_flow {
   bool face_here[6] = {false, false, false, false, false, false};  // this rank holds the face
   std::vector<int> bc_order;                                       // faces in BCApply's execution order
   double *bc_vals[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool pressure_outlet[6] = {false, false, false, false, false, false};  // flow%bc_flags(b) .eq. BC_PRESSURE_OUTLET
+  double outlet_pressure[6] = {0., 0., 0., 0., 0., 0.};                  // flow%bc_data(1,b)
   // free-slip walls (900-902): slots rewritten after every push (bc_kernels.cuh)
   uint32_t *spec_dst = nullptr, *spec_src = nullptr;
   double *spec_tmp = nullptr;
@@ -1196,12 +1198,40 @@ static int bc_apply(txg_flow *h) {
 static int one_step_bc(txg_flow *h) {
   const Grid &g = h->g;
   cudaStream_t sm = h->s_main;
+  // FlowUpdateBCPressureOutlet (top of FlowApplyBCs, only when ncomponents /= 1, lbm_flow.F90:1965-1972):
+  // it reads the densities the previous step left, i.e. the sums of the populations still in f[cur]
+  if (h->S == 2)
+    for (int b = 0; b < 2 * h->D; ++b) {
+      if (!h->pressure_outlet[b] || !h->face_here[b]) continue;
+      const FaceDesc &fd = h->faces[b];
+      if (!h->bc_vals[b]) TXG_FAIL(h, TXG_ERR_ORDER, "boundary %d is a pressure outlet but txg_set_bc_values was not called for it", b);
+      ScopedKernel sk(h, "k_bc_pressure_outlet", sm);
+      k_bc_pressure_outlet<<<blocks_for((long long)fd.n1 * fd.n2, 128), 128, 0, sm>>>(g, h->Q, fd, h->bc_vals[b], h->S * h->D, h->f[h->cur],
+                                                                                    h->nbmask, h->outlet_pressure[b], h->cfg.gf[1][0]);
+      TXG_CUDA(h, cudaGetLastError());
+    }
   TXG_TRY(run_collide(h, 0, g.NZl, sm));
   TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sm));
   TXG_TRY(apply_specular(h, h->f[h->cur ^ 1], sm));
   h->cur ^= 1;
   TXG_TRY(bc_moments_forces(h, true));
   TXG_TRY(bc_apply(h));
+  return 0;
+}
+
+// FlowParseBC's BC_PRESSURE_OUTLET (lbm_flow.F90:1170-1189) with the checks of FlowUpdateBCPressureOutlet (:2000-2005)
+// and FlowUpdateDensityFromPressure (:2260)
+extern "C" int txg_set_bc_pressure_outlet(txg_handle h, int boundary, double pressure) {
+  if (!h) return TXG_ERR_ARG_NULL;
+  if (boundary < 0 || boundary >= 2 * h->D) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "boundary %d out of range", boundary);
+  if (h->cfg.bc_flags[boundary] != TXG_BC_DIRICHLET)
+    TXG_FAIL(h, TXG_ERR_ARG_WRONG, "a pressure outlet is a BC_DIRICHLET face (lbm_flow.F90:1178): bc_flags[%d] = %d", boundary, h->cfg.bc_flags[boundary]);
+  if (h->S > 2) TXG_FAIL(h, 1, "Invalid number of components for flow");
+  if (h->S == 2 && (fabs(h->cfg.gf[0][0]) > (double)1.e-10f || h->cfg.use_nonideal_eos))
+    TXG_FAIL(h, 1, "Pressure outlet not implemented for non-ideal EOS or g11 or g22 /= 0");
+  if (boundary >= 4 && h->g.NZl < 2) TXG_FAIL(h, TXG_ERR_SUP, "a z pressure outlet needs a slab of at least two planes");
+  h->pressure_outlet[boundary] = true;
+  h->outlet_pressure[boundary] = pressure;
   return 0;
 }
 

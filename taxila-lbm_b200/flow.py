@@ -118,6 +118,10 @@ class Flow:
         self._expect(v, self.shape_bc(boundary), "bc values of boundary %d" % boundary)
         self._check(self.lib.txg_set_bc_values(self.h, int(boundary), _dp(v)))
 
+    def bc_set_pressure_outlet(self, boundary, pressure):
+        """flow%bc_flags(boundary) = BC_PRESSURE_OUTLET, flow%bc_data(1,boundary) = pressure (lbm_flow.F90:1170-1189)."""
+        self._check(self.lib.txg_set_bc_pressure_outlet(self.h, int(boundary), float(pressure)))
+
     def initialize_state(self, rho_rg, u_g=None):
         r = _c(rho_rg)
         self._expect(r, self.shape_rho(), "rho")

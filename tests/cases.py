@@ -184,13 +184,16 @@ def drainage_3d(N=24, NZ=32, inlet=None, outlet=None, order=4, mrt=True, seed=11
     return c, walls, rho, bcs
 
 
-def run_oracle_bc(cfg, walls, rho, bcs, steps, prestream=True):
+def run_oracle_bc(cfg, walls, rho, bcs, steps, prestream=True, outlets=None):
+    """outlets = {boundary: pressure}: faces flagged BC_PRESSURE_OUTLET (lbm_flow.F90:1170-1189)."""
     import oracle
 
     o = oracle.Oracle(cfg)
     o.set_walls(walls)
     for b, v in bcs.items():
         o.set_bc_values(b, v)
+    for b, p in (outlets or {}).items():
+        o.set_bc_pressure_outlet(b, p)
     o.set_prestream(prestream)
     o.set_rho(rho)
     o.fi_init()

@@ -39,14 +39,16 @@ def mass(rho, fluid):
     return np.array([np.sum(rho[..., m][fluid], dtype=np.longdouble) for m in range(rho.shape[-1])], dtype=np.float64)
 
 
-def make_flow_bc(cfg, walls, rho, bcs, device=0):
-    """make_flow with face arrays (BCSetValues) uploaded before FlowFiInit."""
+def make_flow_bc(cfg, walls, rho, bcs, device=0, outlets=None):
+    """make_flow with face arrays (BCSetValues) uploaded before FlowFiInit; outlets = {boundary: pressure}."""
     D = cfg.ndims
     R = cfg.stencil_size_rho
     flow = tx.Flow(cfg, device=device)
     flow.walls_set_values(geo.ghosted(walls, R, cfg.periodic, D, wall_ghost=True))
     for b, v in bcs.items():
         flow.bc_set_values(b, v)
+    for b, p in (outlets or {}).items():
+        flow.bc_set_pressure_outlet(b, p)
     flow.initialize_state(geo.ghosted(rho, R, cfg.periodic, D))
     flow.fi_init()
     flow.update_moments()

@@ -57,6 +57,7 @@ def lib():
             "txo_delta_norm": [],
             "txo_set_bc_values": [C.c_int, dp],
             "txo_set_prestream": [C.c_int],
+            "txo_set_bc_pressure_outlet": [C.c_int, C.c_double],
         }.items():
             fn = getattr(L, name)
             fn.argtypes = [C.c_void_p] + args
@@ -134,6 +135,9 @@ class Oracle:
 
     def eos_bad(self):
         return self.L.txo_eos_bad(self.h)
+
+    def set_bc_pressure_outlet(self, boundary, pressure):
+        self.L.txo_set_bc_pressure_outlet(self.h, int(boundary), float(pressure))
 
     def set_prestream(self, on):
         self.L.txo_set_prestream(self.h, int(on))

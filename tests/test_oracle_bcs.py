@@ -155,3 +155,20 @@ def test_reflecting_face_keeps_a_stale_density():
     assert np.abs(stored - r)[interior].max() < 1e-15
     xp = (walls == 0)[:, :, -1]
     assert np.abs(stored - r)[:, :, -1][xp].max() > 1e-6
+
+
+def test_pressure_outlet_rederives_the_face_densities():
+    """FlowUpdateBCPressureOutlet + FlowUpdateDensityFromPressure (lbm_flow.F90:1993-2263): the densities put on
+    the outlet face give the prescribed pressure p = (rho_1 + rho_2)/3 + c_0 g_21 rho_1 rho_2 at the phase
+    fraction of the node one step inside."""
+    cfg, walls, rho, bcs = cases.channel_2d(inlet=tc.BC_VELOCITY, outlet=tc.BC_DIRICHLET, walls_kind="noslip")
+    p_out = 0.31
+    o = cases.run_oracle_bc(cfg, walls, rho, bcs, 20, outlets={tc.BOUNDARY_XP: p_out})
+    fi, r, mom = _moments(o, cfg)
+    fluid = walls[0, :, -1] == 0
+    face = r[0, :, -1][fluid]                        # BCUpdateRho: what the Dirichlet correction reached
+    g21 = cfg.gf[1][0]
+    p = (face[:, 0] + face[:, 1]) / 3 + 6.0 * g21 * face[:, 0] * face[:, 1]
+    assert np.abs(p - p_out).max() < 1e-13
+    # and it differs from the constant-density outlet the face array started with
+    assert np.abs(face - bcs[tc.BOUNDARY_XP][..., 0, :][fluid]).max() > 1e-3

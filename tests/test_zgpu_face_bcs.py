@@ -17,9 +17,9 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
 
-def compare_bc(cfg, walls, rho, bcs, steps, tol=TOL, kernels=()):
-    o = cases.run_oracle_bc(cfg, walls, rho, bcs, steps)
-    flow = gpu_util.make_flow_bc(cfg, walls, rho, bcs)
+def compare_bc(cfg, walls, rho, bcs, steps, tol=TOL, kernels=(), outlets=None):
+    o = cases.run_oracle_bc(cfg, walls, rho, bcs, steps, outlets=outlets)
+    flow = gpu_util.make_flow_bc(cfg, walls, rho, bcs, outlets=outlets)
     flow.step(steps)
     fi, r, u, F = gpu_util.fields(flow)
     fluid = np.asarray(walls).reshape(r.shape[:3]) == 0
@@ -61,6 +61,15 @@ def test_flux_inlet_freeslip_duct_2d():
     """BC_NEUMANN inlet + the reference's nostick duct (WALL_NORMAL_Y rows): face BCs and mirrors together."""
     compare_bc(*cases.channel_2d(inlet=tc.BC_NEUMANN, outlet=tc.BC_DIRICHLET, walls_kind="freeslip"), steps=60,
                kernels=("k_specular_gather", "k_specular_scatter", "k_bc_apply"))
+
+
+def test_pressure_outlet_2d_and_3d():
+    """bc_pressure_outlet faces: the outlet densities follow the phase fraction arriving at the face
+    (FlowUpdateBCPressureOutlet, lbm_flow.F90:1993-2263), re-derived on the device every step."""
+    compare_bc(*cases.channel_2d(inlet=tc.BC_VELOCITY, outlet=tc.BC_DIRICHLET, walls_kind="noslip"), steps=60,
+               outlets={tc.BOUNDARY_XP: 0.31}, kernels=("k_bc_pressure_outlet",))
+    compare_bc(*cases.drainage_3d(inlet=tc.BC_NEUMANN, outlet=tc.BC_DIRICHLET), steps=30,
+               outlets={tc.BOUNDARY_ZP: 0.30}, kernels=("k_bc_pressure_outlet",))
 
 
 @pytest.mark.parametrize("order", [4, 8])
