@@ -183,7 +183,9 @@ TXG_API int txg_set_bc_values(txg_handle h, int boundary, const double *vals);
  * the face densities are re-derived on the device from the pressure and the phase fraction of the node one
  * step inside.  Fails like the reference for a non-ideal EOS or g_11 /= 0 (:2000-2005) and for more than
  * two components (:2260).  The flux-outlet update (FlowUpdateBCFluxOutlet, :2265-2497) tests for
- * BC_PRESSURE_OUTLET faces only, so a BC_FLUX_OUTLET face keeps its constant BC_NEUMANN values: nothing to call. */
+ * BC_PRESSURE_OUTLET faces only (:2301 ... :2480), so a BC_FLUX_OUTLET face keeps its constant BC_NEUMANN values:
+ * nothing to call.  (A run with both kinds of outlet would have that routine overwrite entries of the
+ * pressure-outlet faces; that interplay is not reproduced.) */
 TXG_API int txg_set_bc_pressure_outlet(txg_handle h, int boundary, double pressure);
 
 /* LBMInitializeState result (lbm.F90:444-453): host rho(S,rg..) and u(S,ndims,g..)
