@@ -135,6 +135,24 @@ class Flow:
         self._expect(f, self.shape_fi(), "fi")
         self._check(self.lib.txg_set_fi(self.h, _dp(f)))
 
+    def initialize_state_restarted(self, prefix, counter):
+        """LBMInitializeStateRestarted (lbm.F90:524-544): fi from <prefix>fiNNN.dat as FlowOutputDiagnostics wrote it."""
+        from . import petsc_io
+
+        self.initialize_state_from_file(petsc_io.output_name(prefix, "fi", counter), "fi")
+
+    def initialize_state_from_file(self, path, kind="fi"):
+        """LBMInitializeStateFromFile (lbm.F90:482-522): -ic_file (kind 'fi': populations, FlowFiInit is then skipped,
+        lbm.F90:208-213) or -ic_file_rho (kind 'rho': densities, followed by the usual fi_init())."""
+        from . import petsc_io
+
+        if kind == "fi":
+            self.set_fi(petsc_io.load_local(path, self.cfg, (self.Q, self.S), 1))
+        elif kind == "rho":
+            self.initialize_state(petsc_io.load_local(path, self.cfg, (self.S,), self.R))
+        else:
+            raise ValueError("kind must be 'fi' or 'rho'")
+
     def fi_init(self):
         self._check(self.lib.txg_fi_init(self.h))
 

@@ -28,3 +28,19 @@ def write_vec(path, array):
 def output_name(prefix, name, counter):
     """<prefix><name>NNN.dat, three digits (lbm_io.F90:71-83, MAXIODIGITS lbm_definitions.h:21)."""
     return "%s%s%03d.dat" % (prefix, name, counter)
+
+
+def load_local(path, cfg, dof_shape, width):
+    """IOLoad / IOLoadFile + DMGlobalToLocal (lbm.F90:482-544, lbm_io.F90:95-122): read a Vec written in DMDA natural
+    ordering ([z][y][x][dofs]) and return this rank's local ghosted array of ghost width `width`
+    ([zl+2w][NY+2w][NX+2w] + dof_shape; periodic ghosts filled, others zero) for the slab in cfg (zs, zl)."""
+    from . import geometry as geo
+
+    D = cfg.ndims
+    NZ = cfg.NZ if D == 3 else 1
+    n = (NZ, cfg.NY, cfg.NX) + tuple(dof_shape)
+    v = read_vec(path)
+    if v.size != int(np.prod(n)):
+        raise ValueError("%s holds %d values, the box needs %d" % (path, v.size, int(np.prod(n))))
+    zs, zl = (cfg.zs, cfg.zl) if D == 3 else (0, 1)
+    return geo.ghosted(v.reshape(n), width, cfg.periodic, D, zs=zs, zl=zl)

@@ -33,3 +33,29 @@ def test_rewriting_the_golden_reproduces_it(tmp_path):
     p = tmp_path / "fi001.dat"
     petsc_io.write_vec(p, v)
     assert p.read_bytes() == GOLDEN.read_bytes()
+
+
+def test_load_local_cuts_the_slab_and_fills_periodic_ghosts(tmp_path):
+    """IOLoad + DMGlobalToLocal (lbm.F90:482-544): a natural-order fi file becomes each rank's ghosted local array."""
+    import cases
+    from taxila_lbm_b200 import geometry as geo
+    from taxila_lbm_b200 import slab
+
+    cfg, walls, rho = cases.porous_3d(12, NZ=10, rmin=2.0, rmax=3.0, periodic=(1, 0, 1))
+    rng = np.random.default_rng(3)
+    fi = rng.uniform(size=(10, 12, 12, 19, 2))
+    p = tmp_path / petsc_io.output_name("r_", "fi", 4)
+    petsc_io.write_vec(p, fi)
+    parts = []
+    for r in range(3):
+        c = slab.local_config(cfg, 3, r)
+        loc = petsc_io.load_local(p, c, (19, 2), 1)
+        assert loc.shape == (c.zl + 2, 14, 14, 19, 2)
+        assert np.array_equal(loc, geo.ghosted(fi, 1, cfg.periodic, 3, zs=c.zs, zl=c.zl))
+        assert np.array_equal(loc[:, :, 0], loc[:, :, -2])      # x periodic: low ghost = last owned column
+        assert np.all(loc[:, 0] == 0.0)                          # y not periodic: ghost rows untouched
+        parts.append(geo.owned(loc, 1, 3))
+    assert np.array_equal(np.concatenate(parts, axis=0), fi)
+    rp = tmp_path / "rho.dat"
+    petsc_io.write_vec(rp, rho)
+    assert np.array_equal(geo.owned(petsc_io.load_local(rp, cfg, (2,), cfg.stencil_size_rho), 1, 3), rho)
