@@ -1,5 +1,4 @@
-"""Restart / IC-from-file on the host mirror.  Written after the round-1 GPU budget was spent: not
-yet run on a GPU; sorted late so that it cannot mask other results."""
+"""Restart / IC-from-file on the host mirror; B200: profiles/r1s_restart_test.log."""
 import numpy as np
 import pytest
 
