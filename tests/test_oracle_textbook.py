@@ -1,0 +1,109 @@
+"""The oracle against a second, independently written model (tests/textbook_lbm.py) on the pieces that no
+reference vector pins (SURVEY.md 8c "parity unpinned"): D3Q19 MRT with general rates, the order-8 / order-10
+force stencils with their line-of-sight rules, bounce-back, mineral (fluid-solid) and body forces.
+Two restatements that share no code agree to accumulated round-off; the textbook model itself is held to
+the reference's golden fi001.dat of tests/bubble_2D."""
+import numpy as np
+import pytest
+
+import cases
+import textbook_lbm as tb
+from taxila_lbm_b200 import config as tc
+from taxila_lbm_b200 import geometry as geo
+
+TOL = 1e-12  # relative to max |field|; the two models sum in different orders (measured: <= 1e-13)
+
+
+def rel(a, b):
+    den = np.abs(b).max()
+    return np.abs(a - b).max() / (den if den > 0 else 1.0)
+
+
+def compare(cfg, walls, rho, steps, tol=TOL):
+    o = cases.run_oracle(cfg, walls, rho, steps)
+    t = tb.from_config(cfg, walls, rho)
+    t.step(steps)
+    fluid = np.asarray(walls).reshape(o.rho().shape[:3]) == 0
+    errs = {"fi": rel(t.fi_natural()[fluid], o.fi()[fluid]), "rho": rel(t.rho_natural()[fluid], o.rho()[fluid]),
+            "u": rel(t.u_natural()[fluid], o.u()[fluid][..., 0])}
+    assert all(np.array_equal(o.u()[..., 0], o.u()[..., m]) for m in range(cfg.ncomponents))  # one common velocity
+    if np.abs(o.forces()).max() > 0:
+        errs["forces"] = rel(t.forces_natural()[fluid], o.forces()[fluid])
+    assert all(v <= tol for v in errs.values()), errs
+    assert np.all(o.fi()[~fluid] == 0.0)
+    o.close()
+    return errs
+
+
+def test_textbook_model_reproduces_the_reference_golden():
+    """tests/bubble_2D/reference_solution/fi001.dat (100 steps) from the textbook model alone."""
+    cfg, walls, rho = cases.bubble_2d()
+    t = tb.from_config(cfg, walls, rho)
+    t.step(100)
+    assert np.abs(t.fi_natural() - cases.golden_bubble_2d()).max() <= 1e-12
+
+
+def test_moment_matrices_match_the_polynomials():
+    """The oracle's moment rows (lbm_discretization_d3q19.F90:177-197, _d2q9.F90:108-118) are the
+    d'Humieres / Lallemand-Luo polynomials: same row norms, and the collision operator M^-1 S M built from the
+    polynomials equals the oracle's (checked through the runs below); here the norms the reference hard-codes."""
+    assert np.allclose((tb.Lattice(3).M ** 2).sum(axis=1),
+                       [19, 2394, 252, 10, 40, 10, 40, 10, 40, 36, 72, 12, 24, 4, 4, 4, 8, 8, 8])
+    assert np.allclose((tb.Lattice(2).M ** 2).sum(axis=1), [9, 36, 36, 6, 12, 6, 12, 4, 4])
+    for D in (2, 3):
+        M = tb.Lattice(D).M
+        G = M @ M.T
+        assert np.allclose(G, np.diag(np.diag(G)))
+
+
+def test_d2q9_mrt_general_rates_order10():
+    """C2 (tests/bubble_2D_hots/input_data): MRT rates all different, derivative order 10 (36 offsets, radius 3)."""
+    compare(*cases.bubble_2d_hots(48), steps=40)
+
+
+def test_d2q9_order8_with_walls_and_minerals():
+    """order-8 stencil (24 offsets) next to walls: every line-of-sight rule of the 2-D blocks is exercised."""
+    cfg, walls, rho = cases.bubble_2d(40, mrt=True, order=8)
+    cfg.stencil_size_rho = 2
+    cfg.nminerals = 2
+    for k in range(2):
+        cfg.gw[k][0], cfg.gw[k][1] = -0.03 * (k + 1), 0.02 * (k + 1)
+    for m in range(2):
+        cfg.s_e[m], cfg.s_e2[m], cfg.s_q[m], cfg.s_nu[m] = 1.3, 0.9, 1.7, 1.0 / (0.8 + 0.3 * m)
+    cfg.body_forces = 1
+    cfg.gvt[0], cfg.gvt[1] = 2e-5, -1e-5
+    tc.finalize_flags(cfg)
+    rng = np.random.default_rng(3)
+    walls = np.zeros((1, 40, 40))
+    solid = rng.random((40, 40)) < 0.22
+    walls[0][solid] = 1 + (rng.integers(0, 2, size=(40, 40))[solid])
+    rho = rho.copy()
+    rho[walls != 0] = 0.0
+    compare(cfg, walls, rho, steps=30)
+
+
+@pytest.mark.parametrize("order", [4, 8])
+def test_d3q19_porous_mrt_minerals_body_force(order):
+    """The C4 recipe (MRT s_e=1.19 s_e2=1.4 s_q=1.2 s_pi=1.4 s_m=1.98, 3 minerals, gvt, bounce-back) at 24^3."""
+    cfg, walls, rho = cases.porous_3d(24, order=order, rmin=3.0, rmax=6.0)
+    if order == 8:
+        cfg.stencil_size_rho = 2
+    compare(cfg, walls, rho, steps=25)
+
+
+def test_d3q19_random_solids_order8_every_sight_rule():
+    """Random 30 % solids: isolated voxels put a wall on every kind of line of sight of the 92 offsets."""
+    cfg, walls, rho = cases.porous_3d(16, order=8, rmin=3.0, rmax=6.0)
+    cfg.stencil_size_rho = 2
+    rng = np.random.default_rng(8)
+    walls = np.where(rng.random((16, 16, 16)) < 0.3, 1.0 + rng.integers(0, 3, size=(16, 16, 16)), 0.0)
+    rho = geo.flushing_rho(cfg, walls, (0.9, 0.1), (0.2, 0.8), "z", 5)
+    compare(cfg, walls, rho, steps=15)
+
+
+def test_d3q19_srt_unequal_masses():
+    """mm /= 1: d_k = 1 - 2 / (3 mm) in the equilibrium, mm-weighted common velocity and body force."""
+    cfg, walls, rho = cases.porous_3d(16, mrt=False, rmin=3.0, rmax=5.0)
+    cfg.mm[0], cfg.mm[1] = 1.0, 1.6
+    cfg.tau[0], cfg.tau[1] = 0.9, 1.3
+    compare(cfg, walls, rho, steps=25)
