@@ -107,3 +107,26 @@ def test_d3q19_srt_unequal_masses():
     cfg.mm[0], cfg.mm[1] = 1.0, 1.6
     cfg.tau[0], cfg.tau[1] = 0.9, 1.3
     compare(cfg, walls, rho, steps=25)
+
+
+def test_nonperiodic_box_is_a_box_inside_a_ghost_wall():
+    """A non-periodic face with no BC is the WALL_GHOST = 999 layer (lbm_walls.F90:190-231): bounce-back off it, no
+    mineral force from it, no fluid-fluid stencil through it.  The textbook model runs the same box padded with a ring of
+    999 nodes (periodic wrap falls inside the ring), orders 4 and 8."""
+    for order in (4, 8):
+        cfg, walls, rho = cases.porous_3d(14, order=order, rmin=3.0, rmax=5.0, periodic=(0, 0, 0))
+        cfg.stencil_size_rho = 2 if order == 8 else 1
+        o = cases.run_oracle(cfg, walls, rho, 20)
+        pad = 3
+        wp = np.pad(walls, pad, constant_values=999.0)
+        rp = np.pad(rho, [(pad, pad)] * 3 + [(0, 0)])
+        pc = cfg.copy()
+        pc.NX = pc.NY = pc.NZ = 14 + 2 * pad
+        t = tb.from_config(pc, wp, rp)
+        t.step(20)
+        inner = (slice(pad, -pad),) * 3
+        fluid = walls == 0
+        assert rel(t.fi_natural()[inner][fluid], o.fi()[fluid]) <= TOL
+        assert rel(t.forces_natural()[inner][fluid], o.forces()[fluid]) <= TOL
+        assert rel(t.u_natural()[inner][fluid], o.u()[fluid][..., 0]) <= TOL
+        o.close()
