@@ -18,6 +18,7 @@
 #include "flow.h"
 #include "setup_kernels.cuh"
 #include "bc_kernels.cuh"
+#include "lag_schedule.h"
 
 using namespace txg;
 
@@ -121,6 +122,15 @@ struct txg_flow {
   uint32_t *nbr_all = nullptr;  // [Q-1][fs] every lattice neighbour: the fused path; nbr (centres only) and Fbuf: the split path
   int pf_blocks = 0;            // L2 prefetch distance of the fused kernel in blocks (TXG_PF)
   bool fused = false;           // forces + collide in one kernel (order-4 stencil; TXG_SPLIT=1 forces the split path)
+  // one-pass step (opt-in, TXG_LAG=1; lag_schedule.h): the fused kernel also sums the next step's densities
+  // out of L2, band by band behind the collision front.  rho_next receives them; the buffers swap every step.
+  bool lag_wanted = false, lag = false;
+  int lag_rows = 128, lag_planes = 1, lag_mpos = 512;  // TXG_LAG_ROWS / TXG_LAG_PLANES / TXG_LAG_MPOS
+  double *rho_next = nullptr;
+  LagRowDev *lag_rows_dev = nullptr;  // schedule rows, copied into the kernel's constant table before every launch
+  unsigned *lag_done = nullptr;       // [rows] C blocks finished, zeroed before every launch
+  LagMeta lag_meta;
+  unsigned lag_nrows = 0, lag_grid_x = 0;
   double *wallrec = nullptr;    // [S*D + D][fs]
   double *Fbuf = nullptr;       // [S*D][fs] forces of the current step (k_forces -> k_collide)
   double *halo_recv = nullptr;  // NCCL staging: [2 faces][S][NCROSS][fluid nodes of the boundary plane]
@@ -458,7 +468,7 @@ extern "C" int txg_destroy(txg_handle h) {
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
                   h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->nbr_all, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt, h->spec_dst, h->spec_src, h->spec_tmp, h->bc_vals[0], h->bc_vals[1],
-                  h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5]};
+                  h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_done};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -516,6 +526,10 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     // measured at 512^3 porous, k_step_fused ms: 0: 11.21, 148: 10.83, 222: 10.84, 296: 10.89, 444: 11.01, 592: 11.15, 888: 11.99
     h->pf_blocks = h->num_sms;
     if (const char *pf = getenv("TXG_PF")) h->pf_blocks = atoi(pf);
+    if (const char *lg = getenv("TXG_LAG")) h->lag_wanted = lg[0] == '1';
+    if (const char *v = getenv("TXG_LAG_ROWS")) h->lag_rows = atoi(v);
+    if (const char *v = getenv("TXG_LAG_PLANES")) h->lag_planes = atoi(v);
+    if (const char *v = getenv("TXG_LAG_MPOS")) h->lag_mpos = atoi(v);
     const char *sp = getenv("TXG_SPLIT");
     for (int b = 0; b < 2 * cfg->ndims; ++b) h->bc_mode = h->bc_mode || cfg->bc_flags[b] >= TXG_BC_REFLECTING;
     // face BCs act between the forces and the collision: they need the split kernels and the force buffer
@@ -777,6 +791,11 @@ static void free_storage(txg_flow *h) {
   }
   if (h->rho_true && h->cfg.use_nonideal_eos) cudaFree(h->rho_true);
   h->rho_true = nullptr;
+  for (void **q : {(void **)&h->rho_next, (void **)&h->lag_rows_dev, (void **)&h->lag_done}) {
+    if (*q) cudaFree(*q);
+    *q = nullptr;
+  }
+  h->lag = false;
   h->alloc_nstore = -1;
 }
 // zeroed array of `bytes`: the existing allocation when the storage is being re-used
@@ -943,6 +962,51 @@ static int apply_specular(txg_flow *h, double *f, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------ walls
+// ------------------------------------------------------------------ one-pass step (opt-in, TXG_LAG=1)
+// Block schedule of k_step_fused_lag for the current geometry (lag_schedule.h), rebuilt at every walls upload.
+// Boxes the schedule does not cover keep the two-kernel step; nothing is refused.
+static int build_lag(txg_flow *h) {
+  static_assert(sizeof(LagRow) == sizeof(LagRowDev), "host / device schedule row layout");
+  for (void **q : {(void **)&h->lag_rows_dev, (void **)&h->lag_done}) {
+    if (*q) cudaFree(*q);
+    *q = nullptr;
+  }
+  h->lag = false;
+  h->lag_nrows = h->lag_grid_x = 0;
+  const Grid &g = h->g;
+  if (!h->lag_wanted || !h->fused || !h->ks.step_fused_lag || h->ks.fused_threads != 128 || h->D != 3 || h->cfg.nranks != 1 ||
+      h->p.eos || h->spec_n || h->bc_mode)
+    return 0;
+  const int nzE = g.NZl + 2 * g.Rz;
+  std::vector<uint32_t> row_off((size_t)nzE * g.NY + 1);
+  if (g.P) {
+    // P[(zz*NY + y)*NX] = position of the first fluid node at or after the start of row (zz, y); P[nE] = nstore
+    TXG_CUDA(h, cudaMemcpy2D(row_off.data(), sizeof(uint32_t), g.P, (size_t)g.NX * sizeof(uint32_t), sizeof(uint32_t),
+                             row_off.size(), cudaMemcpyDeviceToHost));
+  } else {
+    for (size_t i = 0; i < row_off.size(); ++i) row_off[i] = (uint32_t)(i * (size_t)g.NX);
+  }
+  const int PB = 4 * h->ks.npw;
+  const int MB = std::max(PB, h->lag_mpos / PB * PB);
+  const LagSchedule sc = build_lag_schedule(g.NY, g.NZl, g.Rz, g.pery, row_off.data(), PB, MB, h->lag_rows, h->lag_planes, LAG_MAX_ROWS);
+  if (!sc.ok || sc.rows.size() > (size_t)LAG_MAX_ROWS || sc.nbands > 16) return 0;
+  TXG_CUDA(h, cudaMalloc((void **)&h->lag_rows_dev, sc.rows.size() * sizeof(LagRow)));
+  TXG_CUDA(h, cudaMalloc((void **)&h->lag_done, (sc.rows.size() + 1) * sizeof(unsigned)));  // + 1: the gave-up counter
+  TXG_CUDA(h, cudaMemset(h->lag_done, 0, (sc.rows.size() + 1) * sizeof(unsigned)));
+  TXG_CUDA(h, cudaMemcpy(h->lag_rows_dev, sc.rows.data(), sc.rows.size() * sizeof(LagRow), cudaMemcpyHostToDevice));
+  TXG_TRY(fresh_zero(h, (void **)&h->rho_next, (size_t)h->S * g.fs * sizeof(double)));
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  h->lag_meta.rows_per_band = sc.rows_per_band;
+  h->lag_meta.lag = sc.lag;
+  h->lag_meta.MB = sc.MB;
+  for (int b = 0; b < 16; ++b)
+    for (int k = 0; k < 3; ++k) h->lag_meta.depbands[b][k] = b < sc.nbands ? sc.depbands[b][k] : -1;
+  h->lag_nrows = (unsigned)sc.rows.size();
+  h->lag_grid_x = sc.grid_x;
+  h->lag = true;
+  return 0;
+}
+
 extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   if (!h) return TXG_ERR_ARG_NULL;
   if (!walls_rg) TXG_FAIL(h, TXG_ERR_ARG_NULL, "txg_set_walls: null array");
@@ -968,6 +1032,7 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   if (counters[0]) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "walls array holds %d negative or NaN codes", counters[0]);
   TXG_TRY(build_storage(h));
   TXG_TRY(build_specular(h, counters[1]));
+  TXG_TRY(build_lag(h));
   h->walls_set = true;
   return 0;
 }
@@ -1109,6 +1174,37 @@ extern "C" int txg_fi_init(txg_handle h) {
 // forces (every gather of the step), then K2b (momentum + velocity + collision + push-streaming with
 // bounce-back) with the halo of the pushed populations.  Boundary planes run first so that their halos travel on the communication
 // stream while the interior computes.
+// One step as ONE hot launch (opt-in): collide + push every owned plane and, behind the collision front, sum the
+// new densities of planes 1 .. NZl-2 out of L2; the two boundary planes are summed by k_moments once the z halo has
+// delivered their crossing populations.  On entry rho (+ halo) belongs to f[cur]; on exit again.
+static int one_step_lag(txg_flow *h) {
+  const Grid &g = h->g;
+  cudaStream_t sm = h->s_main;
+  if (!h->rho_current) {
+    TXG_TRY(run_moments(h, 0, g.NZl, sm));
+    TXG_TRY(exchange_rho(h, h->rho, sm));
+  }
+  TXG_CUDA(h, cudaMemsetAsync(h->lag_done, 0, (size_t)h->lag_nrows * sizeof(unsigned), sm));
+  // the schedule rows live in a constant table of the kernel's module: another handle may have used it last
+  TXG_CUDA(h, (cudaError_t)h->ks.upload_lag_rows(h->lag_rows_dev, (size_t)h->lag_nrows * sizeof(LagRowDev), sm));
+  {
+    ScopedKernel sk(h, "k_step_fused_lag", sm);
+    h->ks.step_fused_lag<<<dim3(h->lag_grid_x, h->lag_nrows), 128, 0, sm>>>(g, h->p, h->lag_meta, h->f[h->cur], h->f[h->cur ^ 1], h->rho,
+                                                                             h->rho_next, h->lmask, h->nbr_all, h->wallrec, h->lag_done,
+                                                                             h->lag_done + h->lag_nrows, h->pf_blocks);
+    TXG_CUDA(h, cudaGetLastError());
+  }
+  TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sm));
+  h->cur ^= 1;
+  std::swap(h->rho, h->rho_next);
+  h->rho_true = h->rho;  // no EOS on this path
+  TXG_TRY(run_moments(h, 0, 1, sm));
+  TXG_TRY(run_moments(h, g.NZl - 1, 1, sm));
+  TXG_TRY(exchange_rho(h, h->rho, sm));
+  h->rho_current = true;
+  return 0;
+}
+
 static int one_step(txg_flow *h) {
   const Grid &g = h->g;
   const bool split = h->cfg.nranks > 1 && g.NZl >= 4 * g.R + 2;
@@ -1260,12 +1356,14 @@ extern "C" int txg_step(txg_handle h, int nsteps) {
   if (h->bc_mode) {
     if (nsteps > 0 && !h->forces_current) TXG_TRY(bc_moments_forces(h, false));  // FlowUpdateMoments of LBMInit2 (lbm.F90:238)
     for (int i = 0; i < nsteps; ++i) TXG_TRY(one_step_bc(h));
+  } else if (h->lag) {
+    for (int i = 0; i < nsteps; ++i) TXG_TRY(one_step_lag(h));
   } else {
     for (int i = 0; i < nsteps; ++i) TXG_TRY(one_step(h));
   }
   TXG_CUDA(h, cudaEventRecord(h->ev_step1, h->s_main));
   h->last_launches = h->launches - l0;
-  h->rho_current = false;
+  if (!h->lag) h->rho_current = false;  // (the one-pass step leaves rho and its halo current)
   return 0;
 }
 
@@ -1411,6 +1509,13 @@ extern "C" int txg_delta_norm(txg_handle h, double *norm) {
 // EOSApply_PR stops the run when its inner square root goes negative (lbm_eos.F90:337-341); the device
 // kernels count such values and the next synchronising call reports them
 static int check_eos(txg_flow *h) {
+  if (h->lag && h->lag_done) {
+    // the one-pass step gives up waiting after ~1 s instead of hanging the device (block dispatch out of linear order)
+    unsigned gave_up = 0;
+    TXG_CUDA(h, cudaMemcpyAsync(&gave_up, h->lag_done + h->lag_nrows, sizeof gave_up, cudaMemcpyDeviceToHost, h->s_main));
+    TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+    if (gave_up) TXG_FAIL(h, TXG_ERR_LIB, "one-pass step (TXG_LAG=1): %u density blocks gave up waiting for their collision rows; results are invalid", gave_up);
+  }
   bool pr = false;
   for (int m = 0; m < h->S; ++m) pr = pr || (h->cfg.use_nonideal_eos && h->cfg.eos_type[m] == TXG_EOS_PR);
   if (!pr) return 0;

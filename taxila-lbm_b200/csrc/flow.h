@@ -22,6 +22,10 @@ struct KernelSet {
                      const double *, long long, long long, int);
   void (*fi_init_fused)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
                         const uint32_t *, const double *, long long, long long);
+  // one-pass step (opt-in, TXG_LAG=1): step_fused + the density sum of the next step in one launch (lag_schedule.h)
+  void (*step_fused_lag)(Grid, Phys, LagMeta, const double *, double *, const double *, double *, const uint32_t *,
+                         const uint32_t *, const double *, unsigned *, unsigned *, int);
+  int (*upload_lag_rows)(const void *rows, size_t bytes, cudaStream_t s);  // into this translation unit's c_lag_rows
   void (*build_nbr_all)(Grid, uint32_t *);
   void (*build_nbr)(Grid, uint32_t *);
   void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, long long, long long, int);
@@ -56,9 +60,15 @@ KernelSet make_kernel_set(const char *name) {
   if constexpr (ISO == 4) {
     k.step_fused = k_step_fused<L, S, MRT>;
     k.fi_init_fused = k_fi_init_fused<L, S>;
+    k.step_fused_lag = k_step_fused_lag<L, S, MRT>;
+    k.upload_lag_rows = [](const void *rows, size_t bytes, cudaStream_t s) -> int {
+      return (int)cudaMemcpyToSymbolAsync(c_lag_rows, rows, bytes, 0, cudaMemcpyDeviceToDevice, s);
+    };
   } else {
     k.step_fused = nullptr;
     k.fi_init_fused = nullptr;
+    k.step_fused_lag = nullptr;
+    k.upload_lag_rows = nullptr;
   }
   k.fused_threads = TXG_FUSED_THREADS;
   k.npw = Lanes<S>::NPW;

@@ -198,6 +198,162 @@ __global__ void __launch_bounds__(TXG_FUSED_THREADS, 512 / TXG_FUSED_THREADS)
   });
 }
 
+// ------------------------------------------------------------------ one-pass step (opt-in: TXG_LAG=1)
+// k_step_fused with the density sum of the NEXT step folded into the same launch (lag_schedule.h has the
+// schedule and the dependency argument).  2-D grid: blockIdx.y = schedule row, blockIdx.x = block in the row.
+//   x <  nC: C block -- exactly k_step_fused on PB positions of the row's C range, then fence + done[row] += 1;
+//   x >= nC: M block -- wait until the <= 9 dependency rows are complete, then rho_next[m][pos] = sum_n fB[m][n][pos]
+//            (ascending n, DistributionCalcDensityD*, lbm_distribution_function.F90:379-428) for MB positions of the
+//            row's M ranges, read through L2 (ld.global.cg: other SMs wrote them in this launch).
+// The schedule rows sit in constant memory so that range starts and counts stay in uniform registers like the
+// kernel parameters of k_step_fused (a per-block table in global memory costs ~100 bytes of spills at the
+// 128-register cap).  The table is per module and device: the host re-uploads it when another handle used it last.
+// Not used with a non-ideal EOS (psi needs its own pass), free-slip walls (the mirrors rewrite slots after
+// the push), external face BCs or more than one rank.  NOT YET RUN ON A GPU (written in a session without
+// GPU minutes; the schedule is CPU-tested, tests/test_lag_schedule.py).
+struct LagRowDev {
+  uint32_t cfirst, ccount, m0first, m0count, m1first, m1count;  // lag_schedule.h LagRow
+};
+constexpr int LAG_MAX_ROWS = 2560;  // 60 KB of the 64 KB constant bank
+struct LagMeta {
+  int rows_per_band, lag, MB;
+  int depbands[16][3];
+};
+__constant__ LagRowDev c_lag_rows[LAG_MAX_ROWS];
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// the M block of k_step_fused_lag
+template <class L, int S>
+__device__ __forceinline__ void lag_m_block(const Grid &g, const LagMeta &meta, const double *__restrict__ fB,
+                                         double *__restrict__ rho_next, unsigned *__restrict__ done,
+                                         unsigned *__restrict__ gave_up, unsigned xm) {
+  constexpr int Q = L::Q, NPW = Lanes<S>::NPW, PB = 4 * NPW;
+  const LagRowDev &row = c_lag_rows[blockIdx.y];
+  const unsigned MB = (unsigned)meta.MB;
+  const unsigned n0 = (row.m0count + MB - 1) / MB;
+  long long first, count;
+  if (xm < n0) {
+    first = (long long)row.m0first + (long long)xm * MB;
+    count = min((long long)MB, (long long)row.m0count - (long long)xm * MB);
+  } else {
+    const unsigned q = xm - n0;
+    if ((long long)q * MB >= (long long)row.m1count) return;  // padding block of the grid
+    first = (long long)row.m1first + (long long)q * MB;
+    count = min((long long)MB, (long long)row.m1count - (long long)q * MB);
+  }
+  // wait for the collisions that push into these positions: rows (b', zm + dz), b' in depbands[b]
+  if (threadIdx.x < 9) {
+    const int b = (int)blockIdx.y / meta.rows_per_band, k = (int)blockIdx.y - b * meta.rows_per_band;
+    const int bb = meta.depbands[b][threadIdx.x / 3];
+    if (bb >= 0) {
+      const int dep = bb * meta.rows_per_band + (k - 1 - meta.lag) + ((int)threadIdx.x % 3 - 1);
+      const unsigned want = (c_lag_rows[dep].ccount + PB - 1) / PB;
+      // bounded: a schedule bug or out-of-order block dispatch must not hang the device (the host reports gave_up)
+      unsigned spins = 0;
+      while (ld_acquire_u32(done + dep) < want) {
+        if (++spins > (1u << 22)) {
+          atomicAdd(gave_up, 1u);
+          break;
+        }
+        __nanosleep(200);
+      }
+    }
+  }
+  __syncthreads();
+  for (long long w = threadIdx.x >> 5; w * NPW < count; w += 4) {
+    Item it;
+    if (!item_of_lane<S>(first, count, w, it)) break;
+    const double *src = fB + (long long)it.m * Q * g.fs + it.pos;
+    double v[Q];
+#pragma unroll
+    for (int n = 0; n < Q; ++n) v[n] = __ldcg(src + (long long)n * g.fs);
+    double a = 0.;
+#pragma unroll
+    for (int n = 0; n < Q; ++n) a += v[n];
+    if (it.active) rho_next[(long long)it.m * g.fs + it.pos] = a;
+  }
+}
+
+// the C block of k_step_fused_lag: the body of k_step_fused on positions [first, first + count), warp `warp` of them
+template <class L, int S, bool MRT>
+__device__ __forceinline__ void lag_c_warp(const Grid &g, const Phys &p, const double *__restrict__ fA, double *__restrict__ fB,
+                                           const double *__restrict__ rho, const uint32_t *__restrict__ lmask,
+                                           const uint32_t *__restrict__ nbr_all, const double *__restrict__ wallrec,
+                                           long long first, long long count, long long warp) {
+  constexpr int Q = L::Q, D = L::D, ISO = 4;
+  Item it;
+  if (!item_of_lane<S>(first, count, warp, it)) return;
+  const uint32_t mask = __ldg(lmask + it.pos);
+  unsigned npos[Q];
+  npos[0] = (unsigned)it.pos;
+#pragma unroll
+  for (int n = 1; n < Q; ++n) npos[n] = __ldg(nbr_all + (long long)(n - 1) * g.fs + it.pos);
+  const long long mo = (long long)it.m * Q * g.fs + it.pos;
+  double f[Q];
+  {
+    const double *src = fA + mo;
+#pragma unroll
+    for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
+  }
+  const double *psi_field = rho + (long long)it.m * g.fs;
+  double r = 0.;
+#pragma unroll
+  for (int n = 0; n < Q; ++n) r += f[n];
+  double F[D];
+  const double psi_m = p.eos ? __ldg(psi_field + it.pos) : r;  // (p.eos is 0 on this path; kept so that the code generated is k_step_fused's)
+  forces1_inline<L, S, ISO>(g, p, psi_field, nullptr, wallrec, it, 0u, 0, 0, mask, npos, r, psi_m, F);
+  double up[D];
+  common_velocity1<L, S>(p, it, f, r, F, up);
+  collide1<L, MRT>(p, it.m, r, F, up, f);
+  if (!it.active) return;
+  double *out = fB + (long long)it.m * Q * g.fs;
+  const unsigned fs = (unsigned)g.fs, here = (unsigned)it.pos;
+  out[here] = f[0];
+  static_for<1, Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    constexpr int on = opp<L>(n);
+    const bool bounce = (mask >> n) & 1u;
+    const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + npos[n];
+    out[e] = f[n];
+  });
+}
+
+template <class L, int S, bool MRT>
+__global__ void __launch_bounds__(128, 4)
+    k_step_fused_lag(Grid g, Phys p, LagMeta meta, const double *__restrict__ fA, double *__restrict__ fB,
+                     const double *__restrict__ rho, double *__restrict__ rho_next, const uint32_t *__restrict__ lmask,
+                     const uint32_t *__restrict__ nbr_all, const double *__restrict__ wallrec, unsigned *__restrict__ done,
+                     unsigned *__restrict__ gave_up, int pf_blocks) {
+  constexpr int PB = 4 * Lanes<S>::NPW;
+  const LagRowDev &row = c_lag_rows[blockIdx.y];
+  const unsigned nC = (row.ccount + PB - 1) / PB;
+  if (blockIdx.x >= nC) {
+    lag_m_block<L, S>(g, meta, fB, rho_next, done, gave_up, blockIdx.x - nC);
+    return;
+  }
+  // L2 prefetch for the C block pf_blocks further on in launch order: in this row, or at the start of the next one
+  if (pf_blocks > 0) {
+    const unsigned ahead = blockIdx.x + (unsigned)pf_blocks;
+    const bool next = ahead >= nC && blockIdx.y + 1 < gridDim.y;
+    const LagRowDev &pr = c_lag_rows[blockIdx.y + (next ? 1u : 0u)];
+    prefetch_block_rows<L, S>(g, fA, lmask, nbr_all, wallrec, (long long)pr.cfirst, (long long)pr.ccount, (long long)(next ? ahead - nC : ahead));
+  }
+  lag_c_warp<L, S, MRT>(g, p, fA, fB, rho, lmask, nbr_all, wallrec, (long long)row.cfirst, (long long)row.ccount,
+                        ((long long)blockIdx.x * 128 + threadIdx.x) >> 5);
+  // every thread's stores are ordered before the row count: fence, block barrier, one release-add
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) red_release_add_u32(done + blockIdx.y, 1u);
+}
+
 // FlowFiInit for the fused path (FlowFiInit lbm_flow.F90:923-934, FlowFeqBarD* :867-921), one lane per
 // (fluid node, component) like the step kernel: F from rho0 through the same forces routine, then
 // f = (1 - prefactor/2) feq(rho0, u0) into the node's own slots.  u0 is [S][D][nnodes] (dense) or null.
