@@ -268,17 +268,29 @@ __device__ __forceinline__ void lag_m_block(const Grid &g, const LagMeta &meta, 
     }
   }
   __syncthreads();
-  for (long long w = threadIdx.x >> 5; w * NPW < count; w += 4) {
-    Item it;
-    if (!item_of_lane<S>(first, count, w, it)) break;
-    const double *src = fB + (long long)it.m * Q * g.fs + it.pos;
-    double v[Q];
+  // two warps of positions per round: 2 x Q loads in flight per lane
+  for (long long w = threadIdx.x >> 5; w * NPW < count; w += 8) {
+    Item it0, it1;
+    item_of_lane<S>(first, count, w, it0);  // (never beyond the range: the loop condition is its test)
+    const bool two = item_of_lane<S>(first, count, w + 4, it1);
+    if (!two) {
+      it1 = it0;
+      it1.active = false;
+    }
+    const double *src0 = fB + (long long)it0.m * Q * g.fs + it0.pos;
+    const double *src1 = fB + (long long)it1.m * Q * g.fs + it1.pos;
+    double v0[Q], v1[Q];
 #pragma unroll
-    for (int n = 0; n < Q; ++n) v[n] = __ldcg(src + (long long)n * g.fs);
-    double a = 0.;
+    for (int n = 0; n < Q; ++n) v0[n] = __ldcg(src0 + (long long)n * g.fs);
 #pragma unroll
-    for (int n = 0; n < Q; ++n) a += v[n];
-    if (it.active) rho_next[(long long)it.m * g.fs + it.pos] = a;
+    for (int n = 0; n < Q; ++n) v1[n] = __ldcg(src1 + (long long)n * g.fs);
+    double a0 = 0., a1 = 0.;
+#pragma unroll
+    for (int n = 0; n < Q; ++n) a0 += v0[n];
+#pragma unroll
+    for (int n = 0; n < Q; ++n) a1 += v1[n];
+    if (it0.active) rho_next[(long long)it0.m * g.fs + it0.pos] = a0;
+    if (it1.active) rho_next[(long long)it1.m * g.fs + it1.pos] = a1;
   }
 }
 
