@@ -130,3 +130,15 @@ def test_nonperiodic_box_is_a_box_inside_a_ghost_wall():
         assert rel(t.forces_natural()[inner][fluid], o.forces()[fluid]) <= TOL
         assert rel(t.u_natural()[inner][fluid], o.u()[fluid][..., 0]) <= TOL
         o.close()
+
+
+def test_nonideal_eos_kinds_in_the_force():
+    """-flow_use_nonideal_eos: psi(rho) replaces rho in the fluid-fluid gradient and as its prefactor only (EOSApply from
+    FlowCalcForces, lbm_flow.F90:795-801); Peng-Robinson + '94 thermo, and Shan-Chen '93 on both components."""
+    compare(*cases.eos_pr_thermo_3d(16), steps=25)
+    cfg, walls, rho = cases.porous_3d(16, rmin=3.0, rmax=5.0)
+    cfg.use_nonideal_eos = 1
+    for m in range(2):
+        cfg.eos_type[m] = tc.EOS_SC
+        cfg.eos_rho0[m] = 0.8 + 0.3 * m
+    compare(cfg, walls, rho, steps=25)

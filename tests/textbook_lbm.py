@@ -1,7 +1,7 @@
 """A second, independently written CPU model of the flow step -- TEST INFRASTRUCTURE ONLY.
 
 Purpose: SURVEY.md 8c lists what no reference vector pins (D3Q19 MRT with general rates, the order-8/10
-force stencils, bounce-back, mineral and body forces).  For those the oracle (oracle/taxila_oracle.c)
+force stencils, bounce-back, mineral and body forces, the non-ideal EOS kinds).  For those the oracle (oracle/taxila_oracle.c)
 is a line-by-line restatement of the Fortran; this file restates the same *equations* from the
 literature in whole-array numpy form, sharing no code, table or loop structure with the oracle:
 
@@ -203,6 +203,7 @@ class Model:
                     F[m, d] += p["gvt"][d] * self.mm[m] * rho[m]
         gf = np.array(p["gf"], dtype=np.float64)
         if np.abs(gf).max() > 0:
+            psi = self.psi(rho, gf)  # the fluid-fluid term alone sees psi(rho) (identity without -flow_use_nonideal_eos)
             G = np.zeros((self.S, lat.D) + self.fluid.shape)
             W = np.zeros((lat.D,) + self.fluid.shape)
             for off, wgt, alts in self.sten:
@@ -219,14 +220,39 @@ class Model:
                     if off[d]:
                         W[d] += np.where(ok, wgt * off[d] * off[d], 0.0)
                         for m in range(self.S):
-                            G[m, d] += np.where(ok, wgt * off[d] * (shift(rho[m], off) - rho[m]), 0.0)
+                            G[m, d] += np.where(ok, wgt * off[d] * (shift(psi[m], off) - psi[m]), 0.0)
             with np.errstate(divide="ignore", invalid="ignore"):
                 for d in range(lat.D):
                     on = W[d] > 1e-12
                     for m in range(self.S):
                         acc = sum(gf[m, k] * np.where(on, G[k, d] / W[d], 0.0) for k in range(self.S))
-                        F[m, d] -= 6.0 * rho[m] * acc
+                        F[m, d] -= 6.0 * psi[m] * acc
         return F * self.fluid
+
+    def psi(self, rho, gf):
+        """Shan-Chen '93 / '94 and Peng-Robinson pseudo-potentials (Yuan & Schaefer 2006 form
+        psi = sqrt(2 (p_EOS - rho c_s^2) / (c_0 g_mm))); p["eos"][m] = None | ("sc", rho0) | ("thermo", psi0, rho0) |
+        ("pr", a, b, R, T, Tc, omega)."""
+        eos = self.p.get("eos")
+        if not eos:
+            return rho
+        out = np.array(rho, dtype=np.float64, copy=True)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            for m, e in enumerate(eos):
+                r = rho[m]
+                if e is None:
+                    continue
+                if e[0] == "sc":
+                    out[m] = e[1] * (1 - np.exp(-r / e[1]))
+                elif e[0] == "thermo":
+                    out[m] = np.where(r > 0, e[1] * np.exp(-e[2] / np.where(r > 0, r, 1.0)), 0.0)
+                elif e[0] == "pr":
+                    _, a, b, R, T, Tc, om = e
+                    kappa = F32(0.37464) + F32(1.54226) * om - F32(0.26992) * om ** 2  # default-real literals in the reference
+                    alpha = (1 + kappa * (1 - np.sqrt(T / Tc))) ** 2
+                    p_eos = r * R * T / (1 - b * r) - a * alpha * r ** 2 / (1 + 2 * b * r - (b * r) ** 2)
+                    out[m] = np.sqrt(np.maximum(2 * (p_eos - r / 3) / (6.0 * gf[m, m]), 0.0))
+        return out
 
     def moments(self):
         lat = self.lat
@@ -284,6 +310,11 @@ def from_config(cfg, walls, rho):
              mm=[cfg.mm[m] for m in range(S)], gf=[[cfg.gf[m][k] for k in range(S)] for m in range(S)],
              gw=[[cfg.gw[k][m] for m in range(S)] for k in range(cfg.nminerals)],
              gvt=[cfg.gvt[d] for d in range(D)] if cfg.body_forces else None)
+    if cfg.use_nonideal_eos:
+        kinds = {1: lambda m: None, 2: lambda m: ("sc", cfg.eos_rho0[m]), 4: lambda m: ("thermo", cfg.eos_psi0[m], cfg.eos_rho0[m]),
+                 3: lambda m: ("pr", cfg.eos_pr_a[m], cfg.eos_pr_b[m], cfg.eos_pr_R[m], cfg.eos_pr_T[m], cfg.eos_pr_Tc[m],
+                               cfg.eos_pr_omega[m])}
+        p["eos"] = [kinds[cfg.eos_type[m]](m) for m in range(S)]
     w = np.asarray(walls)
     r = np.moveaxis(np.asarray(rho, dtype=np.float64), -1, 0)
     if D == 2:
