@@ -259,7 +259,8 @@ __device__ __forceinline__ void lag_m_block(const Grid &g, const LagMeta &meta, 
       // bounded: a schedule bug or out-of-order block dispatch must not hang the device (the host reports gave_up)
       unsigned spins = 0;
       while (ld_acquire_u32(done + dep) < want) {
-        if (++spins > (1u << 22)) {
+        ++spins;
+        if (spins > (1u << 20) || ((spins & 255u) == 0 && ld_acquire_u32(gave_up) != 0)) {  // ~1 s, or someone else gave up
           atomicAdd(gave_up, 1u);
           break;
         }
