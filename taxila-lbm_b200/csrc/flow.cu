@@ -974,8 +974,9 @@ static int build_lag(txg_flow *h) {
   h->lag = false;
   h->lag_nrows = h->lag_grid_x = 0;
   const Grid &g = h->g;
-  if (!h->lag_wanted || !h->fused || !h->ks.step_fused_lag || h->ks.fused_threads != 128 || h->D != 3 || h->cfg.nranks != 1 ||
-      h->p.eos || h->spec_n || h->bc_mode)
+  // (several ranks: the z halos of the one-pass step run on the main stream, not overlapped with the interior yet)
+  if (!h->lag_wanted || !h->fused || !h->ks.step_fused_lag || h->ks.fused_threads != 128 || h->D != 3 || h->p.eos || h->spec_n ||
+      h->bc_mode)
     return 0;
   const int nzE = g.NZl + 2 * g.Rz;
   std::vector<uint32_t> row_off((size_t)nzE * g.NY + 1);

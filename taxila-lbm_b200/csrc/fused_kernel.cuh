@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(TXG_FUSED_THREADS, 512 / TXG_FUSED_THREADS)
 // kernel parameters of k_step_fused (a per-block table in global memory costs ~100 bytes of spills at the
 // 128-register cap).  The table is per module and device: the host re-uploads it when another handle used it last.
 // Not used with a non-ideal EOS (psi needs its own pass), free-slip walls (the mirrors rewrite slots after
-// the push), external face BCs or more than one rank.  NOT YET RUN ON A GPU (written in a session without
+// the push) or external face BCs.  NOT YET RUN ON A GPU (written in a session without
 // GPU minutes; the schedule is CPU-tested, tests/test_lag_schedule.py).
 struct LagRowDev {
   uint32_t cfirst, ccount, m0first, m0count, m1first, m1count;  // lag_schedule.h LagRow

@@ -65,3 +65,15 @@ def test_lag_step_1000_steps(monkeypatch):
     fluid = walls == 0
     assert gpu_util.rel_err(r1[fluid], o.rho()[fluid]) <= 1e-10
     assert gpu_util.rel_err(u1[fluid], o.u()[fluid]) <= 1e-10
+
+
+def test_lag_step_two_ranks(monkeypatch, tmp_path):
+    """z-slabs: the one-pass step on two ranks against the oracle and bit for bit against one rank (both with TXG_LAG=1)."""
+    import test_multi_gpu as mg
+
+    if mg.ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("TXG_LAG", "1")
+    monkeypatch.setenv("TXG_LAG_ROWS", "8")
+    for case, steps in (("porous_periodic", 30), ("porous_closed_box", 30)):
+        mg.check(mg.run_case(case, 2, steps, tmp_path, 29631))
