@@ -106,6 +106,34 @@ __device__ __forceinline__ void forces1_inline(const Grid &g, const Phys &p, con
 // [first + blk*PB, first + (blk+1)*PB), PB = 4*NPW.  One 128-byte line per lane and round.
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
+// Cache-policy experiments on the population traffic of the fused kernels (build-time, default = plain):
+//   TXG_LDF_MODE 1: loads do not allocate in L1 (the 19 rows are read once; L1 is left to the rho gathers)
+//   TXG_STF_MODE 1: streaming stores (st.global.cs: evict-first), 2: st.global.cg
+#ifndef TXG_LDF_MODE
+#define TXG_LDF_MODE 0
+#endif
+#ifndef TXG_STF_MODE
+#define TXG_STF_MODE 0
+#endif
+__device__ __forceinline__ double load_population(const double *p) {
+#if TXG_LDF_MODE == 1
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ void store_population(double *p, double v) {
+#if TXG_STF_MODE == 1
+  __stcs(p, v);
+#elif TXG_STF_MODE == 2
+  __stcg(p, v);
+#else
+  *p = v;
+#endif
+}
+
 template <class L, int S>
 __device__ __forceinline__ void prefetch_block_rows(const Grid &g, const double *__restrict__ fA,
                                                     const uint32_t *__restrict__ lmask,
@@ -171,7 +199,7 @@ __global__ void __launch_bounds__(TXG_FUSED_THREADS, 512 / TXG_FUSED_THREADS)
   {
     const double *src = fA + mo;
 #pragma unroll
-    for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
+    for (int n = 0; n < Q; ++n) f[n] = load_population(src + (long long)n * g.fs);
   }
   const double *psi_field = rho + (long long)it.m * g.fs;
   double r = 0.;
@@ -188,13 +216,13 @@ __global__ void __launch_bounds__(TXG_FUSED_THREADS, 512 / TXG_FUSED_THREADS)
   // (element indices inside one component's Q*fs block fit 32 bits: checked in txg_set_walls)
   double *out = fB + (long long)it.m * Q * g.fs;
   const unsigned fs = (unsigned)g.fs, here = (unsigned)it.pos;
-  out[here] = f[0];
+  store_population(out + here, f[0]);
   static_for<1, Q>([&](auto n_) {
     constexpr int n = decltype(n_)::value;
     constexpr int on = opp<L>(n);
     const bool bounce = (mask >> n) & 1u;
     const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + npos[n];
-    out[e] = f[n];
+    store_population(out + e, f[n]);
   });
 }
 
@@ -314,7 +342,7 @@ __device__ __forceinline__ void lag_c_warp(const Grid &g, const Phys &p, const d
   {
     const double *src = fA + mo;
 #pragma unroll
-    for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
+    for (int n = 0; n < Q; ++n) f[n] = load_population(src + (long long)n * g.fs);
   }
   const double *psi_field = rho + (long long)it.m * g.fs;
   double r = 0.;
@@ -329,13 +357,13 @@ __device__ __forceinline__ void lag_c_warp(const Grid &g, const Phys &p, const d
   if (!it.active) return;
   double *out = fB + (long long)it.m * Q * g.fs;
   const unsigned fs = (unsigned)g.fs, here = (unsigned)it.pos;
-  out[here] = f[0];
+  store_population(out + here, f[0]);
   static_for<1, Q>([&](auto n_) {
     constexpr int n = decltype(n_)::value;
     constexpr int on = opp<L>(n);
     const bool bounce = (mask >> n) & 1u;
     const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + npos[n];
-    out[e] = f[n];
+    store_population(out + e, f[n]);
   });
 }
 

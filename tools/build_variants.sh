@@ -1,0 +1,18 @@
+#!/bin/bash
+# usage (here, before a gpurun call): tools/build_variants.sh
+# Builds kernel-tuning variants of libtaxila_gpu.so next to the default one (git-ignored, they travel with gpurun):
+#   libtaxila_gpu_ldna.so   population loads without L1 allocation      (-DTXG_LDF_MODE=1)
+#   libtaxila_gpu_stcs.so   streaming population stores                 (-DTXG_STF_MODE=1)
+#   libtaxila_gpu_stcg.so   st.global.cg population stores              (-DTXG_STF_MODE=2)
+#   libtaxila_gpu_ldna_stcs.so  both
+set -e
+cd "$(dirname "$0")/../taxila-lbm_b200/csrc"
+unset CC CXX
+build() { # name flags
+  make -j"$(nproc)" OBJDIR=build_$1 TARGET=../libtaxila_gpu_$1.so EXTRA="$2" > /dev/null
+  echo "built libtaxila_gpu_$1.so ($2)"
+}
+build ldna "-DTXG_LDF_MODE=1"
+build stcs "-DTXG_STF_MODE=1"
+build stcg "-DTXG_STF_MODE=2"
+build ldna_stcs "-DTXG_LDF_MODE=1 -DTXG_STF_MODE=1"
