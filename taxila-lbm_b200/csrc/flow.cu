@@ -126,6 +126,9 @@ struct txg_flow {
   // out of L2, band by band behind the collision front.  rho_next receives them; the buffers swap every step.
   bool lag_wanted = false, lag = false;
   int lag_rows = 128, lag_planes = 1, lag_mpos = 512;  // TXG_LAG_ROWS / TXG_LAG_PLANES / TXG_LAG_MPOS
+  // rho tiles in shared memory (opt-in, TXG_RHOTILE=1): window starts per block of the fused kernel (k_build_rtab)
+  bool tile_wanted = false, tile = false;
+  uint32_t *rtab = nullptr;
   double *rho_next = nullptr;
   LagRowDev *lag_rows_dev = nullptr;  // schedule rows, copied into the kernel's constant table before every launch
   unsigned *lag_done = nullptr;       // [rows] C blocks finished, zeroed before every launch
@@ -468,7 +471,7 @@ extern "C" int txg_destroy(txg_handle h) {
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
                   h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->nbr_all, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt, h->spec_dst, h->spec_src, h->spec_tmp, h->bc_vals[0], h->bc_vals[1],
-                  h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_done};
+                  h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_done, h->rtab};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -526,6 +529,7 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     // measured at 512^3 porous, k_step_fused ms: 0: 11.21, 148: 10.83, 222: 10.84, 296: 10.89, 444: 11.01, 592: 11.15, 888: 11.99
     h->pf_blocks = h->num_sms;
     if (const char *pf = getenv("TXG_PF")) h->pf_blocks = atoi(pf);
+    if (const char *rt = getenv("TXG_RHOTILE")) h->tile_wanted = rt[0] == '1';
     if (const char *lg = getenv("TXG_LAG")) h->lag_wanted = lg[0] == '1';
     if (const char *v = getenv("TXG_LAG_ROWS")) h->lag_rows = atoi(v);
     if (const char *v = getenv("TXG_LAG_PLANES")) h->lag_planes = atoi(v);
@@ -563,7 +567,7 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     TXG_TRY(alloc_zero(h, (void **)&h->cls, (size_t)(g.NZl + 2 * g.Rz) * g.cny * g.cnx));
     TXG_TRY(alloc_zero(h, (void **)&h->nbmask, (size_t)g.nnodes * sizeof(uint32_t)));
     if (h->ks.ff_words) TXG_TRY(alloc_zero(h, (void **)&h->ffmask, (size_t)h->ks.ff_words * g.nnodes * sizeof(uint32_t)));
-    TXG_TRY(alloc_zero(h, (void **)&h->counters, 4 * sizeof(int)));
+    TXG_TRY(alloc_zero(h, (void **)&h->counters, 8 * sizeof(int)));  // [4]: blocks of k_step_fused_tile that gave up waiting
     TXG_TRY(alloc_zero(h, (void **)&h->norm_bits, sizeof(unsigned long long)));
     std::vector<double> gw((size_t)cfg->nminerals * h->S);
     for (int k = 0; k < cfg->nminerals; ++k)
@@ -965,6 +969,24 @@ static int apply_specular(txg_flow *h, double *f, cudaStream_t s) {
 // ------------------------------------------------------------------ one-pass step (opt-in, TXG_LAG=1)
 // Block schedule of k_step_fused_lag for the current geometry (lag_schedule.h), rebuilt at every walls upload.
 // Boxes the schedule does not cover keep the two-kernel step; nothing is refused.
+// window starts of k_step_fused_tile for the current geometry (opt-in), rebuilt at every walls upload
+static int build_rtab(txg_flow *h) {
+  if (h->rtab) cudaFree(h->rtab);
+  h->rtab = nullptr;
+  h->tile = false;
+  const Grid &g = h->g;
+  if (!h->tile_wanted || !h->fused || !h->ks.step_fused_tile || h->ks.fused_threads != 128 || g.own1 <= g.own0) return 0;
+  const int PB = 4 * h->ks.npw;
+  const long long nblocks = (g.own1 - g.own0 + PB - 1) / PB;
+  TXG_CUDA(h, cudaMalloc((void **)&h->rtab, (size_t)nblocks * h->ks.rtab_groups * sizeof(uint32_t)));
+  h->ks.build_rtab<<<blocks_for(nblocks * h->ks.rtab_groups, 128), 128, 0, h->s_main>>>(g, h->nbr_all, PB, nblocks, h->rtab);
+  TXG_CUDA(h, cudaGetLastError());
+  TXG_CUDA(h, cudaMemsetAsync(h->counters + 4, 0, sizeof(int), h->s_main));
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+  h->tile = true;
+  return 0;
+}
+
 static int build_lag(txg_flow *h) {
   static_assert(sizeof(LagRow) == sizeof(LagRowDev), "host / device schedule row layout");
   for (void **q : {(void **)&h->lag_rows_dev, (void **)&h->lag_done}) {
@@ -1034,6 +1056,7 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   TXG_TRY(build_storage(h));
   TXG_TRY(build_specular(h, counters[1]));
   TXG_TRY(build_lag(h));
+  TXG_TRY(build_rtab(h));
   h->walls_set = true;
   return 0;
 }
@@ -1080,6 +1103,15 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   long long first, count;
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
+  if (h->fused && h->tile && first == h->g.own0) {  // (window starts are per block counted from own0: whole-slab launches only)
+    ScopedKernel sk(h, "k_step_fused_tile", s);
+    const long long warps = (count + h->ks.npw - 1) / h->ks.npw;
+    h->ks.step_fused_tile<<<(unsigned)((warps + 3) / 4), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
+                                                                     h->nbr_all, h->wallrec, h->rtab, h->counters + 4, first, count,
+                                                                     h->pf_blocks);
+    TXG_CUDA(h, cudaGetLastError());
+    return 0;
+  }
   if (h->fused) {
     ScopedKernel sk(h, "k_step_fused", s);
     const int wpb = h->ks.fused_threads / 32;  // warps per block
@@ -1516,6 +1548,12 @@ static int check_eos(txg_flow *h) {
     TXG_CUDA(h, cudaMemcpyAsync(&gave_up, h->lag_done + h->lag_nrows, sizeof gave_up, cudaMemcpyDeviceToHost, h->s_main));
     TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
     if (gave_up) TXG_FAIL(h, TXG_ERR_LIB, "one-pass step (TXG_LAG=1): %u density blocks gave up waiting for their collision rows; results are invalid", gave_up);
+  }
+  if (h->tile) {
+    int gave_up = 0;
+    TXG_CUDA(h, cudaMemcpyAsync(&gave_up, h->counters + 4, sizeof gave_up, cudaMemcpyDeviceToHost, h->s_main));
+    TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+    if (gave_up) TXG_FAIL(h, TXG_ERR_LIB, "k_step_fused_tile (TXG_RHOTILE=1): %d threads gave up waiting for their bulk copies; results are invalid", gave_up);
   }
   bool pr = false;
   for (int m = 0; m < h->S; ++m) pr = pr || (h->cfg.use_nonideal_eos && h->cfg.eos_type[m] == TXG_EOS_PR);

@@ -26,6 +26,11 @@ struct KernelSet {
   void (*step_fused_lag)(Grid, Phys, LagMeta, const double *, double *, const double *, double *, const uint32_t *,
                          const uint32_t *, const double *, unsigned *, unsigned *, int);
   int (*upload_lag_rows)(const void *rows, size_t bytes, cudaStream_t s);  // into this translation unit's c_lag_rows
+  // step_fused with the stencil's neighbour densities staged in shared memory by bulk copies (opt-in, TXG_RHOTILE=1)
+  void (*step_fused_tile)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
+                          const double *, const uint32_t *, int *, long long, long long, int);
+  void (*build_rtab)(Grid, const uint32_t *, int, long long, uint32_t *);
+  int rtab_groups;  // window starts per block (RhoTile<L>::NG)
   void (*build_nbr_all)(Grid, uint32_t *);
   void (*build_nbr)(Grid, uint32_t *);
   void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, long long, long long, int);
@@ -61,6 +66,9 @@ KernelSet make_kernel_set(const char *name) {
     k.step_fused = k_step_fused<L, S, MRT>;
     k.fi_init_fused = k_fi_init_fused<L, S>;
     k.step_fused_lag = k_step_fused_lag<L, S, MRT>;
+    k.step_fused_tile = k_step_fused_tile<L, S, MRT>;
+    k.build_rtab = k_build_rtab<L>;
+    k.rtab_groups = RhoTile<L>::NG;
     k.upload_lag_rows = [](const void *rows, size_t bytes, cudaStream_t s) -> int {
       return (int)cudaMemcpyToSymbolAsync(c_lag_rows, rows, bytes, 0, cudaMemcpyDeviceToDevice, s);
     };
@@ -69,6 +77,9 @@ KernelSet make_kernel_set(const char *name) {
     k.fi_init_fused = nullptr;
     k.step_fused_lag = nullptr;
     k.upload_lag_rows = nullptr;
+    k.step_fused_tile = nullptr;
+    k.build_rtab = nullptr;
+    k.rtab_groups = 0;
   }
   k.fused_threads = TXG_FUSED_THREADS;
   k.npw = Lanes<S>::NPW;

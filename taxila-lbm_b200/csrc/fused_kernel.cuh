@@ -19,11 +19,21 @@ namespace txg {
 // compile-time weight sum.  Neighbour densities are loaded unconditionally (a solid neighbour's
 // position is that of the next fluid node -- some valid, finite value) and masked afterwards, so that
 // all loads of a lane are in flight together.  npos[n]: position of X + c_n (order 4 re-uses them).
-template <class L, int S, int ISO>
+// Gather: how the order-4 stencil fetches psi of the lattice neighbour n at position np; the default loads it from global
+// memory, k_step_fused_tile serves it from a shared-memory tile (TileGather below).
+struct GlobalGather {
+  template <int n>
+  __device__ __forceinline__ double get(const double *__restrict__ psi_field, long long np) const {
+    return __ldg(psi_field + np);
+  }
+};
+
+template <class L, int S, int ISO, class Gather = GlobalGather>
 __device__ __forceinline__ void forces1_inline(const Grid &g, const Phys &p, const double *__restrict__ psi_field,
                                         const uint32_t *__restrict__ ffmask, const double *__restrict__ wallrec,
                                         const Item &it, unsigned oe, int x, int y, uint32_t mask,
-                                        const unsigned (&npos)[L::Q], double rho_m, double psi_m, double (&F)[L::D]) {
+                                        const unsigned (&npos)[L::Q], double rho_m, double psi_m, double (&F)[L::D],
+                                        const Gather gather = Gather()) {
   constexpr int D = L::D;
   const bool rec = (mask & MASK_WALLREC) != 0;
   const int m = it.m;
@@ -74,16 +84,18 @@ __device__ __forceinline__ void forces1_inline(const Grid &g, const Phys &p, con
       constexpr int dx = FF::off[e][0], dy = FF::off[e][1], dz = FF::off[e][2];
       bool on;
       long long np;
+      double v;
       if constexpr (ISO == 4) {
         constexpr int n = dir_of<L>(dx, dy, dz);
         on = !((mask >> n) & 1u);
         np = npos[n];
+        v = gather.template get<n>(psi_field, np);
       } else {
         on = (words[e / 32] >> (e % 32)) & 1u;
         np = pos_of(g, (long long)oe + (dz * plane + dyo[dy + RAD] + dxo[dx + RAD]));
+        v = __ldg(psi_field + np);
       }
       constexpr double wgt = L::ffw(ISO, FF::L[e]);
-      const double v = __ldg(psi_field + np);
       const double diff = on ? v - psi_m : 0.;
       if constexpr (dx != 0) G[0] = G[0] + ((double)dx * wgt) * diff;
       if constexpr (dy != 0) G[1] = G[1] + ((double)dy * wgt) * diff;
@@ -224,6 +236,160 @@ __global__ void __launch_bounds__(TXG_FUSED_THREADS, 512 / TXG_FUSED_THREADS)
     const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + npos[n];
     store_population(out + e, f[n]);
   });
+}
+
+// ------------------------------------------------------------------ rho tiles in shared memory (opt-in: TXG_RHOTILE=1)
+// k_step_fused with the neighbour densities of the Shan-Chen stencil staged in shared memory by bulk copies (TMA,
+// cp.async.bulk + mbarrier) issued at block start, so that they travel while the populations do instead of in a second,
+// dependent round trip after the adjacency has arrived (57 % of K2's warp time is long-scoreboard, a quarter of it on the
+// gathers: profiles/r1k_step_fused_ncu_summary.txt; issuing the gathers early costs registers the kernel does not have).
+// Positions ascend in (z, y, x) and X -> X + (0, dy, dz) keeps that order, so the neighbours of a block of consecutive
+// positions in one (dy, dz) row group are (nearly) one run of positions: rtab[blk][r] is the start of that run (set-up
+// kernel k_build_rtab), CAP entries of it are copied per component, and a neighbour outside the window falls back to the
+// global load.  The two same-row neighbours (x +- 1) stay global loads (adjacent lanes: L1 hits).
+// NOT YET RUN ON A GPU (written in a session without GPU minutes).
+template <class L>
+TXG_HD constexpr int row_group(int n) {  // 0 .. NG-1 for the (dy, dz) != (0, 0) row groups, -1 for the node's own row
+  const int cy = L::c(n, 1), cz = L::D == 3 ? L::c(n, 2) : 0;
+  if (cy == 0 && cz == 0) return -1;
+  const int k = L::D == 3 ? (cy + 1) * 3 + (cz + 1) : (cy + 1) * 3 + 1;  // 0..8 without 4
+  return L::D == 3 ? (k < 4 ? k : k - 1) : (cy < 0 ? 0 : 1);
+}
+template <class L>
+struct RhoTile {
+  static constexpr int NG = L::D == 3 ? 8 : 2, CAP = 128;
+};
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <class L, int S>
+struct TileGather {
+  const double *tile;      // [S][NG][CAP] in shared memory
+  const uint32_t *starts;  // [NG] in shared memory
+  int m;
+  template <int n>
+  __device__ __forceinline__ double get(const double *__restrict__ psi_field, long long np) const {
+    constexpr int r = row_group<L>(n);
+    if constexpr (r < 0) {
+      return __ldg(psi_field + np);
+    } else {
+      const unsigned idx = (unsigned)np - starts[r];
+      if (idx < (unsigned)RhoTile<L>::CAP) return tile[(m * RhoTile<L>::NG + r) * RhoTile<L>::CAP + idx];
+      return __ldg(psi_field + np);
+    }
+  }
+};
+
+// rtab[blk * NG + r] = even-aligned start of the window of row group r for the block of PB positions blk (relative to
+// own0): the smallest neighbour position of the block in that group (a solid neighbour's table entry is the position
+// of the next fluid node, close by; the window is a heuristic, the fallback load keeps every value exact).
+template <class L>
+__global__ void k_build_rtab(Grid g, const uint32_t *__restrict__ nbr_all, int PB, long long nblocks, uint32_t *__restrict__ rtab) {
+  constexpr int NG = RhoTile<L>::NG;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nblocks * NG) return;
+  const long long blk = t / NG;
+  const int r = (int)(t - blk * NG);
+  const long long p0 = g.own0 + blk * PB, p1 = min(g.own1, p0 + PB);
+  uint32_t lo = 0xffffffffu;
+  static_for<1, L::Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    if (row_group<L>(n) == r)
+      for (long long pos = p0; pos < p1; ++pos) lo = min(lo, __ldg(nbr_all + (long long)(n - 1) * g.fs + pos));
+  });
+  if (lo == 0xffffffffu) lo = 0;
+  rtab[t] = lo & ~1u;
+}
+
+template <class L, int S, bool MRT>
+__global__ void __launch_bounds__(128, 4)
+    k_step_fused_tile(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ rho,
+                      const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr_all,
+                      const double *__restrict__ wallrec, const uint32_t *__restrict__ rtab, int *__restrict__ gave_up,
+                      long long first, long long count, int pf_blocks) {
+  constexpr int Q = L::Q, D = L::D, ISO = 4, NG = RhoTile<L>::NG, CAP = RhoTile<L>::CAP;
+  __shared__ __align__(128) double tile[S * NG * CAP];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t starts[NG];
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // warp 0: window starts, then one bulk copy per (component, row group); completion is counted on `bar`
+    const int lane = threadIdx.x;
+    uint32_t st = 0;
+    if (lane < NG) {
+      st = __ldg(rtab + (long long)blockIdx.x * NG + lane);
+      starts[lane] = st;
+    }
+    __syncwarp();
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar)), "r"((unsigned)(S * NG * CAP * 8)) : "memory");
+    __syncwarp();
+    for (int idx = lane; idx < S * NG; idx += 32) {
+      const int m = idx / NG, r = idx - m * NG;
+      const uint32_t sr = __shfl_sync(0xffffffffu, st, r);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(tile + (m * NG + r) * CAP)),
+                   "l"(rho + (long long)m * g.fs + sr), "r"((unsigned)(CAP * 8)), "r"(smem_addr(&bar))
+                   : "memory");
+    }
+  }
+  if (pf_blocks > 0) prefetch_block_rows<L, S>(g, fA, lmask, nbr_all, wallrec, first, count, (long long)blockIdx.x + pf_blocks);
+  Item it;
+  const bool have = item_of_lane<S>(first, count, it);
+  if (have) {
+    const uint32_t mask = __ldg(lmask + it.pos);
+    unsigned npos[Q];
+    npos[0] = (unsigned)it.pos;
+#pragma unroll
+    for (int n = 1; n < Q; ++n) npos[n] = __ldg(nbr_all + (long long)(n - 1) * g.fs + it.pos);
+    const long long mo = (long long)it.m * Q * g.fs + it.pos;
+    double f[Q];
+    {
+      const double *src = fA + mo;
+#pragma unroll
+      for (int n = 0; n < Q; ++n) f[n] = load_population(src + (long long)n * g.fs);
+    }
+    const double *psi_field = rho + (long long)it.m * g.fs;
+    double r = 0.;
+#pragma unroll
+    for (int n = 0; n < Q; ++n) r += f[n];
+    const double psi_m = p.eos ? __ldg(psi_field + it.pos) : r;
+    // the tiles must have landed (acquire on the mbarrier also publishes `starts`); bounded, reports instead of hanging
+    {
+      unsigned ok = 0, spins = 0;
+      while (true) {
+        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok) : "r"(smem_addr(&bar)), "r"(0u) : "memory");
+        if (ok) break;
+        if (++spins > (1u << 22)) {
+          atomicAdd(gave_up, 1);
+          break;
+        }
+      }
+    }
+    double F[D];
+    const TileGather<L, S> gather{tile, starts, it.m};
+    forces1_inline<L, S, ISO>(g, p, psi_field, nullptr, wallrec, it, 0u, 0, 0, mask, npos, r, psi_m, F, gather);
+    double up[D];
+    common_velocity1<L, S>(p, it, f, r, F, up);
+    collide1<L, MRT>(p, it.m, r, F, up, f);
+    if (it.active) {
+      double *out = fB + (long long)it.m * Q * g.fs;
+      const unsigned fs = (unsigned)g.fs, here = (unsigned)it.pos;
+      store_population(out + here, f[0]);
+      static_for<1, Q>([&](auto n_) {
+        constexpr int n = decltype(n_)::value;
+        constexpr int on = opp<L>(n);
+        const bool bounce = (mask >> n) & 1u;
+        const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + npos[n];
+        store_population(out + e, f[n]);
+      });
+    }
+  }
+  // a block must not retire while its bulk copies are in flight: warp 0 always has work (and waited above); the other
+  // warps of a short last block leave early, which is harmless -- shared memory lives until the whole block is gone
 }
 
 // ------------------------------------------------------------------ one-pass step (opt-in: TXG_LAG=1)

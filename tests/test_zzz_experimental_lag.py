@@ -1,5 +1,6 @@
 """EXPERIMENTAL, opt-in (TXG_RUN_EXPERIMENTAL=1): the one-pass step (TXG_LAG=1, csrc/lag_schedule.h + k_step_fused_lag)
-against the oracle and, bit for bit, against the default two-kernel step.  The kernel was written in a session
+and the shared-memory density tiles (TXG_RHOTILE=1, k_step_fused_tile) against the oracle and, bit for bit, against the
+default two-kernel step.  The kernel was written in a session
 without GPU minutes and has not run on a GPU yet, so these tests stay out of the default `-m gpu` run (they sort
 last and skip unless asked for); tools/gpu_lag_try.sh runs them first and then times the variants."""
 import os
@@ -15,7 +16,7 @@ pytestmark = [pytest.mark.gpu,
 
 
 def run(cfg, walls, rho, steps, env, monkeypatch, chunks=(None,)):
-    for k in ("TXG_LAG", "TXG_LAG_ROWS", "TXG_LAG_PLANES", "TXG_LAG_MPOS"):
+    for k in ("TXG_LAG", "TXG_LAG_ROWS", "TXG_LAG_PLANES", "TXG_LAG_MPOS", "TXG_RHOTILE"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, str(v))
@@ -77,3 +78,37 @@ def test_lag_step_two_ranks(monkeypatch, tmp_path):
     monkeypatch.setenv("TXG_LAG_ROWS", "8")
     for case, steps in (("porous_periodic", 30), ("porous_closed_box", 30)):
         mg.check(mg.run_case(case, 2, steps, tmp_path, 29631))
+
+
+@pytest.mark.parametrize("case", ["porous", "bubble", "closed", "2d", "s3"])
+def test_rho_tile_kernel_equals_default_step(monkeypatch, case):
+    """TXG_RHOTILE=1 (k_step_fused_tile: neighbour densities staged in shared memory by bulk copies, global fallback
+    outside the window): bit for bit the default fused step."""
+    from taxila_lbm_b200 import config as tc
+    from taxila_lbm_b200 import geometry as geo
+
+    if case == "porous":
+        cfg, walls, rho = cases.porous_3d(32, rmin=4.0, rmax=8.0)
+    elif case == "bubble":
+        cfg, walls, rho = cases.bubble_3d(32)
+    elif case == "closed":
+        cfg, walls, rho = cases.porous_3d(24, rmin=3.0, rmax=6.0, periodic=(0, 0, 0))
+    elif case == "2d":
+        cfg, walls, rho = cases.bubble_2d(64)
+    else:
+        cfg = tc.default_config(3, 3, 24, 24, 24)
+        for d in range(3):
+            cfg.periodic[d] = 1
+        for m in range(3):
+            for k in range(3):
+                if k != m:
+                    cfg.gf[m][k] = 0.05 + 0.01 * (m + k)
+        tc.finalize_flags(cfg)
+        walls = geo.porous_spheres(24, 24, 24, seed=11, rmin=3.0, rmax=6.0, solid_fraction=0.4, nminerals=1)
+        rho = 0.2 + 0.6 * np.random.default_rng(5).random((24, 24, 24, 3))
+        rho[walls != 0] = 0.0
+    steps = 20
+    fi0, r0, u0, F0, k0 = run(cfg, walls, rho, steps, {}, monkeypatch)
+    fi1, r1, u1, F1, k1 = run(cfg, walls, rho, steps, dict(TXG_RHOTILE=1), monkeypatch)
+    assert k1["k_step_fused_tile"][1] == steps, k1
+    assert np.array_equal(fi0, fi1) and np.array_equal(r0, r1) and np.array_equal(u0, u1)

@@ -4,7 +4,7 @@
 # step and of a few (band rows, lag planes, M block size) settings at 512^3, each as one bench.py JSON line under gpurun_out/.
 mkdir -p gpurun_out
 export TXG_ASSUME_GPU=1
-( time TXG_RUN_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zzz_experimental_lag.py -x -q -m gpu --tb=short -p no:cacheprovider ) > gpurun_out/lag_tests.log 2>&1
+( time TXG_RUN_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_zzz_experimental_lag.py -x -q -m gpu --tb=short -p no:cacheprovider ) > gpurun_out/lag_tests.log 2>&1
 tail -15 gpurun_out/lag_tests.log
 run() { # name env...
   n=$1; shift
@@ -17,6 +17,7 @@ print(sys.argv[1], "MLUPS %.0f ms/step %.3f" % (d["value"], d["ms_per_step"]), {
 PY
 }
 run default
+run rhotile TXG_RHOTILE=1
 run r128_l1 TXG_LAG=1 TXG_LAG_ROWS=128 TXG_LAG_PLANES=1
 run r128_l0 TXG_LAG=1 TXG_LAG_ROWS=128 TXG_LAG_PLANES=0
 run r64_l1 TXG_LAG=1 TXG_LAG_ROWS=64 TXG_LAG_PLANES=1
