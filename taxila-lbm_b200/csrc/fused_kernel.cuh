@@ -319,18 +319,14 @@ __global__ void __launch_bounds__(128, 4)
   if (threadIdx.x < 32) {
     // warp 0: window starts, then one bulk copy per (component, row group); completion is counted on `bar`
     const int lane = threadIdx.x;
-    uint32_t st = 0;
-    if (lane < NG) {
-      st = __ldg(rtab + (long long)blockIdx.x * NG + lane);
-      starts[lane] = st;
-    }
+    if (lane < NG) starts[lane] = __ldg(rtab + (long long)blockIdx.x * NG + lane);
     __syncwarp();
     if (lane == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar)), "r"((unsigned)(S * NG * CAP * 8)) : "memory");
     __syncwarp();
     for (int idx = lane; idx < S * NG; idx += 32) {
       const int m = idx / NG, r = idx - m * NG;
-      const uint32_t sr = __shfl_sync(0xffffffffu, st, r);
+      const uint32_t sr = starts[r];
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(tile + (m * NG + r) * CAP)),
                    "l"(rho + (long long)m * g.fs + sr), "r"((unsigned)(CAP * 8)), "r"(smem_addr(&bar))
                    : "memory");
