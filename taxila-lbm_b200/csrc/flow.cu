@@ -865,10 +865,11 @@ static int build_storage(txg_flow *h) {
   TXG_TRY(fresh_zero(h, (void **)&h->f[0], fbytes));
   TXG_TRY(fresh_zero(h, (void **)&h->f[1], fbytes));
   h->cur = 0;
-  TXG_TRY(fresh_zero(h, (void **)&h->rho, (size_t)h->S * g.fs * sizeof(double)));
+  // (+ 256 entries: the bulk-copy windows of k_step_fused_tile may overrun the last position of the last component)
+  TXG_TRY(fresh_zero(h, (void **)&h->rho, ((size_t)h->S * g.fs + 256) * sizeof(double)));
   if (h->cfg.use_nonideal_eos) {
     if (h->rho_true == h->rho) h->rho_true = nullptr;
-    TXG_TRY(fresh_zero(h, (void **)&h->rho_true, (size_t)h->S * g.fs * sizeof(double)));
+    TXG_TRY(fresh_zero(h, (void **)&h->rho_true, ((size_t)h->S * g.fs + 256) * sizeof(double)));
   } else {
     h->rho_true = h->rho;
   }
@@ -1017,7 +1018,7 @@ static int build_lag(txg_flow *h) {
   TXG_CUDA(h, cudaMalloc((void **)&h->lag_done, (sc.rows.size() + 1) * sizeof(unsigned)));  // + 1: the gave-up counter
   TXG_CUDA(h, cudaMemset(h->lag_done, 0, (sc.rows.size() + 1) * sizeof(unsigned)));
   TXG_CUDA(h, cudaMemcpy(h->lag_rows_dev, sc.rows.data(), sc.rows.size() * sizeof(LagRow), cudaMemcpyHostToDevice));
-  TXG_TRY(fresh_zero(h, (void **)&h->rho_next, (size_t)h->S * g.fs * sizeof(double)));
+  TXG_TRY(fresh_zero(h, (void **)&h->rho_next, ((size_t)h->S * g.fs + 256) * sizeof(double)));
   TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
   h->lag_meta.rows_per_band = sc.rows_per_band;
   h->lag_meta.lag = sc.lag;

@@ -21,4 +21,7 @@ for v in ldna stcs stcg ldna_stcs; do
   [ -f taxila-lbm_b200/libtaxila_gpu_$v.so ] && run $v libtaxila_gpu_$v.so
 done
 run lag_default libtaxila_gpu.so TXG_LAG=1
+run tile192 libtaxila_gpu.so TXG_RHOTILE=1
+[ -f taxila-lbm_b200/libtaxila_gpu_cap128.so ] && run tile128 libtaxila_gpu_cap128.so TXG_RHOTILE=1
+[ -f taxila-lbm_b200/libtaxila_gpu_cap256.so ] && run tile256 libtaxila_gpu_cap256.so TXG_RHOTILE=1
 [ -f taxila-lbm_b200/libtaxila_gpu_ldna.so ] && run lag_ldna libtaxila_gpu_ldna.so TXG_LAG=1
