@@ -266,6 +266,28 @@ struct RhoTile {
   static_assert(CAP % 2 == 0 && CAP >= 64 && CAP <= 256, "window of 16-byte granules inside the padding of the position arrays");
 };
 
+// every direction off the node's own x-row falls in exactly one of the NG row groups, and every group is used
+template <class L>
+TXG_HD constexpr bool row_groups_consistent() {
+  int members[RhoTile<L>::NG] = {};
+  for (int n = 0; n < L::Q; ++n) {
+    const int r = row_group<L>(n);
+    const bool own_row = L::c(n, 1) == 0 && (L::D == 2 || L::c(n, 2) == 0);
+    if ((r < 0) != own_row || r >= RhoTile<L>::NG) return false;
+    if (r >= 0) {
+      ++members[r];
+      for (int k = 0; k < n; ++k)  // same group <=> same (dy, dz)
+        if (row_group<L>(k) >= 0 &&
+            (row_group<L>(k) == r) != (L::c(k, 1) == L::c(n, 1) && (L::D == 2 || L::c(k, 2) == L::c(n, 2))))
+          return false;
+    }
+  }
+  for (int r = 0; r < RhoTile<L>::NG; ++r)
+    if (members[r] == 0) return false;
+  return true;
+}
+static_assert(row_groups_consistent<D3Q19>() && row_groups_consistent<D2Q9>(), "row groups of the density tiles");
+
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 template <class L, int S>
