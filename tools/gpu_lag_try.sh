@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage (one gpurun call): tools/gpu_lag_try.sh
+# usage (one gpurun call, about 20 GPU-minutes): gpurun --timeout 1500 -- tools/gpu_lag_try.sh
 # The opt-in one-pass step (TXG_LAG=1): parity first (tests/test_zzz_experimental_lag.py), then kernel times of the default
 # step and of a few (band rows, lag planes, M block size) settings at 512^3, each as one bench.py JSON line under gpurun_out/.
 mkdir -p gpurun_out
