@@ -125,12 +125,13 @@ struct txg_flow {
   // one-pass step (opt-in, TXG_LAG=1; lag_schedule.h): the fused kernel also sums the next step's densities
   // out of L2, band by band behind the collision front.  rho_next receives them; the buffers swap every step.
   bool lag_wanted = false, lag = false;
-  int lag_rows = 128, lag_planes = 1, lag_mpos = 512;  // TXG_LAG_ROWS / TXG_LAG_PLANES / TXG_LAG_MPOS
+  int lag_rows = 64, lag_planes = 2, lag_mpos = 512;  // TXG_LAG_ROWS / TXG_LAG_PLANES / TXG_LAG_MPOS
   // rho tiles in shared memory (opt-in, TXG_RHOTILE=1): window starts per block of the fused kernel (k_build_rtab)
   bool tile_wanted = false, tile = false;
   uint32_t *rtab = nullptr;
   double *rho_next = nullptr;
-  LagRowDev *lag_rows_dev = nullptr;  // schedule rows, copied into the kernel's constant table before every launch
+  LagRowDev *lag_rows_dev = nullptr;  // schedule rows (the M blocks read them)
+  LagCRow *lag_crows_dev = nullptr;   // their C parts, copied into the kernel's constant table before every launch
   unsigned *lag_done = nullptr;       // [rows] C blocks finished, zeroed before every launch
   LagMeta lag_meta;
   unsigned lag_nrows = 0, lag_grid_x = 0;
@@ -471,7 +472,7 @@ extern "C" int txg_destroy(txg_handle h) {
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
                   h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->nbr_all, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt, h->spec_dst, h->spec_src, h->spec_tmp, h->bc_vals[0], h->bc_vals[1],
-                  h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_done, h->rtab};
+                  h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_crows_dev, h->lag_done, h->rtab};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -795,7 +796,7 @@ static void free_storage(txg_flow *h) {
   }
   if (h->rho_true && h->cfg.use_nonideal_eos) cudaFree(h->rho_true);
   h->rho_true = nullptr;
-  for (void **q : {(void **)&h->rho_next, (void **)&h->lag_rows_dev, (void **)&h->lag_done}) {
+  for (void **q : {(void **)&h->rho_next, (void **)&h->lag_rows_dev, (void **)&h->lag_crows_dev, (void **)&h->lag_done}) {
     if (*q) cudaFree(*q);
     *q = nullptr;
   }
@@ -990,7 +991,7 @@ static int build_rtab(txg_flow *h) {
 
 static int build_lag(txg_flow *h) {
   static_assert(sizeof(LagRow) == sizeof(LagRowDev), "host / device schedule row layout");
-  for (void **q : {(void **)&h->lag_rows_dev, (void **)&h->lag_done}) {
+  for (void **q : {(void **)&h->lag_rows_dev, (void **)&h->lag_crows_dev, (void **)&h->lag_done}) {
     if (*q) cudaFree(*q);
     *q = nullptr;
   }
@@ -1018,6 +1019,10 @@ static int build_lag(txg_flow *h) {
   TXG_CUDA(h, cudaMalloc((void **)&h->lag_done, (sc.rows.size() + 1) * sizeof(unsigned)));  // + 1: the gave-up counter
   TXG_CUDA(h, cudaMemset(h->lag_done, 0, (sc.rows.size() + 1) * sizeof(unsigned)));
   TXG_CUDA(h, cudaMemcpy(h->lag_rows_dev, sc.rows.data(), sc.rows.size() * sizeof(LagRow), cudaMemcpyHostToDevice));
+  std::vector<LagCRow> crows(sc.rows.size());
+  for (size_t i = 0; i < sc.rows.size(); ++i) crows[i] = LagCRow{sc.rows[i].cfirst, sc.rows[i].ccount};
+  TXG_CUDA(h, cudaMalloc((void **)&h->lag_crows_dev, crows.size() * sizeof(LagCRow)));
+  TXG_CUDA(h, cudaMemcpy(h->lag_crows_dev, crows.data(), crows.size() * sizeof(LagCRow), cudaMemcpyHostToDevice));
   TXG_TRY(fresh_zero(h, (void **)&h->rho_next, ((size_t)h->S * g.fs + 256) * sizeof(double)));
   TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
   h->lag_meta.rows_per_band = sc.rows_per_band;
@@ -1220,12 +1225,12 @@ static int one_step_lag(txg_flow *h) {
   }
   TXG_CUDA(h, cudaMemsetAsync(h->lag_done, 0, (size_t)h->lag_nrows * sizeof(unsigned), sm));
   // the schedule rows live in a constant table of the kernel's module: another handle may have used it last
-  TXG_CUDA(h, (cudaError_t)h->ks.upload_lag_rows(h->lag_rows_dev, (size_t)h->lag_nrows * sizeof(LagRowDev), sm));
+  TXG_CUDA(h, (cudaError_t)h->ks.upload_lag_rows(h->lag_crows_dev, (size_t)h->lag_nrows * sizeof(LagCRow), sm));
   {
     ScopedKernel sk(h, "k_step_fused_lag", sm);
     h->ks.step_fused_lag<<<dim3(h->lag_grid_x, h->lag_nrows), 128, 0, sm>>>(g, h->p, h->lag_meta, h->f[h->cur], h->f[h->cur ^ 1], h->rho,
-                                                                             h->rho_next, h->lmask, h->nbr_all, h->wallrec, h->lag_done,
-                                                                             h->lag_done + h->lag_nrows, h->pf_blocks);
+                                                                             h->rho_next, h->lmask, h->nbr_all, h->wallrec, h->lag_rows_dev,
+                                                                             h->lag_done, h->lag_done + h->lag_nrows, h->pf_blocks);
     TXG_CUDA(h, cudaGetLastError());
   }
   TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sm));

@@ -24,7 +24,7 @@ struct KernelSet {
                         const uint32_t *, const double *, long long, long long);
   // one-pass step (opt-in, TXG_LAG=1): step_fused + the density sum of the next step in one launch (lag_schedule.h)
   void (*step_fused_lag)(Grid, Phys, LagMeta, const double *, double *, const double *, double *, const uint32_t *,
-                         const uint32_t *, const double *, unsigned *, unsigned *, int);
+                         const uint32_t *, const double *, const LagRowDev *, unsigned *, unsigned *, int);
   int (*upload_lag_rows)(const void *rows, size_t bytes, cudaStream_t s);  // into this translation unit's c_lag_rows
   // step_fused with the stencil's neighbour densities staged in shared memory by bulk copies (opt-in, TXG_RHOTILE=1)
   void (*step_fused_tile)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,

@@ -423,21 +423,25 @@ __global__ void __launch_bounds__(128, 4)
 //   x >= nC: M block -- wait until the <= 9 dependency rows are complete, then rho_next[m][pos] = sum_n fB[m][n][pos]
 //            (ascending n, DistributionCalcDensityD*, lbm_distribution_function.F90:379-428) for MB positions of the
 //            row's M ranges, read through L2 (ld.global.cg: other SMs wrote them in this launch).
-// The schedule rows sit in constant memory so that range starts and counts stay in uniform registers like the
-// kernel parameters of k_step_fused (a per-block table in global memory costs ~100 bytes of spills at the
-// 128-register cap).  The table is per module and device: the host re-uploads it when another handle used it last.
+// The C ranges of the schedule rows sit in constant memory so that range starts and counts stay in uniform registers
+// like the kernel parameters of k_step_fused (a per-block table in global memory costs ~100 bytes of spills at the
+// 128-register cap); the M ranges are read from global memory by the M blocks, which have registers to spare.  The
+// constant table is per module and device: the host uploads it before every launch.
 // Not used with a non-ideal EOS (psi needs its own pass), free-slip walls (the mirrors rewrite slots after
 // the push) or external face BCs.  NOT YET RUN ON A GPU (written in a session without
 // GPU minutes; the schedule is CPU-tested, tests/test_lag_schedule.py).
 struct LagRowDev {
-  uint32_t cfirst, ccount, m0first, m0count, m1first, m1count;  // lag_schedule.h LagRow
+  uint32_t cfirst, ccount, m0first, m0count, m1first, m1count;  // lag_schedule.h LagRow (global memory: the M blocks read it)
 };
-constexpr int LAG_MAX_ROWS = 2560;  // 60 KB of the 64 KB constant bank
+struct LagCRow {
+  uint32_t cfirst, ccount;  // the C part of a row, in constant memory
+};
+constexpr int LAG_MAX_ROWS = 7680;  // 60 KB of the 64 KB constant bank: 14 bands of a 512-plane slab
 struct LagMeta {
   int rows_per_band, lag, MB;
   int depbands[16][3];
 };
-__constant__ LagRowDev c_lag_rows[LAG_MAX_ROWS];
+__constant__ LagCRow c_lag_rows[LAG_MAX_ROWS];
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
   unsigned v;
@@ -451,10 +455,10 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
 // the M block of k_step_fused_lag
 template <class L, int S>
 __device__ __forceinline__ void lag_m_block(const Grid &g, const LagMeta &meta, const double *__restrict__ fB,
-                                         double *__restrict__ rho_next, unsigned *__restrict__ done,
-                                         unsigned *__restrict__ gave_up, unsigned xm) {
+                                         double *__restrict__ rho_next, const LagRowDev *__restrict__ rows,
+                                         unsigned *__restrict__ done, unsigned *__restrict__ gave_up, unsigned xm) {
   constexpr int Q = L::Q, NPW = Lanes<S>::NPW, PB = 4 * NPW;
-  const LagRowDev &row = c_lag_rows[blockIdx.y];
+  const LagRowDev row = rows[blockIdx.y];
   const unsigned MB = (unsigned)meta.MB;
   const unsigned n0 = (row.m0count + MB - 1) / MB;
   long long first, count;
@@ -561,20 +565,21 @@ template <class L, int S, bool MRT>
 __global__ void __launch_bounds__(128, 4)
     k_step_fused_lag(Grid g, Phys p, LagMeta meta, const double *__restrict__ fA, double *__restrict__ fB,
                      const double *__restrict__ rho, double *__restrict__ rho_next, const uint32_t *__restrict__ lmask,
-                     const uint32_t *__restrict__ nbr_all, const double *__restrict__ wallrec, unsigned *__restrict__ done,
-                     unsigned *__restrict__ gave_up, int pf_blocks) {
+                     const uint32_t *__restrict__ nbr_all, const double *__restrict__ wallrec,
+                     const LagRowDev *__restrict__ rows, unsigned *__restrict__ done, unsigned *__restrict__ gave_up,
+                     int pf_blocks) {
   constexpr int PB = 4 * Lanes<S>::NPW;
-  const LagRowDev &row = c_lag_rows[blockIdx.y];
+  const LagCRow &row = c_lag_rows[blockIdx.y];
   const unsigned nC = (row.ccount + PB - 1) / PB;
   if (blockIdx.x >= nC) {
-    lag_m_block<L, S>(g, meta, fB, rho_next, done, gave_up, blockIdx.x - nC);
+    lag_m_block<L, S>(g, meta, fB, rho_next, rows, done, gave_up, blockIdx.x - nC);
     return;
   }
   // L2 prefetch for the C block pf_blocks further on in launch order: in this row, or at the start of the next one
   if (pf_blocks > 0) {
     const unsigned ahead = blockIdx.x + (unsigned)pf_blocks;
     const bool next = ahead >= nC && blockIdx.y + 1 < gridDim.y;
-    const LagRowDev &pr = c_lag_rows[blockIdx.y + (next ? 1u : 0u)];
+    const LagCRow &pr = c_lag_rows[blockIdx.y + (next ? 1u : 0u)];
     prefetch_block_rows<L, S>(g, fA, lmask, nbr_all, wallrec, (long long)pr.cfirst, (long long)pr.ccount, (long long)(next ? ahead - nC : ahead));
   }
   lag_c_warp<L, S, MRT>(g, p, fA, fB, rho, lmask, nbr_all, wallrec, (long long)row.cfirst, (long long)row.ccount,

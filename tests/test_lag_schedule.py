@@ -32,7 +32,7 @@ def _lib():
     return L
 
 
-def build(fluid_ext, pery, PB, MB, BR, lag, max_rows=2560):
+def build(fluid_ext, pery, PB, MB, BR, lag, max_rows=7680):
     """fluid_ext: [NZl + 2][NY][NX] bool (one ghost plane each side).  Returns the schedule as the kernel sees it:
     rows [nrows][6], (nbands, rows_per_band, grid_x, c_blocks, m_blocks), depbands [16][3], and P."""
     nzE, NY, NX = fluid_ext.shape
@@ -79,7 +79,7 @@ def tasks_of(rows, meta, depbands, PB, MB, lag):
     return out
 
 
-def check(NX, NY, NZl, solid_fraction, pery, PB, MB, BR, lag, seed, max_rows=2560):
+def check(NX, NY, NZl, solid_fraction, pery, PB, MB, BR, lag, seed, max_rows=7680):
     rng = np.random.default_rng(seed)
     owned = rng.random((NZl, NY, NX)) >= solid_fraction
     owned[:, :, 0] |= rng.random((NZl, NY)) < 0.5  # some rows start fluid, some do not
