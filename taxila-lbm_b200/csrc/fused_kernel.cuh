@@ -387,7 +387,8 @@ __global__ void __launch_bounds__(128, 4)
       while (true) {
         asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok) : "r"(smem_addr(&bar)), "r"(0u) : "memory");
         if (ok) break;
-        if (++spins > (1u << 22)) {
+        ++spins;
+        if (spins > (1u << 16) || ((spins & 255u) == 0 && *(volatile int *)gave_up != 0)) {  // or someone else gave up
           atomicAdd(gave_up, 1);
           break;
         }
