@@ -142,3 +142,40 @@ def test_nonideal_eos_kinds_in_the_force():
         cfg.eos_type[m] = tc.EOS_SC
         cfg.eos_rho0[m] = 0.8 + 0.3 * m
     compare(cfg, walls, rho, steps=25)
+
+
+def test_freeslip_slit_two_components():
+    """WALL_NORMAL_Z planes (code 902, lbm_distribution_function.F90:687-716) as textbook specular reflection: two
+    components with a density pattern, Shan-Chen force next to the walls, body force along x and y, MRT."""
+    cfg = tc.default_config(3, 2, 14, 12, 10)
+    for d in range(3):
+        cfg.periodic[d] = 1
+    cfg.relaxation_mode = tc.RELAXATION_MODE_MRT
+    for m in range(2):
+        cfg.s_e[m], cfg.s_e2[m], cfg.s_q[m], cfg.s_pi[m], cfg.s_m[m] = 1.19, 1.4, 1.2, 1.4, 1.98
+    cfg.gf[0][1] = cfg.gf[1][0] = 0.1
+    cfg.body_forces = 1
+    cfg.gvt[0], cfg.gvt[1] = 1e-4, -5e-5
+    tc.finalize_flags(cfg)
+    walls = np.zeros((10, 12, 14))
+    walls[0] = walls[-1] = tc.WALL_NORMAL_Z
+    zz, yy, xx = np.mgrid[0:10, 0:12, 0:14]
+    rho = np.zeros((10, 12, 14, 2))
+    rho[..., 0] = 0.6 + 0.3 * np.sin(2 * np.pi * xx / 14) * np.cos(2 * np.pi * yy / 12) + 0.02 * zz
+    rho[..., 1] = 1.0 - rho[..., 0]
+    rho[walls != 0] = 0.0
+    compare(cfg, walls, rho, steps=40)
+
+
+def test_freeslip_duct_2d():
+    """initialize_walls_nostick_duct in 2-D: WALL_NORMAL_Y rows (code 901), x periodic, SRT, order-8 stencil next to the rows."""
+    cfg, walls, rho = cases.bubble_2d(32, order=8, hw=6)
+    cfg.stencil_size_rho = 2
+    cfg.body_forces = 1
+    cfg.gvt[0] = 1e-4
+    tc.finalize_flags(cfg)
+    walls = np.zeros((1, 32, 32))
+    walls[0, 0] = walls[0, -1] = tc.WALL_NORMAL_Y
+    rho = rho.copy()
+    rho[walls != 0] = 0.0
+    compare(cfg, walls, rho, steps=40)

@@ -15,7 +15,7 @@ literature in whole-array numpy form, sharing no code, table or loop structure w
   * fluid-solid force from the mineral id of each lattice neighbour (lbm_forcing.F90:1326-1421, with its
     single-precision weights 1./6., 1./12., 1./3.).
 
-Fully periodic boxes only.  Agreement with the oracle is to accumulated round-off (different summation
+Fully periodic boxes only; free-slip walls (900-902) only as whole planes.  Agreement with the oracle is to accumulated round-off (different summation
 order), checked in tests/test_oracle_textbook.py."""
 import itertools
 
@@ -279,7 +279,20 @@ class Model:
             for k in range(lat.Q):
                 back = tuple(-lat.c[k])
                 src_fluid = shift(self.fluid, back)
-                new[:, k] = np.where(src_fluid, shift(post[:, k], back), post[:, lat.opp[k]])
+                val = np.where(src_fluid, shift(post[:, k], back), post[:, lat.opp[k]])
+                # planar free-slip walls (codes 900 + a, normal along axis a): the population arriving along c_k off such a
+                # wall left the node one tangential step back with the normal component of its velocity reversed
+                src_code = shift(self.walls, back)
+                for a in range(lat.D):
+                    if lat.c[k][a] == 0:
+                        continue
+                    mirrored = lat.c[k].copy()
+                    mirrored[a] = -mirrored[a]
+                    n = [tuple(v) for v in lat.c].index(tuple(mirrored))
+                    tang = lat.c[k].copy()
+                    tang[a] = 0
+                    val = np.where(src_code == 900 + a, shift(post[:, n], tuple(-tang)), val)
+                new[:, k] = val
             self.f = new * self.fluid
             self.moments()
 
