@@ -179,3 +179,52 @@ def test_freeslip_duct_2d():
     rho = rho.copy()
     rho[walls != 0] = 0.0
     compare(cfg, walls, rho, steps=40)
+
+
+def _padded_with_faces(cfg, walls, rho, bcs, pad=3):
+    """Textbook model of a box whose non-periodic axes carry BC_DIRICHLET faces: the box padded with a 999 ring along those
+    axes (the reference's ghost layer), the faces as masks with their (constant) target densities."""
+    D = cfg.ndims
+    S = cfg.ncomponents
+    w = walls if D == 3 else walls[0]
+    r = rho if D == 3 else rho[0]
+    nonper = [d for d in range(D) if not cfg.periodic[d]]          # d = 0: x
+    padw = [(pad, pad) if (D - 1 - ax) in nonper else (0, 0) for ax in range(D)]  # array axes run z, y, x
+    wp = np.pad(w, padw, constant_values=999.0)
+    rp = np.pad(r, padw + [(0, 0)])
+    pc = cfg.copy()
+    for d in nonper:
+        setattr(pc, ("NX", "NY", "NZ")[d], getattr(cfg, ("NX", "NY", "NZ")[d]) + 2 * pad)
+    t = tb.from_config(pc, wp if D == 3 else wp[None], rp if D == 3 else rp[None])
+    faces = []
+    for b in sorted(bcs):
+        d, side = b // 2, b % 2
+        ax = D - 1 - d
+        mask = np.zeros(wp.shape, dtype=bool)
+        idx = [slice(pad, -pad) if (D - 1 - a) in nonper else slice(None) for a in range(D)]
+        idx[ax] = pad if side == 0 else wp.shape[ax] - pad - 1
+        mask[tuple(idx)] = True
+        vals = np.asarray(bcs[b]).reshape(-1, D, S)
+        assert np.all(vals == vals[0])  # constant faces
+        faces.append((ax if False else d, side, mask, [vals[0, 0, m] for m in range(S)]))
+    inner = tuple(slice(pad, -pad) if (D - 1 - a) in nonper else slice(None) for a in range(D))
+    return t, faces, inner
+
+
+def test_dirichlet_faces_2d_and_3d():
+    """bc_density / bc_pressure faces (BCApplyDirichletToRho, BCApplyDirichletNode, BCUpdateRho of lbm_bc.F90 in the order of
+    FlowApplyBCs, lbm_flow.F90:1958-1991): the pressure-driven 2-D channel and the 3-D drainage box with density faces."""
+    for case, steps in ((cases.channel_2d(inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET), 40),
+                        (cases.drainage_3d(N=16, NZ=20, inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET), 25)):
+        cfg, walls, rho, bcs = case
+        o = cases.run_oracle_bc(cfg, walls, rho, bcs, steps)
+        t, faces, inner = _padded_with_faces(cfg, walls, rho, bcs)
+        t.p["dirichlet"] = faces
+        t.step(steps)
+        fluid = np.asarray(walls).reshape(o.rho().shape[:3]) == 0
+        sel = (slice(None),) + inner if cfg.ndims == 2 else inner
+        assert rel(t.fi_natural()[sel][fluid], o.fi()[fluid]) <= TOL
+        assert rel(t.rho_natural()[sel][fluid], o.rho()[fluid]) <= TOL
+        assert rel(t.u_natural()[sel][fluid], o.u()[fluid][..., 0]) <= TOL
+        assert rel(t.forces_natural()[sel][fluid], o.forces()[fluid]) <= TOL
+        o.close()

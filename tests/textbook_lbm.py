@@ -154,7 +154,7 @@ class Model:
         zero = np.zeros((lat.D,) + self.fluid.shape)
         self.f = (1 - 0.5 * self.prefactor(self.rho, self.F, zero)) * self.feq(self.rho, zero)
         self.f *= self.fluid
-        self.moments()
+        self.moments(apply_bcs=False)  # LBMInit2: FlowUpdateMoments, no FlowApplyBCs
 
     # -- pieces
     def feq(self, rho, u):
@@ -254,10 +254,35 @@ class Model:
                     out[m] = np.sqrt(np.maximum(2 * (p_eos - r / 3) / (6.0 * gf[m, m]), 0.0))
         return out
 
-    def moments(self):
+    def moments(self, apply_bcs=True):
         lat = self.lat
         self.rho = self.f.sum(axis=1) * self.fluid
+        faces = self.p.get("dirichlet") if apply_bcs else None  # [(axis, side, mask, rho_target[S])]: density faces
+        if faces:
+            for axis, side, mask, target in faces:  # BCApplyDirichletToRho: the stencil sees the prescribed densities
+                for m in range(self.S):
+                    self.rho[m] = np.where(mask & self.fluid, target[m], self.rho[m])
         self.F = self.forces(self.rho)
+        if faces:
+            # Chang, Liu & Lin (2009) as the reference applies it (BCApplyDirichletNode): the unknown (incoming)
+            # populations of a face node get w_n c_n.Q, Q_normal from the density deficit, Q_tangential cancelling the
+            # tangential momentum; faces in the order given (an edge node of two faces is corrected twice)
+            for axis, side, mask, target in faces:
+                inward = 1 if side == 0 else -1
+                inc = [n for n in range(1, lat.Q) if lat.c[n][axis] == inward]
+                on = mask & self.fluid
+                for m in range(self.S):
+                    fm = self.f[m]
+                    Q = [None] * lat.D
+                    Q[axis] = inward * (target[m] - fm.sum(axis=0)) / sum(lat.w[n] for n in inc)
+                    for d in range(lat.D):
+                        if d != axis:
+                            mom = sum(fm[n] * lat.c[n][d] for n in range(1, lat.Q))
+                            Q[d] = -mom / sum(lat.w[n] for n in inc if lat.c[n][d] != 0)
+                    for n in inc:
+                        fm[n] = np.where(on, fm[n] + lat.w[n] * sum(lat.c[n][d] * Q[d] for d in range(lat.D)), fm[n])
+            for axis, side, mask, target in faces:  # BCUpdateRho
+                self.rho = np.where(mask & self.fluid, self.f.sum(axis=1), self.rho)
         j = np.einsum("mn...,nd->md...", self.f, lat.c.astype(np.float64))
         ue = j + 0.5 * self.F
         wgt = (self.mm * self.s_c).reshape((self.S,) + (1,) * self.fluid.ndim)
