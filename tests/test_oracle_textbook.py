@@ -182,8 +182,8 @@ def test_freeslip_duct_2d():
 
 
 def _padded_with_faces(cfg, walls, rho, bcs, pad=3):
-    """Textbook model of a box whose non-periodic axes carry BC_DIRICHLET faces: the box padded with a 999 ring along those
-    axes (the reference's ghost layer), the faces as masks with their (constant) target densities."""
+    """Textbook model of a box whose non-periodic axes carry face BCs: the box padded with a 999 ring along those axes (the
+    reference's ghost layer), the faces as masks with their (constant) values, in BCApply's order."""
     D = cfg.ndims
     S = cfg.ncomponents
     w = walls if D == 3 else walls[0]
@@ -196,6 +196,7 @@ def _padded_with_faces(cfg, walls, rho, bcs, pad=3):
     for d in nonper:
         setattr(pc, ("NX", "NY", "NZ")[d], getattr(cfg, ("NX", "NY", "NZ")[d]) + 2 * pad)
     t = tb.from_config(pc, wp if D == 3 else wp[None], rp if D == 3 else rp[None])
+    kinds = {tc.BC_DIRICHLET: "dirichlet", tc.BC_NEUMANN: "neumann", tc.BC_VELOCITY: "velocity"}
     faces = []
     for b in sorted(bcs):
         d, side = b // 2, b % 2
@@ -206,25 +207,40 @@ def _padded_with_faces(cfg, walls, rho, bcs, pad=3):
         mask[tuple(idx)] = True
         vals = np.asarray(bcs[b]).reshape(-1, D, S)
         assert np.all(vals == vals[0])  # constant faces
-        faces.append((ax if False else d, side, mask, [vals[0, 0, m] for m in range(S)]))
+        faces.append((kinds[cfg.bc_flags[b]], d, side, mask, vals[0]))
+    first = {}
+    for i, f in enumerate(faces):  # each BC type once, in the order of its first face; faces xm .. zp inside a type
+        first.setdefault(f[0], i)
+    faces.sort(key=lambda f: first[f[0]])
     inner = tuple(slice(pad, -pad) if (D - 1 - a) in nonper else slice(None) for a in range(D))
     return t, faces, inner
+
+
+def _compare_faces(case, steps):
+    cfg, walls, rho, bcs = case
+    o = cases.run_oracle_bc(cfg, walls, rho, bcs, steps)
+    t, faces, inner = _padded_with_faces(cfg, walls, rho, bcs)
+    t.p["faces"] = faces
+    t.step(steps)
+    fluid = np.asarray(walls).reshape(o.rho().shape[:3]) == 0
+    sel = (slice(None),) + inner if cfg.ndims == 2 else inner
+    errs = {"fi": rel(t.fi_natural()[sel][fluid], o.fi()[fluid]), "rho": rel(t.rho_natural()[sel][fluid], o.rho()[fluid]),
+            "u": rel(t.u_natural()[sel][fluid], o.u()[fluid][..., 0]), "forces": rel(t.forces_natural()[sel][fluid], o.forces()[fluid])}
+    assert all(v <= TOL for v in errs.values()), errs
+    o.close()
 
 
 def test_dirichlet_faces_2d_and_3d():
     """bc_density / bc_pressure faces (BCApplyDirichletToRho, BCApplyDirichletNode, BCUpdateRho of lbm_bc.F90 in the order of
     FlowApplyBCs, lbm_flow.F90:1958-1991): the pressure-driven 2-D channel and the 3-D drainage box with density faces."""
-    for case, steps in ((cases.channel_2d(inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET), 40),
-                        (cases.drainage_3d(N=16, NZ=20, inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET), 25)):
-        cfg, walls, rho, bcs = case
-        o = cases.run_oracle_bc(cfg, walls, rho, bcs, steps)
-        t, faces, inner = _padded_with_faces(cfg, walls, rho, bcs)
-        t.p["dirichlet"] = faces
-        t.step(steps)
-        fluid = np.asarray(walls).reshape(o.rho().shape[:3]) == 0
-        sel = (slice(None),) + inner if cfg.ndims == 2 else inner
-        assert rel(t.fi_natural()[sel][fluid], o.fi()[fluid]) <= TOL
-        assert rel(t.rho_natural()[sel][fluid], o.rho()[fluid]) <= TOL
-        assert rel(t.u_natural()[sel][fluid], o.u()[fluid][..., 0]) <= TOL
-        assert rel(t.forces_natural()[sel][fluid], o.forces()[fluid]) <= TOL
-        o.close()
+    _compare_faces(cases.channel_2d(inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET), 40)
+    _compare_faces(cases.drainage_3d(N=16, NZ=20, inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET), 25)
+
+
+def test_flux_and_velocity_faces():
+    """bc_flux (BCApplyNeumannNode) and bc_velocity (BCApplyVelocityNode) inlets with a density outlet; no-slip side walls
+    in 2-D; and the 3-D box with Neumann faces on xm / xp as well, whose edge nodes are corrected by two faces in turn."""
+    _compare_faces(cases.channel_2d(inlet=tc.BC_NEUMANN, outlet=tc.BC_DIRICHLET, walls_kind="noslip"), 40)
+    _compare_faces(cases.channel_2d(inlet=tc.BC_VELOCITY, outlet=tc.BC_DIRICHLET, walls_kind="noslip", mrt=True), 40)
+    _compare_faces(cases.drainage_3d(N=16, NZ=20, inlet=tc.BC_NEUMANN, outlet=tc.BC_DIRICHLET), 25)
+    _compare_faces(cases.drainage_3d(N=16, NZ=20, inlet=tc.BC_VELOCITY, outlet=tc.BC_DIRICHLET, x_bc=tc.BC_NEUMANN), 25)

@@ -15,7 +15,8 @@ literature in whole-array numpy form, sharing no code, table or loop structure w
   * fluid-solid force from the mineral id of each lattice neighbour (lbm_forcing.F90:1326-1421, with its
     single-precision weights 1./6., 1./12., 1./3.).
 
-Fully periodic boxes only; free-slip walls (900-902) only as whole planes.  Agreement with the oracle is to accumulated round-off (different summation
+Fully periodic boxes only (a non-periodic face is a ring of 999 nodes, with optional density / flux / velocity face BCs
+on the nodes next to it); free-slip walls (900-902) only as whole planes.  Agreement with the oracle is to accumulated round-off (different summation
 order), checked in tests/test_oracle_textbook.py."""
 import itertools
 
@@ -257,31 +258,45 @@ class Model:
     def moments(self, apply_bcs=True):
         lat = self.lat
         self.rho = self.f.sum(axis=1) * self.fluid
-        faces = self.p.get("dirichlet") if apply_bcs else None  # [(axis, side, mask, rho_target[S])]: density faces
+        # external face BCs: [(kind, axis, side, mask, vals[D][S])], kind "dirichlet" (vals[0][m] = density), "neumann"
+        # (vals[d][m] = momentum) or "velocity" (vals[d][0] = velocity); given in BCApply's order (by kind, then xm .. zp)
+        faces = self.p.get("faces") if apply_bcs else None
         if faces:
-            for axis, side, mask, target in faces:  # BCApplyDirichletToRho: the stencil sees the prescribed densities
-                for m in range(self.S):
-                    self.rho[m] = np.where(mask & self.fluid, target[m], self.rho[m])
+            for kind, axis, side, mask, vals in faces:  # BCApplyDirichletToRho: the stencil sees the prescribed densities
+                if kind == "dirichlet":
+                    for m in range(self.S):
+                        self.rho[m] = np.where(mask & self.fluid, vals[0][m], self.rho[m])
         self.F = self.forces(self.rho)
         if faces:
-            # Chang, Liu & Lin (2009) as the reference applies it (BCApplyDirichletNode): the unknown (incoming)
-            # populations of a face node get w_n c_n.Q, Q_normal from the density deficit, Q_tangential cancelling the
-            # tangential momentum; faces in the order given (an edge node of two faces is corrected twice)
-            for axis, side, mask, target in faces:
+            # Chang, Liu & Lin (2009) as the reference applies it (BCApply{Dirichlet,Neumann,Velocity}Node): the unknown
+            # (incoming) populations of a face node get w_n c_n.Q with Q chosen so that the density, the momentum (+ F/2)
+            # or the velocity is met; an edge node of two faces is corrected twice
+            for kind, axis, side, mask, vals in faces:
                 inward = 1 if side == 0 else -1
                 inc = [n for n in range(1, lat.Q) if lat.c[n][axis] == inward]
+                wsum = [sum(lat.w[n] for n in inc if lat.c[n][d] != 0) for d in range(lat.D)]
                 on = mask & self.fluid
                 for m in range(self.S):
                     fm = self.f[m]
+                    tot = fm.sum(axis=0)
+                    mom = [sum(fm[n] * lat.c[n][d] for n in range(1, lat.Q)) for d in range(lat.D)]
                     Q = [None] * lat.D
-                    Q[axis] = inward * (target[m] - fm.sum(axis=0)) / sum(lat.w[n] for n in inc)
-                    for d in range(lat.D):
-                        if d != axis:
-                            mom = sum(fm[n] * lat.c[n][d] for n in range(1, lat.Q))
-                            Q[d] = -mom / sum(lat.w[n] for n in inc if lat.c[n][d] != 0)
+                    if kind == "dirichlet":
+                        for d in range(lat.D):
+                            Q[d] = inward * (vals[0][m] - tot) / wsum[d] if d == axis else -mom[d] / wsum[d]
+                    elif kind == "neumann":
+                        for d in range(lat.D):
+                            Q[d] = (vals[d][m] - self.F[m, d] / 2 - mom[d]) / wsum[d]
+                    else:
+                        ua = vals[axis][0]
+                        Q[axis] = (tot * ua - mom[axis] - self.F[m, axis] / 2) / (1 - inward * ua) / wsum[axis]
+                        rho_new = tot + wsum[axis] * Q[axis] * inward
+                        for d in range(lat.D):
+                            if d != axis:
+                                Q[d] = (rho_new * vals[d][0] - self.F[m, d] / 2 - mom[d]) / wsum[d]
                     for n in inc:
                         fm[n] = np.where(on, fm[n] + lat.w[n] * sum(lat.c[n][d] * Q[d] for d in range(lat.D)), fm[n])
-            for axis, side, mask, target in faces:  # BCUpdateRho
+            for kind, axis, side, mask, vals in faces:  # BCUpdateRho
                 self.rho = np.where(mask & self.fluid, self.f.sum(axis=1), self.rho)
         j = np.einsum("mn...,nd->md...", self.f, lat.c.astype(np.float64))
         ue = j + 0.5 * self.F
