@@ -216,11 +216,14 @@ def _padded_with_faces(cfg, walls, rho, bcs, pad=3):
     return t, faces, inner
 
 
-def _compare_faces(case, steps):
+def _compare_faces(case, steps, outlets=None):
     cfg, walls, rho, bcs = case
-    o = cases.run_oracle_bc(cfg, walls, rho, bcs, steps)
+    o = cases.run_oracle_bc(cfg, walls, rho, bcs, steps, outlets=outlets)
     t, faces, inner = _padded_with_faces(cfg, walls, rho, bcs)
     t.p["faces"] = faces
+    if outlets:  # {boundary: pressure} -> {index in faces: pressure}
+        t.p["outlets"] = {i: outlets[2 * f[1] + f[2]] for i, f in enumerate(faces) if (2 * f[1] + f[2]) in outlets}
+        assert len(t.p["outlets"]) == len(outlets)
     t.step(steps)
     fluid = np.asarray(walls).reshape(o.rho().shape[:3]) == 0
     sel = (slice(None),) + inner if cfg.ndims == 2 else inner
@@ -244,3 +247,11 @@ def test_flux_and_velocity_faces():
     _compare_faces(cases.channel_2d(inlet=tc.BC_VELOCITY, outlet=tc.BC_DIRICHLET, walls_kind="noslip", mrt=True), 40)
     _compare_faces(cases.drainage_3d(N=16, NZ=20, inlet=tc.BC_NEUMANN, outlet=tc.BC_DIRICHLET), 25)
     _compare_faces(cases.drainage_3d(N=16, NZ=20, inlet=tc.BC_VELOCITY, outlet=tc.BC_DIRICHLET, x_bc=tc.BC_NEUMANN), 25)
+
+
+def test_pressure_outlet_faces():
+    """bc_pressure_outlet (FlowUpdateBCPressureOutlet + FlowUpdateDensityFromPressure, lbm_flow.F90:1993-2263): the face
+    densities are re-derived every step from the phase fraction one node inside."""
+    _compare_faces(cases.channel_2d(inlet=tc.BC_VELOCITY, outlet=tc.BC_DIRICHLET, walls_kind="noslip"), 40,
+                   outlets={tc.BOUNDARY_XP: 0.31})
+    _compare_faces(cases.drainage_3d(N=16, NZ=20, inlet=tc.BC_NEUMANN, outlet=tc.BC_DIRICHLET), 25, outlets={tc.BOUNDARY_ZP: 0.30})

@@ -257,21 +257,43 @@ class Model:
 
     def moments(self, apply_bcs=True):
         lat = self.lat
+        outlets = self.p.get("outlets") if apply_bcs else None  # {face index: pressure}: bc_pressure_outlet faces
+        targets = {}
+        if outlets:
+            # FlowUpdateBCPressureOutlet: the densities prescribed on the face follow the phase fraction found (in the
+            # densities of the previous step) one node inside, at the given pressure p = (r1 + r2)/3 + c_0 g_21 r1 r2
+            g21 = self.p["gf"][1][0]
+            for i, press in outlets.items():
+                kind, axis, side, mask, vals = self.p["faces"][i]
+                step = [0] * lat.D
+                step[axis] = 1 if side == 0 else -1
+                inside_fluid = shift(self.fluid, tuple(step))
+                r1 = np.where(inside_fluid, shift(self.rho[0], tuple(step)), self.rho[0])
+                r2 = np.where(inside_fluid, shift(self.rho[1], tuple(step)), self.rho[1])
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    frac = r1 / (r1 + r2)
+                    alpha = 1 / (1 / frac - 1)
+                    a = (1 + alpha) / 3
+                    t1 = (-a + np.sqrt(a * a + 4 * 6.0 * g21 * alpha * press)) / (2 * 6.0 * g21)
+                    t2 = t1 / alpha
+                t1 = np.where(frac < 1e-10, 0.0, np.where(frac > 1 - 1e-10, 3 * press, t1))
+                t2 = np.where(frac < 1e-10, 3 * press, np.where(frac > 1 - 1e-10, 0.0, t2))
+                targets[i] = [t1, t2]
         self.rho = self.f.sum(axis=1) * self.fluid
         # external face BCs: [(kind, axis, side, mask, vals[D][S])], kind "dirichlet" (vals[0][m] = density), "neumann"
         # (vals[d][m] = momentum) or "velocity" (vals[d][0] = velocity); given in BCApply's order (by kind, then xm .. zp)
         faces = self.p.get("faces") if apply_bcs else None
         if faces:
-            for kind, axis, side, mask, vals in faces:  # BCApplyDirichletToRho: the stencil sees the prescribed densities
+            for i, (kind, axis, side, mask, vals) in enumerate(faces):  # BCApplyDirichletToRho: the stencil sees the prescribed densities
                 if kind == "dirichlet":
                     for m in range(self.S):
-                        self.rho[m] = np.where(mask & self.fluid, vals[0][m], self.rho[m])
+                        self.rho[m] = np.where(mask & self.fluid, targets[i][m] if i in targets else vals[0][m], self.rho[m])
         self.F = self.forces(self.rho)
         if faces:
             # Chang, Liu & Lin (2009) as the reference applies it (BCApply{Dirichlet,Neumann,Velocity}Node): the unknown
             # (incoming) populations of a face node get w_n c_n.Q with Q chosen so that the density, the momentum (+ F/2)
             # or the velocity is met; an edge node of two faces is corrected twice
-            for kind, axis, side, mask, vals in faces:
+            for i, (kind, axis, side, mask, vals) in enumerate(faces):
                 inward = 1 if side == 0 else -1
                 inc = [n for n in range(1, lat.Q) if lat.c[n][axis] == inward]
                 wsum = [sum(lat.w[n] for n in inc if lat.c[n][d] != 0) for d in range(lat.D)]
@@ -283,7 +305,8 @@ class Model:
                     Q = [None] * lat.D
                     if kind == "dirichlet":
                         for d in range(lat.D):
-                            Q[d] = inward * (vals[0][m] - tot) / wsum[d] if d == axis else -mom[d] / wsum[d]
+                            want = targets[i][m] if i in targets else vals[0][m]
+                            Q[d] = inward * (want - tot) / wsum[d] if d == axis else -mom[d] / wsum[d]
                     elif kind == "neumann":
                         for d in range(lat.D):
                             Q[d] = (vals[d][m] - self.F[m, d] / 2 - mom[d]) / wsum[d]
