@@ -18,7 +18,12 @@
  * the MRT tables through MRT(all rates 1) == SRT, and the D3Q19 tables through a
  * z-invariant extrusion projected onto the same golden.  D3Q19 MRT with general
  * rates, iso-8/10, walls, minerals and body force have no golden in the
- * reference ("parity unpinned" for those features).
+ * reference ("parity unpinned" for those features).  For them
+ * tests/test_oracle_textbook.py holds this file against tests/textbook_lbm.py, an
+ * independently written whole-array model of the same equations (which itself
+ * reproduces the golden): agreement to round-off on MRT with general rates, the
+ * order-8/10 stencils, bounce-back, mineral and body forces, the EOS kinds, planar
+ * free-slip walls, density / flux / velocity faces and pressure outlets.
  *
  * Floating point: compile with -ffp-contract=off and without -ffast-math so the
  * evaluation order below is the one executed.  Default-real Fortran literals
