@@ -255,3 +255,40 @@ def test_pressure_outlet_faces():
     _compare_faces(cases.channel_2d(inlet=tc.BC_VELOCITY, outlet=tc.BC_DIRICHLET, walls_kind="noslip"), 40,
                    outlets={tc.BOUNDARY_XP: 0.31})
     _compare_faces(cases.drainage_3d(N=16, NZ=20, inlet=tc.BC_NEUMANN, outlet=tc.BC_DIRICHLET), 25, outlets={tc.BOUNDARY_ZP: 0.30})
+
+
+def test_three_components_and_one_component():
+    """S = 3 (3 x 3 coupling matrix, unequal masses, two minerals) and S = 1 (no fluid-fluid force, SRT)."""
+    cfg = tc.default_config(3, 3, 14, 14, 14)
+    for d in range(3):
+        cfg.periodic[d] = 1
+    cfg.relaxation_mode = tc.RELAXATION_MODE_MRT
+    for m in range(3):
+        cfg.s_e[m], cfg.s_e2[m], cfg.s_q[m], cfg.s_pi[m], cfg.s_m[m] = 1.19, 1.4, 1.2, 1.4, 1.98
+        cfg.mm[m] = 1.0 + 0.25 * m
+        for k in range(3):
+            if k != m:
+                cfg.gf[m][k] = 0.05 + 0.01 * (m + k)
+    cfg.nminerals = 2
+    for k in range(2):
+        for m in range(3):
+            cfg.gw[k][m] = 0.01 * (k + 1) * (m - 1)
+    cfg.body_forces = 1
+    cfg.gvt[2] = 1e-5
+    tc.finalize_flags(cfg)
+    walls = geo.porous_spheres(14, 14, 14, seed=11, rmin=2.0, rmax=4.0, solid_fraction=0.4, nminerals=2)
+    rho = 0.2 + 0.6 * np.random.default_rng(5).random((14, 14, 14, 3))
+    rho[walls != 0] = 0.0
+    compare(cfg, walls, rho, steps=25)
+
+    cfg = tc.default_config(3, 1, 12, 12, 12)
+    for d in range(3):
+        cfg.periodic[d] = 1
+    cfg.tau[0] = 0.8
+    cfg.body_forces = 1
+    cfg.gvt[0] = 1e-4
+    tc.finalize_flags(cfg)
+    walls = geo.porous_spheres(12, 12, 12, seed=3, rmin=2.0, rmax=3.0, solid_fraction=0.3, nminerals=1)
+    rho = np.ones((12, 12, 12, 1))
+    rho[walls != 0] = 0.0
+    compare(cfg, walls, rho, steps=25)
