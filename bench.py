@@ -337,6 +337,8 @@ def main():
     nodes_local = args.size ** 2 * cfg.zl
     # dominant kernel: the fused forces+collide kernel (order-4 stencil) or the split collide kernel
     dom, dom_bytes = ("k_step_fused", B_K2_FLUID) if ktimes.get("k_step_fused", (0.0, 0))[1] else ("k_collide", B_K2B_FLUID)
+    if ktimes.get("k_step_fused_tile", (0.0, 0))[1]:  # TXG_RHOTILE=1 (opt-in): same bytes as k_step_fused
+        dom, dom_bytes = "k_step_fused_tile", B_K2_FLUID
     if ktimes.get("k_step_fused_lag", (0.0, 0))[1]:  # TXG_LAG=1 (opt-in one-pass step): the whole step's bytes in one launch
         dom, dom_bytes = "k_step_fused_lag", B_ALG_FLUID
     kc_ms, kc_n = ktimes.get(dom, (0.0, 0))
@@ -367,7 +369,7 @@ def main():
     kernels = {k: {"ms": v[0], "launches": v[1]} for k, v in ktimes.items()}
     # per-kernel achieved algorithmic GB/s (the launches of one step add up to the slab)
     for name, b in (("k_moments", B_K1_FLUID), ("k_forces", B_KF_FLUID), ("k_collide", B_K2B_FLUID), ("k_step_fused", B_K2_FLUID),
-                    ("k_step_fused_lag", B_ALG_FLUID)):
+                    ("k_step_fused_tile", B_K2_FLUID), ("k_step_fused_lag", B_ALG_FLUID)):
         if name == "k_moments" and "k_step_fused_lag" in kernels and kernels["k_step_fused_lag"]["launches"]:
             continue  # one-pass step: k_moments only sums the two boundary planes
         if name in kernels and kernels[name]["ms"] > 0:
