@@ -1014,7 +1014,7 @@ static int build_lag(txg_flow *h) {
   const int PB = 4 * h->ks.npw;
   const int MB = std::max(PB, h->lag_mpos / PB * PB);
   const LagSchedule sc = build_lag_schedule(g.NY, g.NZl, g.Rz, g.pery, row_off.data(), PB, MB, h->lag_rows, h->lag_planes, LAG_MAX_ROWS);
-  if (!sc.ok || sc.rows.size() > (size_t)LAG_MAX_ROWS || sc.nbands > 16) return 0;
+  if (!sc.ok || sc.rows.size() > (size_t)LAG_MAX_ROWS || sc.nbands > 16 || (unsigned long long)sc.rows.size() * sc.grid_x >= (1ull << 31)) return 0;
   TXG_CUDA(h, cudaMalloc((void **)&h->lag_rows_dev, sc.rows.size() * sizeof(LagRow)));
   TXG_CUDA(h, cudaMalloc((void **)&h->lag_done, (sc.rows.size() + 1) * sizeof(unsigned)));  // + 1: the gave-up counter
   TXG_CUDA(h, cudaMemset(h->lag_done, 0, (sc.rows.size() + 1) * sizeof(unsigned)));
@@ -1028,6 +1028,8 @@ static int build_lag(txg_flow *h) {
   h->lag_meta.rows_per_band = sc.rows_per_band;
   h->lag_meta.lag = sc.lag;
   h->lag_meta.MB = sc.MB;
+  h->lag_meta.nrows = (int)sc.rows.size();
+  h->lag_meta.row_blocks = (int)sc.grid_x;
   for (int b = 0; b < 16; ++b)
     for (int k = 0; k < 3; ++k) h->lag_meta.depbands[b][k] = b < sc.nbands ? sc.depbands[b][k] : -1;
   h->lag_nrows = (unsigned)sc.rows.size();
@@ -1228,7 +1230,7 @@ static int one_step_lag(txg_flow *h) {
   TXG_CUDA(h, (cudaError_t)h->ks.upload_lag_rows(h->lag_crows_dev, (size_t)h->lag_nrows * sizeof(LagCRow), sm));
   {
     ScopedKernel sk(h, "k_step_fused_lag", sm);
-    h->ks.step_fused_lag<<<dim3(h->lag_grid_x, h->lag_nrows), 128, 0, sm>>>(g, h->p, h->lag_meta, h->f[h->cur], h->f[h->cur ^ 1], h->rho,
+    h->ks.step_fused_lag<<<h->lag_grid_x * h->lag_nrows, 128, 0, sm>>>(g, h->p, h->lag_meta, h->f[h->cur], h->f[h->cur ^ 1], h->rho,
                                                                              h->rho_next, h->lmask, h->nbr_all, h->wallrec, h->lag_rows_dev,
                                                                              h->lag_done, h->lag_done + h->lag_nrows, h->pf_blocks);
     TXG_CUDA(h, cudaGetLastError());

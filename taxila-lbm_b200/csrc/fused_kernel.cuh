@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(128, 4)
 
 // ------------------------------------------------------------------ one-pass step (opt-in: TXG_LAG=1)
 // k_step_fused with the density sum of the NEXT step folded into the same launch (lag_schedule.h has the
-// schedule and the dependency argument).  2-D grid: blockIdx.y = schedule row, blockIdx.x = block in the row.
+// schedule and the dependency argument).  Block index = row * row_blocks + x: schedule row, block in the row.
 //   x <  nC: C block -- exactly k_step_fused on PB positions of the row's C range, then fence + done[row] += 1;
 //   x >= nC: M block -- wait until the <= 9 dependency rows are complete, then rho_next[m][pos] = sum_n fB[m][n][pos]
 //            (ascending n, DistributionCalcDensityD*, lbm_distribution_function.F90:379-428) for MB positions of the
@@ -440,6 +440,7 @@ struct LagCRow {
 constexpr int LAG_MAX_ROWS = 7680;  // 60 KB of the 64 KB constant bank: 14 bands of a 512-plane slab
 struct LagMeta {
   int rows_per_band, lag, MB;
+  int nrows, row_blocks;  // the launch: nrows * row_blocks blocks
   int depbands[16][3];
 };
 __constant__ LagCRow c_lag_rows[LAG_MAX_ROWS];
@@ -457,9 +458,9 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
 template <class L, int S>
 __device__ __forceinline__ void lag_m_block(const Grid &g, const LagMeta &meta, const double *__restrict__ fB,
                                          double *__restrict__ rho_next, const LagRowDev *__restrict__ rows,
-                                         unsigned *__restrict__ done, unsigned *__restrict__ gave_up, unsigned xm) {
+                                         unsigned *__restrict__ done, unsigned *__restrict__ gave_up, unsigned y, unsigned xm) {
   constexpr int Q = L::Q, NPW = Lanes<S>::NPW, PB = 4 * NPW;
-  const LagRowDev row = rows[blockIdx.y];
+  const LagRowDev row = rows[y];
   const unsigned MB = (unsigned)meta.MB;
   const unsigned n0 = (row.m0count + MB - 1) / MB;
   long long first, count;
@@ -474,7 +475,7 @@ __device__ __forceinline__ void lag_m_block(const Grid &g, const LagMeta &meta, 
   }
   // wait for the collisions that push into these positions: rows (b', zm + dz), b' in depbands[b]
   if (threadIdx.x < 9) {
-    const int b = (int)blockIdx.y / meta.rows_per_band, k = (int)blockIdx.y - b * meta.rows_per_band;
+    const int b = (int)y / meta.rows_per_band, k = (int)y - b * meta.rows_per_band;
     const int bb = meta.depbands[b][threadIdx.x / 3];
     if (bb >= 0) {
       const int dep = bb * meta.rows_per_band + (k - 1 - meta.lag) + ((int)threadIdx.x % 3 - 1);
@@ -570,25 +571,27 @@ __global__ void __launch_bounds__(128, 4)
                      const LagRowDev *__restrict__ rows, unsigned *__restrict__ done, unsigned *__restrict__ gave_up,
                      int pf_blocks) {
   constexpr int PB = 4 * Lanes<S>::NPW;
-  const LagCRow &row = c_lag_rows[blockIdx.y];
+  // 1-D launch of nrows * row_blocks blocks (a 1-D grid is dispatched in index order): row y, block x of the row
+  const unsigned y = blockIdx.x / (unsigned)meta.row_blocks, x = blockIdx.x - y * (unsigned)meta.row_blocks;
+  const LagCRow &row = c_lag_rows[y];
   const unsigned nC = (row.ccount + PB - 1) / PB;
-  if (blockIdx.x >= nC) {
-    lag_m_block<L, S>(g, meta, fB, rho_next, rows, done, gave_up, blockIdx.x - nC);
+  if (x >= nC) {
+    lag_m_block<L, S>(g, meta, fB, rho_next, rows, done, gave_up, y, x - nC);
     return;
   }
   // L2 prefetch for the C block pf_blocks further on in launch order: in this row, or at the start of the next one
   if (pf_blocks > 0) {
-    const unsigned ahead = blockIdx.x + (unsigned)pf_blocks;
-    const bool next = ahead >= nC && blockIdx.y + 1 < gridDim.y;
-    const LagCRow &pr = c_lag_rows[blockIdx.y + (next ? 1u : 0u)];
+    const unsigned ahead = x + (unsigned)pf_blocks;
+    const bool next = ahead >= nC && y + 1 < (unsigned)meta.nrows;
+    const LagCRow &pr = c_lag_rows[y + (next ? 1u : 0u)];
     prefetch_block_rows<L, S>(g, fA, lmask, nbr_all, wallrec, (long long)pr.cfirst, (long long)pr.ccount, (long long)(next ? ahead - nC : ahead));
   }
   lag_c_warp<L, S, MRT>(g, p, fA, fB, rho, lmask, nbr_all, wallrec, (long long)row.cfirst, (long long)row.ccount,
-                        ((long long)blockIdx.x * 128 + threadIdx.x) >> 5);
+                        ((long long)x * 128 + threadIdx.x) >> 5);
   // every thread's stores are ordered before the row count: fence, block barrier, one release-add
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) red_release_add_u32(done + blockIdx.y, 1u);
+  if (threadIdx.x == 0) red_release_add_u32(done + blockIdx.x / (unsigned)meta.row_blocks, 1u);  // (recomputed: no register held across the collision)
 }
 
 // FlowFiInit for the fused path (FlowFiInit lbm_flow.F90:923-934, FlowFeqBarD* :867-921), one lane per

@@ -12,8 +12,8 @@
 // in y-bands: band b = rows [b*BR, (b+1)*BR), and inside a band plane by plane.  The rows of one band in one
 // plane are one contiguous range of positions, because positions ascend in (z, y, x).
 //
-// The launch is a 2-D grid: blockIdx.y = schedule row, blockIdx.x = block inside the row; blocks are
-// dispatched in linear order (x fastest), so a row's blocks follow all blocks of earlier rows.  Row
+// The launch is a 1-D grid of nrows * grid_x blocks: block index = row * grid_x + x (schedule row, block inside the
+// row); blocks are dispatched in index order, so a row's blocks follow all blocks of earlier rows.  Row
 // r = b * rows_per_band + k of band b holds
 //   C(b, k)   if k < NZl: collide + push the fluid nodes of rows [b*BR, (b+1)*BR) of owned plane k, PB positions
 //             per block, blocks x = 0 .. nC-1; the last thing a C block does is fence + done[r] += 1;
