@@ -54,7 +54,7 @@ def build(fluid_ext, pery, PB, MB, BR, lag, max_rows=7680):
 
 
 def tasks_of(rows, meta, depbands, PB, MB, lag):
-    """The blocks in linear launch order, decoded exactly as k_step_fused_lag decodes (blockIdx.y, blockIdx.x):
+    """The blocks in linear launch order, decoded exactly as k_step_fused_lag decodes its block index (row = index / grid_x, x = index % grid_x):
     (linear index, first, count, is_m, row, dependency rows)."""
     rpb, gx = int(meta[1]), int(meta[2])
     nblk = lambda c, per: (c + per - 1) // per  # noqa: E731
