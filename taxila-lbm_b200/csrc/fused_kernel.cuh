@@ -454,6 +454,43 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// L2 residency hints of the one-pass step (build-time, -DTXG_LAG_HINTS=1; default off): the streamed input is marked
+// evict-first, the pushed populations evict-last until their density sum has read them (which demotes them again).
+#ifndef TXG_LAG_HINTS
+#define TXG_LAG_HINTS 0
+#endif
+__device__ __forceinline__ double lag_load_input(const double *p) {
+#if TXG_LAG_HINTS
+  unsigned long long pol;
+  double v;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ void lag_store_pushed(double *p, double v) {
+#if TXG_LAG_HINTS
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ double lag_load_pushed(const double *p) {
+#if TXG_LAG_HINTS
+  unsigned long long pol;
+  double v;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+#else
+  return __ldcg(p);
+#endif
+}
+
 // the M block of k_step_fused_lag
 template <class L, int S>
 __device__ __forceinline__ void lag_m_block(const Grid &g, const LagMeta &meta, const double *__restrict__ fB,
@@ -506,9 +543,9 @@ __device__ __forceinline__ void lag_m_block(const Grid &g, const LagMeta &meta, 
     const double *src1 = fB + (long long)it1.m * Q * g.fs + it1.pos;
     double v0[Q], v1[Q];
 #pragma unroll
-    for (int n = 0; n < Q; ++n) v0[n] = __ldcg(src0 + (long long)n * g.fs);
+    for (int n = 0; n < Q; ++n) v0[n] = lag_load_pushed(src0 + (long long)n * g.fs);
 #pragma unroll
-    for (int n = 0; n < Q; ++n) v1[n] = __ldcg(src1 + (long long)n * g.fs);
+    for (int n = 0; n < Q; ++n) v1[n] = lag_load_pushed(src1 + (long long)n * g.fs);
     double a0 = 0., a1 = 0.;
 #pragma unroll
     for (int n = 0; n < Q; ++n) a0 += v0[n];
@@ -538,7 +575,7 @@ __device__ __forceinline__ void lag_c_warp(const Grid &g, const Phys &p, const d
   {
     const double *src = fA + mo;
 #pragma unroll
-    for (int n = 0; n < Q; ++n) f[n] = load_population(src + (long long)n * g.fs);
+    for (int n = 0; n < Q; ++n) f[n] = lag_load_input(src + (long long)n * g.fs);
   }
   const double *psi_field = rho + (long long)it.m * g.fs;
   double r = 0.;
@@ -553,13 +590,13 @@ __device__ __forceinline__ void lag_c_warp(const Grid &g, const Phys &p, const d
   if (!it.active) return;
   double *out = fB + (long long)it.m * Q * g.fs;
   const unsigned fs = (unsigned)g.fs, here = (unsigned)it.pos;
-  store_population(out + here, f[0]);
+  lag_store_pushed(out + here, f[0]);
   static_for<1, Q>([&](auto n_) {
     constexpr int n = decltype(n_)::value;
     constexpr int on = opp<L>(n);
     const bool bounce = (mask >> n) & 1u;
     const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + npos[n];
-    store_population(out + e, f[n]);
+    lag_store_pushed(out + e, f[n]);
   });
 }
 

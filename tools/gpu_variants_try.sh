@@ -25,3 +25,5 @@ run tile192 libtaxila_gpu.so TXG_RHOTILE=1
 [ -f taxila-lbm_b200/libtaxila_gpu_cap128.so ] && run tile128 libtaxila_gpu_cap128.so TXG_RHOTILE=1
 [ -f taxila-lbm_b200/libtaxila_gpu_cap256.so ] && run tile256 libtaxila_gpu_cap256.so TXG_RHOTILE=1
 [ -f taxila-lbm_b200/libtaxila_gpu_ldna.so ] && run lag_ldna libtaxila_gpu_ldna.so TXG_LAG=1
+[ -f taxila-lbm_b200/libtaxila_gpu_laghints.so ] && run lag_hints libtaxila_gpu_laghints.so TXG_LAG=1
+[ -f taxila-lbm_b200/libtaxila_gpu_laghints.so ] && run lag_hints_r128 libtaxila_gpu_laghints.so TXG_LAG=1 TXG_LAG_ROWS=128 TXG_LAG_PLANES=2
