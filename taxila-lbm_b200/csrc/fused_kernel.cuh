@@ -625,8 +625,9 @@ __global__ void __launch_bounds__(128, 4)
   }
   lag_c_warp<L, S, MRT>(g, p, fA, fB, rho, lmask, nbr_all, wallrec, (long long)row.cfirst, (long long)row.ccount,
                         ((long long)x * 128 + threadIdx.x) >> 5);
-  // every thread's stores are ordered before the row count: fence, block barrier, one release-add
-  __threadfence();
+  // every thread's stores are ordered before the row count: release fence (acq_rel, lighter than __threadfence's
+  // sequentially consistent one), block barrier, one release-add
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) red_release_add_u32(done + blockIdx.x / (unsigned)meta.row_blocks, 1u);  // (recomputed: no register held across the collision)
 }
