@@ -129,6 +129,7 @@ struct txg_flow {
   // rho tiles in shared memory (opt-in, TXG_RHOTILE=1): window starts per block of the fused kernel (k_build_rtab)
   bool tile_wanted = false, tile = false;
   uint32_t *rtab = nullptr;
+  uint32_t *rtab_lag = nullptr;  // the same per block of the one-pass launch (TXG_LAG=1 TXG_RHOTILE=1)
   double *rho_next = nullptr;
   LagRowDev *lag_rows_dev = nullptr;  // schedule rows (the M blocks read them)
   LagCRow *lag_crows_dev = nullptr;   // their C parts, copied into the kernel's constant table before every launch
@@ -472,7 +473,7 @@ extern "C" int txg_destroy(txg_handle h) {
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
                   h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->nbr_all, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt, h->spec_dst, h->spec_src, h->spec_tmp, h->bc_vals[0], h->bc_vals[1],
-                  h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_crows_dev, h->lag_done, h->rtab};
+                  h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_crows_dev, h->lag_done, h->rtab, h->rtab_lag};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -796,7 +797,7 @@ static void free_storage(txg_flow *h) {
   }
   if (h->rho_true && h->cfg.use_nonideal_eos) cudaFree(h->rho_true);
   h->rho_true = nullptr;
-  for (void **q : {(void **)&h->rho_next, (void **)&h->lag_rows_dev, (void **)&h->lag_crows_dev, (void **)&h->lag_done}) {
+  for (void **q : {(void **)&h->rho_next, (void **)&h->lag_rows_dev, (void **)&h->lag_crows_dev, (void **)&h->lag_done, (void **)&h->rtab_lag}) {
     if (*q) cudaFree(*q);
     *q = nullptr;
   }
@@ -991,7 +992,7 @@ static int build_rtab(txg_flow *h) {
 
 static int build_lag(txg_flow *h) {
   static_assert(sizeof(LagRow) == sizeof(LagRowDev), "host / device schedule row layout");
-  for (void **q : {(void **)&h->lag_rows_dev, (void **)&h->lag_crows_dev, (void **)&h->lag_done}) {
+  for (void **q : {(void **)&h->lag_rows_dev, (void **)&h->lag_crows_dev, (void **)&h->lag_done, (void **)&h->rtab_lag}) {
     if (*q) cudaFree(*q);
     *q = nullptr;
   }
@@ -1024,6 +1025,15 @@ static int build_lag(txg_flow *h) {
   TXG_CUDA(h, cudaMalloc((void **)&h->lag_crows_dev, crows.size() * sizeof(LagCRow)));
   TXG_CUDA(h, cudaMemcpy(h->lag_crows_dev, crows.data(), crows.size() * sizeof(LagCRow), cudaMemcpyHostToDevice));
   TXG_TRY(fresh_zero(h, (void **)&h->rho_next, ((size_t)h->S * g.fs + 256) * sizeof(double)));
+  if (h->tile_wanted && h->ks.step_fused_lag_tile) {
+    // density tiles in the C blocks too: window starts per block of this launch
+    const long long nblk = (long long)sc.rows.size() * sc.grid_x;
+    TXG_CUDA(h, cudaMalloc((void **)&h->rtab_lag, (size_t)nblk * h->ks.rtab_groups * sizeof(uint32_t)));
+    h->ks.build_rtab_lag<<<blocks_for(nblk * h->ks.rtab_groups, 128), 128, 0, h->s_main>>>(
+        g, h->nbr_all, PB, reinterpret_cast<const uint32_t *>(h->lag_crows_dev), (long long)sc.rows.size(), (int)sc.grid_x, h->rtab_lag);
+    TXG_CUDA(h, cudaGetLastError());
+    TXG_CUDA(h, cudaMemsetAsync(h->counters + 4, 0, sizeof(int), h->s_main));
+  }
   TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
   h->lag_meta.rows_per_band = sc.rows_per_band;
   h->lag_meta.lag = sc.lag;
@@ -1230,9 +1240,9 @@ static int one_step_lag(txg_flow *h) {
   TXG_CUDA(h, (cudaError_t)h->ks.upload_lag_rows(h->lag_crows_dev, (size_t)h->lag_nrows * sizeof(LagCRow), sm));
   {
     ScopedKernel sk(h, "k_step_fused_lag", sm);
-    h->ks.step_fused_lag<<<h->lag_grid_x * h->lag_nrows, 128, 0, sm>>>(g, h->p, h->lag_meta, h->f[h->cur], h->f[h->cur ^ 1], h->rho,
+    (h->rtab_lag ? h->ks.step_fused_lag_tile : h->ks.step_fused_lag)<<<h->lag_grid_x * h->lag_nrows, 128, 0, sm>>>(g, h->p, h->lag_meta, h->f[h->cur], h->f[h->cur ^ 1], h->rho,
                                                                              h->rho_next, h->lmask, h->nbr_all, h->wallrec, h->lag_rows_dev,
-                                                                             h->lag_done, h->lag_done + h->lag_nrows, h->pf_blocks);
+                                                                             h->lag_done, h->lag_done + h->lag_nrows, h->rtab_lag, h->counters + 4, h->pf_blocks);
     TXG_CUDA(h, cudaGetLastError());
   }
   TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sm));
@@ -1557,7 +1567,7 @@ static int check_eos(txg_flow *h) {
     TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
     if (gave_up) TXG_FAIL(h, TXG_ERR_LIB, "one-pass step (TXG_LAG=1): %u density blocks gave up waiting for their collision rows; results are invalid", gave_up);
   }
-  if (h->tile) {
+  if (h->tile || h->rtab_lag) {
     int gave_up = 0;
     TXG_CUDA(h, cudaMemcpyAsync(&gave_up, h->counters + 4, sizeof gave_up, cudaMemcpyDeviceToHost, h->s_main));
     TXG_CUDA(h, cudaStreamSynchronize(h->s_main));

@@ -24,7 +24,11 @@ struct KernelSet {
                         const uint32_t *, const double *, long long, long long);
   // one-pass step (opt-in, TXG_LAG=1): step_fused + the density sum of the next step in one launch (lag_schedule.h)
   void (*step_fused_lag)(Grid, Phys, LagMeta, const double *, double *, const double *, double *, const uint32_t *,
-                         const uint32_t *, const double *, const LagRowDev *, unsigned *, unsigned *, int);
+                         const uint32_t *, const double *, const LagRowDev *, unsigned *, unsigned *, const uint32_t *, int *, int);
+  void (*step_fused_lag_tile)(Grid, Phys, LagMeta, const double *, double *, const double *, double *, const uint32_t *,
+                              const uint32_t *, const double *, const LagRowDev *, unsigned *, unsigned *, const uint32_t *, int *,
+                              int);  // + density tiles (TXG_LAG=1 TXG_RHOTILE=1)
+  void (*build_rtab_lag)(Grid, const uint32_t *, int, const uint32_t *, long long, int, uint32_t *);
   int (*upload_lag_rows)(const void *rows, size_t bytes, cudaStream_t s);  // into this translation unit's c_lag_rows
   // step_fused with the stencil's neighbour densities staged in shared memory by bulk copies (opt-in, TXG_RHOTILE=1)
   void (*step_fused_tile)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
@@ -65,7 +69,9 @@ KernelSet make_kernel_set(const char *name) {
   if constexpr (ISO == 4) {
     k.step_fused = k_step_fused<L, S, MRT>;
     k.fi_init_fused = k_fi_init_fused<L, S>;
-    k.step_fused_lag = k_step_fused_lag<L, S, MRT>;
+    k.step_fused_lag = k_step_fused_lag<L, S, MRT, false>;
+    k.step_fused_lag_tile = k_step_fused_lag<L, S, MRT, true>;
+    k.build_rtab_lag = k_build_rtab_lag<L>;
     k.step_fused_tile = k_step_fused_tile<L, S, MRT>;
     k.build_rtab = k_build_rtab<L>;
     k.rtab_groups = RhoTile<L>::NG;
@@ -76,6 +82,8 @@ KernelSet make_kernel_set(const char *name) {
     k.step_fused = nullptr;
     k.fi_init_fused = nullptr;
     k.step_fused_lag = nullptr;
+    k.step_fused_lag_tile = nullptr;
+    k.build_rtab_lag = nullptr;
     k.upload_lag_rows = nullptr;
     k.step_fused_tile = nullptr;
     k.build_rtab = nullptr;

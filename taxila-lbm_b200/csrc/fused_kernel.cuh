@@ -308,6 +308,39 @@ struct TileGather {
   }
 };
 
+// warp 0 of a block: read the window starts of this block, then one bulk copy per (component, row group) into `tile`;
+// completion is counted on `bar` (initialised by thread 0 + __syncthreads before the call)
+template <class L, int S>
+__device__ __forceinline__ void tile_issue(double *tile, uint32_t *starts, uint64_t *bar, const double *__restrict__ rho,
+                                           long long fs, const uint32_t *__restrict__ rtab_block) {
+  constexpr int NG = RhoTile<L>::NG, CAP = RhoTile<L>::CAP;
+  const int lane = threadIdx.x;
+  if (lane < NG) starts[lane] = __ldg(rtab_block + lane);
+  __syncwarp();
+  if (lane == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"((unsigned)(S * NG * CAP * 8)) : "memory");
+  __syncwarp();
+  for (int idx = lane; idx < S * NG; idx += 32) {
+    const int m = idx / NG, r = idx - m * NG;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(tile + (m * NG + r) * CAP)),
+                 "l"(rho + (long long)m * fs + starts[r]), "r"((unsigned)(CAP * 8)), "r"(smem_addr(bar))
+                 : "memory");
+  }
+}
+// the tiles must have landed (acquire on the mbarrier also publishes `starts`); bounded, reports instead of hanging
+__device__ __forceinline__ void tile_wait(uint64_t *bar, int *gave_up) {
+  unsigned ok = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok) : "r"(smem_addr(bar)), "r"(0u) : "memory");
+    if (ok) break;
+    ++spins;
+    if (spins > (1u << 16) || ((spins & 255u) == 0 && *(volatile int *)gave_up != 0)) {  // or someone else gave up
+      atomicAdd(gave_up, 1);
+      break;
+    }
+  }
+}
+
 // rtab[blk * NG + r] = even-aligned start of the window of row group r for the block of PB positions blk (relative to
 // own0): the smallest neighbour position of the block in that group (a solid neighbour's table entry is the position
 // of the next fluid node, close by; the window is a heuristic, the fallback load keeps every value exact).
@@ -329,6 +362,30 @@ __global__ void k_build_rtab(Grid g, const uint32_t *__restrict__ nbr_all, int P
   rtab[t] = lo & ~1u;
 }
 
+// the same for the blocks of the one-pass launch: block index = row * row_blocks + x, C block x of schedule row `row`
+template <class L>
+__global__ void k_build_rtab_lag(Grid g, const uint32_t *__restrict__ nbr_all, int PB, const uint32_t *__restrict__ crows /*[nrows][2]*/,
+                                 long long nrows, int row_blocks, uint32_t *__restrict__ rtab) {
+  constexpr int NG = RhoTile<L>::NG;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrows * row_blocks * NG) return;
+  const long long blk = t / NG;
+  const int r = (int)(t - blk * NG);
+  const long long row = blk / row_blocks, x = blk - row * row_blocks;
+  const long long cfirst = crows[2 * row], ccount = crows[2 * row + 1];
+  uint32_t lo = 0xffffffffu;
+  if (x * PB < ccount) {
+    const long long p0 = cfirst + x * PB, p1 = min(cfirst + ccount, p0 + PB);
+    static_for<1, L::Q>([&](auto n_) {
+      constexpr int n = decltype(n_)::value;
+      if (row_group<L>(n) == r)
+        for (long long pos = p0; pos < p1; ++pos) lo = min(lo, __ldg(nbr_all + (long long)(n - 1) * g.fs + pos));
+    });
+  }
+  if (lo == 0xffffffffu) lo = 0;
+  rtab[t] = lo & ~1u;
+}
+
 template <class L, int S, bool MRT>
 __global__ void __launch_bounds__(128, 4)
     k_step_fused_tile(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ rho,
@@ -344,22 +401,7 @@ __global__ void __launch_bounds__(128, 4)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    // warp 0: window starts, then one bulk copy per (component, row group); completion is counted on `bar`
-    const int lane = threadIdx.x;
-    if (lane < NG) starts[lane] = __ldg(rtab + (long long)blockIdx.x * NG + lane);
-    __syncwarp();
-    if (lane == 0)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar)), "r"((unsigned)(S * NG * CAP * 8)) : "memory");
-    __syncwarp();
-    for (int idx = lane; idx < S * NG; idx += 32) {
-      const int m = idx / NG, r = idx - m * NG;
-      const uint32_t sr = starts[r];
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(tile + (m * NG + r) * CAP)),
-                   "l"(rho + (long long)m * g.fs + sr), "r"((unsigned)(CAP * 8)), "r"(smem_addr(&bar))
-                   : "memory");
-    }
-  }
+  if (threadIdx.x < 32) tile_issue<L, S>(tile, starts, &bar, rho, g.fs, rtab + (long long)blockIdx.x * NG);
   if (pf_blocks > 0) prefetch_block_rows<L, S>(g, fA, lmask, nbr_all, wallrec, first, count, (long long)blockIdx.x + pf_blocks);
   Item it;
   const bool have = item_of_lane<S>(first, count, it);
@@ -381,19 +423,7 @@ __global__ void __launch_bounds__(128, 4)
 #pragma unroll
     for (int n = 0; n < Q; ++n) r += f[n];
     const double psi_m = p.eos ? __ldg(psi_field + it.pos) : r;
-    // the tiles must have landed (acquire on the mbarrier also publishes `starts`); bounded, reports instead of hanging
-    {
-      unsigned ok = 0, spins = 0;
-      while (true) {
-        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok) : "r"(smem_addr(&bar)), "r"(0u) : "memory");
-        if (ok) break;
-        ++spins;
-        if (spins > (1u << 16) || ((spins & 255u) == 0 && *(volatile int *)gave_up != 0)) {  // or someone else gave up
-          atomicAdd(gave_up, 1);
-          break;
-        }
-      }
-    }
+    tile_wait(&bar, gave_up);
     double F[D];
     const TileGather<L, S> gather{tile, starts, it.m};
     forces1_inline<L, S, ISO>(g, p, psi_field, nullptr, wallrec, it, 0u, 0, 0, mask, npos, r, psi_m, F, gather);
@@ -557,11 +587,12 @@ __device__ __forceinline__ void lag_m_block(const Grid &g, const LagMeta &meta, 
 }
 
 // the C block of k_step_fused_lag: the body of k_step_fused on positions [first, first + count), warp `warp` of them
-template <class L, int S, bool MRT>
+template <class L, int S, bool MRT, bool TILE>
 __device__ __forceinline__ void lag_c_warp(const Grid &g, const Phys &p, const double *__restrict__ fA, double *__restrict__ fB,
                                            const double *__restrict__ rho, const uint32_t *__restrict__ lmask,
                                            const uint32_t *__restrict__ nbr_all, const double *__restrict__ wallrec,
-                                           long long first, long long count, long long warp) {
+                                           long long first, long long count, long long warp, const double *tile,
+                                           const uint32_t *starts, uint64_t *bar, int *tile_gave_up) {
   constexpr int Q = L::Q, D = L::D, ISO = 4;
   Item it;
   if (!item_of_lane<S>(first, count, warp, it)) return;
@@ -583,7 +614,13 @@ __device__ __forceinline__ void lag_c_warp(const Grid &g, const Phys &p, const d
   for (int n = 0; n < Q; ++n) r += f[n];
   double F[D];
   const double psi_m = p.eos ? __ldg(psi_field + it.pos) : r;  // (p.eos is 0 on this path; kept so that the code generated is k_step_fused's)
-  forces1_inline<L, S, ISO>(g, p, psi_field, nullptr, wallrec, it, 0u, 0, 0, mask, npos, r, psi_m, F);
+  if constexpr (TILE) {  // neighbour densities from the shared-memory windows (k_step_fused_tile)
+    tile_wait(bar, tile_gave_up);
+    const TileGather<L, S> gather{tile, starts, it.m};
+    forces1_inline<L, S, ISO>(g, p, psi_field, nullptr, wallrec, it, 0u, 0, 0, mask, npos, r, psi_m, F, gather);
+  } else {
+    forces1_inline<L, S, ISO>(g, p, psi_field, nullptr, wallrec, it, 0u, 0, 0, mask, npos, r, psi_m, F);
+  }
   double up[D];
   common_velocity1<L, S>(p, it, f, r, F, up);
   collide1<L, MRT>(p, it.m, r, F, up, f);
@@ -600,14 +637,20 @@ __device__ __forceinline__ void lag_c_warp(const Grid &g, const Phys &p, const d
   });
 }
 
-template <class L, int S, bool MRT>
+// TILE: the C blocks also stage the stencil's neighbour densities in shared memory (k_step_fused_tile); rtab then holds the
+// window starts per block index of THIS launch (k_build_rtab_lag), tile_gave_up its give-up counter
+template <class L, int S, bool MRT, bool TILE>
 __global__ void __launch_bounds__(128, 4)
     k_step_fused_lag(Grid g, Phys p, LagMeta meta, const double *__restrict__ fA, double *__restrict__ fB,
                      const double *__restrict__ rho, double *__restrict__ rho_next, const uint32_t *__restrict__ lmask,
                      const uint32_t *__restrict__ nbr_all, const double *__restrict__ wallrec,
                      const LagRowDev *__restrict__ rows, unsigned *__restrict__ done, unsigned *__restrict__ gave_up,
-                     int pf_blocks) {
+                     const uint32_t *__restrict__ rtab, int *__restrict__ tile_gave_up, int pf_blocks) {
   constexpr int PB = 4 * Lanes<S>::NPW;
+  constexpr int NG = RhoTile<L>::NG, CAP = RhoTile<L>::CAP;
+  __shared__ __align__(128) double tile[TILE ? S * NG * CAP : 1];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t starts[NG];
   // 1-D launch of nrows * row_blocks blocks (a 1-D grid is dispatched in index order): row y, block x of the row
   const unsigned y = blockIdx.x / (unsigned)meta.row_blocks, x = blockIdx.x - y * (unsigned)meta.row_blocks;
   const LagCRow &row = c_lag_rows[y];
@@ -616,6 +659,14 @@ __global__ void __launch_bounds__(128, 4)
     lag_m_block<L, S>(g, meta, fB, rho_next, rows, done, gave_up, y, x - nC);
     return;
   }
+  if constexpr (TILE) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&bar)), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) tile_issue<L, S>(tile, starts, &bar, rho, g.fs, rtab + (long long)blockIdx.x * NG);
+  }
   // L2 prefetch for the C block pf_blocks further on in launch order: in this row, or at the start of the next one
   if (pf_blocks > 0) {
     const unsigned ahead = x + (unsigned)pf_blocks;
@@ -623,8 +674,8 @@ __global__ void __launch_bounds__(128, 4)
     const LagCRow &pr = c_lag_rows[y + (next ? 1u : 0u)];
     prefetch_block_rows<L, S>(g, fA, lmask, nbr_all, wallrec, (long long)pr.cfirst, (long long)pr.ccount, (long long)(next ? ahead - nC : ahead));
   }
-  lag_c_warp<L, S, MRT>(g, p, fA, fB, rho, lmask, nbr_all, wallrec, (long long)row.cfirst, (long long)row.ccount,
-                        ((long long)x * 128 + threadIdx.x) >> 5);
+  lag_c_warp<L, S, MRT, TILE>(g, p, fA, fB, rho, lmask, nbr_all, wallrec, (long long)row.cfirst, (long long)row.ccount,
+                              ((long long)x * 128 + threadIdx.x) >> 5, tile, starts, &bar, tile_gave_up);
   // every thread's stores are ordered before the row count: release fence (acq_rel, lighter than __threadfence's
   // sequentially consistent one), block barrier, one release-add
   asm volatile("fence.acq_rel.gpu;" ::: "memory");

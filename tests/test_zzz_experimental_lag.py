@@ -112,3 +112,14 @@ def test_rho_tile_kernel_equals_default_step(monkeypatch, case):
     fi1, r1, u1, F1, k1 = run(cfg, walls, rho, steps, dict(TXG_RHOTILE=1), monkeypatch)
     assert k1["k_step_fused_tile"][1] == steps, k1
     assert np.array_equal(fi0, fi1) and np.array_equal(r0, r1) and np.array_equal(u0, u1)
+
+
+def test_lag_step_with_density_tiles(monkeypatch):
+    """TXG_LAG=1 TXG_RHOTILE=1: the C blocks of the one-pass step also stage the neighbour densities in shared memory."""
+    for case in (cases.porous_3d(32, rmin=4.0, rmax=8.0), cases.bubble_3d(32),
+                 cases.porous_3d(24, rmin=3.0, rmax=6.0, periodic=(0, 0, 0))):
+        cfg, walls, rho = case
+        fi0, r0, u0, F0, k0 = run(cfg, walls, rho, 20, {}, monkeypatch)
+        fi1, r1, u1, F1, k1 = run(cfg, walls, rho, 20, dict(TXG_LAG=1, TXG_RHOTILE=1, TXG_LAG_ROWS=8), monkeypatch, chunks=(2, None))
+        assert k1["k_step_fused_lag"][1] == 20, k1
+        assert np.array_equal(fi0, fi1) and np.array_equal(r0, r1) and np.array_equal(u0, u1)

@@ -19,6 +19,7 @@ PY
 run default
 run rhotile TXG_RHOTILE=1
 run r64_l2 TXG_LAG=1 TXG_LAG_ROWS=64 TXG_LAG_PLANES=2     # the default setting
+run r64_l2_tile TXG_LAG=1 TXG_RHOTILE=1 TXG_LAG_ROWS=64 TXG_LAG_PLANES=2   # one-pass step + density tiles
 run r64_l1 TXG_LAG=1 TXG_LAG_ROWS=64 TXG_LAG_PLANES=1
 run r64_l3 TXG_LAG=1 TXG_LAG_ROWS=64 TXG_LAG_PLANES=3
 run r64_l0 TXG_LAG=1 TXG_LAG_ROWS=64 TXG_LAG_PLANES=0
