@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage (one gpurun call, about 25 GPU-minutes): gpurun --timeout 1500 -- tools/gpu_lag_try.sh
+# usage (one gpurun call, about 35 GPU-minutes): gpurun --timeout 2400 -- tools/gpu_lag_try.sh
 # The opt-in one-pass step (TXG_LAG=1): parity first (tests/test_zzz_experimental_lag.py), then kernel times of the default
 # step and of a few (band rows, lag planes, M block size) settings at 512^3, each as one bench.py JSON line under gpurun_out/.
 mkdir -p gpurun_out
@@ -29,5 +29,5 @@ run r256_l1 TXG_LAG=1 TXG_LAG_ROWS=256 TXG_LAG_PLANES=1
 run r64_l2_m2048 TXG_LAG=1 TXG_LAG_ROWS=64 TXG_LAG_PLANES=2 TXG_LAG_MPOS=2048
 run r64_l2_m128 TXG_LAG=1 TXG_LAG_ROWS=64 TXG_LAG_PLANES=2 TXG_LAG_MPOS=128
 # DRAM traffic of the one-pass kernel (the question: do the density reads hit L2?) -- one launch under ncu
-TXG_LAG=1 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:k_step_fused_lag -s 3 -c 1 --csv --log-file gpurun_out/lag_ncu.csv python bench.py --steps 2 --warmup 2 --no-e2e --no-cpu > /dev/null 2> gpurun_out/lag_ncu.err
+TXG_LAG=1 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:k_step_fused_lag -s 4 -c 1 --csv --log-file gpurun_out/lag_ncu.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > /dev/null 2> gpurun_out/lag_ncu.err
 tail -3 gpurun_out/lag_ncu.csv
