@@ -29,7 +29,12 @@ def run_case(case, nproc, steps, tmp_path, port):
            "--case", case, "--steps", str(steps), "--out", str(out), "--single"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(ROOT))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    return json.loads(out.read_text())
+    res = json.loads(out.read_text())
+    log = os.environ.get("TXG_MG_LOG")  # keep the per-case numbers of a hardware run (profiles/r2_parity_*.log)
+    if log:
+        with open(log, "a") as fh:
+            fh.write(json.dumps(res) + "\n")
+    return res
 
 
 def check(res):
