@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Generate oracle/ff_stencil_tables.h from the reference's fluid-fluid forcing source.
 
-TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+TEST INFRASTRUCTURE ONLY (see the header of taxila_oracle.c and DESIGN.md section 1).
 
 The reference hard-codes the Shan-Chen density-gradient stencil as one
 `if (walls(...).eq.0 ...) then ... end if` block per stencil offset

@@ -1,7 +1,7 @@
 """ctypes binding of libtaxila_gpu.so -- exactly the entry points include/taxila_gpu.h declares.
 
 This is what a reference-side binding looks like from Python; the Fortran ISO_C_BINDING
-equivalent is in fortran/taxila_gpu_iso_c.F90 and INTEGRATION.md.  There is no fallback: if
+equivalent is in shim/lbm_gpu_binding.F90 and INTEGRATION.md.  There is no fallback: if
 the CUDA library is missing or a call fails, an exception carries txg_last_error().
 """
 import ctypes as C

@@ -223,7 +223,8 @@ class Flow:
         lbm.F90:424-438): <prefix>{fi,rho,u,rhot,prs}NNN.dat as PETSc binary Vecs in DMDA natural ordering
         (petsc_io.py), so src/testing/check_solution.py and petsc2tec.py read them unchanged.  The velocity
         file is named `u` like the reference's (it holds velt).  With several ranks every rank writes its
-        z-slab -- one contiguous byte range of the natural ordering -- into the same file; returns the paths."""
+        z-slab -- one contiguous byte range of the natural ordering -- into the same file; returns the paths.
+        The file is complete once EVERY rank has returned: synchronise the ranks (a barrier) before reading it."""
         import os
 
         from . import geometry as geo
@@ -253,6 +254,9 @@ class Flow:
             path = petsc_io.output_name(prefix, name, counter)
             fd = os.open(path, os.O_RDWR | os.O_CREAT, 0o644)
             try:
+                # exact size of the PETSc Vec file: a longer file left under this name by another box size or dof
+                # count would keep its stale tail (every rank sets the same length: idempotent, no rank order)
+                os.ftruncate(fd, 8 + NZg * plane * dof * 8)
                 if self.cfg.rank == 0:
                     os.pwrite(fd, np.array([petsc_io.VEC_CLASSID, NZg * plane * dof], dtype=">i4").tobytes(), 0)
                 os.pwrite(fd, a.astype(">f8").tobytes(), 8 + zs * plane * dof * 8)
