@@ -118,11 +118,17 @@ class ClockSampler:
 
 def build_case(size, nranks, rank, scaling, order):
     """Per-rank slab of the workload: (cfg, walls_rg, rho_rg, fluid_fraction, global_nodes)."""
-    import cases
     from taxila_lbm_b200 import geometry as geo
-    from taxila_lbm_b200 import slab
+    from taxila_lbm_b200 import slab, workloads
 
-    cfg, walls, rho = cases.porous_3d(size, order=order)
+    # (sweeps of several bench runs in one GPU call keep the generated geometry: TXG_CASE_CACHE=<dir>)
+    cache = os.environ.get("TXG_CASE_CACHE")
+    cpath = Path(cache) / ("c4_%d_walls.npy" % size) if cache else None
+    walls = np.load(cpath) if cpath is not None and cpath.exists() else None
+    have = walls is not None
+    cfg, walls, rho = workloads.porous_3d(size, order=order, walls=walls)
+    if cpath is not None and not have and rank == 0:
+        np.save(cpath, walls)
     R = cfg.stencil_size_rho
     if nranks == 1 or scaling == "strong":
         # the one size^3 box, split into z-slabs (DMDA ownership ranges)
@@ -146,18 +152,19 @@ def build_case(size, nranks, rank, scaling, order):
     return c, walls_rg, rho_rg, fluid_local, size * size * NZg
 
 
-def run_cpu_sample(order, sample_size, steps, threads):
-    """The oracle (reference structure, OpenMP) on a sample_size^3 crop of the same recipe."""
-    import cases
-    import oracle
+def run_cpu_sample(order, sample_size, steps, threads, warm=1):
+    """The oracle (reference structure, OpenMP) on a sample_size^3 crop of the same recipe: `warm` untimed steps
+    (page faults, caches), then exactly `steps` timed ones.  Returns (MLUPS, seconds per step)."""
+    import oracle  # tests/oracle.py: the ctypes wrapper of oracle/ (CPU legs only)
+    from taxila_lbm_b200 import workloads
 
-    cfg, walls, rho = cases.porous_3d(sample_size, order=order)
+    cfg, walls, rho = workloads.porous_3d(sample_size, order=order)
     o = oracle.Oracle(cfg, threads=threads)
     o.set_walls(walls)
     o.set_rho(rho)
     o.fi_init()
     o.update_moments()
-    o.step(1)  # warm-up (page faults)
+    o.step(max(1, warm))
     t0 = time.perf_counter()
     o.step(steps)
     dt = time.perf_counter() - t0
@@ -174,8 +181,8 @@ def main():
     ap.add_argument("--size", type=int, default=512, help="block edge (512 = BASELINE config)")
     ap.add_argument("--order", type=int, default=4, help="isotropy order of the Shan-Chen stencil")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--cpu-sample", type=int, default=128)
-    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--cpu-sample", type=int, default=256, help="edge of the crop the CPU legs time (SURVEY.md 8d: 256^3)")
+    ap.add_argument("--cpu-steps", type=int, default=10, help="timed oracle steps of the cpu_baseline leg of the CUDA arm")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -198,25 +205,24 @@ def main():
                "bounce-back, iso-%d" % (args.size, args.order)
     config = {"workload": workload, "lattice": "D3Q19", "components": 2, "relaxation": "MRT",
               "box_per_gpu": [args.size] * 3, "isotropy_order": args.order, "geometry": "porous_spheres(seed=20260)",
-              "l2_policy": "inputs larger than L2 (40.8 GB of populations per 512^3 block)"}
+              "l2_policy": "inputs larger than L2 (40.8 GB of populations per 512^3 block)",
+              "cpu_sample_box": [args.cpu_sample] * 3}
 
     # ------------------------------------------------------------------ CPU arm
     if args.impl == "reference":
         if rank != 0:
             return 0
         threads = os.cpu_count() or 1
-        vals = []
-        for _ in range(max(1, min(args.steps, 3))):
-            v, sps = run_cpu_sample(args.order, args.cpu_sample, args.cpu_steps, threads)
-            vals.append((v, sps))
-        v = float(np.median([x[0] for x in vals]))
-        sps = float(np.median([x[1] for x in vals]))
-        sample = "%d^3 crop of the same porous recipe, %d steps per measurement, %d measurements" % (
-            args.cpu_sample, args.cpu_steps, len(vals))
+        # exactly `warmup` untimed and `steps` timed LBM steps of the crop: a step of this arm is one time step of the
+        # bounded sample (config.cpu_sample_box), not of the 512^3 box -- MLUPS is size-normalised
+        v, sps = run_cpu_sample(args.order, args.cpu_sample, args.steps, threads, warm=warmup)
+        sample = "%d^3 crop of the same porous recipe (config.cpu_sample_box): %d untimed + %d timed LBM steps of the crop, " \
+                 "%d OpenMP threads" % (args.cpu_sample, warmup, args.steps, threads)
         line = {
             "impl": "reference", "metric": METRIC, "value": v, "unit": "MLUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": warmup, "ms_per_step": sps * 1e3, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "timed": {"box": [args.cpu_sample] * 3, "steps": args.steps, "warmup": warmup, "ms_per_step_of_that_box": sps * 1e3},
             "cpu_baseline": {"value": v, "unit": "MLUPS", "cores": threads, "kind": "port", "sample": sample,
                              "note": "C restatement of the reference's CPU algorithm in the reference's structure "
                                      "(oracle/), OpenMP; the Fortran+PETSc reference cannot be built in this image"},
@@ -339,6 +345,9 @@ def main():
     dom, dom_bytes = ("k_step_fused", B_K2_FLUID) if ktimes.get("k_step_fused", (0.0, 0))[1] else ("k_collide", B_K2B_FLUID)
     if ktimes.get("k_step_fused_tile", (0.0, 0))[1]:  # TXG_RHOTILE=1 (opt-in): same bytes as k_step_fused
         dom, dom_bytes = "k_step_fused_tile", B_K2_FLUID
+    for alt in ("k_step_stage", "k_step_band", "k_step_band_pull"):  # other forms of K2: same algorithmic bytes as k_step_fused
+        if ktimes.get(alt, (0.0, 0))[1]:
+            dom, dom_bytes = alt, B_K2_FLUID
     if ktimes.get("k_step_fused_lag", (0.0, 0))[1]:  # TXG_LAG=1 (opt-in one-pass step): the whole step's bytes in one launch
         dom, dom_bytes = "k_step_fused_lag", B_ALG_FLUID
     kc_ms, kc_n = ktimes.get(dom, (0.0, 0))
@@ -369,7 +378,8 @@ def main():
     kernels = {k: {"ms": v[0], "launches": v[1]} for k, v in ktimes.items()}
     # per-kernel achieved algorithmic GB/s (the launches of one step add up to the slab)
     for name, b in (("k_moments", B_K1_FLUID), ("k_forces", B_KF_FLUID), ("k_collide", B_K2B_FLUID), ("k_step_fused", B_K2_FLUID),
-                    ("k_step_fused_tile", B_K2_FLUID), ("k_step_fused_lag", B_ALG_FLUID)):
+                    ("k_step_fused_tile", B_K2_FLUID), ("k_step_band", B_K2_FLUID), ("k_step_band_pull", B_K2_FLUID),
+                    ("k_step_stage", B_K2_FLUID), ("k_moments_pull", B_K1_FLUID), ("k_step_fused_lag", B_ALG_FLUID)):
         if name == "k_moments" and "k_step_fused_lag" in kernels and kernels["k_step_fused_lag"]["launches"]:
             continue  # one-pass step: k_moments only sums the two boundary planes
         if name in kernels and kernels[name]["ms"] > 0:
@@ -380,10 +390,10 @@ def main():
     cpu = None
     if not args.no_cpu:
         threads = os.cpu_count() or 1
-        v, sps = run_cpu_sample(args.order, args.cpu_sample, args.cpu_steps, threads)
+        v, sps = run_cpu_sample(args.order, args.cpu_sample, args.cpu_steps, threads, warm=2)
         cpu = {"value": v, "unit": "MLUPS", "cores": threads, "kind": "port",
-               "sample": "%d^3 crop of the same porous recipe, %d steps, oracle/ (reference structure, OpenMP)" % (
-                   args.cpu_sample, args.cpu_steps)}
+               "sample": "%d^3 crop of the same porous recipe, 2 untimed + %d timed steps, oracle/ (reference structure, OpenMP, "
+                         "%d threads), %.1f s" % (args.cpu_sample, args.cpu_steps, threads, sps * args.cpu_steps)}
 
     line = {
         "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": warmup,

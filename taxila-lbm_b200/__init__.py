@@ -3,5 +3,5 @@
 Python here is host-side plumbing only (configuration, synthetic inputs, the ctypes binding of
 libtaxila_gpu.so); the product is the CUDA library built from csrc/.
 """
-from . import config, geometry, petsc_io, slab  # noqa: F401
+from . import config, geometry, petsc_io, slab, workloads  # noqa: F401
 from .flow import Flow  # noqa: F401

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -92,7 +93,7 @@ std::string g_create_error;
 
 // ------------------------------------------------------------------ the handle
 struct KernelTimer {
-  std::string name;
+  const char *name = "";  // a string literal of this file: the pointers txg_kernel_times hands out stay valid
   double ms = 0.;
   int64_t launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
@@ -130,6 +131,23 @@ struct txg_flow {
   bool tile_wanted = false, tile = false;
   uint32_t *rtab = nullptr;
   uint32_t *rtab_lag = nullptr;  // the same per block of the one-pass launch (TXG_LAG=1 TXG_RHOTILE=1)
+  // band blocks (band_kernel.cuh; TXG_BAND=0 switches them off): bit rows instead of the adjacency table, density windows in shared memory
+  bool band_wanted = false, band = false;  // (measured slower than the table kernel: profiles/r2c_band_results.txt)
+  // staged form (stage_kernel.cuh; TXG_STAGE=0 switches it off): the default K2 of the order-4 step
+  bool stage_wanted = true, stage = false;
+  int stage_lb = 0;  // positions per block: TXG_STAGE_CHUNKS (default 8) chunks
+  int band_lb = 1024;                 // positions per block (TXG_BAND_LB)
+  int band_prefetch = 1;              // L2 prefetch of the block's next chunk (TXG_BAND_PF)
+  BitrowEntry *bitrows = nullptr;
+  uint32_t *rowend = nullptr, *xrow = nullptr;
+  BandBlock *band_blocks = nullptr;
+  BandParams band_params;
+  std::vector<int> band_plane_block0;  // [NZl + 1] first block of every owned plane
+  int band_smem = 0;
+  // pull form of the band step (band_kernel.cuh; TXG_PULL=0 keeps the push): the population buffer holds the COLLIDED
+  // populations g of the last step at their own nodes (state_g); the reference's fi = stream + bounce-back of g is
+  // formed by the gathers of the next step, or by materialise() for every path that wants fi itself
+  bool pull_wanted = false, pull = false, state_g = false;
   double *rho_next = nullptr;
   LagRowDev *lag_rows_dev = nullptr;  // schedule rows (the M blocks read them)
   LagCRow *lag_crows_dev = nullptr;   // their C parts, copied into the kernel's constant table before every launch
@@ -173,7 +191,9 @@ struct txg_flow {
   int up = -1, down = -1;  // z-neighbour ranks (or -1)
   // measurement
   bool timing = false;
-  std::vector<KernelTimer> timers;
+  std::deque<KernelTimer> timers;
+  std::vector<cudaEvent_t> ev_pool;  // recycled timing events
+  int timers_pending = 0;
   float last_ms = 0.f;
   int64_t last_launches = 0, launches = 0;
   std::string err;
@@ -211,12 +231,30 @@ struct txg_flow {
 static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 // ------------------------------------------------------------------ kernel timing
+static void drain_timers(txg_flow *h);
+static void release_lag_table(txg_flow *h);
+static int check_eos(txg_flow *h);
 static KernelTimer *timer_for(txg_flow *h, const char *name) {
   for (auto &t : h->timers)
-    if (t.name == name) return &t;
-  h->timers.push_back(KernelTimer());
+    if (t.name == name || strcmp(t.name, name) == 0) return &t;
+  h->timers.push_back(KernelTimer());  // (a deque: the entries of the other kernels stay where they are)
   h->timers.back().name = name;
   return &h->timers.back();
+}
+// timing events are recycled: a long timed run holds at most TIMER_DRAIN_AT pairs
+constexpr int TIMER_DRAIN_AT = 2048;
+static cudaEvent_t timer_event(txg_flow *h) {
+  if (!h->ev_pool.empty()) {
+    cudaEvent_t e = h->ev_pool.back();
+    h->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return e;
 }
 struct ScopedKernel {
   txg_flow *h;
@@ -225,20 +263,25 @@ struct ScopedKernel {
   cudaStream_t s;
   ScopedKernel(txg_flow *h_, const char *name, cudaStream_t s_) : h(h_), s(s_) {
     h->launches++;
+    t = timer_for(h, name);
     if (h->timing) {
-      t = timer_for(h, name);
-      cudaEventCreate(&a);
-      cudaEventCreate(&b);
-      cudaEventRecord(a, s);
-    } else {
-      t = timer_for(h, name);
+      a = timer_event(h);
+      b = timer_event(h);
+      if (a && b) {
+        cudaEventRecord(a, s);
+      } else {  // out of events: this launch is counted, not timed
+        if (a) h->ev_pool.push_back(a);
+        if (b) h->ev_pool.push_back(b);
+        a = b = nullptr;
+      }
     }
     t->launches++;
   }
   ~ScopedKernel() {
-    if (h->timing) {
+    if (a && b) {
       cudaEventRecord(b, s);
       t->pending.emplace_back(a, b);
+      if (++h->timers_pending >= TIMER_DRAIN_AT) drain_timers(h);
     }
   }
 };
@@ -249,11 +292,12 @@ static void drain_timers(txg_flow *h) {
       cudaEventSynchronize(pr.second);
       cudaEventElapsedTime(&ms, pr.first, pr.second);
       t.ms += ms;
-      cudaEventDestroy(pr.first);
-      cudaEventDestroy(pr.second);
+      h->ev_pool.push_back(pr.first);
+      h->ev_pool.push_back(pr.second);
     }
     t.pending.clear();
   }
+  h->timers_pending = 0;
 }
 
 // ------------------------------------------------------------------ set-up
@@ -351,6 +395,9 @@ static int validate(const txg_config *c) {
   if (c->zs < 0 || c->zl < 1 || c->zs + c->zl > c->NZ) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "invalid z-slab [%d, %d) of %d", c->zs, c->zs + c->zl, c->NZ);
   if (c->nranks == 1 && (c->zs != 0 || c->zl != c->NZ)) TXG_FAIL(h, TXG_ERR_ARG_WRONG, "a single rank must own the whole box");
   if (c->nranks > 1 && c->zl < c->stencil_size_rho) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "z-slab thinner than the stencil");
+  // one rank, periodic z: the ghost planes are copies of the R opposite owned planes
+  if (c->ndims == 3 && c->nranks == 1 && c->periodic[2] && c->zl < c->stencil_size_rho)
+    TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "periodic z with NZ = %d thinner than the stencil (%d planes)", c->zl, c->stencil_size_rho);
   for (int b = 0; b < 6; ++b) {
     const int fl = c->bc_flags[b];
     if (fl < TXG_BC_NULL || fl > TXG_BC_VELOCITY)
@@ -469,11 +516,15 @@ extern "C" int txg_destroy(txg_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   drain_timers(h);
+  release_lag_table(h);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  h->ev_pool.clear();
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void *ptrs[] = {h->f[0], h->f[1], h->rho, h->rho_true != h->rho ? h->rho_true : nullptr, h->u0, h->gw, h->cls,
                   h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->nbr_all, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt, h->spec_dst, h->spec_src, h->spec_tmp, h->bc_vals[0], h->bc_vals[1],
-                  h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_crows_dev, h->lag_done, h->rtab, h->rtab_lag};
+                  h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_crows_dev, h->lag_done, h->rtab, h->rtab_lag,
+                  h->bitrows, h->rowend, h->xrow, h->band_blocks};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -536,6 +587,11 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     if (const char *v = getenv("TXG_LAG_ROWS")) h->lag_rows = atoi(v);
     if (const char *v = getenv("TXG_LAG_PLANES")) h->lag_planes = atoi(v);
     if (const char *v = getenv("TXG_LAG_MPOS")) h->lag_mpos = atoi(v);
+    if (const char *v = getenv("TXG_BAND")) h->band_wanted = v[0] != '0';
+    if (const char *v = getenv("TXG_STAGE")) h->stage_wanted = v[0] != '0';
+    if (const char *v = getenv("TXG_BAND_LB")) h->band_lb = std::max(16, atoi(v));
+    if (const char *v = getenv("TXG_BAND_PF")) h->band_prefetch = atoi(v);
+    if (const char *v = getenv("TXG_PULL")) h->pull_wanted = v[0] != '0';
     const char *sp = getenv("TXG_SPLIT");
     for (int b = 0; b < 2 * cfg->ndims; ++b) h->bc_mode = h->bc_mode || cfg->bc_flags[b] >= TXG_BC_REFLECTING;
     // face BCs act between the forces and the collision: they need the split kernels and the force buffer
@@ -730,6 +786,28 @@ static int exchange_rho(txg_flow *h, double *buf, cudaStream_t s) {
   return exchange(h, buf, upv, downv, s);
 }
 
+// Pull form: the collided populations that will cross a z face are read by the neighbour slab out of ITS ghost plane:
+// my top owned plane's c_z > 0 rows fill the up neighbour's bottom ghost plane, my bottom owned plane's c_z < 0 rows the
+// down neighbour's top ghost plane -- one contiguous run of positions per (component, direction), received in place
+// (ghost and owned plane hold the same fluid nodes), no unpack kernel.
+static int exchange_g(txg_flow *h, double *buf, cudaStream_t s) {
+  if (h->D != 3) return 0;
+  const Grid &g = h->g;
+  const int Rz = g.Rz;
+  const std::vector<long long> &po = h->plane_off;
+  const long long gb0 = po[Rz - 1], ob0 = po[Rz], ob1 = po[Rz + 1];
+  const long long ot0 = po[Rz + g.NZl - 1], gt0 = po[Rz + g.NZl], gt1 = po[Rz + g.NZl + 1];
+  std::vector<Chunk> upv, downv;
+  for (int m = 0; m < h->S; ++m)
+    for (int n = 1; n < h->Q; ++n) {
+      const int cz = D3Q19::c(n, 2);
+      const long long blk = (long long)(m * h->Q + n) * g.fs;
+      if (cz > 0) upv.push_back({blk + ot0, blk + gb0, gt0 - ot0, ob0 - gb0});
+      if (cz < 0) downv.push_back({blk + ob0, blk + gt0, ob1 - ob0, gt1 - gt0});
+    }
+  return exchange(h, buf, upv, downv, s);
+}
+
 // ------------------------------------------------------------------ host <-> device layout conversion
 static int ensure_staging(txg_flow *h, size_t bytes) {
   if (h->staging_bytes >= bytes) return 0;
@@ -811,6 +889,11 @@ static int fresh_zero(txg_flow *h, void **p, size_t bytes) {
   return 0;
 }
 
+// entries behind the last component of the density arrays: the bulk-copy windows of the band blocks (<= BAND_CAP_MAX
+// doubles) and of k_step_fused_tile may overrun the last position
+constexpr int BAND_CAP_MAX = 4096;
+constexpr size_t RHO_PAD = BAND_CAP_MAX;
+
 static int build_storage(txg_flow *h) {
   Grid &g = h->g;
   h->have_old = false;
@@ -868,10 +951,10 @@ static int build_storage(txg_flow *h) {
   TXG_TRY(fresh_zero(h, (void **)&h->f[1], fbytes));
   h->cur = 0;
   // (+ 256 entries: the bulk-copy windows of k_step_fused_tile may overrun the last position of the last component)
-  TXG_TRY(fresh_zero(h, (void **)&h->rho, ((size_t)h->S * g.fs + 256) * sizeof(double)));
+  TXG_TRY(fresh_zero(h, (void **)&h->rho, ((size_t)h->S * g.fs + RHO_PAD) * sizeof(double)));
   if (h->cfg.use_nonideal_eos) {
     if (h->rho_true == h->rho) h->rho_true = nullptr;
-    TXG_TRY(fresh_zero(h, (void **)&h->rho_true, ((size_t)h->S * g.fs + 256) * sizeof(double)));
+    TXG_TRY(fresh_zero(h, (void **)&h->rho_true, ((size_t)h->S * g.fs + RHO_PAD) * sizeof(double)));
   } else {
     h->rho_true = h->rho;
   }
@@ -990,8 +1073,18 @@ static int build_rtab(txg_flow *h) {
   return 0;
 }
 
+// The C rows of the schedule live in ONE __constant__ table per device (c_lag_rows), uploaded before every launch on the
+// handle's stream: two handles of one device would overwrite each other's table under a running kernel.  The first
+// handle that enables the one-pass step owns the table until it is destroyed or loses eligibility; others keep the
+// two-kernel step.
+static txg_flow *g_lag_owner[64] = {};
+static void release_lag_table(txg_flow *h) {
+  if (h->device >= 0 && h->device < 64 && g_lag_owner[h->device] == h) g_lag_owner[h->device] = nullptr;
+}
+
 static int build_lag(txg_flow *h) {
   static_assert(sizeof(LagRow) == sizeof(LagRowDev), "host / device schedule row layout");
+  release_lag_table(h);
   for (void **q : {(void **)&h->lag_rows_dev, (void **)&h->lag_crows_dev, (void **)&h->lag_done, (void **)&h->rtab_lag}) {
     if (*q) cudaFree(*q);
     *q = nullptr;
@@ -1003,6 +1096,7 @@ static int build_lag(txg_flow *h) {
   if (!h->lag_wanted || !h->fused || !h->ks.step_fused_lag || h->ks.fused_threads != 128 || h->D != 3 || h->p.eos || h->spec_n ||
       h->bc_mode)
     return 0;
+  if (h->device < 0 || h->device >= 64 || (g_lag_owner[h->device] && g_lag_owner[h->device] != h)) return 0;
   const int nzE = g.NZl + 2 * g.Rz;
   std::vector<uint32_t> row_off((size_t)nzE * g.NY + 1);
   if (g.P) {
@@ -1024,7 +1118,7 @@ static int build_lag(txg_flow *h) {
   for (size_t i = 0; i < sc.rows.size(); ++i) crows[i] = LagCRow{sc.rows[i].cfirst, sc.rows[i].ccount};
   TXG_CUDA(h, cudaMalloc((void **)&h->lag_crows_dev, crows.size() * sizeof(LagCRow)));
   TXG_CUDA(h, cudaMemcpy(h->lag_crows_dev, crows.data(), crows.size() * sizeof(LagCRow), cudaMemcpyHostToDevice));
-  TXG_TRY(fresh_zero(h, (void **)&h->rho_next, ((size_t)h->S * g.fs + 256) * sizeof(double)));
+  TXG_TRY(fresh_zero(h, (void **)&h->rho_next, ((size_t)h->S * g.fs + RHO_PAD) * sizeof(double)));
   if (h->tile_wanted && h->ks.step_fused_lag_tile) {
     // density tiles in the C blocks too: window starts per block of this launch
     const long long nblk = (long long)sc.rows.size() * sc.grid_x;
@@ -1045,6 +1139,99 @@ static int build_lag(txg_flow *h) {
   h->lag_nrows = (unsigned)sc.rows.size();
   h->lag_grid_x = sc.grid_x;
   h->lag = true;
+  g_lag_owner[h->device] = h;
+  return 0;
+}
+
+// ------------------------------------------------------------------ band blocks (band_kernel.cuh)
+// Bit rows, xrow and the block table of k_step_band for the current geometry, rebuilt at every walls upload.  A block
+// owns up to band_lb consecutive positions of one owned plane; its three density windows (planes z-1, z, z+1) start at
+// the first position of row y0 - 1 and must reach the end of row y1 + 1 (y0 .. y1 = the rows the block touches).  The
+// window length `cap` is the longest such run over all blocks, bounded by what two blocks per SM can hold in shared
+// memory; a stencil neighbour outside its window (the wrapped rows of a periodic y, rows too long for the budget) is
+// read from global memory -- same value, so the table is a performance matter only.
+static int build_band(txg_flow *h) {
+  for (void **q : {(void **)&h->bitrows, (void **)&h->rowend, (void **)&h->xrow, (void **)&h->band_blocks}) {
+    if (*q) cudaFree(*q);
+    *q = nullptr;
+  }
+  h->band = false;
+  h->pull = false;
+  h->state_g = false;
+  const Grid &g = h->g;
+  if (!h->band_wanted || !h->fused || !h->ks.step_band || g.own1 <= g.own0) return 0;
+  const int rpp = g.NY + 2, nzE = g.NZl + 2 * g.Rz, NW = (g.NX + 31) / 32;
+  if (g.NX > (1 << BITROW_XBITS) || (long long)nzE * rpp >= (long long)BITROW_MAX_ROWS || g.fs > (long long)BITROW_POSMASK) return 0;
+  // row offsets on the host: row_off[zz * NY + y] = position of the first fluid node at or after the start of the row
+  std::vector<uint32_t> row_off((size_t)nzE * g.NY + 1);
+  if (g.P) {
+    TXG_CUDA(h, cudaMemcpy2D(row_off.data(), sizeof(uint32_t), g.P, (size_t)g.NX * sizeof(uint32_t), sizeof(uint32_t), row_off.size(),
+                             cudaMemcpyDeviceToHost));
+  } else {
+    for (size_t i = 0; i < row_off.size(); ++i) row_off[i] = (uint32_t)(i * (size_t)g.NX);
+  }
+  const int NP = h->ks.band_windows;
+  // shared memory: two blocks per SM
+  int dev_smem = 0;
+  TXG_CUDA(h, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  const int per_block = std::min(dev_smem, (int)(((size_t)dev_smem + 1024) / (512 / h->ks.band_threads) - 2048));
+  int cap_max = std::min(BAND_CAP_MAX, per_block / (NP * h->S * 8)) & ~1;
+  if (cap_max < 64) return 0;
+  std::vector<BandBlock> blocks;
+  h->band_plane_block0.assign((size_t)g.NZl + 1, 0);
+  const int LB = h->band_lb;
+  uint32_t need_max = 0;
+  for (int z = 0; z < g.NZl; ++z) {
+    h->band_plane_block0[(size_t)z] = (int)blocks.size();
+    const int zz = z + g.Rz;
+    const uint32_t *ro = row_off.data() + (size_t)zz * g.NY;  // NY + 1 entries: ro[NY] = start of the next plane
+    const uint32_t p0 = ro[0], p1 = ro[g.NY];
+    int y = 0;
+    for (uint32_t first = p0; first < p1; first += (uint32_t)LB) {
+      const uint32_t count = std::min<uint32_t>((uint32_t)LB, p1 - first), last = first + count - 1;
+      while (ro[y + 1] <= first) ++y;  // row of the first position (rows without fluid nodes are skipped)
+      const int y0 = y;
+      int y1 = y0;
+      while (ro[y1 + 1] <= last) ++y1;
+      BandBlock b{first, count, {0u, 0u, 0u}, {0u, 0u, 0u}};
+      const int ys = std::max(y0 - 1, 0), ye = std::min(y1 + 1, g.NY - 1);
+      for (int pl = 0; pl < NP; ++pl) {
+        const int zp = NP == 3 ? zz + pl - 1 : zz;
+        const uint32_t *rp = row_off.data() + (size_t)zp * g.NY;
+        b.win[pl] = rp[ys] & ~1u;
+        b.len[pl] = std::min<uint32_t>((uint32_t)cap_max, (rp[ye + 1] - b.win[pl] + 1u) & ~1u);
+        need_max = std::max(need_max, b.len[pl]);
+      }
+      blocks.push_back(b);
+    }
+  }
+  h->band_plane_block0[(size_t)g.NZl] = (int)blocks.size();
+  if (blocks.empty()) return 0;
+  const int cap = std::max(64, (int)need_max);
+  h->band_smem = NP * h->S * cap * 8;
+  TXG_CUDA(h, (cudaError_t)h->ks.set_band_smem(h->band_smem));
+  TXG_CUDA(h, cudaMalloc((void **)&h->bitrows, (size_t)nzE * rpp * NW * sizeof(BitrowEntry)));
+  TXG_CUDA(h, cudaMalloc((void **)&h->rowend, (size_t)nzE * rpp * sizeof(uint32_t)));
+  TXG_CUDA(h, cudaMalloc((void **)&h->xrow, (size_t)g.fs * sizeof(uint32_t)));
+  TXG_CUDA(h, cudaMemsetAsync(h->xrow, 0, (size_t)g.fs * sizeof(uint32_t), h->s_main));
+  TXG_CUDA(h, cudaMalloc((void **)&h->band_blocks, blocks.size() * sizeof(BandBlock)));
+  TXG_CUDA(h, cudaMemcpyAsync(h->band_blocks, blocks.data(), blocks.size() * sizeof(BandBlock), cudaMemcpyHostToDevice, h->s_main));
+  k_build_bitrows<<<blocks_for((long long)nzE * rpp * NW, 128), 128, 0, h->s_main>>>(g, h->cls, NW, h->bitrows, h->rowend);
+  TXG_CUDA(h, cudaGetLastError());
+  k_build_xrow<<<blocks_for(h->nstore, 256), 256, 0, h->s_main>>>(g, 0, h->nstore, h->xrow);
+  TXG_CUDA(h, cudaGetLastError());
+  TXG_CUDA(h, cudaStreamSynchronize(h->s_main));  // (`blocks` is a local)
+  h->band_params.rows = h->bitrows;
+  h->band_params.rowend = h->rowend;
+  h->band_params.xrow = h->xrow;
+  h->band_params.blocks = h->band_blocks;
+  h->band_params.NW = NW;
+  h->band_params.rows_per_plane = rpp;
+  h->band_params.cap = cap;
+  h->band = true;
+  // pull form: plain bounce-back walls only (free-slip tables and face BCs work on pushed populations)
+  h->pull = h->pull_wanted && h->ks.step_band_pull && !h->spec_n && !h->bc_mode && !h->lag && !h->tile;
+  if (h->pull) TXG_CUDA(h, (cudaError_t)h->ks.set_band_pull_smem(h->band_smem));
   return 0;
 }
 
@@ -1075,6 +1262,15 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   TXG_TRY(build_specular(h, counters[1]));
   TXG_TRY(build_lag(h));
   TXG_TRY(build_rtab(h));
+  TXG_TRY(build_band(h));
+  // staged form of K2: whenever the fused kernel applies and no opt-in experiment replaces it
+  h->stage = h->stage_wanted && h->fused && h->ks.step_stage && !h->tile && !h->band && !h->lag;
+  if (h->stage) {
+    int chunks = 8;
+    if (const char *v = getenv("TXG_STAGE_CHUNKS")) chunks = std::max(1, atoi(v));
+    h->stage_lb = chunks * h->ks.stage_chunk;
+    TXG_CUDA(h, (cudaError_t)h->ks.set_stage_attrs());
+  }
   h->walls_set = true;
   return 0;
 }
@@ -1099,9 +1295,31 @@ static int run_moments(txg_flow *h, int z0, int nz, cudaStream_t s) {
   long long first, count;
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
+  if (h->state_g) {  // collided populations in the buffer: gather, then sum
+    ScopedKernel sk(h, "k_moments_pull", s);
+    h->ks.moments_pull<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->band_params, h->f[h->cur], nullptr, h->rho, h->rho_true, first, count);
+    TXG_CUDA(h, cudaGetLastError());
+    return 0;
+  }
   ScopedKernel sk(h, "k_moments", s);
   h->ks.moments<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, h->rho_true, first, count);
   TXG_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+// The reference's fi (streamed, bounced-back populations) in the current buffer: a no-op unless the pull form left the
+// collided populations there.  Every path that reads or hands out fi calls this first.
+static int materialise(txg_flow *h) {
+  if (!h->state_g) return 0;
+  const Grid &g = h->g;
+  const long long count = g.own1 - g.own0;
+  if (count > 0) {
+    ScopedKernel sk(h, "k_pull_stream", h->s_main);
+    h->ks.pull_stream<<<hot_blocks(h, count), 128, 0, h->s_main>>>(g, h->p, h->band_params, h->f[h->cur], h->f[h->cur ^ 1], nullptr, nullptr, g.own0, count);
+    TXG_CUDA(h, cudaGetLastError());
+  }
+  h->cur ^= 1;
+  h->state_g = false;
   return 0;
 }
 static int run_forces(txg_flow *h, int z0, int nz, cudaStream_t s) {
@@ -1121,6 +1339,27 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   long long first, count;
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
+  if (h->fused && h->band && !h->tile) {
+    ScopedKernel sk(h, h->pull ? "k_step_band_pull" : "k_step_band", s);
+    const int b0 = h->band_plane_block0[(size_t)z0], b1 = h->band_plane_block0[(size_t)(z0 + nz)];
+    if (h->pull)
+      h->ks.step_band_pull<<<(unsigned)(b1 - b0), h->ks.band_threads, (size_t)h->band_smem, s>>>(h->g, h->p, h->band_params, h->f[h->cur], h->f[h->cur ^ 1],
+                                                                                               h->rho, h->wallrec, b0, h->band_prefetch, h->state_g ? 0 : 1,
+                                                                                               h->counters + 4);
+    else
+      h->ks.step_band<<<(unsigned)(b1 - b0), h->ks.band_threads, (size_t)h->band_smem, s>>>(h->g, h->p, h->band_params, h->f[h->cur], h->f[h->cur ^ 1], h->rho,
+                                                                                          h->wallrec, b0, h->band_prefetch, 0, h->counters + 4);
+    TXG_CUDA(h, cudaGetLastError());
+    return 0;
+  }
+  if (h->fused && h->stage && !h->tile) {
+    ScopedKernel sk(h, "k_step_stage", s);
+    const long long LB = h->stage_lb, blk0 = first / LB, nblk = (first + count - 1) / LB - blk0 + 1;
+    h->ks.step_stage<<<(unsigned)nblk, h->ks.stage_threads, (size_t)h->ks.stage_smem, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
+                                                                                           h->nbr_all, h->wallrec, first, count, blk0, (int)LB);
+    TXG_CUDA(h, cudaGetLastError());
+    return 0;
+  }
   if (h->fused && h->tile && first == h->g.own0) {  // (window starts are per block counted from own0: whole-slab launches only)
     ScopedKernel sk(h, "k_step_fused_tile", s);
     const long long warps = (count + h->ks.npw - 1) / h->ks.npw;
@@ -1150,6 +1389,7 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
 // the populations of the owned nodes are in f[cur]: with push storage that is the whole state
 static int state_ready(txg_flow *h) {
   h->state_set = true;
+  h->state_g = false;  // the buffer holds streamed populations
   h->rho_current = false;
   h->forces_current = false;
   return 0;
@@ -1265,9 +1505,14 @@ static int one_step(txg_flow *h) {
     TXG_TRY(exchange_rho(h, h->rho, sm));
     TXG_TRY(run_forces(h, 0, g.NZl, sm));
     TXG_TRY(run_collide(h, 0, g.NZl, sm));
-    TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sm));
-    TXG_TRY(apply_specular(h, h->f[h->cur ^ 1], sm));
+    if (h->pull) {
+      TXG_TRY(exchange_g(h, h->f[h->cur ^ 1], sm));
+    } else {
+      TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sm));
+      TXG_TRY(apply_specular(h, h->f[h->cur ^ 1], sm));
+    }
     h->cur ^= 1;
+    h->state_g = h->pull;
     return 0;
   }
   const int R = g.R;
@@ -1291,11 +1536,15 @@ static int one_step(txg_flow *h) {
   TXG_TRY(run_collide(h, g.NZl - 1, 1, sm));
   TXG_CUDA(h, cudaEventRecord(h->ev_a, sm));
   TXG_CUDA(h, cudaStreamWaitEvent(sc, h->ev_a, 0));
-  TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sc));
+  if (h->pull)
+    TXG_TRY(exchange_g(h, h->f[h->cur ^ 1], sc));
+  else
+    TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sc));
   TXG_CUDA(h, cudaEventRecord(h->ev_b, sc));
   TXG_TRY(run_collide(h, 1, g.NZl - 2, sm));
   TXG_CUDA(h, cudaStreamWaitEvent(sm, h->ev_b, 0));
   h->cur ^= 1;
+  h->state_g = h->pull;
   return 0;
 }
 
@@ -1409,6 +1658,8 @@ extern "C" int txg_step(txg_handle h, int nsteps) {
     for (int i = 0; i < nsteps; ++i) TXG_TRY(one_step_bc(h));
   } else if (h->lag) {
     for (int i = 0; i < nsteps; ++i) TXG_TRY(one_step_lag(h));
+    // a density block that gave up waiting left wrong densities behind: fail here, not at the next export
+    if (nsteps > 0) TXG_TRY(check_eos(h));
   } else {
     for (int i = 0; i < nsteps; ++i) TXG_TRY(one_step(h));
   }
@@ -1442,6 +1693,7 @@ static int check_eos(txg_flow *h);
 // ------------------------------------------------------------------ state out
 // refresh rho (+halo) from the current populations
 static int refresh_rho(txg_flow *h) {
+  TXG_TRY(materialise(h));
   if (h->bc_mode) return h->forces_current ? 0 : bc_moments_forces(h, false);  // exports read f and Fbuf
   if (h->rho_current) return 0;
   TXG_TRY(run_moments(h, 0, h->g.NZl, h->s_main));
@@ -1480,6 +1732,7 @@ extern "C" int txg_get_fi(txg_handle h, double *fi_g) {
   if (!fi_g) TXG_FAIL(h, TXG_ERR_ARG_NULL, "null array");
   if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "no state on the device yet");
   TXG_CUDA(h, cudaSetDevice(h->device));
+  TXG_TRY(materialise(h));
   TXG_TRY(check_eos(h));
   return export_field(h, fi_g, 1, h->D == 3 ? 1 : 0, h->Q, h->S, h->f[h->cur], 0);
 }
@@ -1509,6 +1762,7 @@ extern "C" int txg_get_diagnostics(txg_handle h, double *rhot, double *prs, doub
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
   TXG_TRY(refresh_rho(h));
+  TXG_TRY(check_eos(h));  // (the reference stops the run in EOSApply, ierr 58; a failed device step must not hand out fields)
   const size_t n = (size_t)g.nnodes;
   if (rhot) TXG_TRY(ensure(h, &h->x_rhot, n));
   if (prs) TXG_TRY(ensure(h, &h->x_prs, n));
@@ -1527,6 +1781,8 @@ extern "C" int txg_delta_norm(txg_handle h, double *norm) {
   if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "no state on the device yet");
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
+  TXG_TRY(materialise(h));
+  TXG_TRY(check_eos(h));
   const long long n = (long long)h->S * h->Q * g.fs;
   if (!h->f_old) {
     TXG_CUDA(h, cudaMalloc((void **)&h->f_old, (size_t)n * 8));
@@ -1567,11 +1823,11 @@ static int check_eos(txg_flow *h) {
     TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
     if (gave_up) TXG_FAIL(h, TXG_ERR_LIB, "one-pass step (TXG_LAG=1): %u density blocks gave up waiting for their collision rows; results are invalid", gave_up);
   }
-  if (h->tile || h->rtab_lag) {
+  if (h->tile || h->rtab_lag || h->band) {
     int gave_up = 0;
     TXG_CUDA(h, cudaMemcpyAsync(&gave_up, h->counters + 4, sizeof gave_up, cudaMemcpyDeviceToHost, h->s_main));
     TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
-    if (gave_up) TXG_FAIL(h, TXG_ERR_LIB, "k_step_fused_tile (TXG_RHOTILE=1): %d threads gave up waiting for their bulk copies; results are invalid", gave_up);
+    if (gave_up) TXG_FAIL(h, TXG_ERR_LIB, "%d threads gave up waiting for the bulk copies of their density windows; results are invalid", gave_up);
   }
   bool pr = false;
   for (int m = 0; m < h->S; ++m) pr = pr || (h->cfg.use_nonideal_eos && h->cfg.eos_type[m] == TXG_EOS_PR);
@@ -1623,7 +1879,7 @@ extern "C" int txg_kernel_times(txg_handle h, int cap, const char **names, doubl
   int k = 0;
   for (auto &t : h->timers) {
     if (k >= cap) break;
-    if (names) names[k] = t.name.c_str();
+    if (names) names[k] = t.name;
     if (ms) ms[k] = t.ms;
     if (launches) launches[k] = t.launches;
     ++k;

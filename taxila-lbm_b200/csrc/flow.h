@@ -4,6 +4,8 @@
 
 #include <cstdint>
 
+#include "band_kernel.cuh"
+#include "stage_kernel.cuh"
 #include "fused_kernel.cuh"
 
 namespace txg {
@@ -34,6 +36,20 @@ struct KernelSet {
   void (*step_fused_tile)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
                           const double *, const uint32_t *, int *, long long, long long, int);
   void (*build_rtab)(Grid, const uint32_t *, int, long long, uint32_t *);
+  // band blocks (band_kernel.cuh): step_fused without adjacency table, neighbour densities from shared-memory windows
+  void (*step_band)(Grid, Phys, BandParams, const double *, double *, const double *, const double *, int, int, int, int *);
+  // pull form (band_kernel.cuh): collided populations at their own nodes, gathered at the start of the next step
+  void (*step_band_pull)(Grid, Phys, BandParams, const double *, double *, const double *, const double *, int, int, int, int *);
+  void (*moments_pull)(Grid, Phys, BandParams, const double *, double *, double *, double *, long long, long long);
+  void (*pull_stream)(Grid, Phys, BandParams, const double *, double *, double *, double *, long long, long long);
+  int (*set_band_pull_smem)(int bytes);
+  // staged form (stage_kernel.cuh): k_step_fused with its streamed rows fetched by bulk copies into a double buffer
+  void (*step_stage)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *, const double *,
+                     long long, long long, long long, int);
+  int (*set_stage_attrs)();          // dynamic shared memory size + carve-out of step_stage
+  int stage_threads, stage_chunk, stage_smem;
+  int (*set_band_smem)(int bytes);  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) of step_band
+  int band_threads, band_windows;   // block size; density windows per component (3 in 3-D, 1 in 2-D)
   int rtab_groups;  // window starts per block (RhoTile<L>::NG)
   void (*build_nbr_all)(Grid, uint32_t *);
   void (*build_nbr)(Grid, uint32_t *);
@@ -75,6 +91,22 @@ KernelSet make_kernel_set(const char *name) {
     k.step_fused_tile = k_step_fused_tile<L, S, MRT>;
     k.build_rtab = k_build_rtab<L>;
     k.rtab_groups = RhoTile<L>::NG;
+    k.step_band = k_step_band<L, S, MRT, false>;
+    k.set_band_smem = [](int bytes) -> int {
+      return (int)cudaFuncSetAttribute(k_step_band<L, S, MRT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    k.step_band_pull = k_step_band<L, S, MRT, true>;
+    k.set_band_pull_smem = [](int bytes) -> int {
+      return (int)cudaFuncSetAttribute(k_step_band<L, S, MRT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    k.step_stage = k_step_stage<L, S, MRT>;
+    k.set_stage_attrs = []() -> int {
+      cudaError_t e = cudaFuncSetAttribute(k_step_stage<L, S, MRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, StageGeom<L, S>::SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_stage<L, S, MRT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      return (int)e;
+    };
+    k.moments_pull = k_moments_pull<L, S, false>;
+    k.pull_stream = k_moments_pull<L, S, true>;
     k.upload_lag_rows = [](const void *rows, size_t bytes, cudaStream_t s) -> int {
       return (int)cudaMemcpyToSymbolAsync(c_lag_rows, rows, bytes, 0, cudaMemcpyDeviceToDevice, s);
     };
@@ -88,8 +120,21 @@ KernelSet make_kernel_set(const char *name) {
     k.step_fused_tile = nullptr;
     k.build_rtab = nullptr;
     k.rtab_groups = 0;
+    k.step_band = nullptr;
+    k.set_band_smem = nullptr;
+    k.step_band_pull = nullptr;
+    k.set_band_pull_smem = nullptr;
+    k.moments_pull = nullptr;
+    k.pull_stream = nullptr;
+    k.step_stage = nullptr;
+    k.set_stage_attrs = nullptr;
   }
+  k.stage_threads = StageGeom<L, S>::NT;
+  k.stage_chunk = StageGeom<L, S>::CH;
+  k.stage_smem = StageGeom<L, S>::SMEM_BYTES;
   k.fused_threads = TXG_FUSED_THREADS;
+  k.band_threads = TXG_BAND_THREADS;
+  k.band_windows = BandGeom<L>::NP;
   k.npw = Lanes<S>::NPW;
   k.ncen = num_centres<L>();
   k.ff_words = ISO == 4 ? 0 : ff_words<L>(ISO);

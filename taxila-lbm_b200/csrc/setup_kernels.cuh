@@ -2,6 +2,8 @@
 #pragma once
 #include <cstdint>
 
+#include "bitrows.cuh"
+
 namespace txg {
 
 // walls(rg..) doubles -> u8 classes (include/taxila_gpu.h TXG_CLASS_*); exact, value by value
@@ -158,6 +160,53 @@ __global__ void k_delta_norm(const double *__restrict__ cur, double *__restrict_
   // warp max then one atomic per warp; doubles >= 0 order like their bit patterns
   for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
   if ((threadIdx.x & 31) == 0 && v > 0.) atomicMax(out_bits, (unsigned long long)__double_as_longlong(v));
+}
+
+// ------------------------------------------------------------------ set-up of the bit rows (once per walls upload)
+// one thread per (extended row incl. the two y ghost rows, word): bits and edge flags from the class array (its ghost
+// rows / columns hold the wrapped classes of a periodic box and wall codes otherwise), the start from the position map
+__global__ void k_build_bitrows(Grid g, const uint8_t *__restrict__ cls, int NW, BitrowEntry *__restrict__ rows,
+                                uint32_t *__restrict__ rowend) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int rpp = g.NY + 2, nzE = g.NZl + 2 * g.Rz;
+  if (t >= (long long)nzE * rpp * NW) return;
+  const int w = (int)(t % NW);
+  const long long row = t / NW;
+  const int zz = (int)(row / rpp), yg = (int)(row - (long long)zz * rpp) - 1;  // yg = -1 .. NY
+  // the class array has R >= 1 ghost rows: row yg sits at yg + R
+  const uint8_t *crow = cls + ((long long)zz * g.cny + (yg + g.R)) * g.cnx + g.R;
+  auto fluid = [&](int x) -> bool { return x >= -1 && x <= g.NX && crow[x] == 0; };
+  uint32_t bits = 0u;
+  for (int b = 0; b < 32; ++b) {
+    const int x = 32 * w + b;
+    if (x < g.NX && fluid(x)) bits |= 1u << b;
+  }
+  // the real row behind a y ghost row (periodic: the wrapped row; otherwise the row is solid and its start is unused)
+  int yr = yg;
+  if (yg < 0) yr = g.pery ? g.NY - 1 : 0;
+  if (yg >= g.NY) yr = g.pery ? 0 : g.NY - 1;
+  const long long oe0 = ((long long)zz * g.NY + yr) * g.NX;
+  const int x0 = min(32 * w, g.NX);
+  const uint32_t start = g.P ? g.P[oe0 + x0] : (uint32_t)(oe0 + x0);
+  uint32_t se = start & BITROW_POSMASK;
+  if (fluid(32 * w - 1)) se |= 1u << 30;
+  if (32 * w + 32 <= g.NX && fluid(32 * w + 32)) se |= 1u << 31;
+  // the flag of x = NX (ghost column) when the row does not end on a word boundary: the bit after the last node.
+  // No prefix count ever includes it (b <= (NX - 1) & 31 for every node of the row).
+  if (32 * w < g.NX && g.NX < 32 * w + 32 && fluid(g.NX)) bits |= 1u << (g.NX & 31);
+  rows[t] = BitrowEntry{se, bits};
+  if (w == 0) rowend[row] = g.P ? g.P[oe0 + g.NX] : (uint32_t)(oe0 + g.NX);
+}
+
+// xrow[pos] = x | rowid << 11 for every stored position (owned and ghost planes)
+__global__ void k_build_xrow(Grid g, long long pos0, long long nstore, uint32_t *__restrict__ xrow) {
+  const long long pos = pos0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= nstore) return;
+  const unsigned oe = g.list ? g.list[pos] : (unsigned)pos;
+  const unsigned plane = (unsigned)g.plane;
+  const unsigned zz = oe / plane, r = oe - zz * plane;
+  const unsigned y = r / (unsigned)g.NX, x = r - y * (unsigned)g.NX;
+  xrow[pos] = x | ((zz * (unsigned)(g.NY + 2) + y + 1u) << BITROW_XBITS);
 }
 
 }  // namespace txg

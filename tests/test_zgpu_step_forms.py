@@ -1,0 +1,153 @@
+"""The forms of the order-4 step on the device give the same bits:
+  * stage (default): k_step_stage -- populations, adjacency rows and mask of a chunk fetched by bulk copies (TMA) into a
+    double buffer in shared memory while the previous chunk is collided
+  * table: k_step_fused (the same per-node adjacency table, every operand by demand loads), TXG_STAGE=0
+  * band / push (opt-in TXG_BAND=1): k_step_band (bit rows instead of the table, density windows in shared memory)
+  * band / pull (opt-in TXG_BAND=1 TXG_PULL=1): k_step_band<PULL> + k_moments_pull -- the population buffer holds collided
+    populations between steps and the reference's fi is gathered at the start of the next step, or by k_pull_stream when
+    fi itself is asked for (exports, restart, delta norm) in the middle of a run.
+Same arithmetic in the same order on the same values, so np.array_equal, not a tolerance; the oracle comparison of the
+default form is tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import cases
+import gpu_util
+from taxila_lbm_b200 import config as tc
+from taxila_lbm_b200 import geometry as geo
+
+pytestmark = pytest.mark.gpu
+
+FORMS = {"table": dict(TXG_STAGE="0"), "stage": {}, "push": dict(TXG_BAND="1"), "pull": dict(TXG_BAND="1", TXG_PULL="1")}
+KERNEL = {"table": "k_step_fused", "stage": "k_step_stage", "push": "k_step_band", "pull": "k_step_band_pull"}
+
+
+def run(cfg, walls, rho, form, monkeypatch, chunks, peek=False):
+    for k in ("TXG_BAND", "TXG_PULL", "TXG_STAGE", "TXG_STAGE_CHUNKS", "TXG_BAND_LB", "TXG_LAG", "TXG_RHOTILE", "TXG_SPLIT"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in FORMS[form].items():
+        monkeypatch.setenv(k, v)
+    flow = gpu_util.make_flow(cfg, walls, rho)
+    mid = []
+    for n in chunks:
+        flow.step(n)
+        if peek:  # an export in the middle of the run: fi is materialised, the next step starts from streamed populations
+            mid.append(gpu_util.fields(flow))
+    flow.synchronize()
+    out = gpu_util.fields(flow)
+    kt = flow.kernel_times()
+    flow.close()
+    return out, mid, kt
+
+
+def three_components(N=24):
+    cfg = tc.default_config(3, 3, N, N, N)
+    for d in range(3):
+        cfg.periodic[d] = 1
+    for m in range(3):
+        for k in range(3):
+            if k != m:
+                cfg.gf[m][k] = 0.05 + 0.01 * (m + k)
+    tc.finalize_flags(cfg)
+    walls = geo.porous_spheres(N, N, N, seed=11, rmin=3.0, rmax=6.0, solid_fraction=0.4, nminerals=1)
+    rho = 0.2 + 0.6 * np.random.default_rng(5).random((N, N, N, 3))
+    rho[walls != 0] = 0.0
+    return cfg, walls, rho
+
+
+CASES = {
+    "porous": lambda: cases.porous_3d(32, rmin=4.0, rmax=8.0),
+    "porous_wide_rows": lambda: cases.porous_3d(96, 40, 12, rmin=4.0, rmax=8.0),  # three bit-row words per row
+    "bubble": lambda: cases.bubble_3d(32),
+    "closed": lambda: cases.porous_3d(24, rmin=3.0, rmax=6.0, periodic=(0, 0, 0)),
+    "mixed_periodic": lambda: cases.porous_3d(24, rmin=3.0, rmax=6.0, periodic=(1, 0, 1)),
+    "x_walls": lambda: cases.porous_3d(24, rmin=3.0, rmax=6.0, periodic=(0, 1, 1)),
+    "2d": lambda: cases.bubble_2d(64),
+    "2d_mrt": lambda: cases.bubble_2d(48, mrt=True),
+    "s3": three_components,
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_forms_bit_identical(monkeypatch, case):
+    cfg, walls, rho = CASES[case]()
+    steps = 20
+    ref, _, k0 = run(cfg, walls, rho, "table", monkeypatch, (steps,))
+    assert k0[KERNEL["table"]][1] == steps, k0
+    for form in ("stage", "push", "pull"):
+        out, _, kt = run(cfg, walls, rho, form, monkeypatch, (3, 1, steps - 4))
+        assert kt[KERNEL[form]][1] == steps, (form, kt)
+        for a, b, name in zip(ref, out, ("fi", "rho", "u", "forces")):
+            assert np.array_equal(a, b), (case, form, name, float(np.abs(a - b).max()))
+
+
+def test_pull_form_with_exports_in_the_middle(monkeypatch):
+    """fi, rho, u, forces read after every chunk: k_pull_stream materialises fi, the following step reads it in place."""
+    cfg, walls, rho = cases.porous_3d(32, rmin=4.0, rmax=8.0)
+    chunks = (1, 2, 5, 4)
+    _, mid0, _ = run(cfg, walls, rho, "table", monkeypatch, chunks, peek=True)
+    _, mid1, kt = run(cfg, walls, rho, "pull", monkeypatch, chunks, peek=True)
+    assert kt["k_pull_stream"][1] == len(chunks), kt
+    for a4, b4 in zip(mid0, mid1):
+        for a, b in zip(a4, b4):
+            assert np.array_equal(a, b)
+
+
+def test_pull_form_with_eos(monkeypatch):
+    cfg, walls, rho = cases.porous_3d(32, rmin=4.0, rmax=8.0)
+    cfg.use_nonideal_eos = 1
+    for m in range(2):
+        cfg.eos_type[m] = tc.EOS_SC
+        cfg.eos_rho0[m] = 0.8 + 0.3 * m
+    ref, _, _ = run(cfg, walls, rho, "table", monkeypatch, (25,))
+    out, _, kt = run(cfg, walls, rho, "pull", monkeypatch, (25,))
+    assert kt["k_step_band_pull"][1] == 25 and kt["k_moments_pull"][1] >= 24, kt
+    for a, b in zip(ref, out):
+        assert np.array_equal(a, b)
+
+
+def test_pull_form_delta_norm_and_restart(monkeypatch):
+    """DistributionCalcDeltaNorm and a restart from fi (txg_get_fi -> txg_set_fi) in the pull form."""
+    cfg, walls, rho = cases.porous_3d(24, rmin=3.0, rmax=6.0)
+    vals = {}
+    for form in ("table", "pull"):
+        for k in ("TXG_BAND", "TXG_PULL", "TXG_STAGE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in FORMS[form].items():
+            monkeypatch.setenv(k, v)
+        flow = gpu_util.make_flow(cfg, walls, rho)
+        flow.step(5)
+        n0 = flow.delta_norm()
+        flow.step(3)
+        n1 = flow.delta_norm()
+        fi = flow.get_fi()
+        flow.close()
+        flow2 = gpu_util.make_flow(cfg, walls, rho)
+        flow2.set_fi(fi)
+        flow2.update_moments()
+        flow2.step(7)
+        vals[form] = (n0, n1, fi, gpu_util.fields(flow2))
+        flow2.close()
+    a, b = vals["table"], vals["pull"]
+    assert a[0] == b[0] == 1e99 and a[1] == b[1]
+    assert np.array_equal(a[2], b[2])
+    for x, y in zip(a[3], b[3]):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_staged_form_block_sizes_and_sub_ranges(monkeypatch, chunks):
+    """k_step_stage with one and three chunks per block (single-chunk blocks never refill a stage); a box whose planes
+    do not start on block boundaries."""
+    cfg, walls, rho = cases.porous_3d(40, 24, 20, rmin=4.0, rmax=8.0)
+    ref, _, _ = run(cfg, walls, rho, "table", monkeypatch, (15,))
+    monkeypatch.delenv("TXG_STAGE", raising=False)
+    monkeypatch.setenv("TXG_STAGE_CHUNKS", str(chunks))
+    flow = gpu_util.make_flow(cfg, walls, rho)
+    flow.step(15)
+    out = gpu_util.fields(flow)
+    kt = flow.kernel_times()
+    flow.close()
+    assert kt["k_step_stage"][1] == 15, kt
+    for a, b in zip(ref, out):
+        assert np.array_equal(a, b)
