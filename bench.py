@@ -116,6 +116,9 @@ class ClockSampler:
         }
 
 
+_WALLS = {}
+
+
 def build_case(size, nranks, rank, scaling, order):
     """Per-rank slab of the workload: (cfg, walls_rg, rho_rg, fluid_fraction, global_nodes)."""
     from taxila_lbm_b200 import geometry as geo
@@ -124,9 +127,12 @@ def build_case(size, nranks, rank, scaling, order):
     # (sweeps of several bench runs in one GPU call keep the generated geometry: TXG_CASE_CACHE=<dir>)
     cache = os.environ.get("TXG_CASE_CACHE")
     cpath = Path(cache) / ("c4_%d_walls.npy" % size) if cache else None
-    walls = np.load(cpath) if cpath is not None and cpath.exists() else None
+    walls = _WALLS.get(size)  # (the strong-scaling sub-measurement re-uses the geometry of the weak one)
+    if walls is None and cpath is not None and cpath.exists():
+        walls = np.load(cpath)
     have = walls is not None
     cfg, walls, rho = workloads.porous_3d(size, order=order, walls=walls)
+    _WALLS[size] = walls
     if cpath is not None and not have and rank == 0:
         np.save(cpath, walls)
     R = cfg.stencil_size_rho
@@ -185,6 +191,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10, help="timed oracle steps of the cpu_baseline leg of the CUDA arm")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1, weak scaling: skip the strong-scaling sub-measurement")
     args = ap.parse_args()
 
     # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner under
@@ -333,6 +340,38 @@ def main():
                "what": "walls+rho upload, FlowFiInit, FlowUpdateMoments, %d steps as the six LBMRun2 procedure calls, "
                        "FlowUpdateDiagnostics fields copied back into page-locked host arrays; host wall clock, max over ranks" % args.steps}
 
+    # ------------------------------------------------------------------ strong scaling beside the weak line (N > 1)
+    # the ONE size^3 box split into N z-slabs, same timed protocol (warm-up, K steps between barriers, CUDA events, max
+    # over ranks): the latency-bound case of SURVEY.md 8e (512 / N planes per GPU)
+    strong = None
+    if world > 1 and args.scaling == "weak" and not args.no_strong:
+        flow.close()
+        cfg_s, walls_s, rho_s, _, nodes_s = build_case(args.size, world, rank, "strong", args.order)
+        ids = [tx.Flow.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        fs_ = tx.Flow(cfg_s, device=local_rank, nccl_id=ids[0])
+        fs_.walls_set_values(walls_s)
+        fs_.initialize_state(rho_s)
+        fs_.fi_init()
+        fs_.update_moments()
+        fs_.step(warmup)
+        fs_.synchronize()
+        barrier()
+        fs_.step(args.steps)
+        fs_.synchronize()
+        barrier()
+        ms_s, launches_s = fs_.last_step_ms()
+        ts = torch.tensor([ms_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        r_s = geo.owned(fs_.get_arrays(u=False, forces=False)[0], cfg_s.stencil_size_rho, 3)
+        assert np.isfinite(r_s).all()
+        fs_.close()
+        ms_s = float(ts.item())
+        strong = {"value": nodes_s * args.steps / (ms_s * 1e-3) / 1e6, "unit": "MLUPS", "ms_per_step": ms_s / args.steps,
+                  "box": [args.size] * 3, "planes_per_gpu": cfg_s.zl, "steps": args.steps, "warmup": warmup,
+                  "launches_per_step_per_rank": launches_s / max(args.steps, 1),
+                  "what": "the one %d^3 box of the N=1 line split into %d z-slabs; efficiency = value / (N x the N=1 value)" % (args.size, world)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -402,6 +441,8 @@ def main():
         "gpu_launches": int(launches) * world, "mass_drift_rel": mass_drift, "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels,
         "cpu_baseline": cpu,
     }
+    if strong is not None:
+        line["strong"] = strong
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -1266,7 +1266,7 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   // staged form of K2: whenever the fused kernel applies and no opt-in experiment replaces it
   h->stage = h->stage_wanted && h->fused && h->ks.step_stage && !h->tile && !h->band && !h->lag;
   if (h->stage) {
-    int chunks = 8;
+    int chunks = 16;  // rounds per block: 16 x 4 warps x 16 positions = 1024 positions (S = 2)
     if (const char *v = getenv("TXG_STAGE_CHUNKS")) chunks = std::max(1, atoi(v));
     h->stage_lb = chunks * h->ks.stage_chunk;
     TXG_CUDA(h, (cudaError_t)h->ks.set_stage_attrs());
@@ -1354,7 +1354,9 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   }
   if (h->fused && h->stage && !h->tile) {
     ScopedKernel sk(h, "k_step_stage", s);
-    const long long LB = h->stage_lb, blk0 = first / LB, nblk = (first + count - 1) / LB - blk0 + 1;
+    // (a launch over a plane or two -- the boundary planes of a slab -- takes short blocks so that it still fills the SMs)
+    const long long LB = count < 1024ll * h->stage_lb ? std::min<long long>(h->stage_lb, 2 * h->ks.stage_chunk) : h->stage_lb;
+    const long long blk0 = first / LB, nblk = (first + count - 1) / LB - blk0 + 1;
     h->ks.step_stage<<<(unsigned)nblk, h->ks.stage_threads, (size_t)h->ks.stage_smem, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
                                                                                            h->nbr_all, h->wallrec, first, count, blk0, (int)LB);
     TXG_CUDA(h, cudaGetLastError());

@@ -130,7 +130,7 @@ KernelSet make_kernel_set(const char *name) {
     k.set_stage_attrs = nullptr;
   }
   k.stage_threads = StageGeom<L, S>::NT;
-  k.stage_chunk = StageGeom<L, S>::CH;
+  k.stage_chunk = StageGeom<L, S>::NW * StageGeom<L, S>::NPW;  // positions one round of a block covers
   k.stage_smem = StageGeom<L, S>::SMEM_BYTES;
   k.fused_threads = TXG_FUSED_THREADS;
   k.band_threads = TXG_BAND_THREADS;

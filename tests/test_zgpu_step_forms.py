@@ -57,7 +57,7 @@ def three_components(N=24):
 
 CASES = {
     "porous": lambda: cases.porous_3d(32, rmin=4.0, rmax=8.0),
-    "porous_wide_rows": lambda: cases.porous_3d(96, 40, 12, rmin=4.0, rmax=8.0),  # three bit-row words per row
+    "porous_wide_rows": lambda: cases.porous_3d(96, 40, 12, rmin=2.0, rmax=4.5),  # three bit-row words per row
     "bubble": lambda: cases.bubble_3d(32),
     "closed": lambda: cases.porous_3d(24, rmin=3.0, rmax=6.0, periodic=(0, 0, 0)),
     "mixed_periodic": lambda: cases.porous_3d(24, rmin=3.0, rmax=6.0, periodic=(1, 0, 1)),
@@ -139,7 +139,7 @@ def test_pull_form_delta_norm_and_restart(monkeypatch):
 def test_staged_form_block_sizes_and_sub_ranges(monkeypatch, chunks):
     """k_step_stage with one and three chunks per block (single-chunk blocks never refill a stage); a box whose planes
     do not start on block boundaries."""
-    cfg, walls, rho = cases.porous_3d(40, 24, 20, rmin=4.0, rmax=8.0)
+    cfg, walls, rho = cases.porous_3d(40, 24, 20, rmin=3.0, rmax=6.0)
     ref, _, _ = run(cfg, walls, rho, "table", monkeypatch, (15,))
     monkeypatch.delenv("TXG_STAGE", raising=False)
     monkeypatch.setenv("TXG_STAGE_CHUNKS", str(chunks))
