@@ -48,6 +48,20 @@ B_K1_FLUID = 320.0  # moments kernel: 8*S*Q + 8*S
 B_KF_FLUID = 65.0   # split forces kernel: 8*S (rho) + 8*S*D (F out) + 1
 
 
+def bind_near_gpu(index):
+    """Run this rank (and the page-locked host arrays it touches first) on the CPUs next to its GPU: with 8 ranks on a
+    two-socket box the host <-> device copies of the e2e leg otherwise cross the socket link.  Host-side placement only."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return "cpus %d" % len(os.sched_getaffinity(0))
+    except Exception as e:  # not fatal: placement is an optimisation
+        return "unbound (%s)" % type(e).__name__
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -119,36 +133,37 @@ class ClockSampler:
 _WALLS = {}
 
 
-def build_case(size, nranks, rank, scaling, order):
+def build_case(size, nranks, rank, scaling, order, nz=None):
     """Per-rank slab of the workload: (cfg, walls_rg, rho_rg, fluid_fraction, global_nodes)."""
     from taxila_lbm_b200 import geometry as geo
     from taxila_lbm_b200 import slab, workloads
 
     # (sweeps of several bench runs in one GPU call keep the generated geometry: TXG_CASE_CACHE=<dir>)
     cache = os.environ.get("TXG_CASE_CACHE")
-    cpath = Path(cache) / ("c4_%d_walls.npy" % size) if cache else None
-    walls = _WALLS.get(size)  # (the strong-scaling sub-measurement re-uses the geometry of the weak one)
+    nz = size if nz is None else nz
+    cpath = Path(cache) / ("c4_%d_%d_walls.npy" % (size, nz)) if cache else None
+    walls = _WALLS.get((size, nz))  # (the strong-scaling sub-measurement re-uses the geometry of the weak one)
     if walls is None and cpath is not None and cpath.exists():
         walls = np.load(cpath)
     have = walls is not None
-    cfg, walls, rho = workloads.porous_3d(size, order=order, walls=walls)
-    _WALLS[size] = walls
+    cfg, walls, rho = workloads.porous_3d(size, size, nz, order=order, walls=walls)
+    _WALLS[(size, nz)] = walls
     if cpath is not None and not have and rank == 0:
         np.save(cpath, walls)
     R = cfg.stencil_size_rho
     if nranks == 1 or scaling == "strong":
         # the one size^3 box, split into z-slabs (DMDA ownership ranges)
         c, walls_rg, rho_rg = slab.local_arrays(cfg, walls, rho, nranks, rank)
-        NZg = size
+        NZg = nz
     else:
         # weak: the global box is the size^3 block tiled nranks times along periodic z and rank r
         # owns tile r, so every halo is a real exchange between different GPUs.  All tiles hold the
         # same geometry, so the ghost planes of a tile are its own opposite planes; the flushing IC
         # puts the invading fluid in the first 10 planes of the GLOBAL box only, i.e. in tile 0.
-        NZg = size * nranks
+        NZg = nz * nranks
         c = cfg.copy()
         c.NZ = NZg
-        c.zs, c.zl = rank * size, size
+        c.zs, c.zl = rank * nz, nz
         c.rank, c.nranks = rank, nranks
         if rank != 0:
             rho = geo.flushing_rho(cfg, walls, (0.03, 0.97), (0.03, 0.97), "z", 10)
@@ -185,6 +200,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=512, help="block edge (512 = BASELINE config)")
+    ap.add_argument("--nz", type=int, default=None, help="planes of the box (default: --size); a thin box is the per-GPU work of strong scaling")
     ap.add_argument("--order", type=int, default=4, help="isotropy order of the Shan-Chen stencil")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-sample", type=int, default=256, help="edge of the crop the CPU legs time (SURVEY.md 8d: 256^3)")
@@ -211,7 +227,7 @@ def main():
     workload = "D3Q19 two-component Shan-Chen MRT, %d^3 random-sphere porous medium per GPU, 3 minerals, body force, " \
                "bounce-back, iso-%d" % (args.size, args.order)
     config = {"workload": workload, "lattice": "D3Q19", "components": 2, "relaxation": "MRT",
-              "box_per_gpu": [args.size] * 3, "isotropy_order": args.order, "geometry": "porous_spheres(seed=20260)",
+              "box_per_gpu": [args.size, args.size, args.nz or args.size], "isotropy_order": args.order, "geometry": "porous_spheres(seed=20260)",
               "l2_policy": "inputs larger than L2 (40.8 GB of populations per 512^3 block)",
               "cpu_sample_box": [args.cpu_sample] * 3}
 
@@ -246,12 +262,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_near_gpu(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import taxila_lbm_b200 as tx
     from taxila_lbm_b200 import geometry as geo
 
-    cfg, walls_rg, rho_rg, fluid_frac, global_nodes = build_case(args.size, world, rank, args.scaling, args.order)
+    cfg, walls_rg, rho_rg, fluid_frac, global_nodes = build_case(args.size, world, rank, args.scaling, args.order, args.nz)
     nccl_id = None
     if world > 1:
         ids = [tx.Flow.nccl_unique_id() if rank == 0 else None]
@@ -428,6 +446,7 @@ def main():
 
     cpu = None
     if not args.no_cpu:
+        os.sched_setaffinity(0, all_cpus)  # the CPU leg gets every host core, as in --impl reference
         threads = os.cpu_count() or 1
         v, sps = run_cpu_sample(args.order, args.cpu_sample, args.cpu_steps, threads, warm=2)
         cpu = {"value": v, "unit": "MLUPS", "cores": threads, "kind": "port",

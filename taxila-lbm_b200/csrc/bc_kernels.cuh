@@ -95,6 +95,43 @@ __global__ void k_bc_pressure_outlet(Grid g, int Q, FaceDesc fd, double *__restr
   vals[idx * nbcs + 1] = r1;
 }
 
+// BCApplyReflectingD3 / D2 (lbm_bc.F90:809-1073) on one face: fi(:, n) = fi(:, p) for the face's (n <- p) list, in
+// sequence (a later assignment may read what an earlier one wrote).  The list is formed on the host from the
+// reference's own tests, face by face (flow.cu reflecting_pairs).
+struct ReflectPairs {
+  int count;
+  unsigned char n[64], p[64];
+};
+__global__ void k_bc_reflect(Grid g, int Q, int S, FaceDesc fd, ReflectPairs rp, double *__restrict__ f,
+                             const uint32_t *__restrict__ nbmask) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long pos;
+  if (!face_node(g, fd, nbmask, idx, pos)) return;
+  for (int m = 0; m < S; ++m) {
+    double *fm = f + (long long)m * Q * g.fs + pos;
+    for (int e = 0; e < rp.count; ++e) fm[(long long)rp.n[e] * g.fs] = fm[(long long)rp.p[e] * g.fs];
+  }
+}
+
+// MASK_STALE on the fluid nodes of one face: set for reflecting faces, then cleared for the faces BCUpdateRho visits
+__global__ void k_bc_mark_stale(Grid g, FaceDesc fd, uint32_t *__restrict__ nbmask, uint32_t *__restrict__ lmask, int set) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long pos;
+  if (!face_node(g, fd, nbmask, idx, pos)) return;
+  int x[3] = {0, 0, 0};
+  x[fd.axis] = fd.coord;
+  x[fd.t1] = (int)(idx % fd.n1);
+  x[fd.t2] = (int)(idx / fd.n1);
+  const long long o = (long long)x[2] * g.plane + (long long)x[1] * g.NX + x[0];
+  if (set) {
+    atomicOr(nbmask + o, MASK_STALE);
+    atomicOr(lmask + pos, MASK_STALE);
+  } else {
+    atomicAnd(nbmask + o, ~MASK_STALE);
+    atomicAnd(lmask + pos, ~MASK_STALE);
+  }
+}
+
 // BCApply -> BCApply{Dirichlet,Neumann,Velocity}D* -> ...Node (lbm_bc.F90:781-807,1075-1865) on one
 // face.  f: the populations after streaming and bounce-back (the incoming directions of a face node
 // hold what the bounce-back off the 999 ghost layer put there); F: forces of FlowCalcRhoForces.

@@ -133,9 +133,12 @@ struct txg_flow {
   uint32_t *rtab_lag = nullptr;  // the same per block of the one-pass launch (TXG_LAG=1 TXG_RHOTILE=1)
   // band blocks (band_kernel.cuh; TXG_BAND=0 switches them off): bit rows instead of the adjacency table, density windows in shared memory
   bool band_wanted = false, band = false;  // (measured slower than the table kernel: profiles/r2c_band_results.txt)
-  // staged form (stage_kernel.cuh; TXG_STAGE=0 switches it off): the default K2 of the order-4 step
-  bool stage_wanted = true, stage = false;
-  int stage_lb = 0;  // positions per block: TXG_STAGE_CHUNKS (default 8) chunks
+  // staged form (stage_kernel.cuh; opt-in TXG_STAGE=1: measured 3-15 % slower than the table kernel, profiles/r2d_stage_results.txt)
+  bool stage_wanted = false, stage = false;
+  bool forces_tile_on = true;  // TXG_FORCES_TILE=0: the map-walking k_forces for the wide stencils
+  unsigned *ticket = nullptr;  // item counter of the persistent launch
+  uint32_t *adjm = nullptr;        // [Q][fs] the adjacency rows and, as row Q-1, the mask row: ONE tensor for the staged kernel
+  CUtensorMap tm_f[2], tm_adj;     // the two population buffers and adjm as 2-D tensors
   int band_lb = 1024;                 // positions per block (TXG_BAND_LB)
   int band_prefetch = 1;              // L2 prefetch of the block's next chunk (TXG_BAND_PF)
   BitrowEntry *bitrows = nullptr;
@@ -177,6 +180,8 @@ struct txg_flow {
   LatticeTab lt;
   FaceDesc faces[6];
   bool face_here[6] = {false, false, false, false, false, false};  // this rank holds the face
+  ReflectPairs reflect[6];  // (n <- p) lists of the BC_REFLECTING faces
+  bool has_reflecting = false;
   std::vector<int> bc_order;                                       // faces in BCApply's execution order
   double *bc_vals[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool pressure_outlet[6] = {false, false, false, false, false, false};  // flow%bc_flags(b) .eq. BC_PRESSURE_OUTLET
@@ -309,15 +314,19 @@ static int select_kernels(txg_flow *h) {
     if (h->S == 1) ok = kernel_set_d3q19_s1(mrt, c.isotropy_order, &h->ks);
     if (h->S == 2) ok = kernel_set_d3q19_s2(mrt, c.isotropy_order, &h->ks);
     if (h->S == 3) ok = kernel_set_d3q19_s3(mrt, c.isotropy_order, &h->ks);
+    if (h->S == 4) ok = kernel_set_d3q19_s4(mrt, c.isotropy_order, &h->ks);
+    if (h->S == 5) ok = kernel_set_d3q19_s5(mrt, c.isotropy_order, &h->ks);
   } else {
     if (h->S == 1) ok = kernel_set_d2q9_s1(mrt, c.isotropy_order, &h->ks);
     if (h->S == 2) ok = kernel_set_d2q9_s2(mrt, c.isotropy_order, &h->ks);
     if (h->S == 3) ok = kernel_set_d2q9_s3(mrt, c.isotropy_order, &h->ks);
+    if (h->S == 4) ok = kernel_set_d2q9_s4(mrt, c.isotropy_order, &h->ks);
+    if (h->S == 5) ok = kernel_set_d2q9_s5(mrt, c.isotropy_order, &h->ks);
   }
   if (!ok)
     TXG_FAIL(h, TXG_ERR_SUP,
              "no device kernels for discretization %d, ncomponents %d, isotropy order %d (built: D3Q19 order 4/8, "
-             "D2Q9 order 4/8/10, 1-3 components; D3 order 10 is an LBMError in the reference too)",
+             "D2Q9 order 4/8/10, 1-5 components; D3 order 10 is an LBMError in the reference too)",
              c.discretization, h->S, c.isotropy_order);
   return 0;
 }
@@ -406,13 +415,10 @@ static int validate(const txg_config *c) {
     if (fl >= TXG_BC_REFLECTING && b < 2 * c->ndims && c->periodic[b / 2])
       TXG_FAIL(h, TXG_ERR_ARG_WRONG, "Multiple BCs provided for boundary %d: periodic and bc_flags = %d (lbm_flow.F90:1069-1071)", b, fl);
   }
-  for (int b = 0; b < 2 * c->ndims; ++b)
-    if (c->bc_flags[b] == TXG_BC_REFLECTING)
-      TXG_FAIL(h, TXG_ERR_SUP,
-               "BC_REFLECTING (boundary %d) is not built on the device: BCUpdateRho skips reflecting faces (lbm_bc.F90:443-445), so the "
-               "reference collides their nodes with the density from BEFORE BCApply rewrote the populations -- a stored per-node density "
-               "the collide kernel does not take -- and its xm tests index the wrong axis (lbm_bc.F90:849, :1001)",
-               b);
+  // BCApplyReflectingD2 on XM reads ci(p, Z_DIRECTION) of a two-column array (lbm_bc.F90:1001: out of bounds in the
+  // reference itself): there is no defined behaviour to reproduce
+  if (c->ndims == 2 && c->bc_flags[TXG_BOUNDARY_XM] == TXG_BC_REFLECTING)
+    TXG_FAIL(h, TXG_ERR_SUP, "BC_REFLECTING on the xm face of a 2-D box indexes ci(:, Z_DIRECTION) out of bounds in the reference (lbm_bc.F90:1001)");
   for (int m = 0; m < c->ncomponents; ++m) {
     if (!(c->tau[m] > 0.) || !(c->mm[m] > 0.)) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "component %d: tau and mm must be positive", m + 1);
     if (c->use_nonideal_eos && (c->eos_type[m] < TXG_EOS_DENSITY || c->eos_type[m] > TXG_EOS_THERMO))
@@ -458,8 +464,41 @@ static void setup_faces(txg_flow *h) {
     // x and y faces exist on every z-slab; zm on the first, zp on the last (info%zs.eq.1, info%ze.eq.NZ)
     h->face_here[b] = f.axis < 2 || (b == TXG_BOUNDARY_ZM ? c.zs == 0 : c.zs + c.zl == c.NZ);
   }
+  // BCApplyReflectingD3 / D2 (lbm_bc.F90:825-1073): for every incoming direction n (ascending) and every p (ascending)
+  // that passes the face's own test, fi(n) = fi(p).  The tests are the mirror rule on every face except XM in 3-D,
+  // which compares ci(n, X) with -ci(p, Z) (:849) -- restated as written.
+  h->has_reflecting = false;
+  for (int b = 0; b < 2 * D; ++b) {
+    ReflectPairs &rp = h->reflect[b];
+    rp.count = 0;
+    if (c.bc_flags[b] != TXG_BC_REFLECTING) continue;
+    h->has_reflecting = true;
+    const FaceDesc &f = h->faces[b];
+    const auto &ci = h->lt.c;
+    auto match = [&](int n, int p) -> bool {
+      if (D == 3) {
+        if (b == 0) return ci[n][1] == ci[p][1] && ci[n][2] == ci[p][2] && ci[n][0] == -ci[p][2];
+        if (b == 1) return ci[n][1] == ci[p][1] && ci[n][2] == ci[p][2] && ci[n][0] == -ci[p][0];
+        if (b < 4) return ci[n][0] == ci[p][0] && ci[n][2] == ci[p][2] && ci[n][1] == -ci[p][1];
+        return ci[n][0] == ci[p][0] && ci[n][1] == ci[p][1] && ci[n][2] == -ci[p][2];
+      }
+      if (b == 1) return ci[n][1] == ci[p][1] && ci[n][0] == -ci[p][0];
+      if (b == 2 || b == 3) return ci[n][0] == ci[p][0] && ci[n][1] == -ci[p][1];
+      return false;
+    };
+    for (int n = 1; n < h->Q; ++n) {
+      if (f.sign * ci[n][f.axis] <= 0) continue;
+      for (int p = 1; p < h->Q; ++p)
+        if (match(n, p) && rp.count < 64) {
+          rp.n[rp.count] = (unsigned char)n;
+          rp.p[rp.count] = (unsigned char)p;
+          ++rp.count;
+        }
+    }
+  }
   // BCApply (lbm_bc.F90:781-807): every BC type once, in the order of its first face; inside a type
   // the faces in the order xm, xp, ym, yp, zm, zp
+  h->bc_order.clear();
   bool done[16] = {false};
   done[TXG_BC_NULL] = done[TXG_BC_PERIODIC] = true;
   for (int side = 0; side < 2 * D; ++side) {
@@ -524,7 +563,7 @@ extern "C" int txg_destroy(txg_handle h) {
                   h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->nbr_all, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt, h->spec_dst, h->spec_src, h->spec_tmp, h->bc_vals[0], h->bc_vals[1],
                   h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_crows_dev, h->lag_done, h->rtab, h->rtab_lag,
-                  h->bitrows, h->rowend, h->xrow, h->band_blocks};
+                  h->bitrows, h->rowend, h->xrow, h->band_blocks, h->adjm, h->ticket};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -572,6 +611,10 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     return fail(TXG_ERR_LIB);
   }
   if ((rc = select_kernels(h))) return fail(rc);
+  if (h->ks.set_forces_tile_smem && h->ks.set_forces_tile_smem() != 0) {
+    cudaGetLastError();
+    h->ks.forces_tile = nullptr;  // (a box that does not fit the device's shared memory: keep k_forces)
+  }
   {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
@@ -589,6 +632,7 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     if (const char *v = getenv("TXG_LAG_MPOS")) h->lag_mpos = atoi(v);
     if (const char *v = getenv("TXG_BAND")) h->band_wanted = v[0] != '0';
     if (const char *v = getenv("TXG_STAGE")) h->stage_wanted = v[0] != '0';
+    if (const char *v = getenv("TXG_FORCES_TILE")) h->forces_tile_on = v[0] != '0';
     if (const char *v = getenv("TXG_BAND_LB")) h->band_lb = std::max(16, atoi(v));
     if (const char *v = getenv("TXG_BAND_PF")) h->band_prefetch = atoi(v);
     if (const char *v = getenv("TXG_PULL")) h->pull_wanted = v[0] != '0';
@@ -1235,6 +1279,44 @@ static int build_band(txg_flow *h) {
   return 0;
 }
 
+// ------------------------------------------------------------------ staged K2 (stage_kernel.cuh, opt-in)
+// Tensor descriptors of the arrays k_step_stage streams: [S * Q][fs] doubles (both population buffers) and [Q][fs] words
+// (adjacency rows + mask row, copied into one array), box = one warp item.  cuTensorMapEncodeTiled is a driver entry
+// point; it is fetched through the runtime so that the library keeps linking against cudart only.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int build_stage_tensors(txg_flow *h) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) {
+      cudaGetLastError();
+      h->stage = false;  // (an old driver: keep the table kernel)
+      return 0;
+    }
+    encode = (EncodeTiledFn)fn;
+  }
+  const Grid &g = h->g;
+  const size_t row = (size_t)g.fs * sizeof(uint32_t);
+  TXG_CUDA(h, cudaMalloc((void **)&h->adjm, (size_t)h->Q * row));
+  TXG_CUDA(h, cudaMemcpyAsync(h->adjm, h->nbr_all, (size_t)(h->Q - 1) * row, cudaMemcpyDeviceToDevice, h->s_main));
+  TXG_CUDA(h, cudaMemcpyAsync(h->adjm + (size_t)(h->Q - 1) * g.fs, h->lmask, row, cudaMemcpyDeviceToDevice, h->s_main));
+  auto make = [&](CUtensorMap *tm, CUtensorMapDataType type, void *base, int esize, int rows) -> bool {
+    const cuuint64_t dims[2] = {(cuuint64_t)g.fs, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)g.fs * (cuuint64_t)esize};
+    const cuuint32_t box[2] = {(cuuint32_t)h->ks.stage_item, (cuuint32_t)rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return encode(tm, type, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  if (!make(&h->tm_f[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, h->f[0], 8, h->ks.stage_rows_f) ||
+      !make(&h->tm_f[1], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, h->f[1], 8, h->ks.stage_rows_f) ||
+      !make(&h->tm_adj, CU_TENSOR_MAP_DATA_TYPE_UINT32, h->adjm, 4, h->ks.stage_rows_a))
+    TXG_FAIL(h, TXG_ERR_LIB, "cuTensorMapEncodeTiled failed for the staged kernel (fs = %lld)", (long long)g.fs);
+  return 0;
+}
+
 extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   if (!h) return TXG_ERR_ARG_NULL;
   if (!walls_rg) TXG_FAIL(h, TXG_ERR_ARG_NULL, "txg_set_walls: null array");
@@ -1263,13 +1345,26 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   TXG_TRY(build_lag(h));
   TXG_TRY(build_rtab(h));
   TXG_TRY(build_band(h));
-  // staged form of K2: whenever the fused kernel applies and no opt-in experiment replaces it
-  h->stage = h->stage_wanted && h->fused && h->ks.step_stage && !h->tile && !h->band && !h->lag;
+  // nodes of BC_REFLECTING faces keep the density from before BCApply (MASK_STALE, kernels.cuh): mark them, then unmark
+  // the nodes the faces of BCUpdateRho (Dirichlet / Neumann / velocity) share with them
+  if (h->has_reflecting)
+    for (int pass = 1; pass >= 0; --pass)
+      for (int b = 0; b < 2 * h->D; ++b) {
+        const FaceDesc &fd = h->faces[b];
+        if (!h->face_here[b] || (pass ? fd.type != TXG_BC_REFLECTING : fd.type < TXG_BC_DIRICHLET)) continue;
+        k_bc_mark_stale<<<blocks_for((long long)fd.n1 * fd.n2, 128), 128, 0, h->s_main>>>(h->g, fd, h->nbmask, h->lmask, pass);
+        TXG_CUDA(h, cudaGetLastError());
+        h->launches++;
+      }
+  // staged form of K2 (opt-in)
+  // (S = 3: 10 positions per item; its word rows start off 16-byte boundaries and the copies never completed on the device)
+  h->stage = h->stage_wanted && h->fused && h->ks.step_stage && !h->tile && !h->band && !h->lag && h->ks.npw % 4 == 0;
+  if (h->adjm) cudaFree(h->adjm);
+  h->adjm = nullptr;
+  if (h->stage) TXG_TRY(build_stage_tensors(h));
   if (h->stage) {
-    int chunks = 16;  // rounds per block: 16 x 4 warps x 16 positions = 1024 positions (S = 2)
-    if (const char *v = getenv("TXG_STAGE_CHUNKS")) chunks = std::max(1, atoi(v));
-    h->stage_lb = chunks * h->ks.stage_chunk;
     TXG_CUDA(h, (cudaError_t)h->ks.set_stage_attrs());
+    if (!h->ticket) TXG_CUDA(h, cudaMalloc((void **)&h->ticket, 64));
   }
   h->walls_set = true;
   return 0;
@@ -1302,7 +1397,22 @@ static int run_moments(txg_flow *h, int z0, int nz, cudaStream_t s) {
     return 0;
   }
   ScopedKernel sk(h, "k_moments", s);
-  h->ks.moments<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, h->rho_true, first, count);
+  h->ks.moments<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, h->rho_true, first, count, count, 0);
+  TXG_CUDA(h, cudaGetLastError());
+  return 0;
+}
+// the planes [za, za + nz) and [zb, zb + nz) (za + nz <= zb) in ONE launch: the boundary planes of a slab are a few hundred
+// blocks each, and two launches of that size cost more in launch gaps and tails than in work
+static int run_moments_pair(txg_flow *h, int za, int zb, int nz, cudaStream_t s) {
+  long long fa, ca, fb, cb;
+  plane_range(h, za, nz, &fa, &ca);
+  plane_range(h, zb, nz, &fb, &cb);
+  if (h->state_g || ca == 0 || cb == 0 || za + nz > zb) {
+    TXG_TRY(run_moments(h, za, nz, s));
+    return run_moments(h, zb, nz, s);
+  }
+  ScopedKernel sk(h, "k_moments", s);
+  h->ks.moments_pair<<<hot_blocks(h, ca + cb), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->rho, h->rho_true, fa, ca + cb, ca, fb - (fa + ca));
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -1328,6 +1438,14 @@ static int run_forces(txg_flow *h, int z0, int nz, cudaStream_t s) {
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
   if (h->fused) return 0;  // the collide launch forms the forces itself
+  if (h->ks.forces_tile && h->forces_tile_on) {  // wide stencils: psi staged as dense tiles in shared memory
+    ScopedKernel sk(h, "k_forces_tile", s);
+    const dim3 grid((unsigned)((h->g.NX + h->ks.forces_tile_tx - 1) / h->ks.forces_tile_tx),
+                    (unsigned)((h->g.NY + h->ks.forces_tile_ty - 1) / h->ks.forces_tile_ty), (unsigned)nz);
+    h->ks.forces_tile<<<grid, 256, (size_t)h->ks.forces_tile_smem, s>>>(h->g, h->p, h->rho, h->rho_true, h->lmask, h->ffmask, h->wallrec, h->Fbuf, z0);
+    TXG_CUDA(h, cudaGetLastError());
+    return 0;
+  }
   ScopedKernel sk(h, "k_forces", s);
   h->ks.forces<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->rho, h->rho_true, h->lmask, h->nbr, h->ffmask, h->wallrec,
                                                      h->Fbuf, first, count);
@@ -1354,11 +1472,13 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   }
   if (h->fused && h->stage && !h->tile) {
     ScopedKernel sk(h, "k_step_stage", s);
-    // (a launch over a plane or two -- the boundary planes of a slab -- takes short blocks so that it still fills the SMs)
-    const long long LB = count < 1024ll * h->stage_lb ? std::min<long long>(h->stage_lb, 2 * h->ks.stage_chunk) : h->stage_lb;
-    const long long blk0 = first / LB, nblk = (first + count - 1) / LB - blk0 + 1;
-    h->ks.step_stage<<<(unsigned)nblk, h->ks.stage_threads, (size_t)h->ks.stage_smem, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
-                                                                                           h->nbr_all, h->wallrec, first, count, blk0, (int)LB);
+    // persistent grid; the warps draw items of npw positions from the ticket counter (cleared on the stream)
+    const long long npw = h->ks.npw, nitems = (first + count - 1) / npw - first / npw + 1;
+    const long long wpb = h->ks.stage_threads / 32;
+    const unsigned nblk = (unsigned)std::min<long long>((nitems + wpb - 1) / wpb, (long long)h->num_sms * h->ks.stage_blocks_per_sm);
+    TXG_CUDA(h, cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), s));
+    h->ks.step_stage<<<nblk, h->ks.stage_threads, (size_t)h->ks.stage_smem, s>>>(h->g, h->p, h->tm_f[h->cur], h->tm_adj, h->f[h->cur ^ 1], h->rho, h->wallrec,
+                                                                                 first, count, h->ticket);
     TXG_CUDA(h, cudaGetLastError());
     return 0;
   }
@@ -1377,13 +1497,30 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
     const long long warps = (count + h->ks.npw - 1) / h->ks.npw;
     h->ks.step_fused<<<(unsigned)((warps + wpb - 1) / wpb), h->ks.fused_threads, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask, h->nbr_all,
                                                            h->wallrec, first, count,
-                                                           h->ks.fused_threads == 128 ? h->pf_blocks : 0);
+                                                           h->ks.fused_threads == 128 ? h->pf_blocks : 0, count, 0);
     TXG_CUDA(h, cudaGetLastError());
     return 0;
   }
   ScopedKernel sk(h, "k_collide", s);
   h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->Fbuf, h->lmask, h->nbr,
-                                                      first, count);
+                                                      first, count, h->has_reflecting ? h->rho_true : nullptr);
+  TXG_CUDA(h, cudaGetLastError());
+  return 0;
+}
+// planes [za, za + 1) and [zb, zb + 1) in one launch of the default K2 (other forms: two launches)
+static int run_collide_pair(txg_flow *h, int za, int zb, cudaStream_t s) {
+  long long fa, ca, fb, cb;
+  plane_range(h, za, 1, &fa, &ca);
+  plane_range(h, zb, 1, &fb, &cb);
+  if (!h->fused || h->band || h->stage || h->tile || !h->ks.step_fused_pair || ca == 0 || cb == 0 || za >= zb) {
+    TXG_TRY(run_collide(h, za, 1, s));
+    return run_collide(h, zb, 1, s);
+  }
+  ScopedKernel sk(h, "k_step_fused", s);
+  const int wpb = h->ks.fused_threads / 32;
+  const long long warps = (ca + cb + h->ks.npw - 1) / h->ks.npw;
+  h->ks.step_fused_pair<<<(unsigned)((warps + wpb - 1) / wpb), h->ks.fused_threads, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
+                                                                                          h->nbr_all, h->wallrec, fa, ca + cb, 0, ca, fb - (fa + ca));
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -1521,8 +1658,7 @@ static int one_step(txg_flow *h) {
   // K1: bottom and top R planes, then their halo on the comm stream; interior K1 and the interior
   // forces (which need no halo) meanwhile.  (Running K1 and the forces of different sub-slabs on two
   // streams was tried and gains nothing: a later grid only gets SMs at the tail of an earlier one.)
-  TXG_TRY(run_moments(h, 0, R, sm));
-  TXG_TRY(run_moments(h, g.NZl - R, R, sm));
+  TXG_TRY(run_moments_pair(h, 0, g.NZl - R, R, sm));
   TXG_CUDA(h, cudaEventRecord(h->ev_a, sm));
   TXG_CUDA(h, cudaStreamWaitEvent(sc, h->ev_a, 0));
   TXG_TRY(exchange_rho(h, h->rho, sc));
@@ -1534,8 +1670,7 @@ static int one_step(txg_flow *h) {
   // comm stream; interior collide meanwhile
   TXG_TRY(run_forces(h, 0, R, sm));
   TXG_TRY(run_forces(h, g.NZl - R, R, sm));
-  TXG_TRY(run_collide(h, 0, 1, sm));
-  TXG_TRY(run_collide(h, g.NZl - 1, 1, sm));
+  TXG_TRY(run_collide_pair(h, 0, g.NZl - 1, sm));
   TXG_CUDA(h, cudaEventRecord(h->ev_a, sm));
   TXG_CUDA(h, cudaStreamWaitEvent(sc, h->ev_a, 0));
   if (h->pull)
@@ -1581,6 +1716,12 @@ static int bc_apply(txg_flow *h) {
   for (int b : h->bc_order) {
     const FaceDesc &fd = h->faces[b];
     if (!h->face_here[b]) continue;
+    if (fd.type == TXG_BC_REFLECTING) {
+      ScopedKernel sk(h, "k_bc_reflect", sm);
+      k_bc_reflect<<<blocks_for((long long)fd.n1 * fd.n2, 128), 128, 0, sm>>>(g, h->Q, h->S, fd, h->reflect[b], h->f[h->cur], h->nbmask);
+      TXG_CUDA(h, cudaGetLastError());
+      continue;
+    }
     if (!h->bc_vals[b])
       TXG_FAIL(h, TXG_ERR_ORDER, "boundary %d has bc_flags = %d but txg_set_bc_values was not called for it", b, fd.type);
     ScopedKernel sk(h, "k_bc_apply", sm);
@@ -1717,7 +1858,8 @@ static int run_export(txg_flow *h, double *rho_o, double *u_o, double *F_o, doub
   const Grid &g = h->g;
   ScopedKernel sk(h, "k_export", h->s_main);
   h->ks.export_state<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->p, h->f[h->cur], h->rho, h->nbmask, h->ffmask, h->cls,
-                                                                        h->bc_mode ? h->Fbuf : nullptr, rho_o, u_o, F_o, rhot, prs, velt,
+                                                                        h->bc_mode ? h->Fbuf : nullptr, h->has_reflecting ? h->rho_true : nullptr, rho_o, u_o,
+                                                                        F_o, rhot, prs, velt,
                                                                         h->cfg.null_pressure, 0, g.NZl);
   TXG_CUDA(h, cudaGetLastError());
   return 0;

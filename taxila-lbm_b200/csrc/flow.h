@@ -14,14 +14,18 @@ namespace txg {
 // spread over inst_*.cu so they compile in parallel.
 struct KernelSet {
   // hot path: one lane per (fluid node, component); (first, count) select the positions
-  void (*moments)(Grid, Phys, const double *, double *, double *, long long, long long);
+  // (the *_pair forms cover two runs of positions in one launch: the bottom and top boundary planes of a z-slab)
+  void (*moments)(Grid, Phys, const double *, double *, double *, long long, long long, long long, long long);
+  void (*moments_pair)(Grid, Phys, const double *, double *, double *, long long, long long, long long, long long);
   void (*forces)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *, const uint32_t *,
                  const double *, double *, long long, long long);
   void (*collide)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *, long long,
-                  long long);
+                  long long, const double *);
   // forces + collide in one kernel (order-4 stencil only; nullptr otherwise), fed by the full adjacency table
   void (*step_fused)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
-                     const double *, long long, long long, int);
+                     const double *, long long, long long, int, long long, long long);
+  void (*step_fused_pair)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
+                          const double *, long long, long long, int, long long, long long);
   void (*fi_init_fused)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
                         const uint32_t *, const double *, long long, long long);
   // one-pass step (opt-in, TXG_LAG=1): step_fused + the density sum of the next step in one launch (lag_schedule.h)
@@ -43,9 +47,15 @@ struct KernelSet {
   void (*moments_pull)(Grid, Phys, BandParams, const double *, double *, double *, double *, long long, long long);
   void (*pull_stream)(Grid, Phys, BandParams, const double *, double *, double *, double *, long long, long long);
   int (*set_band_pull_smem)(int bytes);
+  // tile-staged forces of the wide stencils (orders 8, 10): k_forces_tile (hot_kernels.cuh)
+  void (*forces_tile)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *, const double *, double *, int);
+  int (*set_forces_tile_smem)();
+  int forces_tile_smem, forces_tile_tx, forces_tile_ty;
   // staged form (stage_kernel.cuh): k_step_fused with its streamed rows fetched by bulk copies into a double buffer
-  void (*step_stage)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *, const double *,
-                     long long, long long, long long, int);
+  void (*step_stage)(Grid, Phys, const CUtensorMap, const CUtensorMap, double *, const double *, const double *, long long, long long,
+                     unsigned *);
+  int stage_blocks_per_sm;
+  int stage_item, stage_rows_f, stage_rows_a;  // box of the staged tensors: positions per item, population rows, adjacency + mask rows
   int (*set_stage_attrs)();          // dynamic shared memory size + carve-out of step_stage
   int stage_threads, stage_chunk, stage_smem;
   int (*set_band_smem)(int bytes);  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) of step_band
@@ -58,7 +68,7 @@ struct KernelSet {
   void (*fi_init)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
                   const uint32_t *, const uint8_t *, int, int);
   void (*export_state)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *,
-                       const uint8_t *, const double *, double *, double *, double *, double *, double *, double *,
+                       const uint8_t *, const double *, const double *, double *, double *, double *, double *, double *, double *,
                        double, int, int);
   void (*build_masks)(Grid, const uint8_t *, uint32_t *, uint32_t *, int *);
   void (*build_wallrec)(Grid, Phys, const uint8_t *, const uint32_t *, const uint32_t *, double *);
@@ -72,8 +82,23 @@ struct KernelSet {
 template <class L, int S, bool MRT, int ISO>
 KernelSet make_kernel_set(const char *name) {
   KernelSet k;
-  k.moments = k_moments<L, S>;
+  k.moments = k_moments<L, S, false>;
+  k.moments_pair = k_moments<L, S, true>;
   k.forces = k_forces<L, S, ISO>;
+  if constexpr (ISO != 4) {
+    k.forces_tile = k_forces_tile<L, S, ISO>;
+    k.forces_tile_smem = S * ForceTile<L, ISO>::BOX * (int)sizeof(double);
+    k.forces_tile_tx = ForceTile<L, ISO>::TX;
+    k.forces_tile_ty = ForceTile<L, ISO>::TY;
+    k.set_forces_tile_smem = []() -> int {
+      return (int)cudaFuncSetAttribute(k_forces_tile<L, S, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       S * ForceTile<L, ISO>::BOX * (int)sizeof(double));
+    };
+  } else {
+    k.forces_tile = nullptr;
+    k.set_forces_tile_smem = nullptr;
+    k.forces_tile_smem = k.forces_tile_tx = k.forces_tile_ty = 0;
+  }
   k.collide = k_collide<L, S, MRT>;
   k.halo_unpack = k_halo_unpack<L, S>;
   k.fi_init = k_fi_init<L, S, ISO>;
@@ -83,14 +108,23 @@ KernelSet make_kernel_set(const char *name) {
   k.build_nbr = k_build_nbr<L>;
   k.build_nbr_all = k_build_nbr_all<L>;
   if constexpr (ISO == 4) {
-    k.step_fused = k_step_fused<L, S, MRT>;
+    k.step_fused = k_step_fused<L, S, MRT, false>;
+    k.step_fused_pair = k_step_fused<L, S, MRT, true>;
     k.fi_init_fused = k_fi_init_fused<L, S>;
     k.step_fused_lag = k_step_fused_lag<L, S, MRT, false>;
-    k.step_fused_lag_tile = k_step_fused_lag<L, S, MRT, true>;
-    k.build_rtab_lag = k_build_rtab_lag<L>;
-    k.step_fused_tile = k_step_fused_tile<L, S, MRT>;
-    k.build_rtab = k_build_rtab<L>;
-    k.rtab_groups = RhoTile<L>::NG;
+    if constexpr (S <= 3) {  // (the density tiles of the opt-in experiments are static shared memory: S * 12 KB)
+      k.step_fused_lag_tile = k_step_fused_lag<L, S, MRT, true>;
+      k.build_rtab_lag = k_build_rtab_lag<L>;
+      k.step_fused_tile = k_step_fused_tile<L, S, MRT>;
+      k.build_rtab = k_build_rtab<L>;
+      k.rtab_groups = RhoTile<L>::NG;
+    } else {
+      k.step_fused_lag_tile = nullptr;
+      k.build_rtab_lag = nullptr;
+      k.step_fused_tile = nullptr;
+      k.build_rtab = nullptr;
+      k.rtab_groups = 0;
+    }
     k.step_band = k_step_band<L, S, MRT, false>;
     k.set_band_smem = [](int bytes) -> int {
       return (int)cudaFuncSetAttribute(k_step_band<L, S, MRT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -112,6 +146,7 @@ KernelSet make_kernel_set(const char *name) {
     };
   } else {
     k.step_fused = nullptr;
+    k.step_fused_pair = nullptr;
     k.fi_init_fused = nullptr;
     k.step_fused_lag = nullptr;
     k.step_fused_lag_tile = nullptr;
@@ -132,6 +167,10 @@ KernelSet make_kernel_set(const char *name) {
   k.stage_threads = StageGeom<L, S>::NT;
   k.stage_chunk = StageGeom<L, S>::NW * StageGeom<L, S>::NPW;  // positions one round of a block covers
   k.stage_smem = StageGeom<L, S>::SMEM_BYTES;
+  k.stage_item = StageGeom<L, S>::ITEM;
+  k.stage_blocks_per_sm = StageGeom<L, S>::BLOCKS_PER_SM;
+  k.stage_rows_f = StageGeom<L, S>::NF;
+  k.stage_rows_a = StageGeom<L, S>::NA;
   k.fused_threads = TXG_FUSED_THREADS;
   k.band_threads = TXG_BAND_THREADS;
   k.band_windows = BandGeom<L>::NP;
@@ -146,8 +185,12 @@ KernelSet make_kernel_set(const char *name) {
 bool kernel_set_d3q19_s1(bool mrt, int iso, KernelSet *out);
 bool kernel_set_d3q19_s2(bool mrt, int iso, KernelSet *out);
 bool kernel_set_d3q19_s3(bool mrt, int iso, KernelSet *out);
+bool kernel_set_d3q19_s4(bool mrt, int iso, KernelSet *out);
+bool kernel_set_d3q19_s5(bool mrt, int iso, KernelSet *out);
 bool kernel_set_d2q9_s1(bool mrt, int iso, KernelSet *out);
 bool kernel_set_d2q9_s2(bool mrt, int iso, KernelSet *out);
 bool kernel_set_d2q9_s3(bool mrt, int iso, KernelSet *out);
+bool kernel_set_d2q9_s4(bool mrt, int iso, KernelSet *out);
+bool kernel_set_d2q9_s5(bool mrt, int iso, KernelSet *out);
 
 }  // namespace txg

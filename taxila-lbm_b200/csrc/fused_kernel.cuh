@@ -184,20 +184,25 @@ __device__ __forceinline__ void prefetch_block_rows(const Grid &g, const double 
 // RelaxationCollide* (lbm_relaxation.F90:171-200), DistributionStreamD*, DistributionBouncebackD*
 // (lbm_distribution_function.F90:560-784).
 // (order-4 stencil only: its offsets are the lattice directions, so the gathers re-use npos)
-template <class L, int S, bool MRT>
+// PAIR: two runs of positions in one launch (k_moments has the convention); no prefetch then.
 #ifndef TXG_FUSED_THREADS
 #define TXG_FUSED_THREADS 128
 #endif
+template <class L, int S, bool MRT, bool PAIR = false>
 __global__ void __launch_bounds__(TXG_FUSED_THREADS, 512 / TXG_FUSED_THREADS)
     k_step_fused(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ rho,
                  const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr_all,
-                 const double *__restrict__ wallrec, long long first, long long count, int pf_blocks) {
+                 const double *__restrict__ wallrec, long long first, long long count, int pf_blocks, long long split_at,
+                 long long jump) {
   constexpr int Q = L::Q, D = L::D, ISO = 4;
   // pf_blocks > 0: first ask L2 for the rows (populations, adjacency, mask, wall record) of the block
   // pf_blocks further on -- about one wave of resident blocks ahead -- so that its demand loads hit L2
-  if (pf_blocks > 0) prefetch_block_rows<L, S>(g, fA, lmask, nbr_all, wallrec, first, count, (long long)blockIdx.x + pf_blocks);
+  if (!PAIR && pf_blocks > 0) prefetch_block_rows<L, S>(g, fA, lmask, nbr_all, wallrec, first, count, (long long)blockIdx.x + pf_blocks);
   Item it;
   if (!item_of_lane<S>(first, count, it)) return;
+  if constexpr (PAIR) {
+    if (it.pos - first >= split_at) it.pos += jump;
+  }
   // adjacency row and mask first: the second round of loads (neighbour densities, wall record)
   // hangs on them, the populations are not needed until the arithmetic starts
   const uint32_t mask = __ldg(lmask + it.pos);

@@ -200,11 +200,21 @@ __device__ __forceinline__ void load_round2(const Grid &g, const Phys &p, const 
   }
 }
 
-template <class L, int S, int ISO>
+// WideLookup: how a stencil wider than the lattice (orders 8, 10) fetches psi(X + (dx, dy, dz)): the default walks the
+// node -> position map (two dependent loads per entry); k_forces_tile reads a dense shared-memory tile instead.
+struct WideThroughMap {
+  static constexpr bool tile = false;
+  template <int dx, int dy, int dz>
+  __device__ __forceinline__ double get() const {
+    return 0.;
+  }
+};
+
+template <class L, int S, int ISO, class WideLookup = WideThroughMap>
 __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const double *__restrict__ psi_field,
                                         const uint32_t *__restrict__ ffmask, const Round2<L> &r2,
                                         const Item &it, unsigned oe, int x, int y, uint32_t mask,
-                                        double rho_m, double psi_m, double (&F)[L::D]) {
+                                        double rho_m, double psi_m, double (&F)[L::D], const WideLookup wide = WideLookup()) {
   constexpr int D = L::D;
   const int m = it.m;
 #pragma unroll
@@ -227,10 +237,12 @@ __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const doub
     int dxo[2 * RAD + 1], dyo[2 * RAD + 1];
     uint32_t words[(E + 31) / 32];
     if constexpr (ISO != 4) {
+      if constexpr (!WideLookup::tile) {
 #pragma unroll
-      for (int a = -RAD; a <= RAD; ++a) {
-        dxo[a + RAD] = wrap_delta(x, a, g.NX, g.perx);
-        dyo[a + RAD] = wrap_delta(y, a, g.NY, g.pery) * g.NX;
+        for (int a = -RAD; a <= RAD; ++a) {
+          dxo[a + RAD] = wrap_delta(x, a, g.NX, g.perx);
+          dyo[a + RAD] = wrap_delta(y, a, g.NY, g.pery) * g.NX;
+        }
       }
       const long long o = (long long)oe - (long long)g.Rz * g.plane;  // owned dense index
 #pragma unroll
@@ -249,6 +261,9 @@ __device__ __forceinline__ void forces1(const Grid &g, const Phys &p, const doub
         constexpr int n = dir_of<L>(dx, dy, dz);
         on = !((mask >> n) & 1u);
         v = r2.vn[n];
+      } else if constexpr (WideLookup::tile) {
+        on = (words[e / 32] >> (e % 32)) & 1u;
+        v = wide.template get<dx, dy, dz>();
       } else {
         on = (words[e / 32] >> (e % 32)) & 1u;
         v = __ldg(psi_field + pos_of(g, (long long)oe + (dz * plane + dyo[dy + RAD] + dxo[dx + RAD])));
@@ -442,12 +457,17 @@ __device__ __forceinline__ void common_velocity1(const Phys &p, const Item &it, 
 // K1 moments: rho_m = sum_n f_n (ascending n) of the streamed populations; writes rho (psi with an
 // EOS).  Replaces DistributionCalcDensityD* (lbm_distribution_function.F90:379-428) and EOSApply;
 // streaming and bounce-back happened in the push of the previous collide.
-template <class L, int S>
+// PAIR: the launch covers TWO runs of positions -- [first, first + split_at) and, `jump` positions further on, the rest
+// of `count` (the bottom and top boundary planes of a z-slab in one launch).
+template <class L, int S, bool PAIR = false>
 __global__ void __launch_bounds__(128, 16) k_moments(Grid g, Phys p, const double *__restrict__ fA,
                                                  double *__restrict__ rho, double *__restrict__ rho_true,
-                                                 long long first, long long count) {
+                                                 long long first, long long count, long long split_at, long long jump) {
   Item it;
   if (!item_of_lane<S>(first, count, it)) return;
+  if constexpr (PAIR) {
+    if (it.pos - first >= split_at) it.pos += jump;
+  }
   const double *src = fA + (long long)it.m * L::Q * g.fs + it.pos;
   double f[L::Q];
 #pragma unroll
@@ -516,6 +536,129 @@ __global__ void __launch_bounds__(128, 8) k_forces(Grid g, Phys p, const double 
   for (int d = 0; d < D; ++d) Fbuf[(long long)(it.m * D + d) * g.fs + it.pos] = F[d];
 }
 
+// K2a for the wide stencils (orders 8, 10), tile-staged: the 92 (D3Q19 order 8) gathers of a node through the node ->
+// position map are two dependent loads each (k_forces: 13.8 ms per launch at 512^3, profiles/r1_bench_iso8_split_path.json).
+// Here a block owns a dense tile of TX x TY nodes of one plane; it first copies psi of the tile plus a halo of RAD nodes in
+// x, y (and RAD planes in z) -- every component -- into shared memory as a DENSE box (one coalesced look-up of the position
+// map per box node: (TX + 2 RAD)(TY + 2 RAD)(2 RAD + 1) / (TX TY) = 8.4 look-ups per tile node instead of 92 per fluid node),
+// then its lanes take the tile's FLUID nodes only (found through the row starts of the position map: no lane is spent on a
+// solid node) and read every stencil entry from the box at a compile-time offset.  Same arithmetic and summation order as
+// k_forces: bit-identical forces.  Replaces the same reference procedures (LBMAddFluidFluidForcesD* with the 8th / 10th
+// order stencils, lbm_forcing.F90:51-1299; LBMAddFluidSolidForcesD*, LBMAddBodyForcesD*).
+template <class L, int ISO>
+struct ForceTile {
+  static constexpr int RAD = stencil_radius(ISO);
+  static constexpr int TX = 32, TY = 8;
+  static constexpr int BX = TX + 2 * RAD, BY = TY + 2 * RAD, BZ = L::D == 3 ? 2 * RAD + 1 : 1;
+  static constexpr int BOX = BX * BY * BZ;
+  static constexpr int NT = 256;
+};
+
+template <class L, int ISO>
+struct WideFromTile {
+  static constexpr bool tile = true;
+  const double *centre;  // psi of this lane's component at the node, inside the box
+  template <int dx, int dy, int dz>
+  __device__ __forceinline__ double get() const {
+    using T = ForceTile<L, ISO>;
+    return centre[(dz * T::BY + dy) * T::BX + dx];
+  }
+};
+
+template <class L, int S, int ISO>
+__global__ void __launch_bounds__(ForceTile<L, ISO>::NT) k_forces_tile(Grid g, Phys p, const double *__restrict__ rho,
+                                                                     const double *__restrict__ rho_true,
+                                                                     const uint32_t *__restrict__ lmask,
+                                                                     const uint32_t *__restrict__ ffmask,
+                                                                     const double *__restrict__ wallrec, double *__restrict__ Fbuf,
+                                                                     int z0) {
+  using T = ForceTile<L, ISO>;
+  constexpr int D = L::D, RAD = T::RAD, NPW = Lanes<S>::NPW;
+  extern __shared__ __align__(16) double box[];  // [S][BZ][BY][BX]
+  __shared__ unsigned row_pos[T::TY + 1];         // position of the first fluid node of every tile row; [TY]: running total
+  __shared__ unsigned row_cnt[T::TY + 1];         // exclusive prefix of the fluid-node counts of the tile rows
+  const int x0 = blockIdx.x * T::TX, y0 = blockIdx.y * T::TY, z = z0 + (int)blockIdx.z;  // owned plane z
+  const int zz = z + g.Rz;                                                                // extended plane
+  const int nx = min(T::TX, g.NX - x0), ny = min(T::TY, g.NY - y0);
+  // rows of the tile: fluid nodes of row y are the positions [P(x0, y), P(x0 + nx, y))
+  if (threadIdx.x <= T::TY) {
+    unsigned first_pos = 0u, cnt = 0u;
+    if ((int)threadIdx.x < ny) {
+      const long long oe = ((long long)zz * g.NY + (y0 + (int)threadIdx.x)) * g.NX + x0;
+      first_pos = g.P ? __ldg(g.P + oe) : (unsigned)oe;
+      cnt = (g.P ? __ldg(g.P + oe + nx) : (unsigned)(oe + nx)) - first_pos;
+    }
+    row_pos[threadIdx.x] = first_pos;
+    row_cnt[threadIdx.x] = cnt;
+  }
+  // the dense box of psi: wrapped (periodic) or clamped (the entry masks exclude what lies beyond a closed face) coordinates
+  for (int t = threadIdx.x; t < T::BOX; t += T::NT) {
+    const int bx = t % T::BX, r = t / T::BX, by = r % T::BY, bz = r / T::BY;
+    const int x = wrapc(x0 - RAD + bx, g.NX, g.perx), y = wrapc(y0 - RAD + by, g.NY, g.pery);
+    const int ze = D == 3 ? zz - RAD + bz : 0;
+    const long long oe = ((long long)ze * g.NY + y) * g.NX + x;
+    const long long pos = pos_of(g, oe);
+#pragma unroll
+    for (int m = 0; m < S; ++m) box[m * T::BOX + t] = __ldg(rho + (long long)m * g.fs + pos);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // exclusive prefix over <= 8 rows
+    unsigned acc = 0u;
+    for (int r = 0; r <= T::TY; ++r) {
+      const unsigned c = row_cnt[r];
+      row_cnt[r] = acc;
+      acc += c;
+    }
+  }
+  __syncthreads();
+  const unsigned nfluid = row_cnt[T::TY];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int m = lane / NPW;
+  const int j = lane - m * NPW;
+  bool lane_ok = true;
+  if (m >= S) {
+    m = S - 1;
+    lane_ok = false;
+  }
+  for (unsigned c0 = (unsigned)warp * NPW; c0 < nfluid; c0 += (T::NT / 32) * NPW) {
+    Item it;
+    it.m = m;
+    it.j = j;
+    unsigned c = c0 + (unsigned)j;
+    it.active = lane_ok && c < nfluid;
+    c = min(c, nfluid - 1u);
+    int ry = 0;
+#pragma unroll
+    for (int r = 1; r < T::TY; ++r) ry += (c >= row_cnt[r]) ? 1 : 0;
+    it.pos = (long long)row_pos[ry] + (c - row_cnt[ry]);
+    const unsigned oe = g.list ? __ldg(g.list + it.pos) : (unsigned)it.pos;
+    const int x = (int)(oe % (unsigned)g.NX) - x0;  // column inside the tile
+    const uint32_t mask = __ldg(lmask + it.pos);
+    Round2<L> r2;
+    const bool rec = (mask & MASK_WALLREC) != 0;
+    if (p.fluidsolid) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) r2.A[d] = rec ? __ldg(wallrec + (long long)(m * D + d) * g.fs + it.pos) : 0.;
+    }
+    if (p.fluidfluid) {
+      static_for<0, D>([&](auto d_) {
+        constexpr int d = decltype(d_)::value;
+        constexpr double bulk = 1.0 / bulk_weight_sum<L, ISO>(d);
+        r2.rW[d] = rec ? __ldg(wallrec + (long long)(S * D + d) * g.fs + it.pos) : bulk;
+      });
+    }
+    const double *centre = box + m * T::BOX + ((D == 3 ? RAD : 0) * T::BY + (ry + RAD)) * T::BX + (x + RAD);
+    const double psi_m = *centre;
+    const double r = p.eos ? __ldg(rho_true + (long long)m * g.fs + it.pos) : psi_m;
+    double F[D];
+    forces1<L, S, ISO>(g, p, rho + (long long)m * g.fs, ffmask, r2, it, oe, 0, 0, mask, r, psi_m, F, WideFromTile<L, ISO>{centre});
+    if (it.active) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) Fbuf[(long long)(m * D + d) * g.fs + it.pos] = F[d];
+    }
+  }
+}
+
 // K2b collide + push: node populations and forces in, momentum, common velocity, equilibrium,
 // prefactor, SRT/MRT relaxation, forcing term; the post-collision populations are streamed by the
 // store (bounce-back folded in).  Every load address follows from the position alone.
@@ -529,7 +672,8 @@ __global__ void __launch_bounds__(128, 8) k_forces(Grid g, Phys p, const double 
 template <class L, int S, bool MRT>
 __global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
     k_collide(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ Fbuf,
-              const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr, long long first, long long count) {
+              const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr, long long first, long long count,
+              const double *__restrict__ rho_stale /*[S][fs] density of FlowCalcRhoForces for MASK_STALE nodes, or null*/) {
   constexpr int Q = L::Q, D = L::D, NCEN = num_centres<L>();
   // The adjacency row and the mask are needed by the push only.  They travel into shared memory
   // asynchronously (no register is tied up while the collision runs, and their round trip hides
@@ -553,6 +697,9 @@ __global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
   double r = 0.;
 #pragma unroll
   for (int n = 0; n < Q; ++n) r += f[n];
+  if (rho_stale) {  // (handles with a BC_REFLECTING face only)
+    if (__ldg(lmask + it.pos) & MASK_STALE) r = __ldg(rho_stale + (long long)it.m * g.fs + it.pos);
+  }
   double up[D];
   common_velocity1<L, S>(p, it, f, r, F, up);
 #if TXG_ABL != 2 && TXG_ABL != 5

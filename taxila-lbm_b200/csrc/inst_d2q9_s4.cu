@@ -1,0 +1,22 @@
+// inst_d2q9_s4.cu -- kernel instantiations for D2Q9, 4 component(s)
+#include "flow.h"
+namespace txg {
+bool kernel_set_d2q9_s4(bool mrt, int iso, KernelSet *out) {
+  if (iso == 4) {
+    *out = mrt ? make_kernel_set<D2Q9, 4, true, 4>("d2q9_s4_mrt_iso4")
+               : make_kernel_set<D2Q9, 4, false, 4>("d2q9_s4_srt_iso4");
+    return true;
+  }
+  if (iso == 8) {
+    *out = mrt ? make_kernel_set<D2Q9, 4, true, 8>("d2q9_s4_mrt_iso8")
+               : make_kernel_set<D2Q9, 4, false, 8>("d2q9_s4_srt_iso8");
+    return true;
+  }
+  if (iso == 10) {
+    *out = mrt ? make_kernel_set<D2Q9, 4, true, 10>("d2q9_s4_mrt_iso10")
+               : make_kernel_set<D2Q9, 4, false, 10>("d2q9_s4_srt_iso10");
+    return true;
+  }
+  return false;
+}
+}  // namespace txg

@@ -53,7 +53,7 @@ __device__ __forceinline__ long long pos_of(const Grid &g, long long oe) {
   return g.P ? (long long)__ldg(g.P + oe) : oe;
 }
 
-constexpr int MAXS = 3;  // instantiated component counts: 1..3
+constexpr int MAXS = 5;  // instantiated component counts: 1..5 (NMAX_COMPONENTS of the reference, lbm_definitions.h:71)
 
 struct Phys {
   // per component
@@ -119,6 +119,9 @@ constexpr uint32_t MASK_SOLID = 0x80000000u;    // the node itself is solid
 constexpr uint32_t MASK_WALLREC = 0x40000000u;  // the node has a wall record
 constexpr uint32_t MASK_XLO = 0x10000000u;      // x = 0 and x periodic: the -x neighbours wrap
 constexpr uint32_t MASK_XHI = 0x20000000u;      // x = NX-1 and x periodic: the +x neighbours wrap
+// a fluid node of a BC_REFLECTING face (and of no Dirichlet / Neumann / velocity face): BCUpdateRho skips it
+// (lbm_bc.F90:436-456), so collision, flux and exports take the density FlowCalcRhoForces stored before BCApply
+constexpr uint32_t MASK_STALE = 0x08000000u;
 constexpr uint32_t MASK_DIRS = 0x07ffffffu;     // bit n: neighbour X + c_n is solid
 
 // ------------------------------------------------------------------ forces
@@ -377,6 +380,7 @@ __global__ void __launch_bounds__(128) k_export(Grid g, Phys p, const double *__
                                                 const double *__restrict__ rho, const uint32_t *__restrict__ nbmask,
                                                 const uint32_t *__restrict__ ffmask, const uint8_t *__restrict__ cls,
                                                 const double *__restrict__ Fsrc /*[S*D][fs] or null*/,
+                                                const double *__restrict__ rho_stale /*[S][fs] or null: MASK_STALE nodes*/,
                                                 double *__restrict__ rho_out /*[S][nnodes]*/,
                                                 double *__restrict__ u_out /*[S][D][nnodes]*/,
                                                 double *__restrict__ F_out /*[S][D][nnodes]*/,
@@ -407,6 +411,10 @@ __global__ void __launch_bounds__(128) k_export(Grid g, Phys p, const double *__
   double f[S][Q], r[S], F[S][D], up[D];
   load_node<L, S>(g, fA, nd, f);
   density<L, S>(f, r);
+  if (rho_stale && (mask & MASK_STALE)) {
+#pragma unroll
+    for (int m = 0; m < S; ++m) r[m] = __ldg(rho_stale + (long long)m * g.fs + nd.pos);
+  }
   if (Fsrc) {
     // with external face BCs the forces of the step are the ones FlowCalcRhoForces formed BEFORE
     // BCApply / BCUpdateRho changed the face nodes (lbm_flow.F90:1958-1991): take the stored ones

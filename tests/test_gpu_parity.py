@@ -150,6 +150,38 @@ def test_three_components_mrt():
     compare(cfg, walls, rho, steps=50)
 
 
+@pytest.mark.parametrize("S,ndims,order,mrt", [(4, 3, 4, True), (5, 3, 4, True), (5, 3, 8, False), (4, 2, 10, True), (5, 2, 4, False)])
+def test_four_and_five_components(S, ndims, order, mrt):
+    """NMAX_COMPONENTS = 5 (lbm_definitions.h:71): 8 nodes x 4 components and 6 nodes x 5 components per warp (two spare
+    lanes), full coupling matrix, unequal molecular masses, minerals; fused (order 4) and split (orders 8, 10) paths."""
+    N = 20 if ndims == 3 else 40
+    cfg = tc.default_config(ndims, S, N, N, N if ndims == 3 else 1)
+    for d in range(ndims):
+        cfg.periodic[d] = 1
+    cfg.isotropy_order = order
+    cfg.stencil_size_rho = {4: 1, 8: 2, 10: 3}[order]
+    cfg.relaxation_mode = tc.RELAXATION_MODE_MRT if mrt else tc.RELAXATION_MODE_SRT
+    for m in range(S):
+        cfg.tau[m] = 0.9 + 0.05 * m
+        cfg.s_e[m], cfg.s_e2[m], cfg.s_q[m], cfg.s_pi[m], cfg.s_m[m] = 1.19, 1.4, 1.2, 1.4, 1.98
+        cfg.mm[m] = 1.0 + 0.2 * m
+        for k in range(S):
+            if k != m:
+                cfg.gf[m][k] = 0.03 + 0.005 * (m + k)
+    cfg.nminerals = 2
+    for k in range(2):
+        for m in range(S):
+            cfg.gw[k][m] = 0.01 * (k + 1) * (m - 1.5)
+    cfg.body_forces = 1
+    cfg.gvt[ndims - 1] = 1e-5
+    tc.finalize_flags(cfg)
+    NZ = N if ndims == 3 else 1
+    walls = geo.porous_spheres(N, N, NZ, seed=13, rmin=2.5, rmax=5.0, solid_fraction=0.35, nminerals=2)
+    rho = 0.15 + 0.5 * np.random.default_rng(S).random((NZ, N, N, S))
+    rho[walls != 0] = 0.0
+    compare(cfg, walls, rho, steps=30)
+
+
 def test_porous_srt_nonperiodic_box():
     """Closed box: every face non-periodic -> 999 ghosts, bounce-back off the ghost layer."""
     compare(*cases.porous_3d(32, mrt=False, rmin=4.0, rmax=8.0, periodic=(0, 0, 0)), steps=60)

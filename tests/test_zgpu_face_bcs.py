@@ -83,15 +83,36 @@ def test_drainage_3d_velocity_inlet_and_side_faces():
     compare_bc(*cases.drainage_3d(inlet=tc.BC_VELOCITY, outlet=tc.BC_DIRICHLET, x_bc=tc.BC_NEUMANN), steps=30)
 
 
-def test_reflecting_face_is_refused():
-    """BC_REFLECTING is outside SURVEY.md 8a-22 and not built on the device (the reference collides the nodes of a
-    reflecting face with a stale density, tests/test_oracle_bcs.py::test_reflecting_face_keeps_a_stale_density)."""
+def test_reflecting_faces_3d():
+    """BC_REFLECTING on xm / xp (BCApplyReflectingD3, lbm_bc.F90:825-977; the xm test compares ci(n, X) with -ci(p, Z) as
+    written, :849) between a Dirichlet inlet and outlet on z: the fluid nodes of the reflecting faces collide with the
+    density from before BCApply (BCUpdateRho skips them, :443-445), the edge nodes they share with the z faces do not."""
+    compare_bc(*cases.drainage_3d(inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET, x_bc=tc.BC_REFLECTING), steps=40,
+               kernels=("k_bc_reflect", "k_bc_apply", "k_collide"))
+
+
+def test_reflecting_faces_y_and_flux_inlet_3d():
+    """reflecting ym / yp (the mirror rule) with a flux inlet and a pressure-like Dirichlet outlet, order-8 stencil"""
+    c, walls, rho, bcs = cases.drainage_3d(order=8)
+    c.periodic[1] = 0
+    c.bc_flags[tc.BOUNDARY_YM] = c.bc_flags[tc.BOUNDARY_YP] = tc.BC_REFLECTING
+    compare_bc(c, walls, rho, bcs, steps=30, kernels=("k_bc_reflect", "k_forces_tile"))
+
+
+def test_reflecting_faces_2d():
+    """BCApplyReflectingD2 on ym / yp (lbm_bc.F90:979-1073) of a pressure-driven channel; xm is refused (the reference
+    reads ci(p, Z_DIRECTION) of a two-column array there, :1001)."""
     import taxila_lbm_b200 as tx
 
-    c, walls, rho, bcs = cases.drainage_3d(N=8, NZ=8, x_bc=tc.BC_REFLECTING)
+    c, walls, rho, bcs = cases.channel_2d(inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET)
+    c.periodic[1] = 0
+    c.bc_flags[tc.BOUNDARY_YM] = c.bc_flags[tc.BOUNDARY_YP] = tc.BC_REFLECTING
+    compare_bc(c, walls, rho, bcs, steps=60, kernels=("k_bc_reflect",))
+    c2, walls2, rho2, bcs2 = cases.channel_2d(inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET)
+    c2.bc_flags[tc.BOUNDARY_XM] = tc.BC_REFLECTING
     with pytest.raises(capi.TaxilaGpuError) as e:
-        tx.Flow(c)
-    assert e.value.code == 56 and "BC_REFLECTING" in str(e.value)
+        tx.Flow(c2)
+    assert e.value.code == 56 and "lbm_bc.F90:1001" in str(e.value)
 
 
 def test_freeslip_duct_3d_fused_path():
@@ -116,7 +137,7 @@ def test_freeslip_duct_3d_fused_path():
     rho[..., 0] = np.where(xx < N // 2, 0.9, 0.1)
     rho[..., 1] = 1.0 - rho[..., 0]
     rho[walls != 0] = 0
-    errs = compare_bc(c, walls, rho, {}, steps=50, kernels=("k_step_stage", "k_specular_scatter"))
+    errs = compare_bc(c, walls, rho, {}, steps=50, kernels=("k_step_fused", "k_specular_scatter"))
     # specular reflection conserves the mass of each component
     flow = gpu_util.make_flow_bc(c, walls, rho, {})
     flow.step(50)

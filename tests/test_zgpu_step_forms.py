@@ -1,7 +1,7 @@
 """The forms of the order-4 step on the device give the same bits:
-  * stage (default): k_step_stage -- populations, adjacency rows and mask of a chunk fetched by bulk copies (TMA) into a
-    double buffer in shared memory while the previous chunk is collided
-  * table: k_step_fused (the same per-node adjacency table, every operand by demand loads), TXG_STAGE=0
+  * table (default): k_step_fused (per-node adjacency table, every operand by demand loads)
+  * stage (opt-in TXG_STAGE=1): k_step_stage -- populations, adjacency rows and mask of a warp's next item fetched by bulk
+    copies (TMA) into the warp's double buffer in shared memory while the current item is collided
   * band / push (opt-in TXG_BAND=1): k_step_band (bit rows instead of the table, density windows in shared memory)
   * band / pull (opt-in TXG_BAND=1 TXG_PULL=1): k_step_band<PULL> + k_moments_pull -- the population buffer holds collided
     populations between steps and the reference's fi is gathered at the start of the next step, or by k_pull_stream when
@@ -18,12 +18,12 @@ from taxila_lbm_b200 import geometry as geo
 
 pytestmark = pytest.mark.gpu
 
-FORMS = {"table": dict(TXG_STAGE="0"), "stage": {}, "push": dict(TXG_BAND="1"), "pull": dict(TXG_BAND="1", TXG_PULL="1")}
+FORMS = {"table": {}, "stage": dict(TXG_STAGE="1"), "push": dict(TXG_BAND="1"), "pull": dict(TXG_BAND="1", TXG_PULL="1")}
 KERNEL = {"table": "k_step_fused", "stage": "k_step_stage", "push": "k_step_band", "pull": "k_step_band_pull"}
 
 
 def run(cfg, walls, rho, form, monkeypatch, chunks, peek=False):
-    for k in ("TXG_BAND", "TXG_PULL", "TXG_STAGE", "TXG_STAGE_CHUNKS", "TXG_BAND_LB", "TXG_LAG", "TXG_RHOTILE", "TXG_SPLIT"):
+    for k in ("TXG_BAND", "TXG_PULL", "TXG_STAGE", "TXG_BAND_LB", "TXG_LAG", "TXG_RHOTILE", "TXG_SPLIT"):
         monkeypatch.delenv(k, raising=False)
     for k, v in FORMS[form].items():
         monkeypatch.setenv(k, v)
@@ -135,19 +135,17 @@ def test_pull_form_delta_norm_and_restart(monkeypatch):
         assert np.array_equal(x, y)
 
 
-@pytest.mark.parametrize("chunks", [1, 3])
-def test_staged_form_block_sizes_and_sub_ranges(monkeypatch, chunks):
-    """k_step_stage with one and three chunks per block (single-chunk blocks never refill a stage); a box whose planes
-    do not start on block boundaries."""
+def test_staged_form_on_a_box_whose_planes_straddle_items(monkeypatch):
+    """k_step_stage on a box whose planes do not start on multiples of 16 positions (items clipped at both ends of a
+    launch are replayed lanes), and more items than resident warps (every warp draws several tickets)."""
     cfg, walls, rho = cases.porous_3d(40, 24, 20, rmin=3.0, rmax=6.0)
     ref, _, _ = run(cfg, walls, rho, "table", monkeypatch, (15,))
-    monkeypatch.delenv("TXG_STAGE", raising=False)
-    monkeypatch.setenv("TXG_STAGE_CHUNKS", str(chunks))
-    flow = gpu_util.make_flow(cfg, walls, rho)
-    flow.step(15)
-    out = gpu_util.fields(flow)
-    kt = flow.kernel_times()
-    flow.close()
+    out, _, kt = run(cfg, walls, rho, "stage", monkeypatch, (15,))
     assert kt["k_step_stage"][1] == 15, kt
+    for a, b in zip(ref, out):
+        assert np.array_equal(a, b)
+    cfg, walls, rho = cases.porous_3d(96, 96, 40, rmin=4.0, rmax=9.0)  # 165 k fluid nodes = 10 k items > 2368 resident warps
+    ref, _, _ = run(cfg, walls, rho, "table", monkeypatch, (6,))
+    out, _, kt = run(cfg, walls, rho, "stage", monkeypatch, (2, 4))
     for a, b in zip(ref, out):
         assert np.array_equal(a, b)
