@@ -400,6 +400,10 @@ def main():
     nodes_local = args.size ** 2 * cfg.zl
     # dominant kernel: the fused forces+collide kernel (order-4 stencil) or the split collide kernel
     dom, dom_bytes = ("k_step_fused", B_K2_FLUID) if ktimes.get("k_step_fused", (0.0, 0))[1] else ("k_collide", B_K2B_FLUID)
+    if dom == "k_collide":  # split path (wide stencils, face BCs): whichever of its two kernels takes longer
+        for alt in ("k_forces", "k_forces_tile"):
+            if ktimes.get(alt, (0.0, 0))[0] > ktimes.get(dom, (0.0, 0))[0]:
+                dom, dom_bytes = alt, B_KF_FLUID
     if ktimes.get("k_step_fused_tile", (0.0, 0))[1]:  # TXG_RHOTILE=1 (opt-in): same bytes as k_step_fused
         dom, dom_bytes = "k_step_fused_tile", B_K2_FLUID
     for alt in ("k_step_stage", "k_step_band", "k_step_band_pull"):  # other forms of K2: same algorithmic bytes as k_step_fused
@@ -434,7 +438,7 @@ def main():
                      "mflups": value * fluid_frac}
     kernels = {k: {"ms": v[0], "launches": v[1]} for k, v in ktimes.items()}
     # per-kernel achieved algorithmic GB/s (the launches of one step add up to the slab)
-    for name, b in (("k_moments", B_K1_FLUID), ("k_forces", B_KF_FLUID), ("k_collide", B_K2B_FLUID), ("k_step_fused", B_K2_FLUID),
+    for name, b in (("k_moments", B_K1_FLUID), ("k_forces", B_KF_FLUID), ("k_forces_tile", B_KF_FLUID), ("k_collide", B_K2B_FLUID), ("k_step_fused", B_K2_FLUID),
                     ("k_step_fused_tile", B_K2_FLUID), ("k_step_band", B_K2_FLUID), ("k_step_band_pull", B_K2_FLUID),
                     ("k_step_stage", B_K2_FLUID), ("k_moments_pull", B_K1_FLUID), ("k_step_fused_lag", B_ALG_FLUID)):
         if name == "k_moments" and "k_step_fused_lag" in kernels and kernels["k_step_fused_lag"]["launches"]:

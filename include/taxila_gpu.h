@@ -171,7 +171,8 @@ TXG_API int txg_set_walls(txg_handle h, const double *walls_rg);
  * with nbcs = ndims * ncomponents (lbm_flow.F90:245) viewed by the node routines
  * as (S, ndims): densities in (m,1) for BC_DIRICHLET, momentum (m,d) for BC_NEUMANN,
  * velocity (1,d) for BC_VELOCITY (lbm_bc.F90:1273-1333,1533-1593,1793-1865).
- * Only faces whose bc_flags entry is DIRICHLET / NEUMANN / VELOCITY read values.
+ * Only faces whose bc_flags entry is DIRICHLET / NEUMANN / VELOCITY read values; a BC_REFLECTING face
+ * (BCApplyReflectingD3/D2, lbm_bc.F90:809-1073) needs none.
  * May be called again at any time (the outlet updates of FlowApplyBCs,
  * lbm_flow.F90:1958-1991, stay on the host and re-upload). */
 TXG_API int txg_set_bc_values(txg_handle h, int boundary, const double *vals);

@@ -43,7 +43,7 @@ typedef struct {
   char internal[128];
 } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat64 = 8 };
+enum { ncclInt32 = 2, ncclFloat64 = 8 };
 enum { ncclMax = 2 };
 struct NcclApi {
   void *lib = nullptr;
@@ -133,10 +133,15 @@ struct txg_flow {
   uint32_t *rtab_lag = nullptr;  // the same per block of the one-pass launch (TXG_LAG=1 TXG_RHOTILE=1)
   // band blocks (band_kernel.cuh; TXG_BAND=0 switches them off): bit rows instead of the adjacency table, density windows in shared memory
   bool band_wanted = false, band = false;  // (measured slower than the table kernel: profiles/r2c_band_results.txt)
-  // staged form (stage_kernel.cuh; opt-in TXG_STAGE=1: measured 3-15 % slower than the table kernel, profiles/r2d_stage_results.txt)
-  bool stage_wanted = false, stage = false;
+  // staged form (stage_kernel.cuh; TXG_STAGE=0 switches it off): the default K2 of the order-4 step where it applies --
+  // 2.5-3.5 % faster than the table kernel at 512^3 (profiles/r2d_stage_results.txt)
+  bool stage_wanted = true, stage = false;
   bool forces_tile_on = true;  // TXG_FORCES_TILE=0: the map-walking k_forces for the wide stencils
-  unsigned *ticket = nullptr;  // item counter of the persistent launch
+  // orders 8, 10 without face BCs: k_step_tile = forces + collide + push in one kernel.  Opt-in (TXG_WIDE_FUSED=1): 23.7 ms
+  // against 8.4 + 8.5 ms for k_forces_tile + k_collide at 512^3 (the box fill runs at the collision's 16 warps per SM)
+  bool wide_fused = false;
+  int stage_lb = 0;  // positions per block of the staged kernel
+  int stage_pf = 0;  // its L2 prefetch distance in blocks (TXG_STAGE_PF)
   uint32_t *adjm = nullptr;        // [Q][fs] the adjacency rows and, as row Q-1, the mask row: ONE tensor for the staged kernel
   CUtensorMap tm_f[2], tm_adj;     // the two population buffers and adjm as 2-D tensors
   int band_lb = 1024;                 // positions per block (TXG_BAND_LB)
@@ -182,6 +187,7 @@ struct txg_flow {
   bool face_here[6] = {false, false, false, false, false, false};  // this rank holds the face
   ReflectPairs reflect[6];  // (n <- p) lists of the BC_REFLECTING faces
   bool has_reflecting = false;
+  bool spec_any = false;  // some rank of the run has free-slip contacts: every rank joins exchange_parked
   std::vector<int> bc_order;                                       // faces in BCApply's execution order
   double *bc_vals[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool pressure_outlet[6] = {false, false, false, false, false, false};  // flow%bc_flags(b) .eq. BC_PRESSURE_OUTLET
@@ -563,7 +569,7 @@ extern "C" int txg_destroy(txg_handle h) {
                   h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->nbr_all, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt, h->spec_dst, h->spec_src, h->spec_tmp, h->bc_vals[0], h->bc_vals[1],
                   h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_crows_dev, h->lag_done, h->rtab, h->rtab_lag,
-                  h->bitrows, h->rowend, h->xrow, h->band_blocks, h->adjm, h->ticket};
+                  h->bitrows, h->rowend, h->xrow, h->band_blocks, h->adjm};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -640,6 +646,9 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     for (int b = 0; b < 2 * cfg->ndims; ++b) h->bc_mode = h->bc_mode || cfg->bc_flags[b] >= TXG_BC_REFLECTING;
     // face BCs act between the forces and the collision: they need the split kernels and the force buffer
     h->fused = h->ks.step_fused != nullptr && !(sp && sp[0] == '1') && !h->bc_mode;
+    const char *wf = getenv("TXG_WIDE_FUSED");
+    h->wide_fused = wf && wf[0] == '1' && h->ks.step_tile != nullptr && h->ks.forces_tile != nullptr && h->forces_tile_on && !(sp && sp[0] == '1') &&
+                    !h->bc_mode;
   }
   Grid &g = h->g;
   g.NX = cfg->NX;
@@ -1051,8 +1060,8 @@ static int build_specular(txg_flow *h, int contacts) {
   h->spec_n = 0;
   if (!contacts) return 0;
   const Grid &g = h->g;
-  if (h->cfg.nranks != 1)
-    TXG_FAIL(h, TXG_ERR_SUP, "%d fluid/wall contacts with free-slip codes 900-902 (WALL_NORMAL_X/Y/Z): free-slip walls run on one rank only", contacts);
+  // (several ranks: the table of a slab reads the parked populations of the neighbour slabs' boundary planes out of its
+  //  ghost planes, which exchange_parked fills after every push)
   const long long ncls = (long long)(g.NZl + 2 * g.Rz) * g.cny * g.cnx;
   std::vector<uint8_t> cls((size_t)ncls);
   TXG_CUDA(h, cudaMemcpy(cls.data(), h->cls, (size_t)ncls, cudaMemcpyDeviceToHost));
@@ -1061,7 +1070,8 @@ static int build_specular(txg_flow *h, int contacts) {
     P.resize((size_t)g.nE + 1);
     TXG_CUDA(h, cudaMemcpy(P.data(), g.P, P.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   }
-  const int per[3] = {g.perx, g.pery, h->D == 3 ? h->cfg.periodic[2] : 0};
+  // z: one rank wraps inside its own slab; several ranks look into the ghost planes (the neighbour's nodes)
+  const int per[3] = {g.perx, g.pery, h->D == 3 && h->cfg.nranks == 1 ? h->cfg.periodic[2] : 0};
   SpecularTable t;
   build_specular_table(h->lt, g.NX, g.NY, g.NZl, g.R, g.Rz, per, cls.data(), g.P ? P.data() : nullptr, g.fs, t);
   if (t.parked)
@@ -1079,8 +1089,34 @@ static int build_specular(txg_flow *h, int contacts) {
   return 0;
 }
 
+// Free-slip walls on several ranks: a mirror of axis x or y sends the population that left S along c_n to T = S +
+// tangential(c_n), which lies in the next z-plane when c_n,z != 0 -- possibly in the next slab.  The push parked that
+// population in slot (opp(n), S); the table of T's slab reads it from its ghost-plane position of S.  So after every push
+// each slab's ghost planes take the neighbours' boundary-plane rows of the directions pointing AWAY from this slab (the
+// ghost rows pointing away are free: their own pushes were sent on by exchange_f): my top owned plane's c_z < 0 rows fill
+// the up neighbour's bottom ghost plane, my bottom owned plane's c_z > 0 rows the down neighbour's top ghost plane.
+// (DistributionBouncebackD3, lbm_distribution_function.F90:669-784; the reference gets there through the ghosted fi.)
+static int exchange_parked(txg_flow *h, double *buf, cudaStream_t s) {
+  if (h->D != 3 || h->cfg.nranks == 1 || !h->spec_any) return 0;
+  const Grid &g = h->g;
+  const int Rz = g.Rz;
+  const std::vector<long long> &po = h->plane_off;
+  const long long gb0 = po[Rz - 1], ob0 = po[Rz], ob1 = po[Rz + 1];
+  const long long ot0 = po[Rz + g.NZl - 1], gt0 = po[Rz + g.NZl], gt1 = po[Rz + g.NZl + 1];
+  std::vector<Chunk> upv, downv;
+  for (int m = 0; m < h->S; ++m)
+    for (int n = 1; n < h->Q; ++n) {
+      const int cz = D3Q19::c(n, 2);
+      const long long blk = (long long)(m * h->Q + n) * g.fs;
+      if (cz < 0) upv.push_back({blk + ot0, blk + gb0, gt0 - ot0, ob0 - gb0});
+      if (cz > 0) downv.push_back({blk + ob0, blk + gt0, ob1 - ob0, gt1 - gt0});
+    }
+  return exchange(h, buf, upv, downv, s);
+}
+
 // rewrite the free-slip slots of a freshly pushed buffer (after the z halo)
 static int apply_specular(txg_flow *h, double *f, cudaStream_t s) {
+  TXG_TRY(exchange_parked(h, f, s));
   if (!h->spec_n) return 0;
   const long long n = h->spec_n * h->S, stride = (long long)h->Q * h->g.fs;
   {
@@ -1341,6 +1377,22 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
   if (counters[0]) TXG_FAIL(h, TXG_ERR_ARG_OUTOFRANGE, "walls array holds %d negative or NaN codes", counters[0]);
   TXG_TRY(build_storage(h));
+  // free-slip walls anywhere in the run?  (every rank must join the halo of the parked populations or none)
+  h->spec_any = counters[1] > 0;
+  if (h->cfg.nranks > 1) {
+    if (!h->comm) {
+      if (counters[1]) TXG_FAIL(h, TXG_ERR_ORDER, "free-slip walls (900-902) on %d ranks: call txg_comm_init before txg_set_walls", h->cfg.nranks);
+    } else {
+      int *flag = h->counters + 6;
+      const int mine = counters[1] > 0 ? 1 : 0;
+      TXG_CUDA(h, cudaMemcpyAsync(flag, &mine, sizeof mine, cudaMemcpyHostToDevice, h->s_main));
+      TXG_NCCL(h, g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMax, h->comm, h->s_main));
+      int any = 0;
+      TXG_CUDA(h, cudaMemcpyAsync(&any, flag, sizeof any, cudaMemcpyDeviceToHost, h->s_main));
+      TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+      h->spec_any = any != 0;
+    }
+  }
   TXG_TRY(build_specular(h, counters[1]));
   TXG_TRY(build_lag(h));
   TXG_TRY(build_rtab(h));
@@ -1356,7 +1408,7 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
         TXG_CUDA(h, cudaGetLastError());
         h->launches++;
       }
-  // staged form of K2 (opt-in)
+  // staged form of K2: whenever the fused kernel applies and no opt-in experiment replaces it
   // (S = 3: 10 positions per item; its word rows start off 16-byte boundaries and the copies never completed on the device)
   h->stage = h->stage_wanted && h->fused && h->ks.step_stage && !h->tile && !h->band && !h->lag && h->ks.npw % 4 == 0;
   if (h->adjm) cudaFree(h->adjm);
@@ -1364,7 +1416,11 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   if (h->stage) TXG_TRY(build_stage_tensors(h));
   if (h->stage) {
     TXG_CUDA(h, (cudaError_t)h->ks.set_stage_attrs());
-    if (!h->ticket) TXG_CUDA(h, cudaMalloc((void **)&h->ticket, 64));
+    int rounds = 2;
+    if (const char *v = getenv("TXG_STAGE_ROUNDS")) rounds = std::max(1, atoi(v));
+    h->stage_lb = rounds * h->ks.stage_chunk;
+    h->stage_pf = 0;
+    if (const char *v = getenv("TXG_STAGE_PF")) h->stage_pf = std::max(0, atoi(v));
   }
   h->walls_set = true;
   return 0;
@@ -1437,7 +1493,7 @@ static int run_forces(txg_flow *h, int z0, int nz, cudaStream_t s) {
   long long first, count;
   plane_range(h, z0, nz, &first, &count);
   if (count == 0) return 0;
-  if (h->fused) return 0;  // the collide launch forms the forces itself
+  if (h->fused || h->wide_fused) return 0;  // the collide launch forms the forces itself
   if (h->ks.forces_tile && h->forces_tile_on) {  // wide stencils: psi staged as dense tiles in shared memory
     ScopedKernel sk(h, "k_forces_tile", s);
     const dim3 grid((unsigned)((h->g.NX + h->ks.forces_tile_tx - 1) / h->ks.forces_tile_tx),
@@ -1472,13 +1528,10 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   }
   if (h->fused && h->stage && !h->tile) {
     ScopedKernel sk(h, "k_step_stage", s);
-    // persistent grid; the warps draw items of npw positions from the ticket counter (cleared on the stream)
-    const long long npw = h->ks.npw, nitems = (first + count - 1) / npw - first / npw + 1;
-    const long long wpb = h->ks.stage_threads / 32;
-    const unsigned nblk = (unsigned)std::min<long long>((nitems + wpb - 1) / wpb, (long long)h->num_sms * h->ks.stage_blocks_per_sm);
-    TXG_CUDA(h, cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), s));
-    h->ks.step_stage<<<nblk, h->ks.stage_threads, (size_t)h->ks.stage_smem, s>>>(h->g, h->p, h->tm_f[h->cur], h->tm_adj, h->f[h->cur ^ 1], h->rho, h->wallrec,
-                                                                                 first, count, h->ticket);
+    // short blocks: TXG_STAGE_ROUNDS (default 2) rounds of the block's warps, aligned on absolute multiples of their length
+    const long long LB = h->stage_lb, blk0 = first / LB, nblk = (first + count - 1) / LB - blk0 + 1;
+    h->ks.step_stage<<<(unsigned)nblk, h->ks.stage_threads, (size_t)h->ks.stage_smem, s>>>(h->g, h->p, h->tm_f[h->cur], h->tm_adj, h->f[h->cur ^ 1], h->rho,
+                                                                                           h->wallrec, first, count, blk0, (int)LB, h->stage_pf);
     TXG_CUDA(h, cudaGetLastError());
     return 0;
   }
@@ -1501,6 +1554,15 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
     TXG_CUDA(h, cudaGetLastError());
     return 0;
   }
+  if (h->wide_fused) {
+    ScopedKernel sk(h, "k_step_tile", s);
+    const dim3 grid((unsigned)((h->g.NX + h->ks.forces_tile_tx - 1) / h->ks.forces_tile_tx),
+                    (unsigned)((h->g.NY + h->ks.forces_tile_ty - 1) / h->ks.forces_tile_ty), (unsigned)nz);
+    h->ks.step_tile<<<grid, 256, (size_t)h->ks.forces_tile_smem, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->rho_true, h->lmask, h->nbr,
+                                                                      h->ffmask, h->wallrec, z0);
+    TXG_CUDA(h, cudaGetLastError());
+    return 0;
+  }
   ScopedKernel sk(h, "k_collide", s);
   h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->Fbuf, h->lmask, h->nbr,
                                                       first, count, h->has_reflecting ? h->rho_true : nullptr);
@@ -1512,7 +1574,8 @@ static int run_collide_pair(txg_flow *h, int za, int zb, cudaStream_t s) {
   long long fa, ca, fb, cb;
   plane_range(h, za, 1, &fa, &ca);
   plane_range(h, zb, 1, &fb, &cb);
-  if (!h->fused || h->band || h->stage || h->tile || !h->ks.step_fused_pair || ca == 0 || cb == 0 || za >= zb) {
+  // (the staged form too: both kernels compute the same bits, and one table-kernel launch over two single planes beats two launches)
+  if (!h->fused || h->band || h->tile || !h->ks.step_fused_pair || ca == 0 || cb == 0 || za >= zb) {
     TXG_TRY(run_collide(h, za, 1, s));
     return run_collide(h, zb, 1, s);
   }
@@ -1637,7 +1700,8 @@ static int one_step_lag(txg_flow *h) {
 
 static int one_step(txg_flow *h) {
   const Grid &g = h->g;
-  const bool split = h->cfg.nranks > 1 && g.NZl >= 4 * g.R + 2;
+  // (free-slip walls: their slots are rewritten after the whole push and its halos, on one stream)
+  const bool split = h->cfg.nranks > 1 && g.NZl >= 4 * g.R + 2 && !h->spec_any;
   cudaStream_t sm = h->s_main, sc = h->s_comm;
   if (!split) {
     TXG_TRY(run_moments(h, 0, g.NZl, sm));

@@ -49,11 +49,14 @@ struct KernelSet {
   int (*set_band_pull_smem)(int bytes);
   // tile-staged forces of the wide stencils (orders 8, 10): k_forces_tile (hot_kernels.cuh)
   void (*forces_tile)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *, const double *, double *, int);
+  // ... and the whole K2 of the wide stencils in one kernel (forces from the tile, then collide + push): k_step_tile
+  void (*step_tile)(Grid, Phys, const double *, double *, const double *, const double *, const uint32_t *, const uint32_t *,
+                    const uint32_t *, const double *, int);
   int (*set_forces_tile_smem)();
   int forces_tile_smem, forces_tile_tx, forces_tile_ty;
   // staged form (stage_kernel.cuh): k_step_fused with its streamed rows fetched by bulk copies into a double buffer
   void (*step_stage)(Grid, Phys, const CUtensorMap, const CUtensorMap, double *, const double *, const double *, long long, long long,
-                     unsigned *);
+                     long long, int, int);
   int stage_blocks_per_sm;
   int stage_item, stage_rows_f, stage_rows_a;  // box of the staged tensors: positions per item, population rows, adjacency + mask rows
   int (*set_stage_attrs)();          // dynamic shared memory size + carve-out of step_stage
@@ -87,15 +90,21 @@ KernelSet make_kernel_set(const char *name) {
   k.forces = k_forces<L, S, ISO>;
   if constexpr (ISO != 4) {
     k.forces_tile = k_forces_tile<L, S, ISO>;
+    k.step_tile = k_step_tile<L, S, MRT, ISO>;
     k.forces_tile_smem = S * ForceTile<L, ISO>::BOX * (int)sizeof(double);
     k.forces_tile_tx = ForceTile<L, ISO>::TX;
     k.forces_tile_ty = ForceTile<L, ISO>::TY;
     k.set_forces_tile_smem = []() -> int {
-      return (int)cudaFuncSetAttribute(k_forces_tile<L, S, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       S * ForceTile<L, ISO>::BOX * (int)sizeof(double));
+      cudaError_t e = cudaFuncSetAttribute(k_forces_tile<L, S, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           S * ForceTile<L, ISO>::BOX * (int)sizeof(double));
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_step_tile<L, S, MRT, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 S * ForceTile<L, ISO>::BOX * (int)sizeof(double));
+      return (int)e;
     };
   } else {
     k.forces_tile = nullptr;
+    k.step_tile = nullptr;
     k.set_forces_tile_smem = nullptr;
     k.forces_tile_smem = k.forces_tile_tx = k.forces_tile_ty = 0;
   }

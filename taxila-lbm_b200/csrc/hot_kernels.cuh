@@ -565,13 +565,14 @@ struct WideFromTile {
   }
 };
 
-template <class L, int S, int ISO>
-__global__ void __launch_bounds__(ForceTile<L, ISO>::NT) k_forces_tile(Grid g, Phys p, const double *__restrict__ rho,
-                                                                     const double *__restrict__ rho_true,
-                                                                     const uint32_t *__restrict__ lmask,
-                                                                     const uint32_t *__restrict__ ffmask,
-                                                                     const double *__restrict__ wallrec, double *__restrict__ Fbuf,
-                                                                     int z0) {
+// FUSE: the block does not write the forces; it goes on to collide and push its nodes (k_step_tile below) -- the collide
+// kernel of the split path then neither re-reads the forces nor is launched.
+template <class L, int S, int ISO, bool FUSE, bool MRT>
+__device__ __forceinline__ void forces_tile_body(const Grid &g, const Phys &p, const double *__restrict__ rho,
+                                                 const double *__restrict__ rho_true, const uint32_t *__restrict__ lmask,
+                                                 const uint32_t *__restrict__ ffmask, const double *__restrict__ wallrec,
+                                                 double *__restrict__ Fbuf, int z0, const double *__restrict__ fA,
+                                                 double *__restrict__ fB, const uint32_t *__restrict__ nbr) {
   using T = ForceTile<L, ISO>;
   constexpr int D = L::D, RAD = T::RAD, NPW = Lanes<S>::NPW;
   extern __shared__ __align__(16) double box[];  // [S][BZ][BY][BX]
@@ -591,16 +592,6 @@ __global__ void __launch_bounds__(ForceTile<L, ISO>::NT) k_forces_tile(Grid g, P
     row_pos[threadIdx.x] = first_pos;
     row_cnt[threadIdx.x] = cnt;
   }
-  // the dense box of psi: wrapped (periodic) or clamped (the entry masks exclude what lies beyond a closed face) coordinates
-  for (int t = threadIdx.x; t < T::BOX; t += T::NT) {
-    const int bx = t % T::BX, r = t / T::BX, by = r % T::BY, bz = r / T::BY;
-    const int x = wrapc(x0 - RAD + bx, g.NX, g.perx), y = wrapc(y0 - RAD + by, g.NY, g.pery);
-    const int ze = D == 3 ? zz - RAD + bz : 0;
-    const long long oe = ((long long)ze * g.NY + y) * g.NX + x;
-    const long long pos = pos_of(g, oe);
-#pragma unroll
-    for (int m = 0; m < S; ++m) box[m * T::BOX + t] = __ldg(rho + (long long)m * g.fs + pos);
-  }
   __syncthreads();
   if (threadIdx.x == 0) {  // exclusive prefix over <= 8 rows
     unsigned acc = 0u;
@@ -612,6 +603,35 @@ __global__ void __launch_bounds__(ForceTile<L, ISO>::NT) k_forces_tile(Grid g, P
   }
   __syncthreads();
   const unsigned nfluid = row_cnt[T::TY];
+  if (nfluid == 0u) return;  // a tile inside a grain: nothing to do, nothing to fetch
+  // the dense box of psi: wrapped (periodic) or clamped (the entry masks exclude what lies beyond a closed face)
+  // coordinates.  Two unrolled rounds -- all look-ups of the position map first, then all loads of psi -- so that a
+  // thread has its NIT independent chains in flight together instead of one after the other.
+  {
+    constexpr int NIT = (T::BOX + T::NT - 1) / T::NT;
+    unsigned bpos[NIT];
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int t = min((int)threadIdx.x + k * T::NT, T::BOX - 1);
+      const int bx = t % T::BX, r = t / T::BX, by = r % T::BY, bz = r / T::BY;
+      const int x = wrapc(x0 - RAD + bx, g.NX, g.perx), y = wrapc(y0 - RAD + by, g.NY, g.pery);
+      const int ze = D == 3 ? zz - RAD + bz : 0;
+      const long long oe = ((long long)ze * g.NY + y) * g.NX + x;
+      bpos[k] = (unsigned)pos_of(g, oe);
+    }
+#pragma unroll
+    for (int m = 0; m < S; ++m) {
+      double v[NIT];
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) v[k] = __ldg(rho + (long long)m * g.fs + bpos[k]);
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        const int t = (int)threadIdx.x + k * T::NT;
+        if (t < T::BOX) box[m * T::BOX + t] = v[k];
+      }
+    }
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int m = lane / NPW;
   const int j = lane - m * NPW;
@@ -652,11 +672,67 @@ __global__ void __launch_bounds__(ForceTile<L, ISO>::NT) k_forces_tile(Grid g, P
     const double r = p.eos ? __ldg(rho_true + (long long)m * g.fs + it.pos) : psi_m;
     double F[D];
     forces1<L, S, ISO>(g, p, rho + (long long)m * g.fs, ffmask, r2, it, oe, 0, 0, mask, r, psi_m, F, WideFromTile<L, ISO>{centre});
-    if (it.active) {
+    if constexpr (!FUSE) {
+      if (it.active) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) Fbuf[(long long)(m * D + d) * g.fs + it.pos] = F[d];
+        for (int d = 0; d < D; ++d) Fbuf[(long long)(m * D + d) * g.fs + it.pos] = F[d];
+      }
+    } else {
+      // K2b on the same lane: populations, common velocity, collision, push (k_collide, same arithmetic and order)
+      constexpr int Q = L::Q;
+      Adjacency<L> adj;
+      adj.mask = mask;
+      adj.load(g, nbr, it.pos);
+      double f[Q];
+      {
+        const double *src = fA + (long long)m * Q * g.fs + it.pos;
+#pragma unroll
+        for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
+      }
+      double rr = 0.;
+#pragma unroll
+      for (int n = 0; n < Q; ++n) rr += f[n];
+      double up[D];
+      common_velocity1<L, S>(p, it, f, rr, F, up);
+      collide1<L, MRT>(p, m, rr, F, up, f);
+      if (it.active) {
+        double *out = fB + (long long)m * Q * g.fs;
+        const unsigned fs = (unsigned)g.fs, here = (unsigned)it.pos;
+        out[here] = f[0];
+        static_for<1, Q>([&](auto n_) {
+          constexpr int n = decltype(n_)::value;
+          constexpr int on = opp<L>(n);
+          const bool bounce = (mask >> n) & 1u;
+          const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + adj.template at<n>(g);
+          out[e] = f[n];
+        });
+      }
     }
   }
+}
+
+template <class L, int S, int ISO>
+__global__ void __launch_bounds__(ForceTile<L, ISO>::NT) k_forces_tile(Grid g, Phys p, const double *__restrict__ rho,
+                                                                     const double *__restrict__ rho_true,
+                                                                     const uint32_t *__restrict__ lmask,
+                                                                     const uint32_t *__restrict__ ffmask,
+                                                                     const double *__restrict__ wallrec, double *__restrict__ Fbuf,
+                                                                     int z0) {
+  forces_tile_body<L, S, ISO, false, false>(g, p, rho, rho_true, lmask, ffmask, wallrec, Fbuf, z0, nullptr, nullptr, nullptr);
+}
+
+// K2 of the wide stencils in ONE kernel: forces out of the dense psi tile, then collision and push of the same nodes
+// (k_forces_tile + k_collide without the force buffer in between).  Not used with external face BCs, whose BCApply
+// sits between the forces and the collision.
+template <class L, int S, bool MRT, int ISO>
+__global__ void __launch_bounds__(ForceTile<L, ISO>::NT, 2) k_step_tile(Grid g, Phys p, const double *__restrict__ fA,
+                                                                      double *__restrict__ fB, const double *__restrict__ rho,
+                                                                      const double *__restrict__ rho_true,
+                                                                      const uint32_t *__restrict__ lmask,
+                                                                      const uint32_t *__restrict__ nbr,
+                                                                      const uint32_t *__restrict__ ffmask,
+                                                                      const double *__restrict__ wallrec, int z0) {
+  forces_tile_body<L, S, ISO, true, MRT>(g, p, rho, rho_true, lmask, ffmask, wallrec, nullptr, z0, fA, fB, nbr);
 }
 
 // K2b collide + push: node populations and forces in, momentum, common velocity, equilibrium,

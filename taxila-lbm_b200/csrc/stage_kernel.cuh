@@ -62,6 +62,12 @@ __device__ __forceinline__ void stage_issue(unsigned char *dst, uint64_t *bar, c
   }
 }
 
+// one lane: ask L2 for the two boxes of the item at p0 (descriptor-based prefetch, no shared memory, no completion)
+__device__ __forceinline__ void stage_prefetch_l2(const CUtensorMap *tmF, const CUtensorMap *tmA, long long p0) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmF), "r"((int)p0), "r"(0) : "memory");
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmA), "r"((int)p0), "r"(0) : "memory");
+}
+
 __device__ __forceinline__ void stage_wait(uint64_t *bar, unsigned parity) {
   unsigned ok = 0, spins = 0;
   while (!ok) {
@@ -73,26 +79,40 @@ __device__ __forceinline__ void stage_wait(uint64_t *bar, unsigned parity) {
   }
 }
 
-// One launch covers the positions [first, first + count), cut into items of NPW positions on absolute multiples of NPW.
-// The grid is persistent (at most BLOCKS_PER_SM blocks per SM); every WARP draws its items from a ticket counter, so that
-// at any moment the resident warps work one contiguous, advancing window of positions -- the access pattern of k_step_fused,
-// whose L2 / DRAM page locality a static assignment of long runs to blocks loses (profiles/r2d_stage_results.txt: the more
-// rounds per block, the slower) -- and every warp always has its NEXT item in flight.  A warp holds three tickets: the
-// item it collides, the item whose copies are in flight, and the ticket it has asked for (the atomic's round trip hides
-// behind a whole collision).  *ticket must be 0 at launch (the host clears it on the stream).
+// One launch covers the positions [first, first + count); block b owns the absolute positions [(blk0 + b) * LB, + LB) of it
+// (LB a multiple of NW * NPW; the host passes blk0 = first / LB); inside a block, item k = positions [k * NPW, + NPW) of the
+// block goes to warp k % NW, so that the block's warps walk one contiguous run of positions together.  SHORT blocks (two
+// rounds: LB = 2 * NW * NPW = 128 positions for S = 2) measured fastest: the resident blocks then cover one compact,
+// advancing window of positions like k_step_fused does.  Longer blocks, and persistent warps drawing their items from a
+// ticket counter (one at a time: 11 % of the warp time at the atomic; four at a time: the resident warps spread over
+// several planes and the density gathers start missing L2), were slower -- profiles/r2d_stage_results.txt.
 template <class L, int S, bool MRT>
 __global__ void __launch_bounds__(StageGeom<L, S>::NT, StageGeom<L, S>::BLOCKS_PER_SM)
     k_step_stage(Grid g, Phys p, const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmA,
                  double *__restrict__ fB, const double *__restrict__ rho, const double *__restrict__ wallrec, long long first,
-                 long long count, unsigned *__restrict__ ticket) {
+                 long long count, long long blk0, int LB, int pf_blocks) {
   using G = StageGeom<L, S>;
-  constexpr int Q = L::Q, D = L::D, ISO = 4, NPW = G::NPW, ITEM = G::ITEM;
+  constexpr int Q = L::Q, D = L::D, ISO = 4, NPW = G::NPW, NW = G::NW, ITEM = G::ITEM;
   extern __shared__ __align__(1024) unsigned char stage_mem[];  // [NW][2][STAGE_BYTES]
-  __shared__ __align__(8) uint64_t bars[G::NW][2];
-  const long long lo = first, hi = first + count;     // positions of the launch: [lo, hi)
-  const long long a0 = lo / NPW;                      // first item (absolute index: item a = positions [a * NPW, + NPW))
-  const unsigned nitems = (unsigned)((hi - 1) / NPW - a0 + 1);
+  __shared__ __align__(8) uint64_t bars[NW][2];
+  const long long last = first + count;               // one past the last position of the launch
+  const long long b0 = (blk0 + blockIdx.x) * LB;      // absolute positions of this block: [b0, b0 + LB)
+  const long long lo = max(b0, first), hi = min(b0 + LB, last);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // pf_blocks > 0: first ask L2 for this warp's items of the block pf_blocks further on -- about a quarter of a wave of
+  // resident blocks ahead -- so that the copies of that block's FIRST items (the ones no pipeline has prefetched) hit L2
+  if (pf_blocks > 0 && lane == 0) {
+    const long long pb = b0 + (long long)pf_blocks * LB;
+    for (int k = warp; k * NPW < LB; k += NW) {
+      const long long p0 = pb + (long long)k * NPW;
+      if (p0 < last) stage_prefetch_l2(&tmF, &tmA, p0);
+    }
+  }
+  if (lo >= hi) return;
+  // items of this warp that hold positions of the launch: k = warp (mod NW), k_lo <= k <= k_hi
+  int k_lo = (int)((lo - b0) / NPW), k_hi = (int)((hi - 1 - b0) / NPW);
+  k_lo += (warp - k_lo % NW + NW) % NW;
+  if (k_lo > k_hi) return;
   unsigned char *wmem = stage_mem + (size_t)warp * G::WARP_BYTES;
   uint64_t *wbar = bars[warp];
   if (lane == 0) {
@@ -101,16 +121,7 @@ __global__ void __launch_bounds__(StageGeom<L, S>::NT, StageGeom<L, S>::BLOCKS_P
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  // tickets: t_cur is collided, t_nxt is in flight, t_req is lane 0's pending atomic (broadcast when it becomes t_nxt)
-  unsigned t_cur = 0u, t_nxt = 0u, t_req = 0u;
-  if (lane == 0) {
-    t_cur = atomicAdd(ticket, 2u);  // two consecutive items to start with
-    t_req = atomicAdd(ticket, 1u);
-  }
-  t_cur = __shfl_sync(0xffffffffu, t_cur, 0);
-  t_nxt = t_cur + 1u;
-  if (t_cur >= nitems) return;
-  stage_issue<L, S>(wmem, &wbar[0], &tmF, &tmA, (a0 + t_cur) * NPW);
+  stage_issue<L, S>(wmem, &wbar[0], &tmF, &tmA, b0 + (long long)k_lo * NPW);
   // lane -> (component, node slot) like item_of_lane
   int m = lane / NPW;
   const int j = lane - m * NPW;
@@ -119,15 +130,13 @@ __global__ void __launch_bounds__(StageGeom<L, S>::NT, StageGeom<L, S>::BLOCKS_P
     m = S - 1;
     lane_ok = false;
   }
-  for (unsigned round = 0; t_cur < nitems; ++round) {
+  int round = 0;
+  for (int k = k_lo; k <= k_hi; k += NW, ++round) {
     const int st = round & 1;
     // the other stage was read to the end in the previous round: refill it with this warp's next item
-    if (t_nxt < nitems) stage_issue<L, S>(wmem + (size_t)(st ^ 1) * G::STAGE_BYTES, &wbar[st ^ 1], &tmF, &tmA, (a0 + t_nxt) * NPW);
-    const long long w0 = (a0 + t_cur) * NPW;            // first position of the item
-    // the tickets move up; lane 0 asks for one more (its value is not needed before the next round)
-    t_cur = t_nxt;
-    t_nxt = __shfl_sync(0xffffffffu, t_req, 0);
-    if (lane == 0) t_req = atomicAdd(ticket, 1u);
+    if (k + NW <= k_hi)
+      stage_issue<L, S>(wmem + (size_t)(st ^ 1) * G::STAGE_BYTES, &wbar[st ^ 1], &tmF, &tmA, b0 + (long long)(k + NW) * NPW);
+    const long long w0 = b0 + (long long)k * NPW;       // first position of the item
     Item it;
     it.m = m;
     it.j = j;

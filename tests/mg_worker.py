@@ -34,6 +34,25 @@ def build(name):
         return cases.bubble_3d(24, NZ=30, hw=5)
     if name == "thin_slabs":  # slabs thinner than the boundary/interior split needs
         return cases.porous_3d(24, NZ=10, rmin=2.0, rmax=3.0)
+    if name == "freeslip_duct":  # y-normal mirrors (901), flow along periodic z: reflections cross the slab faces
+        from taxila_lbm_b200 import config as tc
+
+        N, NZ = 20, 24
+        c, walls, rho = cases.bubble_3d(N, NZ=NZ, mrt=True, hw=4)
+        c.periodic[1] = 0
+        for m in range(2):
+            c.s_e[m], c.s_e2[m], c.s_q[m], c.s_pi[m], c.s_m[m] = 1.19, 1.4, 1.2, 1.4, 1.98
+        c.body_forces = 1
+        c.gvt[0], c.gvt[2] = 1e-5, 3e-5
+        c.gw[0][0], c.gw[0][1] = -0.02, 0.02
+        tc.finalize_flags(c)
+        walls = np.zeros((NZ, N, N))
+        walls[:, 0, :] = walls[:, -1, :] = tc.WALL_NORMAL_Y
+        zz, yy, xx = np.mgrid[0:NZ, 0:N, 0:N]
+        walls[(xx - 9.5) ** 2 + (yy - 10) ** 2 + (zz - 12.2) ** 2 <= 10.0] = 1.0  # an obstacle astride the slab face
+        rho = np.asarray(rho).copy()
+        rho[walls != 0] = 0.0
+        return c, walls, rho
     if name == "drainage_bc":  # zm flux inlet, zp pressure outlet, Neumann faces on xm/xp: face BCs on every slab
         from taxila_lbm_b200 import config as tc
 

@@ -53,7 +53,7 @@ def check(res):
 
 @pytest.mark.skipif(ngpus() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("case,steps", [("porous_periodic", 30), ("porous_iso8", 20), ("porous_closed_box", 30),
-                                        ("bubble_srt", 20), ("thin_slabs", 20)])
+                                        ("bubble_srt", 20), ("thin_slabs", 20), ("freeslip_duct", 30)])
 def test_two_ranks(case, steps, tmp_path):
     check(run_case(case, 2, steps, tmp_path, 29611))
 

@@ -137,7 +137,7 @@ def test_freeslip_duct_3d_fused_path():
     rho[..., 0] = np.where(xx < N // 2, 0.9, 0.1)
     rho[..., 1] = 1.0 - rho[..., 0]
     rho[walls != 0] = 0
-    errs = compare_bc(c, walls, rho, {}, steps=50, kernels=("k_step_fused", "k_specular_scatter"))
+    errs = compare_bc(c, walls, rho, {}, steps=50, kernels=("k_step_stage", "k_specular_scatter"))
     # specular reflection conserves the mass of each component
     flow = gpu_util.make_flow_bc(c, walls, rho, {})
     flow.step(50)

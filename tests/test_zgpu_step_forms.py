@@ -1,7 +1,8 @@
 """The forms of the order-4 step on the device give the same bits:
-  * table (default): k_step_fused (per-node adjacency table, every operand by demand loads)
-  * stage (opt-in TXG_STAGE=1): k_step_stage -- populations, adjacency rows and mask of a warp's next item fetched by bulk
-    copies (TMA) into the warp's double buffer in shared memory while the current item is collided
+  * stage (default for 1, 2 and 4 components): k_step_stage -- populations, adjacency rows and mask of a warp's next item
+    fetched by two tensor copies (TMA) into the warp's double buffer in shared memory while the current item is collided
+  * table (TXG_STAGE=0; the default for 3 and 5 components): k_step_fused (per-node adjacency table, every operand by
+    demand loads)
   * band / push (opt-in TXG_BAND=1): k_step_band (bit rows instead of the table, density windows in shared memory)
   * band / pull (opt-in TXG_BAND=1 TXG_PULL=1): k_step_band<PULL> + k_moments_pull -- the population buffer holds collided
     populations between steps and the reference's fi is gathered at the start of the next step, or by k_pull_stream when
@@ -18,7 +19,7 @@ from taxila_lbm_b200 import geometry as geo
 
 pytestmark = pytest.mark.gpu
 
-FORMS = {"table": {}, "stage": dict(TXG_STAGE="1"), "push": dict(TXG_BAND="1"), "pull": dict(TXG_BAND="1", TXG_PULL="1")}
+FORMS = {"table": dict(TXG_STAGE="0"), "stage": {}, "push": dict(TXG_BAND="1"), "pull": dict(TXG_BAND="1", TXG_PULL="1")}
 KERNEL = {"table": "k_step_fused", "stage": "k_step_stage", "push": "k_step_band", "pull": "k_step_band_pull"}
 
 
@@ -76,7 +77,10 @@ def test_forms_bit_identical(monkeypatch, case):
     assert k0[KERNEL["table"]][1] == steps, k0
     for form in ("stage", "push", "pull"):
         out, _, kt = run(cfg, walls, rho, form, monkeypatch, (3, 1, steps - 4))
-        assert kt[KERNEL[form]][1] == steps, (form, kt)
+        if form == "stage" and cfg.ncomponents == 3:
+            assert kt["k_step_fused"][1] == steps, kt  # (10 positions per item: the staged form is not offered, the table kernel runs)
+        else:
+            assert kt[KERNEL[form]][1] == steps, (form, kt)
         for a, b, name in zip(ref, out, ("fi", "rho", "u", "forces")):
             assert np.array_equal(a, b), (case, form, name, float(np.abs(a - b).max()))
 
@@ -137,15 +141,57 @@ def test_pull_form_delta_norm_and_restart(monkeypatch):
 
 def test_staged_form_on_a_box_whose_planes_straddle_items(monkeypatch):
     """k_step_stage on a box whose planes do not start on multiples of 16 positions (items clipped at both ends of a
-    launch are replayed lanes), and more items than resident warps (every warp draws several tickets)."""
+    launch are replayed lanes), with short and long blocks, and on a box of 10 k items."""
     cfg, walls, rho = cases.porous_3d(40, 24, 20, rmin=3.0, rmax=6.0)
     ref, _, _ = run(cfg, walls, rho, "table", monkeypatch, (15,))
     out, _, kt = run(cfg, walls, rho, "stage", monkeypatch, (15,))
     assert kt["k_step_stage"][1] == 15, kt
+    monkeypatch.setenv("TXG_STAGE_ROUNDS", "5")  # longer blocks: every warp refills its stages several times
+    out5, _, _ = run(cfg, walls, rho, "stage", monkeypatch, (15,))
+    monkeypatch.delenv("TXG_STAGE_ROUNDS")
+    for a, b in zip(ref, out5):
+        assert np.array_equal(a, b)
     for a, b in zip(ref, out):
         assert np.array_equal(a, b)
-    cfg, walls, rho = cases.porous_3d(96, 96, 40, rmin=4.0, rmax=9.0)  # 165 k fluid nodes = 10 k items > 2368 resident warps
+    cfg, walls, rho = cases.porous_3d(96, 96, 40, rmin=4.0, rmax=9.0)
     ref, _, _ = run(cfg, walls, rho, "table", monkeypatch, (6,))
     out, _, kt = run(cfg, walls, rho, "stage", monkeypatch, (2, 4))
     for a, b in zip(ref, out):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("case", ["porous_iso8", "closed_iso8", "hots_2d_iso10", "bubble_2d_iso8", "s3_iso8"])
+def test_wide_stencil_forms_bit_identical(monkeypatch, case):
+    """Orders 8 and 10: k_forces_tile (forces out of a dense shared-memory tile of psi) + k_collide (the default) ==
+    k_step_tile (the same, then collide + push in one kernel; opt-in TXG_WIDE_FUSED=1) == the map-walking k_forces +
+    k_collide (TXG_FORCES_TILE=0), bit for bit."""
+    if case == "porous_iso8":
+        cfg, walls, rho = cases.porous_3d(40, 24, 20, order=8, rmin=3.0, rmax=6.0)
+    elif case == "closed_iso8":
+        cfg, walls, rho = cases.porous_3d(24, order=8, rmin=3.0, rmax=6.0, periodic=(0, 1, 0))
+    elif case == "hots_2d_iso10":
+        cfg, walls, rho = cases.bubble_2d_hots(96)
+    elif case == "bubble_2d_iso8":
+        cfg, walls, rho = cases.bubble_2d(70, mrt=True, order=8)
+    else:
+        cfg, walls, rho = three_components(20)
+        cfg.isotropy_order = 8
+        cfg.stencil_size_rho = 2
+        tc.finalize_flags(cfg)
+    steps = 12
+    outs = {}
+    for name, env, kernel in (("tile_fused", dict(TXG_WIDE_FUSED="1"), "k_step_tile"), ("tile_split", {}, "k_forces_tile"),
+                              ("map_split", dict(TXG_FORCES_TILE="0"), "k_forces")):
+        for k in ("TXG_SPLIT", "TXG_FORCES_TILE", "TXG_WIDE_FUSED", "TXG_BAND", "TXG_PULL", "TXG_STAGE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        flow = gpu_util.make_flow(cfg, walls, rho)
+        flow.step(steps)
+        outs[name] = gpu_util.fields(flow)
+        kt = flow.kernel_times()
+        flow.close()
+        assert kt[kernel][1] >= steps, (name, kt)
+    for name in ("tile_split", "tile_fused"):
+        for a, b, what in zip(outs["map_split"], outs[name], ("fi", "rho", "u", "forces")):
+            assert np.array_equal(a, b), (case, name, what, float(np.abs(a - b).max()))
