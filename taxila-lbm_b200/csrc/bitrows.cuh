@@ -16,8 +16,8 @@
 //
 // xrow[pos] = x | rowid << 11 (rowid = zz * (NY + 2) + y + 1) tells a lane where it is: 4 bytes per node, coalesced.
 //
-// Everything here is __host__ __device__: tests/test_bitrows.py compiles it with g++ and checks every neighbour of
-// random porous boxes against the position map.
+// Checked on the device: k_step_band must give the bits of the table-driven kernel on every box of
+// tests/test_zgpu_step_forms.py (periodic and closed faces, rows of several words, 2-D, one to three components).
 #pragma once
 #include <cstdint>
 

@@ -96,6 +96,7 @@ struct KernelTimer {
   const char *name = "";  // a string literal of this file: the pointers txg_kernel_times hands out stay valid
   double ms = 0.;
   int64_t launches = 0;
+  int64_t per_graph[2] = {0, 0};  // launches one replay of the two-step graph of parity p adds
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
 
@@ -142,6 +143,13 @@ struct txg_flow {
   bool wide_fused = false;
   int stage_lb = 0;  // positions per block of the staged kernel
   int stage_pf = 0;  // its L2 prefetch distance in blocks (TXG_STAGE_PF)
+  // Two consecutive steps (buffer parity p -> p) of the default path as ONE CUDA graph: a thin z-slab (strong scaling)
+  // or a small box spends its time in launch gaps and NCCL call overhead, not in kernels.  Built lazily after two eager
+  // steps (the halo staging buffers exist by then), dropped at every walls upload; TXG_GRAPH=0 switches it off.
+  cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
+  int64_t graph_launches[2] = {0, 0};
+  bool graph_wanted = true, graph_failed = false;
+  int eager_steps = 0;
   uint32_t *adjm = nullptr;        // [Q][fs] the adjacency rows and, as row Q-1, the mask row: ONE tensor for the staged kernel
   CUtensorMap tm_f[2], tm_adj;     // the two population buffers and adjm as 2-D tensors
   int band_lb = 1024;                 // positions per block (TXG_BAND_LB)
@@ -244,6 +252,7 @@ static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + 
 // ------------------------------------------------------------------ kernel timing
 static void drain_timers(txg_flow *h);
 static void release_lag_table(txg_flow *h);
+static void drop_step_graphs(txg_flow *h);
 static int check_eos(txg_flow *h);
 static KernelTimer *timer_for(txg_flow *h, const char *name) {
   for (auto &t : h->timers)
@@ -272,8 +281,9 @@ struct ScopedKernel {
   KernelTimer *t = nullptr;
   cudaEvent_t a = nullptr, b = nullptr;
   cudaStream_t s;
-  ScopedKernel(txg_flow *h_, const char *name, cudaStream_t s_) : h(h_), s(s_) {
-    h->launches++;
+  // count = false: a timed span that is not one of this library's kernel launches (the NCCL exchanges)
+  ScopedKernel(txg_flow *h_, const char *name, cudaStream_t s_, bool count = true) : h(h_), s(s_) {
+    if (count) h->launches++;
     t = timer_for(h, name);
     if (h->timing) {
       a = timer_event(h);
@@ -561,6 +571,7 @@ extern "C" int txg_destroy(txg_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   drain_timers(h);
+  drop_step_graphs(h);
   release_lag_table(h);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   h->ev_pool.clear();
@@ -638,6 +649,7 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     if (const char *v = getenv("TXG_LAG_MPOS")) h->lag_mpos = atoi(v);
     if (const char *v = getenv("TXG_BAND")) h->band_wanted = v[0] != '0';
     if (const char *v = getenv("TXG_STAGE")) h->stage_wanted = v[0] != '0';
+    if (const char *v = getenv("TXG_GRAPH")) h->graph_wanted = v[0] != '0';
     if (const char *v = getenv("TXG_FORCES_TILE")) h->forces_tile_on = v[0] != '0';
     if (const char *v = getenv("TXG_BAND_LB")) h->band_lb = std::max(16, atoi(v));
     if (const char *v = getenv("TXG_BAND_PF")) h->band_prefetch = atoi(v);
@@ -668,7 +680,14 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
   g.cny = g.NY + 2 * g.R;
   auto body = [&]() -> int {
     TXG_CUDA(h, cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
-    TXG_CUDA(h, cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking));
+    // the communication stream at the highest priority: the block scheduler then places the few blocks of an NCCL or
+    // unpack kernel ahead of the waiting blocks of the interior kernel; at equal priority they only start when the interior
+    // grid has been dispatched to the end, and the halo is not overlapped at all (measured: halo_f span = interior K2 time)
+    {
+      int prio_low = 0, prio_high = 0;
+      TXG_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+      TXG_CUDA(h, cudaStreamCreateWithPriority(&h->s_comm, cudaStreamNonBlocking, prio_high));
+    }
 
     TXG_CUDA(h, cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     TXG_CUDA(h, cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
@@ -768,6 +787,7 @@ static int exchange(txg_flow *h, double *buf, const std::vector<Chunk> &to_up, c
 // its own node wrote.
 static int exchange_f(txg_flow *h, double *buf, cudaStream_t s) {
   if (h->D != 3) return 0;
+  ScopedKernel span(h, "halo_f", s, false);
   const Grid &g = h->g;
   const int nr = h->cfg.nranks, Rz = g.Rz;
   const std::vector<long long> &po = h->plane_off;
@@ -787,32 +807,28 @@ static int exchange_f(txg_flow *h, double *buf, cudaStream_t s) {
   }
   if (!h->comm) TXG_FAIL(h, TXG_ERR_ORDER, "nranks > 1 but txg_comm_init was not called");
   const int NC = D3Q19::NCROSS;
-  const size_t need = (size_t)h->S * NC * (size_t)(nbot + ntop);
+  const long long nsend_up = gt1 - gt0, nsend_down = ob0 - gb0;  // fluid nodes of my ghost planes
+  // staging: [received from down | received from up | packed for up | packed for down], S * NC rows each
+  const size_t need = (size_t)h->S * NC * (size_t)(nbot + ntop + nsend_up + nsend_down);
   if (h->halo_recv_doubles < need) {
     if (h->halo_recv) cudaFree(h->halo_recv);
     h->halo_recv = nullptr;
     TXG_CUDA(h, cudaMalloc((void **)&h->halo_recv, std::max<size_t>(need, 1) * sizeof(double)));
     h->halo_recv_doubles = need;
   }
-  double *from_down = h->halo_recv, *from_up = h->halo_recv + (size_t)h->S * NC * (size_t)nbot;
-  const long long nsend_up = gt1 - gt0, nsend_down = ob0 - gb0;  // fluid nodes of my ghost planes
+  const size_t rows = (size_t)h->S * NC;
+  double *from_down = h->halo_recv, *from_up = from_down + rows * (size_t)nbot;
+  double *to_up = from_up + rows * (size_t)ntop, *to_down = to_up + rows * (size_t)nsend_up;
+  // the crossing rows of each ghost plane packed into one message per neighbour (k_halo_pack), received packed
+  if (h->up >= 0 && nsend_up) h->ks.halo_pack<<<blocks_for(nsend_up, 256), 256, 0, s>>>(g, buf, to_up, gt0, nsend_up, 1);
+  if (h->down >= 0 && nsend_down) h->ks.halo_pack<<<blocks_for(nsend_down, 256), 256, 0, s>>>(g, buf, to_down, gb0, nsend_down, 0);
+  TXG_CUDA(h, cudaGetLastError());
+  h->launches += 2;
   TXG_NCCL(h, g_nccl.GroupStart());
-  for (int m = 0; m < h->S; ++m) {
-    int ku = 0, kd = 0;
-    for (int n = 1; n < h->Q; ++n) {
-      const int cz = D3Q19::c(n, 2);
-      const long long blk = (long long)(m * h->Q + n) * g.fs;
-      if (cz > 0) {  // my top ghost plane -> up; the same directions arrive from down
-        if (h->up >= 0 && nsend_up) TXG_NCCL(h, g_nccl.Send(buf + blk + gt0, (size_t)nsend_up, ncclFloat64, h->up, h->comm, s));
-        if (h->down >= 0 && nbot) TXG_NCCL(h, g_nccl.Recv(from_down + (size_t)(m * NC + ku) * nbot, (size_t)nbot, ncclFloat64, h->down, h->comm, s));
-        ++ku;
-      } else if (cz < 0) {  // my bottom ghost plane -> down; the same directions arrive from up
-        if (h->down >= 0 && nsend_down) TXG_NCCL(h, g_nccl.Send(buf + blk + gb0, (size_t)nsend_down, ncclFloat64, h->down, h->comm, s));
-        if (h->up >= 0 && ntop) TXG_NCCL(h, g_nccl.Recv(from_up + (size_t)(m * NC + kd) * ntop, (size_t)ntop, ncclFloat64, h->up, h->comm, s));
-        ++kd;
-      }
-    }
-  }
+  if (h->up >= 0 && nsend_up) TXG_NCCL(h, g_nccl.Send(to_up, rows * (size_t)nsend_up, ncclFloat64, h->up, h->comm, s));
+  if (h->down >= 0 && nbot) TXG_NCCL(h, g_nccl.Recv(from_down, rows * (size_t)nbot, ncclFloat64, h->down, h->comm, s));
+  if (h->down >= 0 && nsend_down) TXG_NCCL(h, g_nccl.Send(to_down, rows * (size_t)nsend_down, ncclFloat64, h->down, h->comm, s));
+  if (h->up >= 0 && ntop) TXG_NCCL(h, g_nccl.Recv(from_up, rows * (size_t)ntop, ncclFloat64, h->up, h->comm, s));
   TXG_NCCL(h, g_nccl.GroupEnd());
   if (h->down >= 0 && nbot) h->ks.halo_unpack<<<blocks_for(nbot, 256), 256, 0, s>>>(g, buf, from_down, 0, 1, h->lmask, ob0, nbot, 1);
   if (h->up >= 0 && ntop) h->ks.halo_unpack<<<blocks_for(ntop, 256), 256, 0, s>>>(g, buf, from_up, 0, 1, h->lmask, ot0, ntop, 0);
@@ -825,6 +841,7 @@ static int exchange_f(txg_flow *h, double *buf, cudaStream_t s) {
 // both are contiguous runs of positions with matching fluid-node counts.
 static int exchange_rho(txg_flow *h, double *buf, cudaStream_t s) {
   if (h->D != 3) return 0;
+  ScopedKernel span(h, "halo_rho", s, false);
   const Grid &g = h->g;
   const int Rz = g.Rz;
   const std::vector<long long> &po = h->plane_off;
@@ -1356,6 +1373,7 @@ static int build_stage_tensors(txg_flow *h) {
 extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
   if (!h) return TXG_ERR_ARG_NULL;
   if (!walls_rg) TXG_FAIL(h, TXG_ERR_ARG_NULL, "txg_set_walls: null array");
+  drop_step_graphs(h);
   TXG_CUDA(h, cudaSetDevice(h->device));
   const Grid &g = h->g;
   const long long n = (long long)(g.NZl + 2 * g.Rz) * g.cny * g.cnx;
@@ -1853,6 +1871,54 @@ extern "C" int txg_set_bc_values(txg_handle h, int boundary, const double *vals)
   return 0;
 }
 
+static void drop_step_graphs(txg_flow *h) {
+  for (int p = 0; p < 2; ++p) {
+    if (h->step_graph[p]) cudaGraphExecDestroy(h->step_graph[p]);
+    h->step_graph[p] = nullptr;
+  }
+  h->eager_steps = 0;
+  h->graph_failed = false;
+}
+
+// capture one_step twice (parity p -> p ^ 1 -> p) on the main stream; the communication stream joins the capture through
+// the events of the split schedule.  Nothing executes here.
+static int build_step_graph(txg_flow *h, int p) {
+  const int64_t l0 = h->launches;
+  const int cur0 = h->cur;
+  std::deque<KernelTimer> counts = h->timers;  // (the per-kernel launch counters move during the capture too)
+  if (cudaStreamBeginCapture(h->s_main, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    h->graph_failed = true;
+    return 0;
+  }
+  int rc = one_step(h);
+  if (!rc) rc = one_step(h);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(h->s_main, &g);
+  h->graph_launches[p] = h->launches - l0;
+  h->launches = l0;
+  h->cur = cur0;
+  // remember what one replay adds to every kernel's launch counter, then put the counters back
+  for (size_t i = 0; i < h->timers.size(); ++i) {
+    const int64_t before = i < counts.size() ? counts[i].launches : 0;
+    h->timers[i].per_graph[p] = h->timers[i].launches - before;
+    h->timers[i].launches = before;
+  }
+  if (rc || e != cudaSuccess || !g) {
+    cudaGetLastError();
+    if (g) cudaGraphDestroy(g);
+    h->graph_failed = true;  // keep the eager step
+    return rc;
+  }
+  if (cudaGraphInstantiate(&h->step_graph[p], g, 0) != cudaSuccess) {
+    cudaGetLastError();
+    h->step_graph[p] = nullptr;
+    h->graph_failed = true;
+  }
+  cudaGraphDestroy(g);
+  return 0;
+}
+
 extern "C" int txg_step(txg_handle h, int nsteps) {
   if (!h) return TXG_ERR_ARG_NULL;
   if (!h->state_set) TXG_FAIL(h, TXG_ERR_ORDER, "txg_step before txg_fi_init / txg_set_fi");
@@ -1868,7 +1934,23 @@ extern "C" int txg_step(txg_handle h, int nsteps) {
     // a density block that gave up waiting left wrong densities behind: fail here, not at the next export
     if (nsteps > 0) TXG_TRY(check_eos(h));
   } else {
-    for (int i = 0; i < nsteps; ++i) TXG_TRY(one_step(h));
+    int i = 0;
+    // two warm-up steps eagerly, then pairs of steps as graph replays (not while kernels are being timed one by one)
+    for (; i < nsteps && h->eager_steps < 2; ++i, ++h->eager_steps) TXG_TRY(one_step(h));
+    // (one rank only: replaying a graph that holds NCCL nodes costs 0.8 ms of host time per step, measured on 2 B200)
+    const bool graphs = h->graph_wanted && !h->graph_failed && !h->timing && !h->pull && !h->state_g && h->cfg.nranks == 1;
+    if (graphs && nsteps - i >= 2) {
+      const int p = h->cur;
+      if (!h->step_graph[p]) TXG_TRY(build_step_graph(h, p));
+      if (h->step_graph[p]) {
+        for (; nsteps - i >= 2; i += 2) {
+          TXG_CUDA(h, cudaGraphLaunch(h->step_graph[p], h->s_main));
+          h->launches += h->graph_launches[p];
+          for (auto &t : h->timers) t.launches += t.per_graph[p];
+        }
+      }
+    }
+    for (; i < nsteps; ++i) TXG_TRY(one_step(h));
   }
   TXG_CUDA(h, cudaEventRecord(h->ev_step1, h->s_main));
   h->last_launches = h->launches - l0;

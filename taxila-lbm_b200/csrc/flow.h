@@ -67,6 +67,7 @@ struct KernelSet {
   void (*build_nbr_all)(Grid, uint32_t *);
   void (*build_nbr)(Grid, uint32_t *);
   void (*halo_unpack)(Grid, double *, const double *, long long, int, const uint32_t *, long long, long long, int);
+  void (*halo_pack)(Grid, const double *, double *, long long, long long, int);
   // set-up and export
   void (*fi_init)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
                   const uint32_t *, const uint8_t *, int, int);
@@ -110,6 +111,7 @@ KernelSet make_kernel_set(const char *name) {
   }
   k.collide = k_collide<L, S, MRT>;
   k.halo_unpack = k_halo_unpack<L, S>;
+  k.halo_pack = k_halo_pack<L, S>;
   k.fi_init = k_fi_init<L, S, ISO>;
   k.export_state = k_export<L, S, ISO>;
   k.build_masks = k_build_masks<L, ISO>;

@@ -947,4 +947,24 @@ __global__ void k_halo_unpack(Grid g, double *__restrict__ f, const double *__re
   });
 }
 
+// The crossing populations of a ghost plane as ONE contiguous message: dst[(m*NCROSS + k) * count + i] =
+// f[(m*Q + n) * fs + first + i], k the rank of n among the directions with c_z > 0 (up != 0) or < 0 -- the layout
+// k_halo_unpack reads on the other side.  One send and one receive per neighbour instead of S * NCROSS of each.
+template <class L, int S>
+__global__ void k_halo_pack(Grid g, const double *__restrict__ f, double *__restrict__ dst, long long first, long long count, int up) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int k = 0;
+  static_for<1, L::Q>([&](auto n_) {
+    constexpr int n = decltype(n_)::value;
+    if constexpr (L::c(n, 2) != 0) {
+      if ((L::c(n, 2) > 0) == (up != 0)) {
+#pragma unroll
+        for (int m = 0; m < S; ++m) dst[(long long)(m * L::NCROSS + k) * count + i] = f[(long long)(m * L::Q + n) * g.fs + first + i];
+        ++k;
+      }
+    }
+  });
+}
+
 }  // namespace txg

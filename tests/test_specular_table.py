@@ -208,3 +208,133 @@ def test_obstacle_touching_a_mirror_is_refused():
     walls[0, 1, 4] = 1.0
     got, want, parked, n = _replay(_cfg(2, NX, NY, 1, (1, 0, 0)), walls)
     assert parked > 0
+
+
+# ------------------------------------------------------------------ two z-slabs (the device's sequence, replayed in numpy)
+def _replay_two_slabs(cfg, walls, zsplit, seed=5):
+    """The multi-rank device sequence on two z-slabs [0, zsplit) and [zsplit, NZ) of a 3-D box, slab by slab:
+    push inside the extended slab (pushes across a z face land in ghost-plane positions) -> exchange_f (the crossing
+    rows of a ghost plane go to the neighbour's boundary plane, masked: a slot whose streaming source is solid keeps what
+    its own node wrote) -> exchange_parked (the boundary planes' rows that point AWAY from the neighbour are copied into the
+    neighbour's ghost plane) -> the slab's free-slip table, built with z NOT periodic so that it looks into the ghost
+    planes.  Returns (assembled device-style result, oracle result, parked)."""
+    D, Q = 3, cfg.Q
+    NZ, NY, NX = walls.shape
+    R = Rz = 1
+    o = oracle.Oracle(cfg)
+    o.set_walls(walls)
+    ci = o.lattice()["ci"].astype(np.int32)
+    opp = o.lattice()["opposites"]
+    rng = np.random.default_rng(seed)
+    fstar = rng.uniform(0.01, 1.0, size=(NZ, NY, NX, Q, 1))
+    fstar[walls != 0] = 0.0
+    L = _lib()
+    ip, up = C.POINTER(C.c_int), C.POINTER(C.c_uint32)
+    slabs = []
+    for zs, zl in ((0, zsplit), (zsplit, NZ - zsplit)):
+        cls = _classes(geo.ghosted(walls, R, cfg.periodic, D, zs=zs, zl=zl, wall_ghost=True))
+        ext_fluid = cls[:, R:R + NY, R:R + NX] == 0
+        P = np.zeros(ext_fluid.size + 1, dtype=np.uint32)
+        P[1:] = np.cumsum(ext_fluid.ravel())
+        fs = ((int(P[-1]) + 128 + 127) // 128) * 128
+        cap = 19 * ext_fluid.size
+        dst = np.zeros(cap, dtype=np.uint32)
+        src = np.zeros(cap, dtype=np.uint32)
+        parked = C.c_longlong()
+        per = np.array([cfg.periodic[0], cfg.periodic[1], 0], dtype=np.int32)  # several ranks: z looks into the ghost planes
+        n = L.spec_build(Q, D, np.ascontiguousarray(ci).ctypes.data_as(ip), NX, NY, zl, R, Rz, per.ctypes.data_as(ip),
+                         np.ascontiguousarray(cls).ctypes.data_as(C.POINTER(C.c_uint8)), P.ctypes.data_as(up), fs,
+                         dst.ctypes.data_as(up), src.ctypes.data_as(up), cap, C.byref(parked))
+        slabs.append(dict(zs=zs, zl=zl, cls=cls, P=P, fs=fs, dst=dst[:n], src=src[:n], parked=parked.value,
+                          out=np.full(Q * fs, np.nan)))
+
+    def pos(s, x, y, zloc):  # zloc = -1 .. zl: local plane incl. the ghost planes
+        return int(s["P"][((zloc + Rz) * NY + y) * NX + x])
+
+    # push, slab by slab (x, y wrap inside the slab; z never wraps: plane -1 / zl are the ghost planes)
+    for s in slabs:
+        for zloc in range(s["zl"]):
+            z = s["zs"] + zloc
+            for y in range(NY):
+                for x in range(NX):
+                    if walls[z, y, x] != 0:
+                        continue
+                    here = pos(s, x, y, zloc)
+                    for q in range(Q):
+                        cx, cy, cz = (int(v) for v in ci[q])
+                        v = fstar[z, y, x, q, 0]
+                        if s["cls"][zloc + Rz + cz, y + R + cy, x + R + cx] != 0:
+                            s["out"][opp[q] * s["fs"] + here] = v
+                        else:
+                            tx, ty = x + cx, y + cy
+                            if cfg.periodic[0]:
+                                tx %= NX
+                            if cfg.periodic[1]:
+                                ty %= NY
+                            s["out"][q * s["fs"] + pos(s, tx, ty, zloc + cz)] = v
+    # z halos between slab a (below) and slab b (above) across BOTH faces of the periodic box
+    a, b = slabs
+    faces = [(a, a["zl"] - 1, b, 0)] + ([(b, b["zl"] - 1, a, 0)] if cfg.periodic[2] else [])
+    snapshot = [s["out"].copy() for s in slabs]  # every exchange reads what the push left (sends precede receives)
+    for lo, zt, hi, zb in faces:  # lo's top plane zt faces hi's bottom plane zb
+        lo_snap = snapshot[slabs.index(lo)]
+        hi_snap = snapshot[slabs.index(hi)]
+        for y in range(NY):
+            for x in range(NX):
+                zg_lo, zg_hi = lo["zs"] + zt, hi["zs"] + zb
+                # exchange_f: lo's top ghost plane (the image of hi's plane zb) -> hi's plane zb, directions c_z > 0
+                if walls[zg_hi, y, x] == 0:
+                    for q in range(Q):
+                        cx, cy, cz = (int(v) for v in ci[q])
+                        sx, sy = (x - cx) % NX if cfg.periodic[0] else x - cx, (y - cy) % NY if cfg.periodic[1] else y - cy
+                        inside = 0 <= sx < NX and 0 <= sy < NY
+                        if cz > 0 and inside and walls[zg_lo, sy, sx] == 0:
+                            hi["out"][q * hi["fs"] + pos(hi, x, y, zb)] = lo_snap[q * lo["fs"] + pos(lo, x, y, zt + 1)]
+                        # exchange_parked: hi's bottom plane rows c_z > 0 -> lo's top ghost plane
+                        if cz > 0:
+                            lo["out"][q * lo["fs"] + pos(lo, x, y, zt + 1)] = hi_snap[q * hi["fs"] + pos(hi, x, y, zb)]
+                if walls[zg_lo, y, x] == 0:
+                    for q in range(Q):
+                        cx, cy, cz = (int(v) for v in ci[q])
+                        sx, sy = (x - cx) % NX if cfg.periodic[0] else x - cx, (y - cy) % NY if cfg.periodic[1] else y - cy
+                        inside = 0 <= sx < NX and 0 <= sy < NY
+                        if cz < 0 and inside and walls[zg_hi, sy, sx] == 0:
+                            lo["out"][q * lo["fs"] + pos(lo, x, y, zt)] = hi_snap[q * hi["fs"] + pos(hi, x, y, zb - 1)]
+                        if cz < 0:
+                            hi["out"][q * hi["fs"] + pos(hi, x, y, zb - 1)] = lo_snap[q * lo["fs"] + pos(lo, x, y, zt)]
+    got = np.zeros((NZ, NY, NX, Q))
+    for s in slabs:
+        out = s["out"]
+        tmp = np.where(s["src"] == 0xFFFFFFFF, 0.0, out[np.minimum(s["src"], out.size - 1)])
+        out[s["dst"]] = tmp
+        for zloc in range(s["zl"]):
+            z = s["zs"] + zloc
+            for y in range(NY):
+                for x in range(NX):
+                    if walls[z, y, x] == 0:
+                        got[z, y, x] = out[np.arange(Q) * s["fs"] + pos(s, x, y, zloc)]
+    o.set_fi(fstar)
+    o.phase("communicate_fi")
+    o.phase("stream")
+    o.phase("bounceback")
+    return got, o.fi()[..., 0], sum(s["parked"] for s in slabs)
+
+
+@pytest.mark.parametrize("axis,zper", [(1, 1), (0, 1), (1, 0)])
+def test_duct_3d_on_two_slabs(axis, zper):
+    """Free-slip walls with normal x or y in a box cut into two z-slabs: reflections with c_z != 0 cross the slab face,
+    and an obstacle sits astride it.  The exchanged ghost rows + the per-slab tables reproduce the oracle's sweep bit for bit."""
+    N = [9, 8, 10]
+    walls = np.zeros((N[2], N[1], N[0]))
+    sl = [slice(None)] * 3
+    for idx in (0, -1):
+        sl[2 - axis] = idx
+        walls[tuple(sl)] = 900.0 + axis
+    walls[4, 4, 4] = walls[5, 4, 4] = walls[5, 3, 4] = 3.0  # astride the face between planes 4 and 5
+    per = [1, 1, zper]
+    per[axis] = 0
+    cfg = _cfg(3, N[0], N[1], N[2], per)
+    got, want, parked = _replay_two_slabs(cfg, walls, zsplit=5)
+    assert parked == 0
+    fluid = walls == 0
+    assert np.array_equal(got[fluid], want[fluid]), float(np.nanmax(np.abs(got[fluid] - want[fluid])))
