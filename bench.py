@@ -348,14 +348,24 @@ def main():
         walls_rg, rho_rg = walls_h, rho_h
         barrier()
         t0 = time.perf_counter()
+        marks = [("start", t0)]
+
+        def mark(name):  # (host clock; the calls before a mark are synchronous except the steps, which the last mark covers)
+            marks.append((name, time.perf_counter()))
+
         flow.walls_set_values(walls_rg)
+        mark("walls_set_values")
         flow.initialize_state(rho_rg)
+        mark("initialize_state")
         flow.fi_init()
         flow.update_moments()
+        mark("fi_init+update_moments (queued)")
         for _ in range(args.steps):
             flow.collision(); flow.communicate_fi(); flow.stream(); flow.bounceback(); flow.apply_bcs(); flow.update_flux()
+        mark("steps (queued)")
         out = flow.update_diagnostics(out=diag_h)
         flow.synchronize()
+        mark("update_diagnostics incl. the wait for the steps")
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -367,7 +377,9 @@ def main():
         e2e = {"value": global_nodes * args.steps / dt / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                "what": "walls+rho upload, FlowFiInit, FlowUpdateMoments, %d steps as the six LBMRun2 procedure calls, "
-                       "FlowUpdateDiagnostics fields copied back into page-locked host arrays; host wall clock, max over ranks" % args.steps}
+                       "FlowUpdateDiagnostics fields copied back into page-locked host arrays; host wall clock, max over ranks" % args.steps,
+               "host_placement": numa,
+               "breakdown_ms": {marks[i][0]: round((marks[i][1] - marks[i - 1][1]) * 1e3, 2) for i in range(1, len(marks))}}
 
     # ------------------------------------------------------------------ strong scaling beside the weak line (N > 1)
     # the ONE size^3 box split into N z-slabs, same timed protocol (warm-up, K steps between barriers, CUDA events, max

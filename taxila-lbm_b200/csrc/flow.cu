@@ -2058,10 +2058,11 @@ extern "C" int txg_get_diagnostics(txg_handle h, double *rhot, double *prs, doub
   if (prs) TXG_TRY(ensure(h, &h->x_prs, n));
   if (velt) TXG_TRY(ensure(h, &h->x_velt, n * h->D));
   TXG_TRY(run_export(h, nullptr, nullptr, nullptr, rhot ? h->x_rhot : nullptr, prs ? h->x_prs : nullptr, velt ? h->x_velt : nullptr));
+  // the export kernel writes all three fields in the host arrays' own (natural, owned-only) layout: three plain copies
   if (rhot) TXG_CUDA(h, cudaMemcpyAsync(rhot, h->x_rhot, n * 8, cudaMemcpyDeviceToHost, h->s_main));
   if (prs) TXG_CUDA(h, cudaMemcpyAsync(prs, h->x_prs, n * 8, cudaMemcpyDeviceToHost, h->s_main));
+  if (velt) TXG_CUDA(h, cudaMemcpyAsync(velt, h->x_velt, n * h->D * 8, cudaMemcpyDeviceToHost, h->s_main));
   TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
-  if (velt) TXG_TRY(export_field(h, velt, 0, 0, h->D, 1, h->x_velt, 1));
   return 0;
 }
 

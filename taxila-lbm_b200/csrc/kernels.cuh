@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(128) k_export(Grid g, Phys p, const double *__
                                                 double *__restrict__ u_out /*[S][D][nnodes]*/,
                                                 double *__restrict__ F_out /*[S][D][nnodes]*/,
                                                 double *__restrict__ rhot, double *__restrict__ prs,
-                                                double *__restrict__ velt /*[D][nnodes]*/, double null_pressure,
+                                                double *__restrict__ velt /*[nnodes][D]: the host array's own layout*/, double null_pressure,
                                                 int z0, int nz) {
   NodeIdx nd;
   if (!node_of_thread(g, z0, nz, nd)) return;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(128) k_export(Grid g, Phys p, const double *__
     if (prs) prs[nd.o] = null_pressure;
     if (velt)
 #pragma unroll
-      for (int d = 0; d < D; ++d) velt[(long long)d * g.nnodes + nd.o] = 0.;
+      for (int d = 0; d < D; ++d) velt[(long long)nd.o * D + d] = 0.;
     return;
   }
   double f[S][Q], r[S], F[S][D], up[D];
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(128) k_export(Grid g, Phys p, const double *__
           });
           a += (j + .5 * F[m][d]) * p.mm[m];
         }
-        velt[(long long)d * g.nnodes + nd.o] = a / rt;
+        velt[(long long)nd.o * D + d] = a / rt;
       });
     }
   }
