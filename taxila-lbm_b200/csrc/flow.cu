@@ -138,6 +138,7 @@ struct txg_flow {
   // 2.5-3.5 % faster than the table kernel at 512^3 (profiles/r2d_stage_results.txt)
   bool stage_wanted = true, stage = false;
   bool forces_tile_on = true;  // TXG_FORCES_TILE=0: the map-walking k_forces for the wide stencils
+  int tile_march = 16;         // planes a block of k_forces_tile marches over (TXG_TILE_MARCH)
   // orders 8, 10 without face BCs: k_step_tile = forces + collide + push in one kernel.  Opt-in (TXG_WIDE_FUSED=1): 23.7 ms
   // against 8.4 + 8.5 ms for k_forces_tile + k_collide at 512^3 (the box fill runs at the collision's 16 warps per SM)
   bool wide_fused = false;
@@ -651,6 +652,7 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     if (const char *v = getenv("TXG_STAGE")) h->stage_wanted = v[0] != '0';
     if (const char *v = getenv("TXG_GRAPH")) h->graph_wanted = v[0] != '0';
     if (const char *v = getenv("TXG_FORCES_TILE")) h->forces_tile_on = v[0] != '0';
+    if (const char *v = getenv("TXG_TILE_MARCH")) h->tile_march = std::max(1, atoi(v));
     if (const char *v = getenv("TXG_BAND_LB")) h->band_lb = std::max(16, atoi(v));
     if (const char *v = getenv("TXG_BAND_PF")) h->band_prefetch = atoi(v);
     if (const char *v = getenv("TXG_PULL")) h->pull_wanted = v[0] != '0';
@@ -1514,9 +1516,13 @@ static int run_forces(txg_flow *h, int z0, int nz, cudaStream_t s) {
   if (h->fused || h->wide_fused) return 0;  // the collide launch forms the forces itself
   if (h->ks.forces_tile && h->forces_tile_on) {  // wide stencils: psi staged as dense tiles in shared memory
     ScopedKernel sk(h, "k_forces_tile", s);
+    // a block marches over zc planes (ring of psi planes in shared memory): long marches amortise the ring's prologue,
+    // short ones keep enough blocks for a thin slab
+    const int zc = h->D == 3 ? std::max(1, std::min(h->tile_march, nz)) : 1;
     const dim3 grid((unsigned)((h->g.NX + h->ks.forces_tile_tx - 1) / h->ks.forces_tile_tx),
-                    (unsigned)((h->g.NY + h->ks.forces_tile_ty - 1) / h->ks.forces_tile_ty), (unsigned)nz);
-    h->ks.forces_tile<<<grid, 256, (size_t)h->ks.forces_tile_smem, s>>>(h->g, h->p, h->rho, h->rho_true, h->lmask, h->ffmask, h->wallrec, h->Fbuf, z0);
+                    (unsigned)((h->g.NY + h->ks.forces_tile_ty - 1) / h->ks.forces_tile_ty), (unsigned)((nz + zc - 1) / zc));
+    h->ks.forces_tile<<<grid, 256, (size_t)h->ks.forces_tile_smem, s>>>(h->g, h->p, h->rho, h->rho_true, h->lmask, h->ffmask, h->wallrec, h->Fbuf, z0,
+                                                                        nz, zc);
     TXG_CUDA(h, cudaGetLastError());
     return 0;
   }
@@ -1574,10 +1580,11 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   }
   if (h->wide_fused) {
     ScopedKernel sk(h, "k_step_tile", s);
+    const int zc = h->D == 3 ? std::max(1, std::min(h->tile_march, nz)) : 1;
     const dim3 grid((unsigned)((h->g.NX + h->ks.forces_tile_tx - 1) / h->ks.forces_tile_tx),
-                    (unsigned)((h->g.NY + h->ks.forces_tile_ty - 1) / h->ks.forces_tile_ty), (unsigned)nz);
+                    (unsigned)((h->g.NY + h->ks.forces_tile_ty - 1) / h->ks.forces_tile_ty), (unsigned)((nz + zc - 1) / zc));
     h->ks.step_tile<<<grid, 256, (size_t)h->ks.forces_tile_smem, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->rho_true, h->lmask, h->nbr,
-                                                                      h->ffmask, h->wallrec, z0);
+                                                                      h->ffmask, h->wallrec, z0, nz, zc);
     TXG_CUDA(h, cudaGetLastError());
     return 0;
   }

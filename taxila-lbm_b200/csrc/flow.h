@@ -48,10 +48,11 @@ struct KernelSet {
   void (*pull_stream)(Grid, Phys, BandParams, const double *, double *, double *, double *, long long, long long);
   int (*set_band_pull_smem)(int bytes);
   // tile-staged forces of the wide stencils (orders 8, 10): k_forces_tile (hot_kernels.cuh)
-  void (*forces_tile)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *, const double *, double *, int);
+  void (*forces_tile)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *, const double *, double *, int, int,
+                      int);
   // ... and the whole K2 of the wide stencils in one kernel (forces from the tile, then collide + push): k_step_tile
   void (*step_tile)(Grid, Phys, const double *, double *, const double *, const double *, const uint32_t *, const uint32_t *,
-                    const uint32_t *, const double *, int);
+                    const uint32_t *, const double *, int, int, int);
   int (*set_forces_tile_smem)();
   int forces_tile_smem, forces_tile_tx, forces_tile_ty;
   // staged form (stage_kernel.cuh): k_step_fused with its streamed rows fetched by bulk copies into a double buffer

@@ -538,30 +538,35 @@ __global__ void __launch_bounds__(128, 8) k_forces(Grid g, Phys p, const double 
 
 // K2a for the wide stencils (orders 8, 10), tile-staged: the 92 (D3Q19 order 8) gathers of a node through the node ->
 // position map are two dependent loads each (k_forces: 13.8 ms per launch at 512^3, profiles/r1_bench_iso8_split_path.json).
-// Here a block owns a dense tile of TX x TY nodes of one plane; it first copies psi of the tile plus a halo of RAD nodes in
-// x, y (and RAD planes in z) -- every component -- into shared memory as a DENSE box (one coalesced look-up of the position
-// map per box node: (TX + 2 RAD)(TY + 2 RAD)(2 RAD + 1) / (TX TY) = 8.4 look-ups per tile node instead of 92 per fluid node),
-// then its lanes take the tile's FLUID nodes only (found through the row starts of the position map: no lane is spent on a
-// solid node) and read every stencil entry from the box at a compile-time offset.  Same arithmetic and summation order as
-// k_forces: bit-identical forces.  Replaces the same reference procedures (LBMAddFluidFluidForcesD* with the 8th / 10th
-// order stencils, lbm_forcing.F90:51-1299; LBMAddFluidSolidForcesD*, LBMAddBodyForcesD*).
+// Here a block owns a dense column of TX x TY nodes and MARCHES along z over `zc` planes.  It keeps psi of the column plus a
+// halo of RAD nodes in x and y for the 2 RAD + 1 planes around the current one -- every component -- in shared memory as a
+// ring of dense planes, filling ONE new plane per step (one coalesced look-up of the position map per box node:
+// (TX + 2 RAD)(TY + 2 RAD) / (TX TY) = 1.7 look-ups per tile node and plane instead of 92 per fluid node; the first form
+// of this kernel re-filled the whole 5-plane box per plane: 8.4).  Its lanes then take the plane's FLUID nodes only (found
+// through the row starts of the position map: no lane is spent on a solid node) and read every stencil entry from the
+// ring at a compile-time offset.  Same arithmetic and summation order as k_forces: bit-identical forces.  Replaces the
+// same reference procedures (LBMAddFluidFluidForcesD* with the 8th / 10th order stencils, lbm_forcing.F90:51-1299;
+// LBMAddFluidSolidForcesD*, LBMAddBodyForcesD*).
 template <class L, int ISO>
 struct ForceTile {
   static constexpr int RAD = stencil_radius(ISO);
   static constexpr int TX = 32, TY = 8;
   static constexpr int BX = TX + 2 * RAD, BY = TY + 2 * RAD, BZ = L::D == 3 ? 2 * RAD + 1 : 1;
-  static constexpr int BOX = BX * BY * BZ;
+  static constexpr int PLANE = BX * BY;
+  static constexpr int RING = L::D == 3 ? BZ + 1 : 1;  // one plane more than the stencil reads: the next plane lands meanwhile
+  static constexpr int BOX = PLANE * RING;
   static constexpr int NT = 256;
+  static constexpr int NIT = (PLANE + NT - 1) / NT;    // box nodes of one plane per thread
 };
 
 template <class L, int ISO>
 struct WideFromTile {
   static constexpr bool tile = true;
-  const double *centre;  // psi of this lane's component at the node, inside the box
+  const double *pl[ForceTile<L, ISO>::BZ];  // psi of this lane's component at (x, y) in the ring planes z - RAD .. z + RAD
   template <int dx, int dy, int dz>
   __device__ __forceinline__ double get() const {
     using T = ForceTile<L, ISO>;
-    return centre[(dz * T::BY + dy) * T::BX + dx];
+    return pl[L::D == 3 ? dz + T::RAD : 0][dy * T::BX + dx];
   }
 };
 
@@ -571,68 +576,80 @@ template <class L, int S, int ISO, bool FUSE, bool MRT>
 __device__ __forceinline__ void forces_tile_body(const Grid &g, const Phys &p, const double *__restrict__ rho,
                                                  const double *__restrict__ rho_true, const uint32_t *__restrict__ lmask,
                                                  const uint32_t *__restrict__ ffmask, const double *__restrict__ wallrec,
-                                                 double *__restrict__ Fbuf, int z0, const double *__restrict__ fA,
+                                                 double *__restrict__ Fbuf, int z0, int nz, int zc, const double *__restrict__ fA,
                                                  double *__restrict__ fB, const uint32_t *__restrict__ nbr) {
   using T = ForceTile<L, ISO>;
   constexpr int D = L::D, RAD = T::RAD, NPW = Lanes<S>::NPW;
-  extern __shared__ __align__(16) double box[];  // [S][BZ][BY][BX]
-  __shared__ unsigned row_pos[T::TY + 1];         // position of the first fluid node of every tile row; [TY]: running total
-  __shared__ unsigned row_cnt[T::TY + 1];         // exclusive prefix of the fluid-node counts of the tile rows
-  const int x0 = blockIdx.x * T::TX, y0 = blockIdx.y * T::TY, z = z0 + (int)blockIdx.z;  // owned plane z
-  const int zz = z + g.Rz;                                                                // extended plane
+  extern __shared__ __align__(16) double box[];  // [S][RING][BY][BX]: ring slot of extended plane e = e % RING
+  __shared__ unsigned row_pos[2][T::TY + 1];      // position of the first fluid node of every tile row (plane parity)
+  __shared__ unsigned row_cnt[2][T::TY + 1];      // exclusive prefix of the fluid-node counts of the tile rows; [TY]: total
+  const int x0 = blockIdx.x * T::TX, y0 = blockIdx.y * T::TY;
+  const int zb = z0 + (int)blockIdx.z * zc, ze = min(z0 + nz, zb + zc);  // owned planes [zb, ze) of this block
+  if (zb >= ze) return;
   const int nx = min(T::TX, g.NX - x0), ny = min(T::TY, g.NY - y0);
-  // rows of the tile: fluid nodes of row y are the positions [P(x0, y), P(x0 + nx, y))
-  if (threadIdx.x <= T::TY) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // One dense plane of psi for the ring, in two halves so that the loads travel while the block computes: look-ups of the
+  // position map + loads of psi into registers (wrapped or clamped coordinates: the entry masks exclude what lies beyond
+  // a closed face), and later the stores into the ring slot.
+  auto plane_load = [&](int e, double (&v)[S][T::NIT]) {
+    unsigned bpos[T::NIT];
+#pragma unroll
+    for (int k = 0; k < T::NIT; ++k) {
+      const int t = min((int)threadIdx.x + k * T::NT, T::PLANE - 1);
+      const int bx = t % T::BX, by = t / T::BX;
+      const int x = wrapc(x0 - RAD + bx, g.NX, g.perx), y = wrapc(y0 - RAD + by, g.NY, g.pery);
+      bpos[k] = (unsigned)pos_of(g, ((long long)e * g.NY + y) * g.NX + x);
+    }
+#pragma unroll
+    for (int mm = 0; mm < S; ++mm)
+#pragma unroll
+      for (int k = 0; k < T::NIT; ++k) v[mm][k] = __ldg(rho + (long long)mm * g.fs + bpos[k]);
+  };
+  auto plane_store = [&](int e, const double (&v)[S][T::NIT]) {
+    const int slot = D == 3 ? e % T::RING : 0;
+#pragma unroll
+    for (int mm = 0; mm < S; ++mm)
+#pragma unroll
+      for (int k = 0; k < T::NIT; ++k) {
+        const int t = (int)threadIdx.x + k * T::NT;
+        if (t < T::PLANE) box[(mm * T::RING + slot) * T::PLANE + t] = v[mm][k];
+      }
+  };
+  // rows of the tile in owned plane z: fluid nodes of row y are the positions [P(x0, y), P(x0 + nx, y)); exclusive prefix
+  // of the counts by a shuffle scan inside warp 0 (no block-wide step)
+  auto rows_of = [&](int z) {
+    const int par = z & 1;
     unsigned first_pos = 0u, cnt = 0u;
-    if ((int)threadIdx.x < ny) {
-      const long long oe = ((long long)zz * g.NY + (y0 + (int)threadIdx.x)) * g.NX + x0;
+    if (lane < ny) {
+      const long long oe = ((long long)(z + g.Rz) * g.NY + (y0 + lane)) * g.NX + x0;
       first_pos = g.P ? __ldg(g.P + oe) : (unsigned)oe;
       cnt = (g.P ? __ldg(g.P + oe + nx) : (unsigned)(oe + nx)) - first_pos;
     }
-    row_pos[threadIdx.x] = first_pos;
-    row_cnt[threadIdx.x] = cnt;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {  // exclusive prefix over <= 8 rows
-    unsigned acc = 0u;
-    for (int r = 0; r <= T::TY; ++r) {
-      const unsigned c = row_cnt[r];
-      row_cnt[r] = acc;
-      acc += c;
+    unsigned incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+      const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
     }
-  }
-  __syncthreads();
-  const unsigned nfluid = row_cnt[T::TY];
-  if (nfluid == 0u) return;  // a tile inside a grain: nothing to do, nothing to fetch
-  // the dense box of psi: wrapped (periodic) or clamped (the entry masks exclude what lies beyond a closed face)
-  // coordinates.  Two unrolled rounds -- all look-ups of the position map first, then all loads of psi -- so that a
-  // thread has its NIT independent chains in flight together instead of one after the other.
+    if (lane <= T::TY) {
+      row_pos[par][lane] = first_pos;
+      row_cnt[par][lane] = incl - cnt;  // lanes >= ny hold cnt = 0: entry [TY] is the total
+    }
+  };
   {
-    constexpr int NIT = (T::BOX + T::NT - 1) / T::NT;
-    unsigned bpos[NIT];
-#pragma unroll
-    for (int k = 0; k < NIT; ++k) {
-      const int t = min((int)threadIdx.x + k * T::NT, T::BOX - 1);
-      const int bx = t % T::BX, r = t / T::BX, by = r % T::BY, bz = r / T::BY;
-      const int x = wrapc(x0 - RAD + bx, g.NX, g.perx), y = wrapc(y0 - RAD + by, g.NY, g.pery);
-      const int ze = D == 3 ? zz - RAD + bz : 0;
-      const long long oe = ((long long)ze * g.NY + y) * g.NX + x;
-      bpos[k] = (unsigned)pos_of(g, oe);
-    }
-#pragma unroll
-    for (int m = 0; m < S; ++m) {
-      double v[NIT];
-#pragma unroll
-      for (int k = 0; k < NIT; ++k) v[k] = __ldg(rho + (long long)m * g.fs + bpos[k]);
-#pragma unroll
-      for (int k = 0; k < NIT; ++k) {
-        const int t = (int)threadIdx.x + k * T::NT;
-        if (t < T::BOX) box[m * T::BOX + t] = v[k];
+    double v[S][T::NIT];
+    if constexpr (D == 3) {
+      for (int dz = -RAD; dz <= RAD; ++dz) {  // (Rz >= RAD: the ghost planes exist)
+        plane_load(zb + g.Rz + dz, v);
+        plane_store(zb + g.Rz + dz, v);
       }
+    } else {
+      plane_load(0, v);
+      plane_store(0, v);
     }
   }
+  if (warp == 0) rows_of(zb);
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int m = lane / NPW;
   const int j = lane - m * NPW;
   bool lane_ok = true;
@@ -640,85 +657,106 @@ __device__ __forceinline__ void forces_tile_body(const Grid &g, const Phys &p, c
     m = S - 1;
     lane_ok = false;
   }
-  for (unsigned c0 = (unsigned)warp * NPW; c0 < nfluid; c0 += (T::NT / 32) * NPW) {
-    Item it;
-    it.m = m;
-    it.j = j;
-    unsigned c = c0 + (unsigned)j;
-    it.active = lane_ok && c < nfluid;
-    c = min(c, nfluid - 1u);
-    int ry = 0;
-#pragma unroll
-    for (int r = 1; r < T::TY; ++r) ry += (c >= row_cnt[r]) ? 1 : 0;
-    it.pos = (long long)row_pos[ry] + (c - row_cnt[ry]);
-    const unsigned oe = g.list ? __ldg(g.list + it.pos) : (unsigned)it.pos;
-    const int x = (int)(oe % (unsigned)g.NX) - x0;  // column inside the tile
-    const uint32_t mask = __ldg(lmask + it.pos);
-    Round2<L> r2;
-    const bool rec = (mask & MASK_WALLREC) != 0;
-    if (p.fluidsolid) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) r2.A[d] = rec ? __ldg(wallrec + (long long)(m * D + d) * g.fs + it.pos) : 0.;
+  for (int z = zb; z < ze; ++z) {
+    const int zz = z + g.Rz;  // extended plane
+    const int par = z & 1;
+    // the next step's plane and row tables start travelling now; they land after this plane's arithmetic
+    double vnext[S][T::NIT];
+    const bool more = z + 1 < ze;
+    if (more) {
+      plane_load(zz + RAD + 1, vnext);
+      if (warp == 0) rows_of(z + 1);
     }
-    if (p.fluidfluid) {
-      static_for<0, D>([&](auto d_) {
-        constexpr int d = decltype(d_)::value;
-        constexpr double bulk = 1.0 / bulk_weight_sum<L, ISO>(d);
-        r2.rW[d] = rec ? __ldg(wallrec + (long long)(S * D + d) * g.fs + it.pos) : bulk;
-      });
-    }
-    const double *centre = box + m * T::BOX + ((D == 3 ? RAD : 0) * T::BY + (ry + RAD)) * T::BX + (x + RAD);
-    const double psi_m = *centre;
-    const double r = p.eos ? __ldg(rho_true + (long long)m * g.fs + it.pos) : psi_m;
-    double F[D];
-    forces1<L, S, ISO>(g, p, rho + (long long)m * g.fs, ffmask, r2, it, oe, 0, 0, mask, r, psi_m, F, WideFromTile<L, ISO>{centre});
-    if constexpr (!FUSE) {
-      if (it.active) {
+    const unsigned nfluid = row_cnt[par][T::TY];
+    for (unsigned c0 = (unsigned)warp * NPW; c0 < nfluid; c0 += (T::NT / 32) * NPW) {
+      Item it;
+      it.m = m;
+      it.j = j;
+      unsigned c = c0 + (unsigned)j;
+      it.active = lane_ok && c < nfluid;
+      c = min(c, nfluid - 1u);
+      int ry = 0;
 #pragma unroll
-        for (int d = 0; d < D; ++d) Fbuf[(long long)(m * D + d) * g.fs + it.pos] = F[d];
+      for (int r = 1; r < T::TY; ++r) ry += (c >= row_cnt[par][r]) ? 1 : 0;
+      it.pos = (long long)row_pos[par][ry] + (c - row_cnt[par][ry]);
+      const unsigned oe = g.list ? __ldg(g.list + it.pos) : (unsigned)it.pos;
+      const int x = (int)(oe % (unsigned)g.NX) - x0;  // column inside the tile
+      const uint32_t mask = __ldg(lmask + it.pos);
+      Round2<L> r2;
+      const bool rec = (mask & MASK_WALLREC) != 0;
+      if (p.fluidsolid) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) r2.A[d] = rec ? __ldg(wallrec + (long long)(m * D + d) * g.fs + it.pos) : 0.;
       }
-    } else {
-      // K2b on the same lane: populations, common velocity, collision, push (k_collide, same arithmetic and order)
-      constexpr int Q = L::Q;
-      Adjacency<L> adj;
-      adj.mask = mask;
-      adj.load(g, nbr, it.pos);
-      double f[Q];
-      {
-        const double *src = fA + (long long)m * Q * g.fs + it.pos;
-#pragma unroll
-        for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
-      }
-      double rr = 0.;
-#pragma unroll
-      for (int n = 0; n < Q; ++n) rr += f[n];
-      double up[D];
-      common_velocity1<L, S>(p, it, f, rr, F, up);
-      collide1<L, MRT>(p, m, rr, F, up, f);
-      if (it.active) {
-        double *out = fB + (long long)m * Q * g.fs;
-        const unsigned fs = (unsigned)g.fs, here = (unsigned)it.pos;
-        out[here] = f[0];
-        static_for<1, Q>([&](auto n_) {
-          constexpr int n = decltype(n_)::value;
-          constexpr int on = opp<L>(n);
-          const bool bounce = (mask >> n) & 1u;
-          const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + adj.template at<n>(g);
-          out[e] = f[n];
+      if (p.fluidfluid) {
+        static_for<0, D>([&](auto d_) {
+          constexpr int d = decltype(d_)::value;
+          constexpr double bulk = 1.0 / bulk_weight_sum<L, ISO>(d);
+          r2.rW[d] = rec ? __ldg(wallrec + (long long)(S * D + d) * g.fs + it.pos) : bulk;
         });
       }
+      WideFromTile<L, ISO> wide;
+      const int inplane = (ry + RAD) * T::BX + (x + RAD);
+#pragma unroll
+      for (int k = 0; k < T::BZ; ++k) {
+        const int slot = D == 3 ? (zz + k - RAD) % T::RING : 0;
+        wide.pl[k] = box + (m * T::RING + slot) * T::PLANE + inplane;
+      }
+      const double psi_m = *wide.pl[D == 3 ? RAD : 0];
+      const double r = p.eos ? __ldg(rho_true + (long long)m * g.fs + it.pos) : psi_m;
+      double F[D];
+      forces1<L, S, ISO>(g, p, rho + (long long)m * g.fs, ffmask, r2, it, oe, 0, 0, mask, r, psi_m, F, wide);
+      if constexpr (!FUSE) {
+        if (it.active) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) Fbuf[(long long)(m * D + d) * g.fs + it.pos] = F[d];
+        }
+      } else {
+        // K2b on the same lane: populations, common velocity, collision, push (k_collide, same arithmetic and order)
+        constexpr int Q = L::Q;
+        Adjacency<L> adj;
+        adj.mask = mask;
+        adj.load(g, nbr, it.pos);
+        double f[Q];
+        {
+          const double *src = fA + (long long)m * Q * g.fs + it.pos;
+#pragma unroll
+          for (int n = 0; n < Q; ++n) f[n] = __ldg(src + (long long)n * g.fs);
+        }
+        double rr = 0.;
+#pragma unroll
+        for (int n = 0; n < Q; ++n) rr += f[n];
+        double up[D];
+        common_velocity1<L, S>(p, it, f, rr, F, up);
+        collide1<L, MRT>(p, m, rr, F, up, f);
+        if (it.active) {
+          double *out = fB + (long long)m * Q * g.fs;
+          const unsigned fs = (unsigned)g.fs, here = (unsigned)it.pos;
+          out[here] = f[0];
+          static_for<1, Q>([&](auto n_) {
+            constexpr int n = decltype(n_)::value;
+            constexpr int on = opp<L>(n);
+            const bool bounce = (mask >> n) & 1u;
+            const unsigned e = bounce ? (unsigned)on * fs + here : (unsigned)n * fs + adj.template at<n>(g);
+            out[e] = f[n];
+          });
+        }
+      }
     }
+    // the next plane goes into the one ring slot this step did not read (RING = stencil planes + 1)
+    if (more) plane_store(zz + RAD + 1, vnext);
+    __syncthreads();  // ONE barrier per plane: ring and row tables of the next step are complete, this step's are free
   }
 }
 
 template <class L, int S, int ISO>
-__global__ void __launch_bounds__(ForceTile<L, ISO>::NT) k_forces_tile(Grid g, Phys p, const double *__restrict__ rho,
+__global__ void __launch_bounds__(ForceTile<L, ISO>::NT, 3) k_forces_tile(Grid g, Phys p, const double *__restrict__ rho,
                                                                      const double *__restrict__ rho_true,
                                                                      const uint32_t *__restrict__ lmask,
                                                                      const uint32_t *__restrict__ ffmask,
                                                                      const double *__restrict__ wallrec, double *__restrict__ Fbuf,
-                                                                     int z0) {
-  forces_tile_body<L, S, ISO, false, false>(g, p, rho, rho_true, lmask, ffmask, wallrec, Fbuf, z0, nullptr, nullptr, nullptr);
+                                                                     int z0, int nz, int zc) {
+  forces_tile_body<L, S, ISO, false, false>(g, p, rho, rho_true, lmask, ffmask, wallrec, Fbuf, z0, nz, zc, nullptr, nullptr, nullptr);
 }
 
 // K2 of the wide stencils in ONE kernel: forces out of the dense psi tile, then collision and push of the same nodes
@@ -731,8 +769,8 @@ __global__ void __launch_bounds__(ForceTile<L, ISO>::NT, 2) k_step_tile(Grid g, 
                                                                       const uint32_t *__restrict__ lmask,
                                                                       const uint32_t *__restrict__ nbr,
                                                                       const uint32_t *__restrict__ ffmask,
-                                                                      const double *__restrict__ wallrec, int z0) {
-  forces_tile_body<L, S, ISO, true, MRT>(g, p, rho, rho_true, lmask, ffmask, wallrec, nullptr, z0, fA, fB, nbr);
+                                                                      const double *__restrict__ wallrec, int z0, int nz, int zc) {
+  forces_tile_body<L, S, ISO, true, MRT>(g, p, rho, rho_true, lmask, ffmask, wallrec, nullptr, z0, nz, zc, fA, fB, nbr);
 }
 
 // K2b collide + push: node populations and forces in, momentum, common velocity, equilibrium,
