@@ -1440,7 +1440,7 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
     if (const char *v = getenv("TXG_STAGE_ROUNDS")) rounds = std::max(1, atoi(v));
     h->stage_lb = rounds * h->ks.stage_chunk;
     h->stage_pf = 0;
-    if (const char *v = getenv("TXG_STAGE_PF")) h->stage_pf = std::max(0, atoi(v));
+    if (const char *v = getenv("TXG_STAGE_PF")) h->stage_pf = atoi(v);  // > 0: tensor prefetch, < 0: plain prefetch lines
   }
   h->walls_set = true;
   return 0;
@@ -1555,7 +1555,8 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
     // short blocks: TXG_STAGE_ROUNDS (default 2) rounds of the block's warps, aligned on absolute multiples of their length
     const long long LB = h->stage_lb, blk0 = first / LB, nblk = (first + count - 1) / LB - blk0 + 1;
     h->ks.step_stage<<<(unsigned)nblk, h->ks.stage_threads, (size_t)h->ks.stage_smem, s>>>(h->g, h->p, h->tm_f[h->cur], h->tm_adj, h->f[h->cur ^ 1], h->rho,
-                                                                                           h->wallrec, first, count, blk0, (int)LB, h->stage_pf);
+                                                                                           h->wallrec, first, count, blk0, (int)LB, h->stage_pf, h->f[h->cur],
+                                                                                           h->adjm);
     TXG_CUDA(h, cudaGetLastError());
     return 0;
   }

@@ -57,7 +57,7 @@ struct KernelSet {
   int forces_tile_smem, forces_tile_tx, forces_tile_ty;
   // staged form (stage_kernel.cuh): k_step_fused with its streamed rows fetched by bulk copies into a double buffer
   void (*step_stage)(Grid, Phys, const CUtensorMap, const CUtensorMap, double *, const double *, const double *, long long, long long,
-                     long long, int, int);
+                     long long, int, int, const double *, const uint32_t *);
   int stage_blocks_per_sm;
   int stage_item, stage_rows_f, stage_rows_a;  // box of the staged tensors: positions per item, population rows, adjacency + mask rows
   int (*set_stage_attrs)();          // dynamic shared memory size + carve-out of step_stage

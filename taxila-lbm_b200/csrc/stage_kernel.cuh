@@ -90,7 +90,8 @@ template <class L, int S, bool MRT>
 __global__ void __launch_bounds__(StageGeom<L, S>::NT, StageGeom<L, S>::BLOCKS_PER_SM)
     k_step_stage(Grid g, Phys p, const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmA,
                  double *__restrict__ fB, const double *__restrict__ rho, const double *__restrict__ wallrec, long long first,
-                 long long count, long long blk0, int LB, int pf_blocks) {
+                 long long count, long long blk0, int LB, int pf_blocks, const double *__restrict__ fA_rows,
+                 const uint32_t *__restrict__ adj_rows) {
   using G = StageGeom<L, S>;
   constexpr int Q = L::Q, D = L::D, ISO = 4, NPW = G::NPW, NW = G::NW, ITEM = G::ITEM;
   extern __shared__ __align__(1024) unsigned char stage_mem[];  // [NW][2][STAGE_BYTES]
@@ -106,6 +107,24 @@ __global__ void __launch_bounds__(StageGeom<L, S>::NT, StageGeom<L, S>::BLOCKS_P
     for (int k = warp; k * NPW < LB; k += NW) {
       const long long p0 = pb + (long long)k * NPW;
       if (p0 < last) stage_prefetch_l2(&tmF, &tmA, p0);
+    }
+  }
+  // pf_blocks < 0: the same with plain prefetch.global.L2 instructions, one 128-byte line per thread and round (what
+  // k_step_fused does for its rows)
+  if (pf_blocks < 0) {
+    const long long pb = b0 + (long long)(-pf_blocks) * LB;
+    if (pb < last) {
+      const int fl = LB / 16, al = LB / 32;  // lines per population row / per adjacency row of one block
+      const int total = G::NF * fl + G::NA * al;
+      for (int t = threadIdx.x; t < total; t += G::NT) {
+        if (t < G::NF * fl) {
+          const int row = t / fl, seg = t - row * fl;
+          prefetch_l2(fA_rows + (long long)row * g.fs + pb + seg * 16);
+        } else {
+          const int u = t - G::NF * fl, row = u / al, seg = u - row * al;
+          prefetch_l2(adj_rows + (long long)row * g.fs + pb + seg * 32);
+        }
+      }
     }
   }
   if (lo >= hi) return;
