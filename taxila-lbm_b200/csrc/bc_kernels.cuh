@@ -10,30 +10,7 @@
 
 namespace txg {
 
-// One face of the box in the numbering of lbm_definitions.h:45-50 (0-based: XM, XP, YM, YP, ZM, ZP).
-// The node routines of lbm_bc.F90 are written for one boundary and rotated onto the others with
-// DiscSetLocalDirections (lbm_discretization_d3q19.F90:566-714, lbm_discretization_d2q9.F90:372-434);
-// all they take from the rotation is ci(directions(local_normal), normal axis) -- the inward normal
-// sign on every boundary -- and the set of tangential axes, each handled independently.
-struct FaceDesc {
-  int axis, sign, coord;  // normal axis, inward sign, coordinate of the face plane (owned, local in z)
-  int t1, t2, n1, n2;     // tangential axes (t1 fastest in the face array) and their local extents
-  int type;               // TXG_BC_DIRICHLET / NEUMANN / VELOCITY (lbm_definitions.h:32-34)
-};
-
-// (owned dense index, position) of face entry idx; false for a solid node or past the end
-__device__ __forceinline__ bool face_node(const Grid &g, const FaceDesc &fd, const uint32_t *__restrict__ nbmask,
-                                          long long idx, long long &pos) {
-  if (idx >= (long long)fd.n1 * fd.n2) return false;
-  int x[3] = {0, 0, 0};
-  x[fd.axis] = fd.coord;
-  x[fd.t1] = (int)(idx % fd.n1);
-  x[fd.t2] = (int)(idx / fd.n1);
-  const long long o = (long long)x[2] * g.plane + (long long)x[1] * g.NX + x[0];
-  if (nbmask[o] >> 31) return false;
-  pos = pos_of(g, o + (long long)g.Rz * g.plane);
-  return true;
-}
+// (FaceDesc and face_node: kernels.cuh -- the face variants of the hot kernels use them too)
 
 // BCApplyDirichletToRho -> _D2/_D3 (lbm_bc.F90:252-434): rho(m, face node) = vals(m) on the fluid
 // nodes of a Dirichlet face, before the density halo and the forces.

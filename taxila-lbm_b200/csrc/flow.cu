@@ -191,6 +191,11 @@ struct txg_flow {
   // The step then runs in the reference's own order (collide first, FlowApplyBCs last) on the split
   // kernels, and Fbuf holds the forces of FlowCalcRhoForces between steps.
   bool bc_mode = false, forces_current = false;
+  // face BCs on the fused K2 (order 4; TXG_SPLIT=1: off): every node is collided by k_step_fused with forces re-formed from
+  // the stored densities; the nodes of the BC faces -- whose populations BCApply changed after those densities were summed --
+  // are then collided AGAIN by k_collide<FACE> with the forces FlowCalcRhoForces stored for them (same push targets: the
+  // second result replaces the first)
+  bool bc_fused = false;
   LatticeTab lt;
   FaceDesc faces[6];
   bool face_here[6] = {false, false, false, false, false, false};  // this rank holds the face
@@ -660,6 +665,7 @@ extern "C" int txg_create(txg_handle *out, const txg_config *cfg, int device) {
     for (int b = 0; b < 2 * cfg->ndims; ++b) h->bc_mode = h->bc_mode || cfg->bc_flags[b] >= TXG_BC_REFLECTING;
     // face BCs act between the forces and the collision: they need the split kernels and the force buffer
     h->fused = h->ks.step_fused != nullptr && !(sp && sp[0] == '1') && !h->bc_mode;
+    h->bc_fused = h->ks.step_fused != nullptr && !(sp && sp[0] == '1') && h->bc_mode;
     const char *wf = getenv("TXG_WIDE_FUSED");
     h->wide_fused = wf && wf[0] == '1' && h->ks.step_tile != nullptr && h->ks.forces_tile != nullptr && h->forces_tile_on && !(sp && sp[0] == '1') &&
                     !h->bc_mode;
@@ -1034,15 +1040,11 @@ static int build_storage(txg_flow *h) {
   TXG_TRY(fresh_zero(h, (void **)&h->lmask, (size_t)g.fs * sizeof(uint32_t)));
   const long long nown = g.own1 - g.own0;
   int nrec = 0;
-  if (h->fused)
-    TXG_TRY(fresh_zero(h, (void **)&h->nbr_all, (size_t)(h->Q - 1) * g.fs * sizeof(uint32_t)));
-  else
-    TXG_TRY(fresh_zero(h, (void **)&h->nbr, (size_t)h->ks.ncen * g.fs * sizeof(uint32_t)));
+  if (h->fused || h->bc_fused) TXG_TRY(fresh_zero(h, (void **)&h->nbr_all, (size_t)(h->Q - 1) * g.fs * sizeof(uint32_t)));
+  if (!h->fused) TXG_TRY(fresh_zero(h, (void **)&h->nbr, (size_t)h->ks.ncen * g.fs * sizeof(uint32_t)));
   if (nown) {
-    if (h->fused)
-      h->ks.build_nbr_all<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->nbr_all);
-    else
-      h->ks.build_nbr<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->nbr);
+    if (h->fused || h->bc_fused) h->ks.build_nbr_all<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->nbr_all);
+    if (!h->fused) h->ks.build_nbr<<<blocks_for(nown, 128), 128, 0, h->s_main>>>(g, h->nbr);
     TXG_CUDA(h, cudaGetLastError());
     TXG_CUDA(h, cudaMemsetAsync(h->counters + 2, 0, sizeof(int), h->s_main));
     k_gather_mask<<<blocks_for(nown, 256), 256, 0, h->s_main>>>(g, h->nbmask, h->list, h->lmask, h->counters + 2);
@@ -1528,7 +1530,7 @@ static int run_forces(txg_flow *h, int z0, int nz, cudaStream_t s) {
   }
   ScopedKernel sk(h, "k_forces", s);
   h->ks.forces<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->rho, h->rho_true, h->lmask, h->nbr, h->ffmask, h->wallrec,
-                                                     h->Fbuf, first, count);
+                                                     h->Fbuf, first, count, FaceDesc(), nullptr);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -1591,7 +1593,7 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
   }
   ScopedKernel sk(h, "k_collide", s);
   h->ks.collide<<<hot_blocks(h, count), 128, 0, s>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->Fbuf, h->lmask, h->nbr,
-                                                      first, count, h->has_reflecting ? h->rho_true : nullptr);
+                                                      first, count, h->has_reflecting ? h->rho_true : nullptr, FaceDesc(), nullptr);
   TXG_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -1793,7 +1795,20 @@ static int bc_moments_forces(txg_flow *h, bool dirichlet) {
       TXG_CUDA(h, cudaGetLastError());
     }
   TXG_TRY(exchange_rho(h, h->rho, sm));
-  TXG_TRY(run_forces(h, 0, g.NZl, sm));
+  if (h->bc_fused) {
+    // only BCApply and the second collision of the face nodes read stored forces: form them on the BC faces alone
+    for (int b = 0; b < 2 * h->D; ++b) {
+      const FaceDesc &fd = h->faces[b];
+      if (!h->face_here[b] || fd.type < TXG_BC_REFLECTING) continue;
+      const long long n = (long long)fd.n1 * fd.n2;
+      ScopedKernel sk(h, "k_forces_face", sm);
+      h->ks.forces_face<<<hot_blocks(h, n), 128, 0, sm>>>(g, h->p, h->rho, h->rho_true, h->lmask, h->nbr, h->ffmask, h->wallrec, h->Fbuf, 0, n, fd,
+                                                          h->nbmask);
+      TXG_CUDA(h, cudaGetLastError());
+    }
+  } else {
+    TXG_TRY(run_forces(h, 0, g.NZl, sm));
+  }
   h->forces_current = true;
   return 0;
 }
@@ -1839,7 +1854,30 @@ static int one_step_bc(txg_flow *h) {
                                                                                     h->nbmask, h->outlet_pressure[b], h->cfg.gf[1][0]);
       TXG_CUDA(h, cudaGetLastError());
     }
-  TXG_TRY(run_collide(h, 0, g.NZl, sm));
+  if (h->bc_fused) {
+    long long first, count;
+    plane_range(h, 0, g.NZl, &first, &count);
+    if (count) {
+      ScopedKernel sk(h, "k_step_fused", sm);
+      const int wpb = h->ks.fused_threads / 32;
+      const long long warps = (count + h->ks.npw - 1) / h->ks.npw;
+      h->ks.step_fused<<<(unsigned)((warps + wpb - 1) / wpb), h->ks.fused_threads, 0, sm>>>(h->g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->rho, h->lmask,
+                                                                                          h->nbr_all, h->wallrec, first, count,
+                                                                                          h->ks.fused_threads == 128 ? h->pf_blocks : 0, count, 0);
+      TXG_CUDA(h, cudaGetLastError());
+    }
+    for (int b = 0; b < 2 * h->D; ++b) {
+      const FaceDesc &fd = h->faces[b];
+      if (!h->face_here[b] || fd.type < TXG_BC_REFLECTING) continue;
+      const long long n = (long long)fd.n1 * fd.n2;
+      ScopedKernel sk(h, "k_collide_face", sm);
+      h->ks.collide_face<<<hot_blocks(h, n), 128, 0, sm>>>(g, h->p, h->f[h->cur], h->f[h->cur ^ 1], h->Fbuf, h->lmask, h->nbr, 0, n,
+                                                           h->has_reflecting ? h->rho_true : nullptr, fd, h->nbmask);
+      TXG_CUDA(h, cudaGetLastError());
+    }
+  } else {
+    TXG_TRY(run_collide(h, 0, g.NZl, sm));
+  }
   TXG_TRY(exchange_f(h, h->f[h->cur ^ 1], sm));
   TXG_TRY(apply_specular(h, h->f[h->cur ^ 1], sm));
   h->cur ^= 1;
@@ -2008,11 +2046,20 @@ extern "C" int txg_update_moments(txg_handle h) {
   return refresh_rho(h);
 }
 
+// bit b: box face b carries an external BC and lies on this rank
+static int bc_faces_here(const txg_flow *h) {
+  int bits = 0;
+  for (int b = 0; b < 2 * h->D; ++b)
+    if (h->face_here[b] && h->faces[b].type >= TXG_BC_REFLECTING) bits |= 1 << b;
+  return bits;
+}
+
 static int run_export(txg_flow *h, double *rho_o, double *u_o, double *F_o, double *rhot, double *prs, double *velt) {
   const Grid &g = h->g;
   ScopedKernel sk(h, "k_export", h->s_main);
   h->ks.export_state<<<blocks_for(g.nnodes, 128), 128, 0, h->s_main>>>(g, h->p, h->f[h->cur], h->rho, h->nbmask, h->ffmask, h->cls,
-                                                                        h->bc_mode ? h->Fbuf : nullptr, h->has_reflecting ? h->rho_true : nullptr, rho_o, u_o,
+                                                                        h->bc_mode ? h->Fbuf : nullptr, h->has_reflecting ? h->rho_true : nullptr,
+                                                                        h->bc_fused ? bc_faces_here(h) : 0, rho_o, u_o,
                                                                         F_o, rhot, prs, velt,
                                                                         h->cfg.null_pressure, 0, g.NZl);
   TXG_CUDA(h, cudaGetLastError());

@@ -18,9 +18,14 @@ struct KernelSet {
   void (*moments)(Grid, Phys, const double *, double *, double *, long long, long long, long long, long long);
   void (*moments_pair)(Grid, Phys, const double *, double *, double *, long long, long long, long long, long long);
   void (*forces)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *, const uint32_t *,
-                 const double *, double *, long long, long long);
+                 const double *, double *, long long, long long, FaceDesc, const uint32_t *);
+  void (*forces_face)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *, const uint32_t *,
+                      const double *, double *, long long, long long, FaceDesc, const uint32_t *);
   void (*collide)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *, long long,
-                  long long, const double *);
+                  long long, const double *, FaceDesc, const uint32_t *);
+  // the same over the fluid nodes of one box face (fused step with external face BCs)
+  void (*collide_face)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *, long long,
+                       long long, const double *, FaceDesc, const uint32_t *);
   // forces + collide in one kernel (order-4 stencil only; nullptr otherwise), fed by the full adjacency table
   void (*step_fused)(Grid, Phys, const double *, double *, const double *, const uint32_t *, const uint32_t *,
                      const double *, long long, long long, int, long long, long long);
@@ -73,7 +78,7 @@ struct KernelSet {
   void (*fi_init)(Grid, Phys, double *, const double *, const double *, const double *, const uint32_t *,
                   const uint32_t *, const uint8_t *, int, int);
   void (*export_state)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *,
-                       const uint8_t *, const double *, const double *, double *, double *, double *, double *, double *, double *,
+                       const uint8_t *, const double *, const double *, int, double *, double *, double *, double *, double *, double *,
                        double, int, int);
   void (*build_masks)(Grid, const uint8_t *, uint32_t *, uint32_t *, int *);
   void (*build_wallrec)(Grid, Phys, const uint8_t *, const uint32_t *, const uint32_t *, double *);
@@ -89,7 +94,8 @@ KernelSet make_kernel_set(const char *name) {
   KernelSet k;
   k.moments = k_moments<L, S, false>;
   k.moments_pair = k_moments<L, S, true>;
-  k.forces = k_forces<L, S, ISO>;
+  k.forces = k_forces<L, S, ISO, false>;
+  k.forces_face = k_forces<L, S, ISO, true>;
   if constexpr (ISO != 4) {
     k.forces_tile = k_forces_tile<L, S, ISO>;
     k.step_tile = k_step_tile<L, S, MRT, ISO>;
@@ -110,7 +116,8 @@ KernelSet make_kernel_set(const char *name) {
     k.set_forces_tile_smem = nullptr;
     k.forces_tile_smem = k.forces_tile_tx = k.forces_tile_ty = 0;
   }
-  k.collide = k_collide<L, S, MRT>;
+  k.collide = k_collide<L, S, MRT, false>;
+  k.collide_face = k_collide<L, S, MRT, true>;
   k.halo_unpack = k_halo_unpack<L, S>;
   k.halo_pack = k_halo_pack<L, S>;
   k.fi_init = k_fi_init<L, S, ISO>;

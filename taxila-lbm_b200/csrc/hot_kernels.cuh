@@ -499,15 +499,24 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // needs few registers and runs at full occupancy; inside the register-heavy collide kernel the same
 // gathers cost 3.5 ms per step against 1.4 ms here (tools/membench/layoutbench.cu, 512^3 porous).
 // Replaces LBMAddFluidSolidForcesD*, LBMAddBodyForcesD*, LBMAddFluidFluidForcesD* (lbm_forcing.F90).
-template <class L, int S, int ISO>
+// FACE: the launch covers the fluid nodes of ONE box face (entry i of the face array -> node, face_node) instead of a run
+// of positions: with external face BCs on the fused step only the face nodes need their forces stored (BCApply reads them,
+// and the face nodes are collided again with them, flow.cu one_step_bc).
+template <class L, int S, int ISO, bool FACE = false>
 __global__ void __launch_bounds__(128, 8) k_forces(Grid g, Phys p, const double *__restrict__ rho,
                                                 const double *__restrict__ rho_true, const uint32_t *__restrict__ lmask,
                                                 const uint32_t *__restrict__ nbr, const uint32_t *__restrict__ ffmask,
                                                 const double *__restrict__ wallrec, double *__restrict__ Fbuf,
-                                                long long first, long long count) {
+                                                long long first, long long count, FaceDesc fd, const uint32_t *__restrict__ nbmask) {
   constexpr int Q = L::Q, D = L::D;
   Item it;
   if (!item_of_lane<S>(first, count, it)) return;
+  if constexpr (FACE) {  // (first = 0, count = entries of the face; a solid entry replays some fluid node and stores nothing)
+    long long pos = g.own0;
+    const bool fluid = face_node(g, fd, nbmask, it.pos, pos);
+    it.active = it.active && fluid;
+    it.pos = pos;
+  }
   Adjacency<L> adj;
   adj.mask = __ldg(lmask + it.pos);
   adj.load(g, nbr, it.pos);
@@ -783,11 +792,12 @@ __global__ void __launch_bounds__(ForceTile<L, ISO>::NT, 2) k_step_tile(Grid g, 
 #ifndef TXG_COLLIDE_MIN_BLOCKS
 #define TXG_COLLIDE_MIN_BLOCKS 4
 #endif
-template <class L, int S, bool MRT>
+template <class L, int S, bool MRT, bool FACE = false>
 __global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
     k_collide(Grid g, Phys p, const double *__restrict__ fA, double *__restrict__ fB, const double *__restrict__ Fbuf,
               const uint32_t *__restrict__ lmask, const uint32_t *__restrict__ nbr, long long first, long long count,
-              const double *__restrict__ rho_stale /*[S][fs] density of FlowCalcRhoForces for MASK_STALE nodes, or null*/) {
+              const double *__restrict__ rho_stale /*[S][fs] density of FlowCalcRhoForces for MASK_STALE nodes, or null*/,
+              FaceDesc fd, const uint32_t *__restrict__ nbmask /*FACE (k_forces has the convention)*/) {
   constexpr int Q = L::Q, D = L::D, NCEN = num_centres<L>();
   // The adjacency row and the mask are needed by the push only.  They travel into shared memory
   // asynchronously (no register is tied up while the collision runs, and their round trip hides
@@ -795,6 +805,12 @@ __global__ void __launch_bounds__(128, TXG_COLLIDE_MIN_BLOCKS)
   __shared__ uint32_t adj_col[NCEN + 1][128];
   Item it;
   if (!item_of_lane<S>(first, count, it)) return;
+  if constexpr (FACE) {
+    long long pos = g.own0;
+    const bool fluid = face_node(g, fd, nbmask, it.pos, pos);
+    it.active = it.active && fluid;
+    it.pos = pos;
+  }
 #pragma unroll
   for (int k = 0; k < NCEN; ++k) cp_async4(&adj_col[k][threadIdx.x], nbr + (long long)k * g.fs + it.pos);
   cp_async4(&adj_col[NCEN][threadIdx.x], lmask + it.pos);

@@ -53,6 +53,31 @@ __device__ __forceinline__ long long pos_of(const Grid &g, long long oe) {
   return g.P ? (long long)__ldg(g.P + oe) : oe;
 }
 
+// One face of the box in the numbering of lbm_definitions.h:45-50 (0-based: XM, XP, YM, YP, ZM, ZP).
+// The node routines of lbm_bc.F90 are written for one boundary and rotated onto the others with
+// DiscSetLocalDirections (lbm_discretization_d3q19.F90:566-714, lbm_discretization_d2q9.F90:372-434);
+// all they take from the rotation is ci(directions(local_normal), normal axis) -- the inward normal
+// sign on every boundary -- and the set of tangential axes, each handled independently.
+struct FaceDesc {
+  int axis, sign, coord;  // normal axis, inward sign, coordinate of the face plane (owned, local in z)
+  int t1, t2, n1, n2;     // tangential axes (t1 fastest in the face array) and their local extents
+  int type;               // TXG_BC_DIRICHLET / NEUMANN / VELOCITY (lbm_definitions.h:32-34)
+};
+
+// (owned dense index, position) of face entry idx; false for a solid node or past the end
+__device__ __forceinline__ bool face_node(const Grid &g, const FaceDesc &fd, const uint32_t *__restrict__ nbmask,
+                                          long long idx, long long &pos) {
+  if (idx >= (long long)fd.n1 * fd.n2) return false;
+  int x[3] = {0, 0, 0};
+  x[fd.axis] = fd.coord;
+  x[fd.t1] = (int)(idx % fd.n1);
+  x[fd.t2] = (int)(idx / fd.n1);
+  const long long o = (long long)x[2] * g.plane + (long long)x[1] * g.NX + x[0];
+  if (nbmask[o] >> 31) return false;
+  pos = pos_of(g, o + (long long)g.Rz * g.plane);
+  return true;
+}
+
 constexpr int MAXS = 5;  // instantiated component counts: 1..5 (NMAX_COMPONENTS of the reference, lbm_definitions.h:71)
 
 struct Phys {
@@ -381,6 +406,7 @@ __global__ void __launch_bounds__(128) k_export(Grid g, Phys p, const double *__
                                                 const uint32_t *__restrict__ ffmask, const uint8_t *__restrict__ cls,
                                                 const double *__restrict__ Fsrc /*[S*D][fs] or null*/,
                                                 const double *__restrict__ rho_stale /*[S][fs] or null: MASK_STALE nodes*/,
+                                                int fsrc_faces /*bit b: Fsrc holds the nodes of face b only (0: every node)*/,
                                                 double *__restrict__ rho_out /*[S][nnodes]*/,
                                                 double *__restrict__ u_out /*[S][D][nnodes]*/,
                                                 double *__restrict__ F_out /*[S][D][nnodes]*/,
@@ -415,7 +441,16 @@ __global__ void __launch_bounds__(128) k_export(Grid g, Phys p, const double *__
 #pragma unroll
     for (int m = 0; m < S; ++m) r[m] = __ldg(rho_stale + (long long)m * g.fs + nd.pos);
   }
-  if (Fsrc) {
+  bool stored = Fsrc != nullptr;
+  if (stored && fsrc_faces) {
+    // fused step with face BCs: only the nodes of the BC faces have stored forces; elsewhere the sum of the populations
+    // IS the density the forces were formed from, and they are re-formed like without BCs
+    const int c[3] = {nd.x, nd.y, nd.z}, n[3] = {g.NX, g.NY, g.NZl};
+    stored = false;
+    for (int b = 0; b < 2 * D; ++b)
+      if ((fsrc_faces >> b) & 1) stored = stored || c[b / 2] == ((b & 1) ? n[b / 2] - 1 : 0);
+  }
+  if (stored) {
     // with external face BCs the forces of the step are the ones FlowCalcRhoForces formed BEFORE
     // BCApply / BCUpdateRho changed the face nodes (lbm_flow.F90:1958-1991): take the stored ones
 #pragma unroll

@@ -50,7 +50,7 @@ def compare_bc(cfg, walls, rho, bcs, steps, tol=TOL, kernels=(), outlets=None):
 def test_pressure_driven_channel_2d():
     """bc_density / bc_pressure faces (BC_DIRICHLET) on xm and xp, y periodic, SRT."""
     compare_bc(*cases.channel_2d(inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET), steps=60,
-               kernels=("k_bc_dirichlet_rho", "k_bc_apply", "k_forces", "k_collide"))
+               kernels=("k_bc_dirichlet_rho", "k_bc_apply", "k_step_fused", "k_forces_face", "k_collide_face"))
 
 
 def test_velocity_inlet_noslip_channel_2d_mrt():
@@ -88,7 +88,18 @@ def test_reflecting_faces_3d():
     written, :849) between a Dirichlet inlet and outlet on z: the fluid nodes of the reflecting faces collide with the
     density from before BCApply (BCUpdateRho skips them, :443-445), the edge nodes they share with the z faces do not."""
     compare_bc(*cases.drainage_3d(inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET, x_bc=tc.BC_REFLECTING), steps=40,
-               kernels=("k_bc_reflect", "k_bc_apply", "k_collide"))
+               kernels=("k_bc_reflect", "k_bc_apply", "k_step_fused", "k_collide_face"))
+
+
+def test_face_bcs_on_the_split_kernels(monkeypatch):
+    """TXG_SPLIT=1: the same face-BC steps on k_forces + k_collide over every node (the form of round 1; the default
+    collides every node with the fused kernel and the face nodes a second time with their stored forces)."""
+    monkeypatch.setenv("TXG_SPLIT", "1")
+    compare_bc(*cases.drainage_3d(inlet=tc.BC_VELOCITY, outlet=tc.BC_DIRICHLET, x_bc=tc.BC_NEUMANN), steps=30,
+               kernels=("k_forces", "k_collide", "k_bc_apply"))
+    compare_bc(*cases.drainage_3d(inlet=tc.BC_DIRICHLET, outlet=tc.BC_DIRICHLET, x_bc=tc.BC_REFLECTING), steps=30,
+               kernels=("k_forces", "k_collide", "k_bc_reflect"))
+    compare_bc(*cases.channel_2d(inlet=tc.BC_NEUMANN, outlet=tc.BC_DIRICHLET, walls_kind="freeslip"), steps=40, kernels=("k_collide",))
 
 
 def test_reflecting_faces_y_and_flux_inlet_3d():
