@@ -473,7 +473,7 @@ def main():
             kernels[name]["frac_of_peak"] = kernels[name]["algorithmic_gbs"] / peak
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # (the CPU leg beside the N = 1 line only; the CPU arm proper is --impl reference)
         os.sched_setaffinity(0, all_cpus)  # the CPU leg gets every host core, as in --impl reference
         threads = os.cpu_count() or 1
         v, sps = run_cpu_sample(args.order, args.cpu_sample, args.cpu_steps, threads, warm=2)
