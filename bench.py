@@ -146,7 +146,8 @@ def build_case(size, nranks, rank, scaling, order, nz=None):
     if walls is None and cpath is not None and cpath.exists():
         walls = np.load(cpath)
     have = walls is not None
-    cfg, walls, rho = workloads.porous_3d(size, size, nz, order=order, walls=walls)
+    # TXG_BENCH_SRT=1: timing ablation only (how much of K2 is the MRT transform); the line then says relaxation SRT
+    cfg, walls, rho = workloads.porous_3d(size, size, nz, order=order, walls=walls, mrt=os.environ.get("TXG_BENCH_SRT") != "1")
     _WALLS[(size, nz)] = walls
     if cpath is not None and not have and rank == 0:
         np.save(cpath, walls)
@@ -226,7 +227,9 @@ def main():
     warmup = max(args.warmup, 3)
     workload = "D3Q19 two-component Shan-Chen MRT, %d^3 random-sphere porous medium per GPU, 3 minerals, body force, " \
                "bounce-back, iso-%d" % (args.size, args.order)
-    config = {"workload": workload, "lattice": "D3Q19", "components": 2, "relaxation": "MRT",
+    if os.environ.get("TXG_BENCH_SRT") == "1":
+        workload = "ABLATION (SRT instead of MRT): " + workload
+    config = {"workload": workload, "lattice": "D3Q19", "components": 2, "relaxation": "SRT" if os.environ.get("TXG_BENCH_SRT") == "1" else "MRT",
               "box_per_gpu": [args.size, args.size, args.nz or args.size], "isotropy_order": args.order, "geometry": "porous_spheres(seed=20260)",
               "l2_policy": "inputs larger than L2 (40.8 GB of populations per 512^3 block)",
               "cpu_sample_box": [args.cpu_sample] * 3}
@@ -429,7 +432,7 @@ def main():
                 dom, dom_bytes = alt, B_KF_FLUID
     if ktimes.get("k_step_fused_tile", (0.0, 0))[1]:  # TXG_RHOTILE=1 (opt-in): same bytes as k_step_fused
         dom, dom_bytes = "k_step_fused_tile", B_K2_FLUID
-    for alt in ("k_step_stage", "k_step_band", "k_step_band_pull"):  # other forms of K2: same algorithmic bytes as k_step_fused
+    for alt in ("k_step_stage", "k_step_stage_clc", "k_step_band", "k_step_band_pull"):  # other forms of K2: same algorithmic bytes as k_step_fused
         if ktimes.get(alt, (0.0, 0))[1]:
             dom, dom_bytes = alt, B_K2_FLUID
     if ktimes.get("k_step_fused_lag", (0.0, 0))[1]:  # TXG_LAG=1 (opt-in one-pass step): the whole step's bytes in one launch
@@ -464,7 +467,7 @@ def main():
     # per-kernel achieved algorithmic GB/s (the launches of one step add up to the slab)
     for name, b in (("k_moments", B_K1_FLUID), ("k_forces", B_KF_FLUID), ("k_forces_tile", B_KF_FLUID), ("k_collide", B_K2B_FLUID), ("k_step_fused", B_K2_FLUID),
                     ("k_step_fused_tile", B_K2_FLUID), ("k_step_band", B_K2_FLUID), ("k_step_band_pull", B_K2_FLUID),
-                    ("k_step_stage", B_K2_FLUID), ("k_moments_pull", B_K1_FLUID), ("k_step_fused_lag", B_ALG_FLUID)):
+                    ("k_step_stage", B_K2_FLUID), ("k_step_stage_clc", B_K2_FLUID), ("k_moments_pull", B_K1_FLUID), ("k_step_fused_lag", B_ALG_FLUID)):
         if name == "k_moments" and "k_step_fused_lag" in kernels and kernels["k_step_fused_lag"]["launches"]:
             continue  # one-pass step: k_moments only sums the two boundary planes
         if name in kernels and kernels[name]["ms"] > 0:

@@ -144,6 +144,11 @@ struct txg_flow {
   bool wide_fused = false;
   int stage_lb = 0;  // positions per block of the staged kernel
   int stage_pf = 0;  // its L2 prefetch distance in blocks (TXG_STAGE_PF)
+  bool stage_clc = false;  // k_step_stage_clc: blocks take over the next block of the grid (TXG_STAGE_CLC)
+  unsigned char *adjc = nullptr;  // compressed adjacency records of the staged kernel (TXG_STAGE_ADJC; stage_kernel.cuh AdjcGeom)
+  bool stage_adjc = false;
+  int stage_pg = 0;  // TXG_STAGE_PG: the staged kernel prefetches the gathers of a warp's next item into L1
+  int stage_v = 0;         // block shape of the staged kernel: index into KernelSet::stage_warps (TXG_STAGE_WARPS = 4, 6, 12)
   // Two consecutive steps (buffer parity p -> p) of the default path as ONE CUDA graph: a thin z-slab (strong scaling)
   // or a small box spends its time in launch gaps and NCCL call overhead, not in kernels.  Built lazily after two eager
   // steps (the halo staging buffers exist by then), dropped at every walls upload; TXG_GRAPH=0 switches it off.
@@ -586,7 +591,7 @@ extern "C" int txg_destroy(txg_handle h) {
                   h->nbmask, h->ffmask, h->P, h->list, h->lmask, h->nbr, h->nbr_all, h->wallrec, h->halo_recv, h->counters, h->Fbuf, h->staging, h->f_old, h->norm_bits, h->x_rho, h->x_u, h->x_F,
                   h->x_rhot, h->x_prs, h->x_velt, h->spec_dst, h->spec_src, h->spec_tmp, h->bc_vals[0], h->bc_vals[1],
                   h->bc_vals[2], h->bc_vals[3], h->bc_vals[4], h->bc_vals[5], h->rho_next, h->lag_rows_dev, h->lag_crows_dev, h->lag_done, h->rtab, h->rtab_lag,
-                  h->bitrows, h->rowend, h->xrow, h->band_blocks, h->adjm};
+                  h->bitrows, h->rowend, h->xrow, h->band_blocks, h->adjm, h->adjc};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -1432,17 +1437,47 @@ extern "C" int txg_set_walls(txg_handle h, const double *walls_rg) {
       }
   // staged form of K2: whenever the fused kernel applies and no opt-in experiment replaces it
   // (S = 3: 10 positions per item; its word rows start off 16-byte boundaries and the copies never completed on the device)
-  h->stage = h->stage_wanted && h->fused && h->ks.step_stage && !h->tile && !h->band && !h->lag && h->ks.npw % 4 == 0;
+  h->stage = h->stage_wanted && h->fused && h->ks.step_stage[0] && !h->tile && !h->band && !h->lag && h->ks.npw % 4 == 0;
   if (h->adjm) cudaFree(h->adjm);
   h->adjm = nullptr;
   if (h->stage) TXG_TRY(build_stage_tensors(h));
   if (h->stage) {
-    TXG_CUDA(h, (cudaError_t)h->ks.set_stage_attrs());
+    h->stage_v = 0;
+    if (const char *v = getenv("TXG_STAGE_WARPS")) {
+      const int w = atoi(v);
+      for (int i = 0; i < 3; ++i)
+        if (h->ks.stage_warps[i] == w) h->stage_v = i;
+    }
+    // shared-memory carve-out: what the resident blocks of this shape need (+ 1 KB per block the driver reserves, + the static
+    // barriers), the rest of the 256 KB stays L1 for the density gathers
+    int carve = (h->ks.stage_blocks_v[h->stage_v] * (h->ks.stage_smem_v[h->stage_v] + 2048) * 100 + 228 * 1024 - 1) / (228 * 1024);
+    carve = std::min(100, std::max(carve, 1));
+    if (const char *v = getenv("TXG_STAGE_CARVE")) carve = atoi(v);
+    TXG_CUDA(h, (cudaError_t)h->ks.set_stage_attrs(h->stage_v, carve));
     int rounds = 2;
     if (const char *v = getenv("TXG_STAGE_ROUNDS")) rounds = std::max(1, atoi(v));
-    h->stage_lb = rounds * h->ks.stage_chunk;
+    h->stage_lb = rounds * h->ks.stage_warps[h->stage_v] * h->ks.npw;
     h->stage_pf = 0;
     if (const char *v = getenv("TXG_STAGE_PF")) h->stage_pf = atoi(v);  // > 0: tensor prefetch, < 0: plain prefetch lines
+    h->stage_clc = false;
+    if (const char *v = getenv("TXG_STAGE_CLC")) h->stage_clc = v[0] != '0';
+    h->stage_pg = 0;
+    if (const char *v = getenv("TXG_STAGE_PG")) h->stage_pg = atoi(v);
+    h->stage_adjc = false;
+    if (const char *v = getenv("TXG_STAGE_ADJC")) h->stage_adjc = v[0] != '0';
+    h->stage_adjc = h->stage_adjc && h->stage_v == 0 && !h->stage_clc;
+    if (h->adjc) cudaFree(h->adjc);
+    h->adjc = nullptr;
+    if (h->stage_adjc) {
+      // one record per item of ITEM positions; items are aligned on absolute multiples of ITEM (= the warp items of the kernel)
+      const long long item0 = h->g.own0 / h->ks.stage_item, item1 = (h->g.own1 + h->ks.stage_item - 1) / h->ks.stage_item;
+      TXG_CUDA(h, cudaMalloc((void **)&h->adjc, (size_t)(h->g.fs / h->ks.stage_item + 1) * h->ks.adjc_rec_bytes));
+      if (item1 > item0) {
+        h->ks.build_adjc<<<blocks_for(item1 - item0, 128), 128, 0, h->s_main>>>(h->g, h->nbr_all, h->lmask, h->adjc, item0, item1 - item0);
+        TXG_CUDA(h, cudaGetLastError());
+      }
+      TXG_CUDA(h, cudaStreamSynchronize(h->s_main));
+    }
   }
   h->walls_set = true;
   return 0;
@@ -1553,12 +1588,24 @@ static int run_collide(txg_flow *h, int z0, int nz, cudaStream_t s) {
     return 0;
   }
   if (h->fused && h->stage && !h->tile) {
-    ScopedKernel sk(h, "k_step_stage", s);
     // short blocks: TXG_STAGE_ROUNDS (default 2) rounds of the block's warps, aligned on absolute multiples of their length
     const long long LB = h->stage_lb, blk0 = first / LB, nblk = (first + count - 1) / LB - blk0 + 1;
-    h->ks.step_stage<<<(unsigned)nblk, h->ks.stage_threads, (size_t)h->ks.stage_smem, s>>>(h->g, h->p, h->tm_f[h->cur], h->tm_adj, h->f[h->cur ^ 1], h->rho,
-                                                                                           h->wallrec, first, count, blk0, (int)LB, h->stage_pf, h->f[h->cur],
-                                                                                           h->adjm);
+    if (h->stage_clc) {
+      ScopedKernel sk(h, "k_step_stage_clc", s);
+      h->ks.step_stage_clc[h->stage_v]<<<(unsigned)nblk, 32 * h->ks.stage_warps[h->stage_v], (size_t)h->ks.stage_smem_v[h->stage_v], s>>>(h->g, h->p, h->tm_f[h->cur], h->tm_adj, h->f[h->cur ^ 1],
+                                                                                                 h->rho, h->wallrec, first, count, blk0, (int)LB, h->stage_pg);
+      TXG_CUDA(h, cudaGetLastError());
+      return 0;
+    }
+    ScopedKernel sk(h, "k_step_stage", s);
+    if (h->stage_adjc)
+      h->ks.step_stage_adjc<<<(unsigned)nblk, 32 * h->ks.stage_warps[0], (size_t)h->ks.stage_smem_adjc, s>>>(
+          h->g, h->p, h->tm_f[h->cur], h->tm_adj, h->f[h->cur ^ 1], h->rho, h->wallrec, first, count, blk0, (int)LB, 0, h->f[h->cur], h->adjm, h->adjc,
+          h->nbr_all, h->stage_pg);
+    else
+      h->ks.step_stage[h->stage_v]<<<(unsigned)nblk, 32 * h->ks.stage_warps[h->stage_v], (size_t)h->ks.stage_smem_v[h->stage_v], s>>>(
+          h->g, h->p, h->tm_f[h->cur], h->tm_adj, h->f[h->cur ^ 1], h->rho, h->wallrec, first, count, blk0, (int)LB, h->stage_pf, h->f[h->cur], h->adjm,
+          nullptr, nullptr, h->stage_pg);
     TXG_CUDA(h, cudaGetLastError());
     return 0;
   }

@@ -61,12 +61,20 @@ struct KernelSet {
   int (*set_forces_tile_smem)();
   int forces_tile_smem, forces_tile_tx, forces_tile_ty;
   // staged form (stage_kernel.cuh): k_step_fused with its streamed rows fetched by bulk copies into a double buffer
-  void (*step_stage)(Grid, Phys, const CUtensorMap, const CUtensorMap, double *, const double *, const double *, long long, long long,
-                     long long, int, int, const double *, const uint32_t *);
-  int stage_blocks_per_sm;
+  // staged K2 in three block shapes (STAGE_VARIANTS: 4 warps x 4 blocks per SM, 6 x 2, 12 x 1; stage_kernel.cuh)
+  void (*step_stage[3])(Grid, Phys, const CUtensorMap, const CUtensorMap, double *, const double *, const double *, long long, long long,
+                        long long, int, int, const double *, const uint32_t *, const unsigned char *, const uint32_t *, int);
+  // 4 warps x 4 blocks with the compressed adjacency records (AdjcGeom) instead of the adjacency + mask rows; their builder
+  void (*step_stage_adjc)(Grid, Phys, const CUtensorMap, const CUtensorMap, double *, const double *, const double *, long long, long long,
+                          long long, int, int, const double *, const uint32_t *, const unsigned char *, const uint32_t *, int);
+  void (*build_adjc)(Grid, const uint32_t *, const uint32_t *, unsigned char *, long long, long long);
+  int adjc_rec_bytes, stage_smem_adjc;
+  // the same with blocks that take over the next block of the grid (cluster launch control)
+  void (*step_stage_clc[3])(Grid, Phys, const CUtensorMap, const CUtensorMap, double *, const double *, const double *, long long, long long,
+                            long long, int, int);
+  int stage_warps[3], stage_smem_v[3], stage_blocks_v[3];
   int stage_item, stage_rows_f, stage_rows_a;  // box of the staged tensors: positions per item, population rows, adjacency + mask rows
-  int (*set_stage_attrs)();          // dynamic shared memory size + carve-out of step_stage
-  int stage_threads, stage_chunk, stage_smem;
+  int (*set_stage_attrs)(int variant, int carveout_pct);  // dynamic shared memory size + carve-out of step_stage[variant] and its clc form
   int (*set_band_smem)(int bytes);  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) of step_band
   int band_threads, band_windows;   // block size; density windows per component (3 in 3-D, 1 in 2-D)
   int rtab_groups;  // window starts per block (RhoTile<L>::NG)
@@ -152,11 +160,30 @@ KernelSet make_kernel_set(const char *name) {
     k.set_band_pull_smem = [](int bytes) -> int {
       return (int)cudaFuncSetAttribute(k_step_band<L, S, MRT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     };
-    k.step_stage = k_step_stage<L, S, MRT>;
-    k.set_stage_attrs = []() -> int {
-      cudaError_t e = cudaFuncSetAttribute(k_step_stage<L, S, MRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, StageGeom<L, S>::SMEM_BYTES);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_stage<L, S, MRT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      return (int)e;
+    k.step_stage[0] = k_step_stage<L, S, MRT, 4>;
+    k.step_stage[1] = k_step_stage<L, S, MRT, 6>;
+    k.step_stage[2] = k_step_stage<L, S, MRT, 12>;
+    k.step_stage_adjc = k_step_stage<L, S, MRT, 4, true>;
+    k.build_adjc = k_build_adjc<L, S>;
+    k.step_stage_clc[0] = k_step_stage_clc<L, S, MRT, 4>;
+    k.step_stage_clc[1] = k_step_stage_clc<L, S, MRT, 6>;
+    k.step_stage_clc[2] = k_step_stage_clc<L, S, MRT, 12>;
+    k.set_stage_attrs = [](int variant, int carveout_pct) -> int {
+      auto set2 = [&](auto *kernel, auto *kernel_clc, int bytes) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel_clc, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel_clc, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
+        return e;
+      };
+      if (variant == 0) {
+        cudaError_t e = cudaFuncSetAttribute(k_step_stage<L, S, MRT, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, StageGeom<L, S, 4, true>::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_stage<L, S, MRT, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
+        if (e != cudaSuccess) return (int)e;
+        return (int)set2(k_step_stage<L, S, MRT, 4>, k_step_stage_clc<L, S, MRT, 4>, StageGeom<L, S, 4>::SMEM_BYTES);
+      }
+      if (variant == 1) return (int)set2(k_step_stage<L, S, MRT, 6>, k_step_stage_clc<L, S, MRT, 6>, StageGeom<L, S, 6>::SMEM_BYTES);
+      return (int)set2(k_step_stage<L, S, MRT, 12>, k_step_stage_clc<L, S, MRT, 12>, StageGeom<L, S, 12>::SMEM_BYTES);
     };
     k.moments_pull = k_moments_pull<L, S, false>;
     k.pull_stream = k_moments_pull<L, S, true>;
@@ -180,14 +207,18 @@ KernelSet make_kernel_set(const char *name) {
     k.set_band_pull_smem = nullptr;
     k.moments_pull = nullptr;
     k.pull_stream = nullptr;
-    k.step_stage = nullptr;
+    for (int v = 0; v < 3; ++v) k.step_stage[v] = nullptr, k.step_stage_clc[v] = nullptr;
+    k.step_stage_adjc = nullptr;
+    k.build_adjc = nullptr;
     k.set_stage_attrs = nullptr;
   }
-  k.stage_threads = StageGeom<L, S>::NT;
-  k.stage_chunk = StageGeom<L, S>::NW * StageGeom<L, S>::NPW;  // positions one round of a block covers
-  k.stage_smem = StageGeom<L, S>::SMEM_BYTES;
+  k.stage_warps[0] = 4, k.stage_warps[1] = 6, k.stage_warps[2] = 12;
+  k.stage_smem_v[0] = StageGeom<L, S, 4>::SMEM_BYTES, k.stage_smem_v[1] = StageGeom<L, S, 6>::SMEM_BYTES, k.stage_smem_v[2] = StageGeom<L, S, 12>::SMEM_BYTES;
+  k.stage_blocks_v[0] = StageGeom<L, S, 4>::BLOCKS_PER_SM, k.stage_blocks_v[1] = StageGeom<L, S, 6>::BLOCKS_PER_SM;
+  k.stage_blocks_v[2] = StageGeom<L, S, 12>::BLOCKS_PER_SM;
   k.stage_item = StageGeom<L, S>::ITEM;
-  k.stage_blocks_per_sm = StageGeom<L, S>::BLOCKS_PER_SM;
+  k.adjc_rec_bytes = AdjcGeom<L, S>::REC_BYTES;
+  k.stage_smem_adjc = StageGeom<L, S, 4, true>::SMEM_BYTES;
   k.stage_rows_f = StageGeom<L, S>::NF;
   k.stage_rows_a = StageGeom<L, S>::NA;
   k.fused_threads = TXG_FUSED_THREADS;

@@ -5,6 +5,7 @@ tests/bubble_2D/reference_solution/fi001.dat: full distribution function after 1
 steps of the shipped D2Q9 two-component bubble (the file `make test` compares with
 src/testing/check_solution.py at eps = 1e-5)."""
 import numpy as np
+import pytest
 
 import cases
 
@@ -71,3 +72,24 @@ def test_mrt_rows_orthogonal():
         gram = lat["mt"] @ lat["mt"].T
         assert np.array_equal(gram, np.diag(lat["mmt"]))
         assert abs(lat["weights"].sum() - 1.0) < 1e-15
+
+
+@pytest.mark.parametrize("stem", ["c3_bubble3d_256_1000", "c4_porous_256_1000"])
+def test_large_golden_samples_are_well_formed(stem):
+    """The committed samples of the oracle's 256^3 x 1000-step runs (tests/golden/make_large_golden.py) that the GPU parity tests read:
+    shapes, finiteness, sorted unique node indices inside the box, positive mass."""
+    import json
+    from pathlib import Path
+
+    path = Path(__file__).resolve().parent / "golden" / (stem + ".npz")
+    if not path.exists():
+        pytest.skip("sample not generated")
+    g = np.load(path)
+    meta = json.loads(str(g["meta"]))
+    nodes = int(np.prod(meta["box"]))
+    idx = g["idx"]
+    assert meta["steps"] == 1000 and idx.ndim == 1 and np.all(np.diff(idx) > 0) and 0 <= idx[0] and idx[-1] < nodes
+    assert g["rho"].shape == (idx.size, 2) and g["u"].shape[0] == idx.size and g["fi"].shape[1] == 38
+    for k in ("rho", "u", "fi", "mass"):
+        assert np.isfinite(g[k]).all(), k
+    assert (g["mass"] > 0).all() and (g["rho"] >= 0).all()

@@ -71,3 +71,58 @@ def test_bubble_3d_as_shipped_128_cubed_100_steps():
 
 def test_bubble_3d_256_cubed_50_steps():
     _compare("C3 bubble_3D scaled to 256^3 (SRT)", *cases.bubble_3d(256, hw=20), steps=50)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# 256^3 x 1000 steps against committed samples of the oracle's result (tests/golden/make_large_golden.py made them in the build
+# container: 1.5 h of oracle time per case does not fit the GPU box's clock).  Same deterministic builders, same seeds.
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _compare_golden(name, stem, cfg, walls, rho, steps):
+    path = os.path.join(GOLD, stem + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("no golden sample %s (tests/golden/make_large_golden.py)" % stem)
+    g = np.load(path)
+    meta = json.loads(str(g["meta"]))
+    assert meta["box"] == [cfg.NX, cfg.NY, cfg.NZ] and meta["steps"] == steps, meta
+    t0 = time.time()
+    flow = gpu_util.make_flow(cfg, walls, rho)
+    flow.step(steps)
+    fi, r, u, F = gpu_util.fields(flow)
+    t_gpu = time.time() - t0
+    n = np.asarray(walls).size
+    idx = g["idx"]
+    fluid = np.asarray(walls).reshape(-1) == 0
+    assert fluid[idx].all()
+    errs = {
+        "rho": float(np.abs(r.reshape(n, -1)[idx] - g["rho"]).max() / g["rho_max"].max()),
+        "u": float(np.abs(u.reshape(n, -1)[idx] - g["u"]).max() / g["u_max"]),
+        "fi": float(np.abs(fi.reshape(n, -1)[idx[:g["fi"].shape[0]]] - g["fi"]).max() / g["fi_max"]),
+    }
+    fl3 = fluid.reshape(r.shape[:3])
+    m0 = gpu_util.mass(np.asarray(rho).reshape(r.shape), fl3)
+    m1 = gpu_util.mass(r, fl3)
+    drift = float(np.max(np.abs(m1 - m0) / np.abs(m0)))
+    kernels = {k: int(v[1]) for k, v in flow.kernel_times().items()}
+    flow.close()
+    rec = {"case": name, "box": [cfg.NX, cfg.NY, cfg.NZ], "steps": steps, "against": "tests/golden/%s.npz" % stem, "sampled_nodes": int(idx.size),
+           "max_rel_err": errs, "mass_drift_rel": drift, "tol": TOL, "oracle_s": meta["oracle_s"], "oracle_threads": meta["threads"],
+           "gpu_s_incl_transfers": round(t_gpu, 1), "kernels": kernels}
+    print(json.dumps(rec))
+    if os.environ.get("TXG_PARITY_LOG"):
+        with open(os.environ["TXG_PARITY_LOG"], "a") as fh:
+            fh.write(json.dumps(rec) + "\n")
+    for k, v in errs.items():
+        assert v <= TOL, (k, v, errs)
+    assert drift <= 1e-12, drift
+
+
+def test_bubble_3d_256_cubed_1000_steps_vs_golden_sample():
+    """BASELINE.json configs[2] at its full size and the north star's 1000 steps."""
+    _compare_golden("C3 bubble_3D scaled to 256^3 (SRT), 1000 steps", "c3_bubble3d_256_1000", *cases.bubble_3d(256, hw=20), steps=1000)
+
+
+def test_c4_recipe_256_cubed_1000_steps_vs_golden_sample():
+    """The C4 recipe on the 256^3 sample SURVEY.md 8d names, 1000 steps."""
+    _compare_golden("C4 porous MRT 3 minerals body force, 256^3", "c4_porous_256_1000", *cases.porous_3d(256), steps=1000)

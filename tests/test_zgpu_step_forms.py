@@ -1,6 +1,10 @@
 """The forms of the order-4 step on the device give the same bits:
   * stage (default for 1, 2 and 4 components): k_step_stage -- populations, adjacency rows and mask of a warp's next item
     fetched by two tensor copies (TMA) into the warp's double buffer in shared memory while the current item is collided
+  * clc (TXG_STAGE_CLC=1/0): k_step_stage_clc -- the staged form whose blocks take over the next block of the grid through
+    cluster launch control instead of ending, so that every item of a warp but its first is prefetched
+  * adjc (TXG_STAGE_ADJC=1/0): k_step_stage fed with one compressed adjacency record per item (bases + byte offsets, 27 instead of
+    76 bytes per node) instead of the adjacency and mask rows
   * table (TXG_STAGE=0; the default for 3 and 5 components): k_step_fused (per-node adjacency table, every operand by
     demand loads)
   * band / push (opt-in TXG_BAND=1): k_step_band (bit rows instead of the table, density windows in shared memory)
@@ -19,12 +23,14 @@ from taxila_lbm_b200 import geometry as geo
 
 pytestmark = pytest.mark.gpu
 
-FORMS = {"table": dict(TXG_STAGE="0"), "stage": {}, "push": dict(TXG_BAND="1"), "pull": dict(TXG_BAND="1", TXG_PULL="1")}
-KERNEL = {"table": "k_step_fused", "stage": "k_step_stage", "push": "k_step_band", "pull": "k_step_band_pull"}
+FORMS = {"table": dict(TXG_STAGE="0"), "stage": dict(TXG_STAGE_CLC="0", TXG_STAGE_ADJC="0"), "adjc": dict(TXG_STAGE_CLC="0", TXG_STAGE_ADJC="1"),
+         "clc": dict(TXG_STAGE_CLC="1"), "push": dict(TXG_BAND="1"), "pull": dict(TXG_BAND="1", TXG_PULL="1")}
+KERNEL = {"table": "k_step_fused", "stage": "k_step_stage", "adjc": "k_step_stage", "clc": "k_step_stage_clc", "push": "k_step_band",
+          "pull": "k_step_band_pull"}
 
 
 def run(cfg, walls, rho, form, monkeypatch, chunks, peek=False):
-    for k in ("TXG_BAND", "TXG_PULL", "TXG_STAGE", "TXG_BAND_LB", "TXG_LAG", "TXG_RHOTILE", "TXG_SPLIT"):
+    for k in ("TXG_BAND", "TXG_PULL", "TXG_STAGE", "TXG_STAGE_CLC", "TXG_STAGE_ADJC", "TXG_STAGE_PG", "TXG_STAGE_WARPS", "TXG_BAND_LB", "TXG_LAG", "TXG_RHOTILE", "TXG_SPLIT"):
         monkeypatch.delenv(k, raising=False)
     for k, v in FORMS[form].items():
         monkeypatch.setenv(k, v)
@@ -75,9 +81,9 @@ def test_forms_bit_identical(monkeypatch, case):
     steps = 20
     ref, _, k0 = run(cfg, walls, rho, "table", monkeypatch, (steps,))
     assert k0[KERNEL["table"]][1] == steps, k0
-    for form in ("stage", "push", "pull"):
+    for form in ("stage", "adjc", "clc", "push", "pull"):
         out, _, kt = run(cfg, walls, rho, form, monkeypatch, (3, 1, steps - 4))
-        if form == "stage" and cfg.ncomponents == 3:
+        if form in ("stage", "adjc", "clc") and cfg.ncomponents == 3:
             assert kt["k_step_fused"][1] == steps, kt  # (10 positions per item: the staged form is not offered, the table kernel runs)
         else:
             assert kt[KERNEL[form]][1] == steps, (form, kt)
@@ -153,11 +159,65 @@ def test_staged_form_on_a_box_whose_planes_straddle_items(monkeypatch):
         assert np.array_equal(a, b)
     for a, b in zip(ref, out):
         assert np.array_equal(a, b)
+    outc, _, kt = run(cfg, walls, rho, "clc", monkeypatch, (15,))
+    assert kt["k_step_stage_clc"][1] == 15, kt
+    for a, b in zip(ref, outc):
+        assert np.array_equal(a, b)
+    # 10 k items: more blocks than are resident at once, so that the blocks of the clc form do take over later ones
     cfg, walls, rho = cases.porous_3d(96, 96, 40, rmin=4.0, rmax=9.0)
     ref, _, _ = run(cfg, walls, rho, "table", monkeypatch, (6,))
-    out, _, kt = run(cfg, walls, rho, "stage", monkeypatch, (2, 4))
-    for a, b in zip(ref, out):
-        assert np.array_equal(a, b)
+    for form in ("stage", "adjc", "clc"):
+        out, _, kt = run(cfg, walls, rho, form, monkeypatch, (2, 4))
+        for a, b in zip(ref, out):
+            assert np.array_equal(a, b), form
+
+
+def test_compressed_adjacency_escape_items(monkeypatch):
+    """TXG_STAGE_ADJC=1 on boxes whose rows are longer than 256 fluid nodes and periodic in x: the items at the two ends of a row
+    hold neighbour positions a whole row apart, their byte offsets overflow and the lanes fall back to the full table; and on a box
+    with clipped items at both ends of the owned range."""
+    for cfg, walls, rho in (cases.bubble_3d(288, 4), cases.porous_3d(40, 24, 20, rmin=3.0, rmax=6.0)):
+        ref, _, _ = run(cfg, walls, rho, "table", monkeypatch, (8,))
+        out, _, kt = run(cfg, walls, rho, "adjc", monkeypatch, (3, 5))
+        assert kt["k_step_stage"][1] == 8, kt
+        for a, b in zip(ref, out):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("form", ["stage", "adjc", "clc"])
+def test_staged_forms_with_gather_prefetch(monkeypatch, form):
+    """TXG_STAGE_PG=1: a warp prefetches the densities and the wall record of its next item into L1 while it collides the current one
+    (it waits for the next item's adjacency in the middle of the current item): same bits, blocks of 1, 2 and 5 rounds."""
+    cfg, walls, rho = cases.porous_3d(96, 96, 40, rmin=4.0, rmax=9.0)
+    ref, _, _ = run(cfg, walls, rho, "table", monkeypatch, (6,))
+    for rounds in (1, 2, 5):
+        FORMS["_pg"] = dict(FORMS[form], TXG_STAGE_PG="1", TXG_STAGE_ROUNDS=str(rounds))
+        try:
+            out, _, kt = run(cfg, walls, rho, "_pg", monkeypatch, (2, 4))
+        finally:
+            del FORMS["_pg"]
+            monkeypatch.delenv("TXG_STAGE_ROUNDS", raising=False)
+        assert kt[KERNEL[form]][1] == 6, kt
+        for a, b in zip(ref, out):
+            assert np.array_equal(a, b), (form, rounds)
+
+
+@pytest.mark.parametrize("warps", [6, 12])
+def test_staged_block_shapes(monkeypatch, warps):
+    """The staged K2 with 6 warps x 2 blocks and 12 warps x 1 block per SM (TXG_STAGE_WARPS; room for L1), static blocks and
+    blocks that take over the next one (TXG_STAGE_CLC=1), short and long blocks: the same bits as the table kernel."""
+    cfg, walls, rho = cases.porous_3d(96, 96, 40, rmin=4.0, rmax=9.0)
+    ref, _, _ = run(cfg, walls, rho, "table", monkeypatch, (6,))
+    for form, rounds in (("stage", 2), ("stage", 5), ("clc", 1), ("clc", 4)):
+        FORMS["_shape"] = dict(FORMS[form], TXG_STAGE_WARPS=str(warps), TXG_STAGE_ROUNDS=str(rounds))
+        try:
+            out, _, kt = run(cfg, walls, rho, "_shape", monkeypatch, (2, 4))
+        finally:
+            del FORMS["_shape"]
+            monkeypatch.delenv("TXG_STAGE_ROUNDS", raising=False)
+        assert kt[KERNEL[form]][1] == 6, kt
+        for a, b in zip(ref, out):
+            assert np.array_equal(a, b), (form, rounds)
 
 
 @pytest.mark.parametrize("case", ["porous_iso8", "closed_iso8", "hots_2d_iso10", "bubble_2d_iso8", "s3_iso8"])
