@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 evidence on one B200 (gpurun --timeout 2400 -- tools/gpu_r2_evidence.sh): the whole -m gpu suite incl. the large-size
 # oracle comparisons, the default bench line, the CPU arm, the ncu launch list of the same command, one full ncu capture per hot kernel.
-O=gpurun_out; R=r2z
+O=gpurun_out; R=${R:-r2zz}
 mkdir -p $O /tmp/txg_cache
 export TXG_CASE_CACHE=/tmp/txg_cache
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $O/${R}_nvsmi.csv 2>&1
