@@ -353,7 +353,11 @@ def main():
         t0 = time.perf_counter()
         marks = [("start", t0)]
 
+        sync_marks = os.environ.get("TXG_BENCH_SYNC_MARKS") == "1"  # diagnosis only: wait for the device at every mark
+
         def mark(name):  # (host clock; the calls before a mark are synchronous except the steps, which the last mark covers)
+            if sync_marks:
+                flow.synchronize()
             marks.append((name, time.perf_counter()))
 
         flow.walls_set_values(walls_rg)
@@ -361,6 +365,8 @@ def main():
         flow.initialize_state(rho_rg)
         mark("initialize_state")
         flow.fi_init()
+        if sync_marks:
+            mark("fi_init")
         flow.update_moments()
         mark("fi_init+update_moments (queued)")
         for _ in range(args.steps):

@@ -2159,8 +2159,25 @@ extern "C" int txg_get_diagnostics(txg_handle h, double *rhot, double *prs, doub
   if (rhot) TXG_TRY(ensure(h, &h->x_rhot, n));
   if (prs) TXG_TRY(ensure(h, &h->x_prs, n));
   if (velt) TXG_TRY(ensure(h, &h->x_velt, n * h->D));
-  TXG_TRY(run_export(h, nullptr, nullptr, nullptr, rhot ? h->x_rhot : nullptr, prs ? h->x_prs : nullptr, velt ? h->x_velt : nullptr));
-  // the export kernel writes all three fields in the host arrays' own (natural, owned-only) layout: three plain copies
+  const bool fast = h->fused && h->ks.export_diag_fused && h->nbr_all && h->lmask && !h->band && !h->pull && !h->lag && !h->bc_mode && !h->bc_fused &&
+                    !h->has_reflecting && getenv("TXG_EXPORT_GENERIC") == nullptr;
+  if (fast) {
+    // fused path: the fluid nodes by one lane per (node, component) over the position-indexed rows, the solid nodes by a fill
+    ScopedKernel sk(h, "k_export_diag_fused", h->s_main);
+    k_export_fill_solid<<<blocks_for(g.nnodes, 256), 256, 0, h->s_main>>>(g, h->nbmask, h->D, rhot ? h->x_rhot : nullptr, prs ? h->x_prs : nullptr,
+                                                                          velt ? h->x_velt : nullptr, h->cfg.null_pressure);
+    TXG_CUDA(h, cudaGetLastError());
+    const long long nown = g.own1 - g.own0;
+    if (nown) {
+      h->ks.export_diag_fused<<<hot_blocks(h, nown), 128, 0, h->s_main>>>(g, h->p, h->f[h->cur], h->rho, h->lmask, h->nbr_all, h->wallrec, g.own0, nown,
+                                                                          rhot ? h->x_rhot : nullptr, prs ? h->x_prs : nullptr,
+                                                                          velt ? h->x_velt : nullptr);
+      TXG_CUDA(h, cudaGetLastError());
+    }
+  } else {
+    TXG_TRY(run_export(h, nullptr, nullptr, nullptr, rhot ? h->x_rhot : nullptr, prs ? h->x_prs : nullptr, velt ? h->x_velt : nullptr));
+  }
+  // the export kernels write all three fields in the host arrays' own (natural, owned-only) layout: three plain copies
   if (rhot) TXG_CUDA(h, cudaMemcpyAsync(rhot, h->x_rhot, n * 8, cudaMemcpyDeviceToHost, h->s_main));
   if (prs) TXG_CUDA(h, cudaMemcpyAsync(prs, h->x_prs, n * 8, cudaMemcpyDeviceToHost, h->s_main));
   if (velt) TXG_CUDA(h, cudaMemcpyAsync(velt, h->x_velt, n * h->D * 8, cudaMemcpyDeviceToHost, h->s_main));

@@ -67,6 +67,8 @@ struct KernelSet {
   // 4 warps x 4 blocks with the compressed adjacency records (AdjcGeom) instead of the adjacency + mask rows; their builder
   void (*step_stage_adjc)(Grid, Phys, const CUtensorMap, const CUtensorMap, double *, const double *, const double *, long long, long long,
                           long long, int, int, const double *, const uint32_t *, const unsigned char *, const uint32_t *, int);
+  void (*export_diag_fused)(Grid, Phys, const double *, const double *, const uint32_t *, const uint32_t *, const double *, long long, long long,
+                            double *, double *, double *);
   void (*build_adjc)(Grid, const uint32_t *, const uint32_t *, unsigned char *, long long, long long);
   int adjc_rec_bytes, stage_smem_adjc;
   // the same with blocks that take over the next block of the grid (cluster launch control)
@@ -138,6 +140,7 @@ KernelSet make_kernel_set(const char *name) {
     k.step_fused = k_step_fused<L, S, MRT, false>;
     k.step_fused_pair = k_step_fused<L, S, MRT, true>;
     k.fi_init_fused = k_fi_init_fused<L, S>;
+    k.export_diag_fused = k_export_diag_fused<L, S>;
     k.step_fused_lag = k_step_fused_lag<L, S, MRT, false>;
     if constexpr (S <= 3) {  // (the density tiles of the opt-in experiments are static shared memory: S * 12 KB)
       k.step_fused_lag_tile = k_step_fused_lag<L, S, MRT, true>;
@@ -194,6 +197,7 @@ KernelSet make_kernel_set(const char *name) {
     k.step_fused = nullptr;
     k.step_fused_pair = nullptr;
     k.fi_init_fused = nullptr;
+    k.export_diag_fused = nullptr;
     k.step_fused_lag = nullptr;
     k.step_fused_lag_tile = nullptr;
     k.build_rtab_lag = nullptr;

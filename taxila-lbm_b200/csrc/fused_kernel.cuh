@@ -729,6 +729,83 @@ __global__ void __launch_bounds__(128, 4)
   for (int n = 0; n < Q; ++n) dst[(long long)n * g.fs] = (1. - 0.5 * pref[n]) * feq[n];
 }
 
+// FlowUpdateDiagnosticsD* (lbm_flow.F90:654-758) for the fused path: rhot, prs and velt of the FLUID nodes, one lane per (fluid node,
+// component) like the step kernel -- populations as position-aligned rows, forces through the adjacency table and the wall records, the
+// component sums by shuffles in ascending component order.  The solid nodes of the dense output arrays are filled by
+// k_export_fill_solid.  (k_export walks the dense box, holds both components of a node in one thread and looks every neighbour up
+// through the position map and the class bytes: 27 ms at 512^3 against this kernel's few; it stays the path of the face-BC modes, of
+// the wide stencils and of rho / u / forces exports.)  Same formulas in the same order as k_export.
+template <class L, int S>
+__global__ void __launch_bounds__(128, 4)
+    k_export_diag_fused(Grid g, Phys p, const double *__restrict__ fA, const double *__restrict__ psi, const uint32_t *__restrict__ lmask,
+                        const uint32_t *__restrict__ nbr_all, const double *__restrict__ wallrec, long long first, long long count,
+                        double *__restrict__ rhot, double *__restrict__ prs, double *__restrict__ velt /*[nnodes][D]*/) {
+  constexpr int Q = L::Q, D = L::D;
+  Item it;
+  if (!item_of_lane<S>(first, count, it)) return;
+  const uint32_t mask = __ldg(lmask + it.pos);
+  unsigned npos[Q];
+  npos[0] = (unsigned)it.pos;
+#pragma unroll
+  for (int n = 1; n < Q; ++n) npos[n] = __ldg(nbr_all + (long long)(n - 1) * g.fs + it.pos);
+  double f[Q];
+  const double *src = fA + (long long)it.m * Q * g.fs + it.pos;
+#pragma unroll
+  for (int n = 0; n < Q; ++n) f[n] = load_population(src + (long long)n * g.fs);
+  double r = 0.;
+#pragma unroll
+  for (int n = 0; n < Q; ++n) r += f[n];
+  const double *psi_field = psi + (long long)it.m * g.fs;
+  const double psi_m = p.eos ? __ldg(psi_field + it.pos) : r;
+  double F[D];
+  forces1_inline<L, S, 4>(g, p, psi_field, nullptr, wallrec, it, 0u, 0, 0, mask, npos, r, psi_m, F);
+  // rhot = sum_m rho_m mm_m
+  const double rmm = r * p.mm[it.m];
+  double rt = 0.;
+#pragma unroll
+  for (int k = 0; k < S; ++k) rt += from_component<S>(rmm, k, it.j);
+  // prs = rhot / 3 + (c_0 / 2) sum_m psi_m sum_m' g_mm' psi_m'
+  double pr = rt / 3.;
+  if (p.eos || S > 1) {
+    const double ps_own = p.eos ? eos_psi(p, it.m, r) : r;
+    double ps[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) ps[k] = from_component<S>(ps_own, k, it.j);
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      double acc = 0.;
+#pragma unroll
+      for (int kp = 0; kp < S; ++kp) acc += p.gf[k][kp] * ps[kp];
+      pr = pr + 6.0 / 2. * ps[k] * acc;
+    }
+  }
+  // velt_d = sum_m (j_m,d + F_m,d / 2) mm_m / rhot
+  double vt[D];
+  static_for<0, D>([&](auto d_) {
+    constexpr int d = decltype(d_)::value;
+    double j = 0.;
+    static_for<0, Q>([&](auto n_) {
+      constexpr int n = decltype(n_)::value;
+      if constexpr (L::c(n, d) != 0) j += f[n] * (double)L::c(n, d);
+    });
+    const double term = (j + .5 * F[d]) * p.mm[it.m];
+    double a = 0.;
+#pragma unroll
+    for (int k = 0; k < S; ++k) a += from_component<S>(term, k, it.j);
+    vt[d] = a / rt;
+  });
+  if (!it.active) return;
+  const long long o = (g.list ? (long long)__ldg(g.list + it.pos) : it.pos) - (long long)g.Rz * g.plane;
+  if (it.m == 0) {
+    if (rhot) rhot[o] = rt;
+    if (prs) prs[o] = pr;
+  }
+  if (it.m == S - 1 && velt) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) velt[o * D + d] = vt[d];
+  }
+}
+
 // Adjacency table (one thread per owned position): nbr[(n-1)*fs + pos] = position of X + c_n, with
 // the periodic wrap in x and y applied.  For a solid or out-of-domain neighbour the entry is some
 // valid position that the mask bit keeps from being used.

@@ -315,15 +315,16 @@ __device__ __forceinline__ void common_velocity(const Phys &p, const double (&f)
   }
 }
 
-// equilibrium (DiscretizationEquilf_D3Q19/D2Q9) for one component
+// equilibrium (DiscretizationEquilf_D3Q19/D2Q9) for one component.  The reference divides by c_s2 = 1/3 and 2 c_s2^2; here the
+// factors 3 and 4.5 are multiplied in, as collide1 does (a correctly rounded fp64 division is ~20 instructions and a branch: with the
+// 37 divisions of the literal form FlowFiInit took 20 ms at 512^3, profiles/r2aj_e2e_sync_marks.json; the difference is one rounding).
 template <class L>
 __device__ __forceinline__ void equilibrium(double rho, double d_k, const double (&u)[L::D], double (&feq)[L::Q]) {
-  constexpr double c_s2 = 1.0 / 3.0;
   double usqr = 0.;
 #pragma unroll
   for (int d = 0; d < L::D; ++d) usqr += u[d] * u[d];
   feq[0] = rho * L::feq0(d_k, usqr);
-  const double base = 1.5 * (1. - d_k) - usqr / (2. * c_s2);
+  const double base = 1.5 * (1. - d_k) - 1.5 * usqr;
   static_for<1, L::Q>([&](auto n_) {
     constexpr int n = decltype(n_)::value;
     double udote = 0.;
@@ -331,7 +332,7 @@ __device__ __forceinline__ void equilibrium(double rho, double d_k, const double
       constexpr int d = decltype(d_)::value;
       if constexpr (L::c(n, d) != 0) udote += (double)L::c(n, d) * u[d];
     });
-    feq[n] = L::w(n) * rho * (base + udote / c_s2 + udote * udote / (2. * c_s2 * c_s2));
+    feq[n] = L::w(n) * rho * (base + 3. * udote + 4.5 * (udote * udote));
   });
 }
 
@@ -339,7 +340,7 @@ __device__ __forceinline__ void equilibrium(double rho, double d_k, const double
 template <class L>
 __device__ __forceinline__ void prefactor(double rho, const double (&F)[L::D], const double (&u)[L::D],
                                           double (&pref)[L::Q]) {
-  const double inv = 1. / (rho * (1.0 / 3.0));
+  const double inv = 3.0 / rho;  // 1 / (rho c_s2)
   static_for<0, L::Q>([&](auto n_) {
     constexpr int n = decltype(n_)::value;
     double a = 0.;

@@ -209,4 +209,15 @@ __global__ void k_build_xrow(Grid g, long long pos0, long long nstore, uint32_t 
   xrow[pos] = x | ((zz * (unsigned)(g.NY + 2) + y + 1u) << BITROW_XBITS);
 }
 
+// the solid nodes of the dense diagnostics arrays: rhot = 0, prs = null_pressure, velt = 0 (what k_export writes there)
+__global__ void k_export_fill_solid(Grid g, const uint32_t *__restrict__ nbmask, int D, double *__restrict__ rhot, double *__restrict__ prs,
+                                    double *__restrict__ velt, double null_pressure) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= g.nnodes || !(nbmask[o] >> 31)) return;
+  if (rhot) rhot[o] = 0.;
+  if (prs) prs[o] = null_pressure;
+  if (velt)
+    for (int d = 0; d < D; ++d) velt[o * D + d] = 0.;
+}
+
 }  // namespace txg

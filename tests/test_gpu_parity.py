@@ -274,6 +274,39 @@ def test_diagnostics_vs_oracle():
     assert gpu_util.rel_err(velt, ovelt) <= TOL
 
 
+@pytest.mark.parametrize("case", ["porous", "bubble_2d", "eos", "closed"])
+def test_fused_diagnostics_export_equals_the_generic_one(monkeypatch, case):
+    """FlowUpdateDiagnostics on the fused path (k_export_diag_fused: one lane per fluid node and component over the position-indexed
+    rows + a fill of the solid nodes) against the generic k_export (TXG_EXPORT_GENERIC=1, read at the call) on the same device state,
+    and against the oracle."""
+    if case == "porous":
+        cfg, walls, rho = cases.porous_3d(40, 24, 20, rmin=3.0, rmax=6.0)
+    elif case == "bubble_2d":
+        cfg, walls, rho = cases.bubble_2d(64)
+    elif case == "closed":
+        cfg, walls, rho = cases.porous_3d(24, rmin=3.0, rmax=6.0, periodic=(0, 1, 0))
+    else:
+        cfg, walls, rho = cases.porous_3d(32, rmin=4.0, rmax=8.0)
+        cfg.use_nonideal_eos = 1
+        for m in range(2):
+            cfg.eos_type[m] = tc.EOS_SC
+            cfg.eos_rho0[m] = 0.8 + 0.3 * m
+    monkeypatch.delenv("TXG_EXPORT_GENERIC", raising=False)
+    flow = gpu_util.make_flow(cfg, walls, rho)
+    flow.step(15)
+    fast = [a.copy() for a in flow.update_diagnostics()]
+    assert flow.kernel_times()["k_export_diag_fused"][1] == 1
+    monkeypatch.setenv("TXG_EXPORT_GENERIC", "1")
+    slow = [a.copy() for a in flow.update_diagnostics()]
+    assert flow.kernel_times()["k_export"][1] >= 1
+    flow.close()
+    o = cases.run_oracle(cfg, walls, rho, 15)
+    for a, b, c, name in zip(fast, slow, o.diagnostics(), ("rhot", "prs", "velt")):
+        assert gpu_util.rel_err(a, b) <= 1e-14, (name, gpu_util.rel_err(a, b))
+        assert gpu_util.rel_err(a, c) <= TOL, name
+        assert np.array_equal(a == 0, b == 0) or name == "prs"
+
+
 def test_delta_norm_vs_oracle():
     cfg, walls, rho = cases.bubble_3d(16, hw=3)
     o = cases.run_oracle(cfg, walls, rho, 5)
