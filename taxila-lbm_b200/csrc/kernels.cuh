@@ -317,7 +317,7 @@ __device__ __forceinline__ void common_velocity(const Phys &p, const double (&f)
 
 // equilibrium (DiscretizationEquilf_D3Q19/D2Q9) for one component.  The reference divides by c_s2 = 1/3 and 2 c_s2^2; here the
 // factors 3 and 4.5 are multiplied in, as collide1 does (a correctly rounded fp64 division is ~20 instructions and a branch: with the
-// 37 divisions of the literal form FlowFiInit took 20 ms at 512^3, profiles/r2aj_e2e_sync_marks.json; the difference is one rounding).
+// 37 divisions of the literal form FlowFiInit took 20 ms at 512^3, profiles/r2aj_e2e_sync_marks_before.json -> r2ak_e2e_sync_marks.json; the difference is one rounding).
 template <class L>
 __device__ __forceinline__ void equilibrium(double rho, double d_k, const double (&u)[L::D], double (&feq)[L::Q]) {
   double usqr = 0.;
